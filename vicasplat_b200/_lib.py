@@ -1,0 +1,139 @@
+"""ctypes binding of the C-ABI in ``include/vicasplat_b200.h``.
+
+There is no CPU fallback: if the shared library is missing or a symbol is absent, loading raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import re
+from pathlib import Path
+
+_ROOT = Path(__file__).resolve().parent
+LIB_PATH = _ROOT / "lib" / "libvicasplat_b200.so"
+HEADER_PATH = _ROOT.parent / "include" / "vicasplat_b200.h"
+
+VS_F32, VS_BF16, VS_F16, VS_F64 = 0, 1, 2, 3
+VS_ACT_NONE, VS_ACT_GELU, VS_ACT_RELU = 0, 1, 2
+
+_vp, _i32, _i64, _f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+
+
+class GemmParams(C.Structure):
+    _fields_ = [
+        ("A", _vp), ("a_mode", _i32), ("a_rows", _i32), ("a_groups", _i32),
+        ("a_row_stride", _i64), ("a_group_stride", _i64),
+        ("cn", _i32), ("ch", _i32), ("cw", _i32), ("cin", _i32), ("kh", _i32), ("kw", _i32),
+        ("pad", _i32),
+        ("W", _vp), ("w_row_stride", _i64), ("N", _i32), ("K", _i32),
+        ("bias", _vp), ("act", _i32),
+        ("gate", _vp), ("gate_ld", _i64), ("gate_rows", _i32), ("first_row_mode", _i32),
+        ("res1", _vp), ("res2", _vp), ("res_dtype", _i32), ("res_ld", _i64),
+        ("C", _vp), ("c_dtype", _i32), ("ldc", _i64),
+        ("C2", _vp), ("ldc2", _i64),
+        ("out_gin", _i32), ("out_gout", _i32), ("out_off", _i32), ("block_n", _i32),
+    ]
+
+
+class LayerNormParams(C.Structure):
+    _fields_ = [
+        ("x", _vp), ("ldx", _i64), ("rows", _i32), ("C", _i32),
+        ("w", _vp), ("b", _vp), ("w0", _vp), ("b0", _vp),
+        ("scale", _vp), ("shift", _vp), ("mod_ld", _i64), ("rows_per_frame", _i32),
+        ("eps", _f32), ("normalize", _i32),
+        ("y_bf16", _vp), ("ldy_bf16", _i64), ("y_f32", _vp), ("ldy_f32", _i64),
+    ]
+
+
+class AttentionParams(C.Structure):
+    _fields_ = [
+        ("Q", _vp), ("K", _vp), ("V", _vp), ("O", _vp),
+        ("ldq", _i64), ("ldk", _i64), ("ldv", _i64), ("ldo", _i64),
+        ("q_rows", _i32), ("kv_rows", _i32), ("heads", _i32), ("items", _i32),
+        ("q_start", _vp), ("q_len", _vp), ("kv_start0", _vp), ("kv_len0", _vp),
+        ("kv_start1", _vp), ("kv_len1", _vp),
+        ("max_q_len", _i32), ("causal_block", _i32), ("scale", _f32),
+    ]
+
+
+class RasterParams(C.Structure):
+    _fields_ = [
+        ("V", _i32), ("G", _i32), ("H", _i32), ("W", _i32), ("gaussians_shared", _i32),
+        ("means3D", _vp), ("cov3D", _vp), ("opacities", _vp), ("shs", _vp),
+        ("sh_M", _i32), ("sh_degree", _i32), ("sh_stride_coef", _i32), ("sh_stride_chan", _i32),
+        ("colors_precomp", _vp), ("viewmatrix", _vp), ("projmatrix", _vp), ("campos", _vp),
+        ("tanfov", _vp), ("bg", _vp), ("scale_modifier", _f32),
+        ("out_color", _vp), ("out_depth", _vp), ("out_alpha", _vp), ("radii", _vp),
+        ("n_touched", _vp), ("final_T", _vp), ("n_contrib", _vp),
+        ("workspace", _vp), ("workspace_bytes", _i64), ("max_pairs", _i64),
+        ("num_pairs_out", _vp),
+    ]
+
+
+class RasterBwdParams(C.Structure):
+    _fields_ = [
+        ("fwd", RasterParams),
+        ("dL_dcolor", _vp), ("dL_ddepth", _vp), ("dL_dalpha", _vp),
+        ("dL_dmeans3D", _vp), ("dL_dcov3D", _vp), ("dL_dopacity", _vp), ("dL_dshs", _vp),
+        ("dL_dcolors", _vp), ("dL_dtau", _vp),
+    ]
+
+
+STRUCTS = {
+    "vs_gemm_params": GemmParams,
+    "vs_layernorm_params": LayerNormParams,
+    "vs_attention_params": AttentionParams,
+    "vs_raster_params": RasterParams,
+    "vs_raster_bwd_params": RasterBwdParams,
+}
+
+_DECL = re.compile(r"^\s*(?:const\s+char\s*\*|int64_t|int)\s+(vs_\w+)\s*\(", re.M)
+
+
+def declared_symbols() -> list[str]:
+    """Every function the public header declares."""
+    return sorted(set(_DECL.findall(HEADER_PATH.read_text())))
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: run `python __graft_entry__.py` (build()) first. "
+            "vicasplat_b200 has no CPU fallback.")
+    lib = C.CDLL(str(LIB_PATH))
+    missing = [s for s in declared_symbols() if not hasattr(lib, s)]
+    if missing:
+        raise RuntimeError(f"{LIB_PATH} does not export: {missing}")
+    lib.vs_last_error.restype = C.c_char_p
+    lib.vs_raster_workspace_bytes.restype = _i64
+    lib.vs_raster_workspace_bytes.argtypes = [_i32, _i32, _i32, _i32, _i64]
+    lib.vs_struct_size.restype = _i64
+    lib.vs_struct_size.argtypes = [C.c_char_p]
+    for name, cls in STRUCTS.items():
+        n = lib.vs_struct_size(name.encode())
+        if n != C.sizeof(cls):
+            raise RuntimeError(f"ctypes layout of {name} ({C.sizeof(cls)} B) != C layout ({n} B)")
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = "") -> None:
+    """Turn a negative VS_ERR_* code into the RuntimeError the reference ops raise (TORCH_CHECK)."""
+    if rc != 0:
+        msg = load().vs_last_error().decode(errors="replace")
+        raise RuntimeError(f"{what + ': ' if what else ''}{msg} (code {rc})")
+
+
+def ptr(t) -> int | None:
+    """Device pointer of a torch tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def stream_ptr() -> int:
+    import torch
+    return torch.cuda.current_stream().cuda_stream

@@ -1,0 +1,298 @@
+// Flash-style attention for head_dim 64 on tcgen05 (sm_100a).
+//
+// One CTA = one (item, head, 128-query tile).  Warp roles (192 threads):
+//   warp 0      TMA producer: Q tile once, then one K tile and one V tile (128 rows x 64) per step
+//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer:
+//                 S[128x128] = Q K^T   (both operands K-major, 128B-swizzled, straight from TMA)
+//                 O'[128x64] = P V     (P written by the softmax warps as a K-major swizzled tile,
+//                                       V consumed as an MN-major operand: no transpose anywhere)
+//   warps 2..5  softmax: thread r owns query row r (TMEM lane r): two passes over S in TMEM (row
+//               max, then exp2 / row sum / bf16 P -> shared memory), then folds the fresh O' tile
+//               into its fp32 register accumulator with the running-max correction.
+// The exponentials (MUFU) bound this kernel at hd = 64, not the tensor pipe, so S is single
+// buffered and two CTAs per SM interleave their softmax and MMA phases.
+//
+// Replaces: explicit softmax attention croco/blocks.py:105-109; F.scaled_dot_product_attention in
+// VideoCameraAttention / CrossNeighborAttention, backbone_vica.py:116-121,188; the blocked-causal
+// camera mask backbone_vica.py:585-593.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "common.h"
+#include "ptx.cuh"
+#include "tmap.h"
+
+namespace vs {
+namespace {
+
+constexpr int QT = 128;   // queries per CTA
+constexpr int KT = 128;   // keys per step
+constexpr int HD = 64;
+constexpr int TILE_BYTES = 128 * 128;  // 128 rows x 128 B
+constexpr int SMEM_BYTES = 5 * TILE_BYTES /*Q,K,V,P(2)*/ + 1024 /*align*/ + 128 /*barriers*/;
+constexpr int TMEM_COLS = 256;  // S: [0,128)  O': [128,192)
+
+struct AttnDev {
+  __nv_bfloat16* O;
+  long long ldo;
+  const int *q_start, *q_len, *kv_start0, *kv_len0, *kv_start1, *kv_len1;
+  int causal_block;
+  float scale_log2;
+};
+
+__global__ void __launch_bounds__(192, 2)
+    attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                     const __grid_constant__ CUtensorMap tmV, const AttnDev a) {
+  const int item = blockIdx.z, head = blockIdx.y, qt = blockIdx.x;
+  const int q_len = a.q_len[item];
+  if (qt * QT >= q_len) return;  // uniform for the CTA, before any barrier / allocation
+  const int q_row0 = a.q_start[item] + qt * QT;
+  const int s0 = a.kv_start0[item], l0 = a.kv_len0[item];
+  const int s1 = a.kv_start1 ? a.kv_start1[item] : 0, l1 = a.kv_len1 ? a.kv_len1[item] : 0;
+  const int n0 = (l0 + KT - 1) / KT, n1 = (l1 + KT - 1) / KT;
+  const int nt = n0 + n1;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = smem + TILE_BYTES;
+  uint8_t* sV = smem + 2 * TILE_BYTES;
+  uint8_t* sP = smem + 3 * TILE_BYTES;  // two 64-wide k-blocks
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 5 * TILE_BYTES);
+  uint64_t *q_full = bars, *k_full = bars + 1, *k_empty = bars + 2, *v_full = bars + 3,
+           *v_empty = bars + 4, *s_full = bars + 5, *p_full = bars + 6, *o_full = bars + 7;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(q_full, 1);
+    mbar_init(k_full, 1);
+    mbar_init(k_empty, 1);
+    mbar_init(v_full, 1);
+    mbar_init(v_empty, 1);
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 128);
+    mbar_init(o_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(q_full, TILE_BYTES);
+      tma_load_2d(sQ, &tmQ, q_full, head * HD, q_row0);
+      for (int j = 0; j < nt; ++j) {
+        const int row = j < n0 ? s0 + j * KT : s1 + (j - n0) * KT;
+        const uint32_t ph = j & 1;
+        mbar_wait(k_empty, ph ^ 1);
+        mbar_expect_tx(k_full, TILE_BYTES);
+        tma_load_2d(sK, &tmK, k_full, head * HD, row);
+        mbar_wait(v_empty, ph ^ 1);
+        mbar_expect_tx(v_full, TILE_BYTES);
+        tma_load_2d(sV, &tmV, v_full, head * HD, row);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(QT, KT, 0);
+      constexpr uint32_t idesc_o = umma_idesc_bf16(QT, HD, 1);
+      const uint32_t q_addr = smem_u32(sQ), k_addr = smem_u32(sK), v_addr = smem_u32(sV),
+                     p_addr = smem_u32(sP);
+      mbar_wait(q_full, 0);
+      for (int j = 0; j < nt; ++j) {
+        const uint32_t ph = j & 1;
+        mbar_wait(k_full, ph);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k)
+          umma_bf16_ss(tmem_base, umma_desc_k_sw128(q_addr + k * 32),
+                       umma_desc_k_sw128(k_addr + k * 32), idesc_s, k != 0 ? 1u : 0u);
+        umma_commit(k_empty);
+        umma_commit(s_full);
+        mbar_wait(v_full, ph);
+        mbar_wait(p_full, ph);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < KT / 16; ++k)
+          umma_bf16_ss(tmem_base + 128,
+                       umma_desc_k_sw128(p_addr + (k >> 2) * TILE_BYTES + (k & 3) * 32),
+                       umma_desc_mn_sw128(v_addr + k * 2048), idesc_o, k != 0 ? 1u : 0u);
+        umma_commit(v_empty);
+        umma_commit(o_full);
+      }
+    }
+  } else {
+    const int q = warp & 3;  // TMEM lane quarter of this warp
+    const int r = q * 32 + lane;
+    const int grow = q_row0 + r;  // absolute query row
+    const bool row_valid = (qt * QT + r) < q_len;
+    int lim = 0x7fffffff;
+    if (a.causal_block > 0 && (grow % a.causal_block) == 0)
+      lim = (grow / a.causal_block + 1) * a.causal_block;
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    float m = -INFINITY, l = 0.f;
+    float o[HD];
+#pragma unroll
+    for (int i = 0; i < HD; ++i) o[i] = 0.f;
+    uint8_t* p_row = sP + r * 128;
+    const int sw = r & 7;
+
+    for (int j = 0; j < nt; ++j) {
+      const uint32_t ph = j & 1;
+      const int row0 = j < n0 ? s0 + j * KT : s1 + (j - n0) * KT;
+      const int seg_left = j < n0 ? l0 - j * KT : l1 - (j - n0) * KT;
+      const int nvalid = min(min(seg_left, KT), lim - row0);  // keys [0, nvalid) of this tile count
+      mbar_wait(s_full, ph);
+      tc_fence_after();
+      // ---- pass 1: row maximum
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < KT / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(t_lane + c * 32, v);
+        tmem_ld_wait();
+        if (nvalid >= (c + 1) * 32) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c * 32 + i < nvalid) mx = fmaxf(mx, __uint_as_float(v[i]));
+        }
+      }
+      const float m_new = fmaxf(m, mx * a.scale_log2);
+      const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+      // ---- pass 2: probabilities -> bf16 P tile (K-major, 128B swizzle), row sum
+      float rs = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < KT / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(t_lane + c * 32, v);
+        tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float p0 = exp2f(__uint_as_float(v[i]) * a.scale_log2 - m_use);
+          float p1 = exp2f(__uint_as_float(v[i + 1]) * a.scale_log2 - m_use);
+          if (c * 32 + i >= nvalid) p0 = 0.f;
+          if (c * 32 + i + 1 >= nvalid) p1 = 0.f;
+          rs += p0 + p1;
+          const __nv_bfloat162 b2 = __floats2bfloat162_rn(p0, p1);
+          pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&b2);
+        }
+        // columns [c*32, c*32+32) = k-block (c>>1), 16-byte chunks (c&1)*4 .. +3 of the 128-B row
+        uint8_t* blk = p_row + (c >> 1) * TILE_BYTES;
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          const int chunk = ((c & 1) * 4 + ch) ^ sw;
+          *reinterpret_cast<uint4*>(blk + chunk * 16) =
+              make_uint4(pk[ch * 4], pk[ch * 4 + 1], pk[ch * 4 + 2], pk[ch * 4 + 3]);
+        }
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(p_full);
+      const float alpha = exp2f(m - m_use);  // m == -inf -> 0
+      l = l * alpha + rs;
+      m = m_new;
+      // ---- fold O' = P V into the accumulator
+      mbar_wait(o_full, ph);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < HD / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(t_lane + 128 + c * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[c * 32 + i] = o[c * 32 + i] * alpha + __uint_as_float(v[i]);
+      }
+      tc_fence_before();
+    }
+    if (row_valid) {
+      const float inv = l > 0.f ? 1.0f / l : 0.f;
+      __nv_bfloat16* dst = a.O + static_cast<long long>(grow) * a.ldo + head * HD;
+#pragma unroll
+      for (int ch = 0; ch < HD / 8; ++ch) {
+        uint32_t w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const __nv_bfloat162 b2 =
+              __floats2bfloat162_rn(o[ch * 8 + 2 * i] * inv, o[ch * 8 + 2 * i + 1] * inv);
+          w[i] = *reinterpret_cast<const uint32_t*>(&b2);
+        }
+        *reinterpret_cast<uint4*>(dst + ch * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+int make_map(CUtensorMap* map, const void* base, int heads, int rows, long long ld) {
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(heads) * HD, static_cast<cuuint64_t>(rows)};
+  cuuint64_t str[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {HD, 128};
+  return encode_map(map, base, 2, dims, str, box);
+}
+
+}  // namespace
+}  // namespace vs
+
+extern "C" int vs_attention(const vs_attention_params* p, vs_stream_t stream_) {
+  using namespace vs;
+  VS_REQUIRE(p != nullptr, "vs_attention: null params");
+  VS_REQUIRE(p->Q && p->K && p->V && p->O, "vs_attention: null tensor");
+  VS_REQUIRE(p->heads > 0 && p->items >= 0 && p->max_q_len >= 0, "vs_attention: bad sizes");
+  VS_REQUIRE(p->q_start && p->q_len && p->kv_start0 && p->kv_len0,
+             "vs_attention: item arrays missing");
+  VS_REQUIRE((p->kv_start1 == nullptr) == (p->kv_len1 == nullptr),
+             "vs_attention: kv_start1 / kv_len1 go together");
+  VS_REQUIRE(p->ldq % 8 == 0 && p->ldk % 8 == 0 && p->ldv % 8 == 0 && p->ldo % 8 == 0,
+             "vs_attention: leading dimensions must be multiples of 8 elements");
+  VS_REQUIRE(((reinterpret_cast<uintptr_t>(p->Q) | reinterpret_cast<uintptr_t>(p->K) |
+               reinterpret_cast<uintptr_t>(p->V) | reinterpret_cast<uintptr_t>(p->O)) & 15) == 0,
+             "vs_attention: tensors must be 16-byte aligned");
+  VS_REQUIRE(p->q_rows > 0 && p->kv_rows > 0, "vs_attention: q_rows / kv_rows must be positive");
+  if (p->items == 0 || p->max_q_len == 0) return VS_OK;
+  CUtensorMap tmQ, tmK, tmV;
+  int rc = make_map(&tmQ, p->Q, p->heads, p->q_rows, p->ldq);
+  if (rc) return rc;
+  rc = make_map(&tmK, p->K, p->heads, p->kv_rows, p->ldk);
+  if (rc) return rc;
+  rc = make_map(&tmV, p->V, p->heads, p->kv_rows, p->ldv);
+  if (rc) return rc;
+  AttnDev a{};
+  a.O = static_cast<__nv_bfloat16*>(p->O);
+  a.ldo = p->ldo;
+  a.q_start = p->q_start;
+  a.q_len = p->q_len;
+  a.kv_start0 = p->kv_start0;
+  a.kv_len0 = p->kv_len0;
+  a.kv_start1 = p->kv_start1;
+  a.kv_len1 = p->kv_len1;
+  a.causal_block = p->causal_block;
+  a.scale_log2 = p->scale * 1.4426950408889634f;
+  static bool configured = false;
+  if (!configured) {
+    VS_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 SMEM_BYTES));
+    configured = true;
+  }
+  dim3 grid(ceil_div(p->max_q_len, QT), p->heads, p->items);
+  attention_kernel<<<grid, 192, SMEM_BYTES, to_stream(stream_)>>>(tmQ, tmK, tmV, a);
+  VS_LAUNCH_CHECK();
+  return VS_OK;
+}

@@ -1,0 +1,648 @@
+// Bandwidth-bound fused ops of the encoder path (everything that is not a GEMM or attention):
+// RoPE (curope replacement), LayerNorm + AdaLN modulate, patch / im2col gathers, bilinear x2,
+// pixel shuffle, token initialisers, camera head, pts-head tail and the Gaussian adapter.
+// All kernels are written for coalesced 16-byte accesses with the innermost (channel) dimension on
+// the lanes; none of them needs shared-memory tiling (no reuse).
+#include <cuda_bf16.h>
+
+#include "common.h"
+
+namespace vs {
+namespace {
+
+using bf16 = __nv_bfloat16;
+
+template <typename T> __device__ __forceinline__ float to_f(T v);
+template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f<__half>(__half v) { return __half2float(v); }
+template <> __device__ __forceinline__ float to_f<bf16>(bf16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ __half from_f<__half>(float v) { return __float2half(v); }
+template <> __device__ __forceinline__ bf16 from_f<bf16>(float v) { return __float2bfloat16(v); }
+
+// ------------------------------------------------------------------ curope.rope_2d
+// One warp per token; lanes stride over the D/2 (u,v) pairs, heads in the inner loop so that
+// cos/sin are computed once per pair per token (kernels.cu:44-81 computes them once per thread).
+template <typename T>
+__global__ void rope_2d_kernel(T* __restrict__ tokens, int B, int N, int H, int D,
+                               long long stride_b, long long stride_n,
+                               const long long* __restrict__ pos, float base, float fwd) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= B * N) return;
+  const int b = warp / N, n = warp - b * N;
+  const int Q = D / 4;
+  T* tok = tokens + b * stride_b + n * stride_n;
+  for (int p = lane; p < D / 2; p += 32) {
+    const int X = p / Q, d = p - X * Q;
+    const float inv_freq = fwd / powf(base, d / static_cast<float>(Q));
+    const float ang = static_cast<float>(pos[(static_cast<long long>(warp)) * 2 + X]) * inv_freq;
+    float s, c;
+    sincosf(ang, &s, &c);
+    const int iu = X * (D / 2) + d, iv = iu + Q;
+    for (int h = 0; h < H; ++h) {
+      const float u = to_f<T>(tok[h * D + iu]), v = to_f<T>(tok[h * D + iv]);
+      tok[h * D + iu] = from_f<T>(u * c - v * s);
+      tok[h * D + iv] = from_f<T>(v * c + u * s);
+    }
+  }
+}
+
+// Row-wise rope on a packed bf16 qkv buffer, head_dim 64: one warp per row, each lane owns the
+// element pair (2*lane, 2*lane+1) of every head; the image rope's partner (e +- 16) lives in
+// lane ^ 8, the camera rope's partner is inside the lane.
+__global__ void rope_rows_kernel(bf16* __restrict__ qkv, long long ld, int rows, int H, int q_col,
+                                 int k_col, const int* __restrict__ pos, float base,
+                                 float cam_theta) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const int py = pos[row * 2 + 0], px = pos[row * 2 + 1];
+  const bool cam = py < 0;
+  float c0, s0, c1, s1;
+  bool upper = false;  // lane holds the "v" element of an image pair
+  if (cam) {
+    const float t = static_cast<float>(-1 - py);
+    const float ang = t / powf(cam_theta, (2 * lane) / 64.0f);
+    sincosf(ang, &s0, &c0);
+    c1 = c0; s1 = s0;
+  } else {
+    const int e0 = 2 * lane;
+    const int half = e0 >> 5;         // 0: y block, 1: x block
+    const int within = e0 & 31;
+    upper = within >= 16;
+    const int d0 = within & 15;
+    const float p = static_cast<float>(half ? px : py);
+    sincosf(p / powf(base, d0 / 16.0f), &s0, &c0);
+    sincosf(p / powf(base, (d0 + 1) / 16.0f), &s1, &c1);
+  }
+  bf16* r = qkv + static_cast<long long>(row) * ld;
+#pragma unroll 1
+  for (int which = 0; which < 2; ++which) {
+    bf16* base_ptr = r + (which == 0 ? q_col : k_col);
+    for (int h = 0; h < H; ++h) {
+      __nv_bfloat162* p2 = reinterpret_cast<__nv_bfloat162*>(base_ptr + h * 64) + lane;
+      const float2 me = __bfloat1622float2(*p2);
+      float2 out;
+      if (cam) {
+        out.x = me.x * c0 - me.y * s0;
+        out.y = me.y * c0 + me.x * s0;
+        // keep the shuffles below convergent
+        (void)__shfl_xor_sync(0xffffffffu, me.x, 8);
+        (void)__shfl_xor_sync(0xffffffffu, me.y, 8);
+      } else {
+        const float ox = __shfl_xor_sync(0xffffffffu, me.x, 8);
+        const float oy = __shfl_xor_sync(0xffffffffu, me.y, 8);
+        if (!upper) {  // me = u, other = v
+          out.x = me.x * c0 - ox * s0;
+          out.y = me.y * c1 - oy * s1;
+        } else {       // me = v, other = u
+          out.x = me.x * c0 + ox * s0;
+          out.y = me.y * c1 + oy * s1;
+        }
+      }
+      *p2 = __floats2bfloat162_rn(out.x, out.y);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ LayerNorm (+ modulate)
+// One warp per row, row kept in registers (C <= 1024, C % 128 == 0): two-pass mean / variance.
+__global__ void layernorm_kernel(vs_layernorm_params p) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= p.rows) return;
+  const int nv = p.C / 128;  // float4 per lane
+  const float4* x4 = reinterpret_cast<const float4*>(p.x + static_cast<long long>(row) * p.ldx);
+  float4 v[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    if (i < nv) v[i] = x4[i * 32 + lane];
+  float mean = 0.f, rstd = 1.f;
+  if (p.normalize) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (i < nv) s += v[i].x + v[i].y + v[i].z + v[i].w;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    mean = s / p.C;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (i < nv) {
+        const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+        q += a * a + b * b + c * c + d * d;
+      }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    rstd = rsqrtf(q / p.C + p.eps);
+  }
+  const bool framed = p.rows_per_frame > 0;
+  const int frame = framed ? row / p.rows_per_frame : 0;
+  const bool first = framed && (row - frame * p.rows_per_frame) == 0 && p.w0 != nullptr;
+  const float4* w4 = reinterpret_cast<const float4*>(first ? p.w0 : p.w);
+  const float4* b4 = reinterpret_cast<const float4*>(first ? p.b0 : p.b);
+  const bool mod = p.scale != nullptr && !first;
+  const float4* sc4 =
+      mod ? reinterpret_cast<const float4*>(p.scale + static_cast<long long>(frame) * p.mod_ld)
+          : nullptr;
+  const float4* sh4 =
+      mod ? reinterpret_cast<const float4*>(p.shift + static_cast<long long>(frame) * p.mod_ld)
+          : nullptr;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    if (i < nv) {
+      const int idx = i * 32 + lane;
+      float4 y = v[i];
+      if (p.normalize) {
+        y.x = (y.x - mean) * rstd; y.y = (y.y - mean) * rstd;
+        y.z = (y.z - mean) * rstd; y.w = (y.w - mean) * rstd;
+      }
+      if (w4 != nullptr) {
+        const float4 w = w4[idx], b = b4[idx];
+        y.x = y.x * w.x + b.x; y.y = y.y * w.y + b.y; y.z = y.z * w.z + b.z; y.w = y.w * w.w + b.w;
+      }
+      if (mod) {
+        const float4 sc = sc4[idx], sh = sh4[idx];
+        y.x = y.x * (1.f + sc.x) + sh.x; y.y = y.y * (1.f + sc.y) + sh.y;
+        y.z = y.z * (1.f + sc.z) + sh.z; y.w = y.w * (1.f + sc.w) + sh.w;
+      }
+      if (p.y_f32 != nullptr)
+        reinterpret_cast<float4*>(p.y_f32 + static_cast<long long>(row) * p.ldy_f32)[idx] = y;
+      if (p.y_bf16 != nullptr) {
+        __nv_bfloat162 lo = __floats2bfloat162_rn(y.x, y.y), hi = __floats2bfloat162_rn(y.z, y.w);
+        uint2 pk;
+        pk.x = *reinterpret_cast<uint32_t*>(&lo);
+        pk.y = *reinterpret_cast<uint32_t*>(&hi);
+        reinterpret_cast<uint2*>(static_cast<bf16*>(p.y_bf16) +
+                                 static_cast<long long>(row) * p.ldy_bf16)[idx] = pk;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ gathers
+__global__ void patchify_kernel(const float* __restrict__ img, bf16* __restrict__ out, int n, int h,
+                                int w, int P) {
+  const long long total = static_cast<long long>(n) * 3 * h * w;
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  // i indexes the OUTPUT: [token][c][py][px]
+  const int K = 3 * P * P;
+  const long long tok = i / K;
+  int k = static_cast<int>(i - tok * K);
+  const int c = k / (P * P);
+  k -= c * P * P;
+  const int py = k / P, px = k - py * P;
+  const int gw = w / P, gh = h / P;
+  const int im = static_cast<int>(tok / (gw * gh));
+  const int t = static_cast<int>(tok - static_cast<long long>(im) * gw * gh);
+  const int ty = t / gw, tx = t - ty * gw;
+  const float v = img[((static_cast<long long>(im) * 3 + c) * h + ty * P + py) * w + tx * P + px];
+  out[i] = __float2bfloat16(v);
+}
+
+__global__ void im2col_kernel(const void* __restrict__ src, int nchw_f32, bf16* __restrict__ out,
+                              int n, int h, int w, int c, int k, int stride, int pad, int kpad,
+                              int ho, int wo) {
+  const long long total = static_cast<long long>(n) * ho * wo * kpad;
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const long long row = i / kpad;
+  const int col = static_cast<int>(i - row * kpad);
+  float v = 0.f;
+  if (col < k * k * c) {
+    const int tap = col / c, ch = col - tap * c;
+    const int dy = tap / k, dx = tap - dy * k;
+    const int im = static_cast<int>(row / (ho * wo));
+    const int r = static_cast<int>(row - static_cast<long long>(im) * ho * wo);
+    const int yo = r / wo, xo = r - yo * wo;
+    const int y = yo * stride + dy - pad, x = xo * stride + dx - pad;
+    if (y >= 0 && y < h && x >= 0 && x < w) {
+      if (nchw_f32)
+        v = static_cast<const float*>(src)[((static_cast<long long>(im) * c + ch) * h + y) * w + x];
+      else
+        v = __bfloat162float(
+            static_cast<const bf16*>(src)[((static_cast<long long>(im) * h + y) * w + x) * c + ch]);
+    }
+  }
+  out[i] = __float2bfloat16(v);
+}
+
+// bilinear x2 align_corners=True on NHWC bf16; one thread per 8 channels of an output pixel
+__global__ void upsample2x_kernel(const bf16* __restrict__ src, bf16* __restrict__ dst, int n,
+                                  int h, int w, int c) {
+  const int c8 = c / 8;
+  const int ho = 2 * h, wo = 2 * w;
+  const long long total = static_cast<long long>(n) * ho * wo * c8;
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int cc = static_cast<int>(i % c8);
+  long long r = i / c8;
+  const int xo = static_cast<int>(r % wo); r /= wo;
+  const int yo = static_cast<int>(r % ho);
+  const int im = static_cast<int>(r / ho);
+  const float sy = ho > 1 ? static_cast<float>(h - 1) / (ho - 1) : 0.f;
+  const float sx = wo > 1 ? static_cast<float>(w - 1) / (wo - 1) : 0.f;
+  const float fy = yo * sy, fx = xo * sx;
+  const int y0 = static_cast<int>(fy), x0 = static_cast<int>(fx);
+  const int y1 = min(y0 + 1, h - 1), x1 = min(x0 + 1, w - 1);
+  const float ly = fy - y0, lx = fx - x0;
+  const float w00 = (1 - ly) * (1 - lx), w01 = (1 - ly) * lx, w10 = ly * (1 - lx), w11 = ly * lx;
+  auto ld = [&](int y, int x) {
+    return *reinterpret_cast<const uint4*>(src + ((static_cast<long long>(im) * h + y) * w + x) * c +
+                                           cc * 8);
+  };
+  const uint4 a = ld(y0, x0), b = ld(y0, x1), cq = ld(y1, x0), d = ld(y1, x1);
+  uint4 o;
+  const uint32_t* pa = &a.x; const uint32_t* pb = &b.x; const uint32_t* pc = &cq.x;
+  const uint32_t* pd = &d.x; uint32_t* po = &o.x;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 fa = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(pa + j));
+    const float2 fb = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(pb + j));
+    const float2 fc = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(pc + j));
+    const float2 fd = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(pd + j));
+    const __nv_bfloat162 r2 =
+        __floats2bfloat162_rn(w00 * fa.x + w01 * fb.x + w10 * fc.x + w11 * fd.x,
+                              w00 * fa.y + w01 * fb.y + w10 * fc.y + w11 * fd.y);
+    po[j] = *reinterpret_cast<const uint32_t*>(&r2);
+  }
+  *reinterpret_cast<uint4*>(dst + ((static_cast<long long>(im) * ho + yo) * wo + xo) * c + cc * 8) =
+      o;
+}
+
+__global__ void pixel_shuffle_kernel(const bf16* __restrict__ src, bf16* __restrict__ dst, int n,
+                                     int h, int w, int c, int k) {
+  const int c8 = c / 8;
+  const int ho = h * k, wo = w * k;
+  const long long total = static_cast<long long>(n) * ho * wo * c8;
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int cc = static_cast<int>(i % c8);
+  long long r = i / c8;
+  const int xo = static_cast<int>(r % wo); r /= wo;
+  const int yo = static_cast<int>(r % ho);
+  const int im = static_cast<int>(r / ho);
+  const int y = yo / k, dy = yo - y * k, x = xo / k, dx = xo - x * k;
+  const long long srow = (static_cast<long long>(im) * h + y) * w + x;
+  const uint4 v = *reinterpret_cast<const uint4*>(src + srow * (static_cast<long long>(k) * k * c) +
+                                                  (dy * k + dx) * c + cc * 8);
+  *reinterpret_cast<uint4*>(dst + ((static_cast<long long>(im) * ho + yo) * wo + xo) * c + cc * 8) =
+      v;
+}
+
+__global__ void intrinsic_token_kernel(const float* __restrict__ K9, const float* __restrict__ w,
+                                       const float* __restrict__ b, float* __restrict__ x,
+                                       int frames, int E, int rows_per_frame, int row_off) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= frames * E) return;
+  const int f = i / E, e = i - f * E;
+  float acc = b[e];
+#pragma unroll
+  for (int j = 0; j < 9; ++j) acc += K9[f * 9 + j] * w[e * 9 + j];
+  x[(static_cast<long long>(f) * rows_per_frame + row_off) * E + e] = acc;
+}
+
+__global__ void camera_tokens_kernel(const float* __restrict__ intr, const float* __restrict__ extr,
+                                     float* __restrict__ x, int frames, int T, int C,
+                                     int rows_per_frame) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= frames * C) return;
+  const int f = i / C, c = i - f * C;
+  float v = intr[c];
+  if (f % T != 0) v += extr[c];
+  x[static_cast<long long>(f) * rows_per_frame * C + c] = v;
+}
+
+__global__ void silu_bf16_kernel(const float* __restrict__ x, long long ldx, bf16* __restrict__ y,
+                                 long long ldy, int rows, int C) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * C) return;
+  const int r = i / C, c = i - r * C;
+  const float v = x[r * ldx + c];
+  y[r * ldy + c] = __float2bfloat16(v / (1.0f + expf(-v)));
+}
+
+// one block (8 warps) per (b, t): warp j computes output channel j of Linear(C->8) on relu(feat)
+__global__ void camera_head_kernel(const float* __restrict__ feat, long long ld,
+                                   const float* __restrict__ w, const float* __restrict__ bias,
+                                   int B, int T, int C, float* __restrict__ pred,
+                                   float* __restrict__ c2w) {
+  __shared__ float o[8];
+  const int bt = blockIdx.x;
+  const int b = bt / T, t = bt - b * T;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* M = c2w + static_cast<long long>(bt) * 16;
+  if (t == 0) {
+    if (threadIdx.x < 16) M[threadIdx.x] = (threadIdx.x % 5 == 0) ? 1.f : 0.f;
+    return;
+  }
+  const float* f = feat + static_cast<long long>(bt) * ld;
+  float acc = 0.f;
+  for (int c = lane; c < C; c += 32) acc += fmaxf(f[c], 0.f) * w[warp * C + c];
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+  if (lane == 0) o[warp] = acc + bias[warp];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float q[8];
+    for (int i = 0; i < 8; ++i) q[i] = o[i];
+    q[3] += 1.0f;
+    const float nrm = sqrtf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+    for (int i = 0; i < 8; ++i) q[i] /= nrm;
+    float* pd = pred + (static_cast<long long>(b) * (T - 1) + (t - 1)) * 8;
+    for (int i = 0; i < 8; ++i) pd[i] = q[i];
+    const float x = q[0], y = q[1], z = q[2], ww = q[3];
+    // rotation of the unit quaternion (xyzw)
+    const float R[9] = {1 - 2 * (y * y + z * z), 2 * (x * y - z * ww),     2 * (x * z + y * ww),
+                        2 * (x * y + z * ww),     1 - 2 * (x * x + z * z), 2 * (y * z - x * ww),
+                        2 * (x * z - y * ww),     2 * (y * z + x * ww),     1 - 2 * (x * x + y * y)};
+    // translation = (2 q_d) * conj(q_r), vector part (Hamilton product, xyzw)
+    const float x1 = 2 * q[4], y1 = 2 * q[5], z1 = 2 * q[6], w1 = 2 * q[7];
+    const float x2 = -x, y2 = -y, z2 = -z, w2 = ww;
+    const float tx = w1 * x2 + x1 * w2 + y1 * z2 - z1 * y2;
+    const float ty = w1 * y2 - x1 * z2 + y1 * w2 + z1 * x2;
+    const float tz = w1 * z2 + x1 * y2 - y1 * x2 + z1 * w2;
+    M[0] = R[0]; M[1] = R[1]; M[2] = R[2];  M[3] = tx;
+    M[4] = R[3]; M[5] = R[4]; M[6] = R[5];  M[7] = ty;
+    M[8] = R[6]; M[9] = R[7]; M[10] = R[8]; M[11] = tz;
+    M[12] = 0.f; M[13] = 0.f; M[14] = 0.f;  M[15] = 1.f;
+  }
+}
+
+// one warp per pixel: 3 dot products over Cf channels, then the exp-depth postprocess
+__global__ void pts_tail_kernel(const bf16* __restrict__ feat, int Cf, const float* __restrict__ w,
+                                const float* __restrict__ b, float* __restrict__ raw,
+                                long long raw_ld, long long px) {
+  const long long pix = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (pix >= px) return;
+  const bf16* f = feat + pix * Cf;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+  for (int c = lane * 2; c < Cf; c += 64) {
+    const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(f + c));
+    a0 += v.x * w[c] + v.y * w[c + 1];
+    a1 += v.x * w[Cf + c] + v.y * w[Cf + c + 1];
+    a2 += v.x * w[2 * Cf + c] + v.y * w[2 * Cf + c + 1];
+  }
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) {
+    a0 += __shfl_xor_sync(0xffffffffu, a0, s);
+    a1 += __shfl_xor_sync(0xffffffffu, a1, s);
+    a2 += __shfl_xor_sync(0xffffffffu, a2, s);
+  }
+  if (lane == 0) {
+    a0 += b[0]; a1 += b[1]; a2 += b[2];
+    const float d = sqrtf(a0 * a0 + a1 * a1 + a2 * a2);
+    const float sc = expm1f(d) / fmaxf(d, 1e-8f);
+    float* o = raw + pix * raw_ld;
+    o[0] = a0 * sc; o[1] = a1 * sc; o[2] = a2 * sc;
+  }
+}
+
+// Gaussian adapter, part 1: per-Gaussian scalars (thread per Gaussian)
+__global__ void adapter_params_kernel(const float* __restrict__ raw, long long raw_ld, long long G,
+                                      float* __restrict__ means, float* __restrict__ cov,
+                                      float* __restrict__ cov6, float* __restrict__ opac,
+                                      float* __restrict__ scales, float* __restrict__ rot) {
+  const long long g = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (g >= G) return;
+  const float* r = raw + g * raw_ld;
+  if (means) { means[g * 3] = r[0]; means[g * 3 + 1] = r[1]; means[g * 3 + 2] = r[2]; }
+  const float o = 1.0f / (1.0f + expf(-r[3]));
+  if (opac) opac[g] = o;
+  float s[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const float x = r[4 + i];
+    const float sp = x > 20.0f ? x : log1pf(expf(x));  // F.softplus (beta 1, threshold 20)
+    s[i] = fminf(0.001f * sp, 0.3f);
+  }
+  float q[4] = {r[7], r[8], r[9], r[10]};
+  const float qn = fmaxf(sqrtf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]), 1e-12f);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) q[i] /= qn;
+  if (scales) { scales[g * 3] = s[0]; scales[g * 3 + 1] = s[1]; scales[g * 3 + 2] = s[2]; }
+  if (rot) { rot[g * 4] = q[0]; rot[g * 4 + 1] = q[1]; rot[g * 4 + 2] = q[2]; rot[g * 4 + 3] = q[3]; }
+  const float i_ = q[0], j_ = q[1], k_ = q[2], rr = q[3];
+  const float two_s = 2.0f / (i_ * i_ + j_ * j_ + k_ * k_ + rr * rr + 1e-8f);
+  const float R[9] = {1 - two_s * (j_ * j_ + k_ * k_), two_s * (i_ * j_ - k_ * rr),
+                      two_s * (i_ * k_ + j_ * rr),     two_s * (i_ * j_ + k_ * rr),
+                      1 - two_s * (i_ * i_ + k_ * k_), two_s * (j_ * k_ - i_ * rr),
+                      two_s * (i_ * k_ - j_ * rr),     two_s * (j_ * k_ + i_ * rr),
+                      1 - two_s * (i_ * i_ + j_ * j_)};
+  const float s2[3] = {s[0] * s[0], s[1] * s[1], s[2] * s[2]};
+  float Cm[9];
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int bb = 0; bb < 3; ++bb)
+      Cm[a * 3 + bb] = R[a * 3 + 0] * s2[0] * R[bb * 3 + 0] + R[a * 3 + 1] * s2[1] * R[bb * 3 + 1] +
+                       R[a * 3 + 2] * s2[2] * R[bb * 3 + 2];
+  if (cov) {
+#pragma unroll
+    for (int a = 0; a < 9; ++a) cov[g * 9 + a] = Cm[a];
+  }
+  if (cov6) {
+    cov6[g * 6 + 0] = Cm[0]; cov6[g * 6 + 1] = Cm[1]; cov6[g * 6 + 2] = Cm[2];
+    cov6[g * 6 + 3] = Cm[4]; cov6[g * 6 + 4] = Cm[5]; cov6[g * 6 + 5] = Cm[8];
+  }
+}
+
+// Gaussian adapter, part 2: SH = raw[..., 11:] * sh_mask, flat and fully coalesced
+__global__ void adapter_sh_kernel(const float* __restrict__ raw, long long raw_ld, long long G,
+                                  int d_sh, const float* __restrict__ mask,
+                                  float* __restrict__ sh) {
+  const long long per = 3ll * d_sh;
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= G * per) return;
+  const long long g = i / per;
+  const int j = static_cast<int>(i - g * per);
+  sh[i] = raw[g * raw_ld + 11 + j] * mask[j % d_sh];
+}
+
+inline unsigned blocks_for(long long n, int threads) {
+  return static_cast<unsigned>((n + threads - 1) / threads);
+}
+
+}  // namespace
+}  // namespace vs
+
+using namespace vs;
+
+extern "C" int vs_rope_2d(void* tokens, int dtype, int B, int N, int H, int D, int64_t stride_b,
+                          int64_t stride_n, const int64_t* positions, float base, float fwd,
+                          vs_stream_t stream) {
+  VS_REQUIRE(tokens && positions, "rope_2d: null tensor");
+  VS_REQUIRE(D % 4 == 0, "token dim must be multiple of 4");  // kernels.cu:94
+  VS_REQUIRE(B >= 0 && N >= 0 && H >= 0, "rope_2d: negative size");
+  if (B * N == 0 || H == 0) return VS_OK;
+  const int threads = 256;
+  const unsigned blocks = blocks_for(static_cast<long long>(B) * N * 32, threads);
+  cudaStream_t s = to_stream(stream);
+  const long long* pos = reinterpret_cast<const long long*>(positions);
+  if (dtype == VS_F32)
+    rope_2d_kernel<float><<<blocks, threads, 0, s>>>(static_cast<float*>(tokens), B, N, H, D,
+                                                     stride_b, stride_n, pos, base, fwd);
+  else if (dtype == VS_F16)
+    rope_2d_kernel<__half><<<blocks, threads, 0, s>>>(static_cast<__half*>(tokens), B, N, H, D,
+                                                      stride_b, stride_n, pos, base, fwd);
+  else if (dtype == VS_BF16)
+    rope_2d_kernel<bf16><<<blocks, threads, 0, s>>>(static_cast<bf16*>(tokens), B, N, H, D,
+                                                    stride_b, stride_n, pos, base, fwd);
+  else {
+    set_error("rope_2d: unsupported dtype %d", dtype);
+    return VS_ERR_UNSUPPORTED;
+  }
+  VS_LAUNCH_CHECK();
+  return VS_OK;
+}
+
+extern "C" int vs_rope_rows(void* qkv, int64_t ld, int rows, int H, int q_col, int k_col,
+                            const int32_t* pos, float base, float cam_theta, vs_stream_t stream) {
+  VS_REQUIRE(qkv && pos, "rope_rows: null tensor");
+  VS_REQUIRE(ld % 2 == 0 && q_col % 2 == 0 && k_col % 2 == 0, "rope_rows: columns must be even");
+  if (rows <= 0) return VS_OK;
+  rope_rows_kernel<<<blocks_for(static_cast<long long>(rows) * 32, 256), 256, 0,
+                     to_stream(stream)>>>(static_cast<bf16*>(qkv), ld, rows, H, q_col, k_col, pos,
+                                          base, cam_theta);
+  VS_LAUNCH_CHECK();
+  return VS_OK;
+}
+
+extern "C" int vs_layernorm(const vs_layernorm_params* p, vs_stream_t stream) {
+  VS_REQUIRE(p && p->x, "layernorm: null input");
+  VS_REQUIRE(p->C % 128 == 0 && p->C <= 1024 && p->C > 0, "layernorm: C must be k*128 <= 1024");
+  VS_REQUIRE(p->ldx % 4 == 0 && p->ldy_f32 % 4 == 0 && p->ldy_bf16 % 4 == 0 && p->mod_ld % 4 == 0,
+             "layernorm: leading dimensions must be multiples of 4");
+  VS_REQUIRE((p->scale == nullptr) == (p->shift == nullptr), "layernorm: scale/shift go together");
+  VS_REQUIRE(p->scale == nullptr || p->rows_per_frame > 0, "layernorm: modulation needs frames");
+  if (p->rows <= 0) return VS_OK;
+  layernorm_kernel<<<blocks_for(static_cast<long long>(p->rows) * 32, 256), 256, 0,
+                     to_stream(stream)>>>(*p);
+  VS_LAUNCH_CHECK();
+  return VS_OK;
+}
+
+extern "C" int vs_patchify(const float* img, void* out, int n, int h, int w, int P,
+                           vs_stream_t stream) {
+  VS_REQUIRE(img && out, "patchify: null tensor");
+  VS_REQUIRE(P > 0 && h % P == 0 && w % P == 0, "Input image size is not a multiple of patch size");
+  const long long total = static_cast<long long>(n) * 3 * h * w;
+  if (total == 0) return VS_OK;
+  patchify_kernel<<<blocks_for(total, 256), 256, 0, to_stream(stream)>>>(
+      img, static_cast<bf16*>(out), n, h, w, P);
+  VS_LAUNCH_CHECK();
+  return VS_OK;
+}
+
+extern "C" int vs_im2col(const void* src, int src_nchw_f32, void* out, int n, int h, int w, int c,
+                         int k, int stride, int pad, int kpad, vs_stream_t stream) {
+  VS_REQUIRE(src && out, "im2col: null tensor");
+  VS_REQUIRE(k > 0 && stride > 0 && kpad >= k * k * c, "im2col: bad geometry");
+  const int ho = (h + 2 * pad - k) / stride + 1, wo = (w + 2 * pad - k) / stride + 1;
+  const long long total = static_cast<long long>(n) * ho * wo * kpad;
+  if (total <= 0) return VS_OK;
+  im2col_kernel<<<blocks_for(total, 256), 256, 0, to_stream(stream)>>>(
+      src, src_nchw_f32, static_cast<bf16*>(out), n, h, w, c, k, stride, pad, kpad, ho, wo);
+  VS_LAUNCH_CHECK();
+  return VS_OK;
+}
+
+extern "C" int vs_upsample2x(const void* src, void* dst, int n, int h, int w, int c,
+                             vs_stream_t stream) {
+  VS_REQUIRE(src && dst, "upsample2x: null tensor");
+  VS_REQUIRE(c % 8 == 0, "upsample2x: channels must be a multiple of 8");
+  const long long total = static_cast<long long>(n) * 4 * h * w * (c / 8);
+  if (total == 0) return VS_OK;
+  upsample2x_kernel<<<blocks_for(total, 256), 256, 0, to_stream(stream)>>>(
+      static_cast<const bf16*>(src), static_cast<bf16*>(dst), n, h, w, c);
+  VS_LAUNCH_CHECK();
+  return VS_OK;
+}
+
+extern "C" int vs_pixel_shuffle(const void* src, void* dst, int n, int h, int w, int c, int k,
+                                vs_stream_t stream) {
+  VS_REQUIRE(src && dst, "pixel_shuffle: null tensor");
+  VS_REQUIRE(c % 8 == 0 && k > 0, "pixel_shuffle: channels must be a multiple of 8");
+  const long long total = static_cast<long long>(n) * h * k * w * k * (c / 8);
+  if (total == 0) return VS_OK;
+  pixel_shuffle_kernel<<<blocks_for(total, 256), 256, 0, to_stream(stream)>>>(
+      static_cast<const bf16*>(src), static_cast<bf16*>(dst), n, h, w, c, k);
+  VS_LAUNCH_CHECK();
+  return VS_OK;
+}
+
+extern "C" int vs_intrinsic_token(const float* K9, const float* w, const float* b, float* x,
+                                  int frames, int E, int rows_per_frame, int row_off,
+                                  vs_stream_t stream) {
+  VS_REQUIRE(K9 && w && b && x, "intrinsic_token: null tensor");
+  if (frames * E == 0) return VS_OK;
+  intrinsic_token_kernel<<<blocks_for(static_cast<long long>(frames) * E, 256), 256, 0,
+                           to_stream(stream)>>>(K9, w, b, x, frames, E, rows_per_frame, row_off);
+  VS_LAUNCH_CHECK();
+  return VS_OK;
+}
+
+extern "C" int vs_camera_tokens(const float* intr_tok, const float* extr_tok, float* x, int frames,
+                                int T, int C, int rows_per_frame, vs_stream_t stream) {
+  VS_REQUIRE(intr_tok && extr_tok && x && T > 0, "camera_tokens: bad arguments");
+  if (frames * C == 0) return VS_OK;
+  camera_tokens_kernel<<<blocks_for(static_cast<long long>(frames) * C, 256), 256, 0,
+                         to_stream(stream)>>>(intr_tok, extr_tok, x, frames, T, C, rows_per_frame);
+  VS_LAUNCH_CHECK();
+  return VS_OK;
+}
+
+extern "C" int vs_silu_bf16(const float* x, int64_t ldx, void* y, int64_t ldy, int rows, int C,
+                            vs_stream_t stream) {
+  VS_REQUIRE(x && y, "silu: null tensor");
+  if (rows * C == 0) return VS_OK;
+  silu_bf16_kernel<<<blocks_for(static_cast<long long>(rows) * C, 256), 256, 0,
+                     to_stream(stream)>>>(x, ldx, static_cast<bf16*>(y), ldy, rows, C);
+  VS_LAUNCH_CHECK();
+  return VS_OK;
+}
+
+extern "C" int vs_camera_head(const float* cam_feat, int64_t ld, const float* w, const float* b,
+                              int B, int T, int C, float* pred_dq, float* c2w, vs_stream_t stream) {
+  VS_REQUIRE(cam_feat && w && b && pred_dq && c2w, "camera_head: null tensor");
+  VS_REQUIRE(T >= 1 && B >= 1, "camera_head: bad sizes");
+  camera_head_kernel<<<B * T, 256, 0, to_stream(stream)>>>(cam_feat, ld, w, b, B, T, C, pred_dq,
+                                                           c2w);
+  VS_LAUNCH_CHECK();
+  return VS_OK;
+}
+
+extern "C" int vs_pts_tail(const void* feat, int Cf, const float* w, const float* b, float* raw,
+                           int64_t raw_ld, int64_t px, vs_stream_t stream) {
+  VS_REQUIRE(feat && w && b && raw, "pts_tail: null tensor");
+  VS_REQUIRE(Cf % 64 == 0, "pts_tail: Cf must be a multiple of 64");
+  if (px == 0) return VS_OK;
+  pts_tail_kernel<<<blocks_for(px * 32, 256), 256, 0, to_stream(stream)>>>(
+      static_cast<const bf16*>(feat), Cf, w, b, raw, raw_ld, px);
+  VS_LAUNCH_CHECK();
+  return VS_OK;
+}
+
+extern "C" int vs_gaussian_adapter(const float* raw, int64_t raw_ld, int64_t G, int d_sh,
+                                   const float* sh_mask, float* means, float* cov, float* cov6,
+                                   float* sh, float* opac, float* scales, float* rot,
+                                   vs_stream_t stream) {
+  VS_REQUIRE(raw, "gaussian_adapter: null input");
+  VS_REQUIRE(raw_ld >= 11 + 3 * d_sh, "gaussian_adapter: raw_ld too small");
+  if (G == 0) return VS_OK;
+  adapter_params_kernel<<<blocks_for(G, 256), 256, 0, to_stream(stream)>>>(
+      raw, raw_ld, G, means, cov, cov6, opac, scales, rot);
+  VS_LAUNCH_CHECK();
+  if (sh != nullptr) {
+    VS_REQUIRE(sh_mask != nullptr, "gaussian_adapter: sh_mask required");
+    adapter_sh_kernel<<<blocks_for(G * 3 * d_sh, 256), 256, 0, to_stream(stream)>>>(
+        raw, raw_ld, G, d_sh, sh_mask, sh);
+    VS_LAUNCH_CHECK();
+  }
+  return VS_OK;
+}

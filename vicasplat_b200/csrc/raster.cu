@@ -1,0 +1,521 @@
+// Tile-based differentiable 3-D Gaussian splatting rasterizer for sm_100a (forward).
+//
+// Semantics follow the diff_gaussian_rasterization extension the reference calls at
+// src/model/decoder/cuda_splatting.py:207-235 (EWA projection, 16x16 tiles, depth-sorted
+// front-to-back alpha compositing; constants in SURVEY.md Appendix D).  The organisation is new:
+//   * all V views of a scene are rendered by ONE launch chain: the Gaussians are read once
+//     (coalesced, SH staged through shared memory), each thread projects its Gaussian into every
+//     view, and the (view, tile, depth) keys of all views go through a single radix sort;
+//   * per-view intermediates are SoA so the blend kernel's gathers are 16-byte vector loads;
+//   * the blend kernel stages 256-splat batches of a tile's list in shared memory, each warp
+//     ballots its done-mask for early exit.
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
+#include "common.h"
+
+namespace vs {
+namespace {
+
+constexpr int TILE = 16;
+constexpr int BLEND_THREADS = TILE * TILE;
+
+// upstream constants (named so the oracle and the kernel agree)
+constexpr float kNearCullZ = 0.2f;
+constexpr float kLowpass = 0.3f;
+constexpr float kFovClamp = 1.3f;
+constexpr float kLambdaFloor = 0.1f;
+constexpr float kAlphaMax = 0.99f;
+constexpr float kAlphaMin = 1.0f / 255.0f;
+constexpr float kTStop = 1e-4f;
+constexpr float kWEps = 1e-7f;
+constexpr float kNTouchedT = 0.5f;
+
+constexpr float SH_C0 = 0.28209479177387814f;
+constexpr float SH_C1 = 0.4886025119029199f;
+__constant__ float SH_C2[5] = {1.0925484305920792f, -1.0925484305920792f, 0.31539156525252005f,
+                               -1.0925484305920792f, 0.5462742152960396f};
+__constant__ float SH_C3[7] = {-0.5900435899266435f, 2.890611442640554f,  -0.4570457994644658f,
+                               0.3731763325901154f,  -0.4570457994644658f, 1.445305721320277f,
+                               -0.5900435899266435f};
+
+struct Workspace {
+  float2* xy;        // (V*G)
+  float4* conic_o;   // (V*G)  conic a,b,c + opacity
+  float4* rgbd;      // (V*G)  rgb + view-space depth
+  uint32_t* tiles;   // (V*G)  tiles touched
+  uint32_t* offsets; // (V*G)  inclusive scan of tiles
+  int32_t* radii;    // (V*G)  (only used when the caller passes radii == NULL)
+  uint64_t* keys_in;
+  uint64_t* keys_out;
+  uint32_t* vals_in;
+  uint32_t* vals_out;
+  uint2* ranges;     // (V*tiles)
+  void* cub_tmp;
+  size_t cub_bytes;
+  size_t total;
+};
+
+inline size_t align256(size_t x) { return (x + 255) & ~static_cast<size_t>(255); }
+
+Workspace carve(void* base, int V, int G, int H, int W, int64_t max_pairs) {
+  Workspace w{};
+  const size_t vg = static_cast<size_t>(V) * G;
+  const size_t nt = static_cast<size_t>(V) * ceil_div(H, TILE) * ceil_div(W, TILE);
+  size_t scan_bytes = 0, sort_bytes = 0;
+  cub::DeviceScan::InclusiveSum(nullptr, scan_bytes, static_cast<uint32_t*>(nullptr),
+                                static_cast<uint32_t*>(nullptr), static_cast<int>(vg));
+  cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, static_cast<uint64_t*>(nullptr),
+                                  static_cast<uint64_t*>(nullptr), static_cast<uint32_t*>(nullptr),
+                                  static_cast<uint32_t*>(nullptr), static_cast<int>(max_pairs), 0,
+                                  64);
+  w.cub_bytes = scan_bytes > sort_bytes ? scan_bytes : sort_bytes;
+  uint8_t* p = static_cast<uint8_t*>(base);
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    void* r = p ? p + off : nullptr;
+    off += align256(bytes);
+    return r;
+  };
+  w.xy = static_cast<float2*>(take(vg * sizeof(float2)));
+  w.conic_o = static_cast<float4*>(take(vg * sizeof(float4)));
+  w.rgbd = static_cast<float4*>(take(vg * sizeof(float4)));
+  w.tiles = static_cast<uint32_t*>(take(vg * 4));
+  w.offsets = static_cast<uint32_t*>(take(vg * 4));
+  w.radii = static_cast<int32_t*>(take(vg * 4));
+  w.keys_in = static_cast<uint64_t*>(take(static_cast<size_t>(max_pairs) * 8));
+  w.keys_out = static_cast<uint64_t*>(take(static_cast<size_t>(max_pairs) * 8));
+  w.vals_in = static_cast<uint32_t*>(take(static_cast<size_t>(max_pairs) * 4));
+  w.vals_out = static_cast<uint32_t*>(take(static_cast<size_t>(max_pairs) * 4));
+  w.ranges = static_cast<uint2*>(take(nt * sizeof(uint2)));
+  w.cub_tmp = take(w.cub_bytes);
+  w.total = off;
+  return w;
+}
+
+struct View {
+  float vm[16];  // column-major view matrix (as passed by the reference, transposed)
+  float pm[16];  // column-major full projection
+  float cam[3];
+  float tanx, tany;
+};
+
+__device__ __forceinline__ void tile_rect(float px, float py, int radius, int gx, int gy,
+                                          int& x0, int& x1, int& y0, int& y1) {
+  x0 = min(gx, max(0, static_cast<int>((px - radius) / TILE)));
+  y0 = min(gy, max(0, static_cast<int>((py - radius) / TILE)));
+  x1 = min(gx, max(0, static_cast<int>((px + radius + TILE - 1) / TILE)));
+  y1 = min(gy, max(0, static_cast<int>((py + radius + TILE - 1) / TILE)));
+}
+
+// ------------------------------------------------------------------ preprocess
+// One thread per Gaussian; loops over the views [v_begin, v_end) (all V when the set is shared,
+// exactly one when every view has its own set).  SH coefficients of the warp's 32 Gaussians are
+// staged through shared memory with coalesced 16-byte loads.
+__global__ void __launch_bounds__(128)
+    preprocess_kernel(int G, int V, int shared_set, int H, int W, const float* __restrict__ means,
+                      const float* __restrict__ cov6, const float* __restrict__ opac,
+                      const float* __restrict__ shs, int M, int sh_cs, int sh_ch, int degree,
+                      const float* __restrict__ colors, const float* __restrict__ viewm,
+                      const float* __restrict__ projm, const float* __restrict__ campos,
+                      const float* __restrict__ tanfov, float2* __restrict__ xy,
+                      float4* __restrict__ conic_o, float4* __restrict__ rgbd,
+                      uint32_t* __restrict__ tiles, int32_t* __restrict__ radii) {
+  extern __shared__ float sh_smem[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  const int v_begin = shared_set ? 0 : blockIdx.y;
+  const int v_end = shared_set ? V : blockIdx.y + 1;
+  const size_t set_off = shared_set ? 0 : static_cast<size_t>(blockIdx.y) * G;
+  const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
+
+  // ---- stage SH for this warp
+  const int n_sh = (degree >= 3 ? 16 : (degree + 1) * (degree + 1));
+  float* my_sh = nullptr;
+  if (shs != nullptr) {
+    const int per = 3 * M;
+    float* ws = sh_smem + static_cast<size_t>(warp) * 32 * per;
+    const int gbase = blockIdx.x * blockDim.x + warp * 32;
+    const int cnt = max(0, min(32, G - gbase)) * per;
+    const float* src = shs + (set_off + gbase) * per;
+    if ((cnt & 3) == 0 && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
+      const float4* s4 = reinterpret_cast<const float4*>(src);
+      float4* d4 = reinterpret_cast<float4*>(ws);
+      for (int i = lane; i < cnt / 4; i += 32) d4[i] = __ldg(s4 + i);
+    } else {
+      for (int i = lane; i < cnt; i += 32) ws[i] = __ldg(src + i);
+    }
+    __syncwarp();
+    my_sh = ws + lane * per;
+  }
+  if (g >= G) return;
+
+  const size_t gi = set_off + g;
+  const float mx = means[gi * 3 + 0], my = means[gi * 3 + 1], mz = means[gi * 3 + 2];
+  float c6[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) c6[i] = cov6[gi * 6 + i];
+  const float op = opac[gi];
+
+  for (int v = v_begin; v < v_end; ++v) {
+    const float* vm = viewm + v * 16;
+    const float* pm = projm + v * 16;
+    const size_t o = static_cast<size_t>(v) * G + g;
+    // view-space point
+    const float tx = vm[0] * mx + vm[4] * my + vm[8] * mz + vm[12];
+    const float ty = vm[1] * mx + vm[5] * my + vm[9] * mz + vm[13];
+    const float tz = vm[2] * mx + vm[6] * my + vm[10] * mz + vm[14];
+    int radius = 0;
+    uint32_t ntiles = 0;
+    if (tz > kNearCullZ) {
+      const float hx = pm[0] * mx + pm[4] * my + pm[8] * mz + pm[12];
+      const float hy = pm[1] * mx + pm[5] * my + pm[9] * mz + pm[13];
+      const float hw = pm[3] * mx + pm[7] * my + pm[11] * mz + pm[15];
+      const float pw = 1.0f / (hw + kWEps);
+      const float px = ((hx * pw + 1.0f) * W - 1.0f) * 0.5f;
+      const float py = ((hy * pw + 1.0f) * H - 1.0f) * 0.5f;
+      // EWA 2-D covariance
+      const float tanx = tanfov[v * 2 + 0], tany = tanfov[v * 2 + 1];
+      const float fx = W / (2.0f * tanx), fy = H / (2.0f * tany);
+      const float limx = kFovClamp * tanx, limy = kFovClamp * tany;
+      const float txc = fminf(limx, fmaxf(-limx, tx / tz)) * tz;
+      const float tyc = fminf(limy, fmaxf(-limy, ty / tz)) * tz;
+      const float j00 = fx / tz, j02 = -fx * txc / (tz * tz);
+      const float j11 = fy / tz, j12 = -fy * tyc / (tz * tz);
+      // T = J * Wrot, Wrot[r][c] = vm[c*4 + r]
+      const float t00 = j00 * vm[0] + j02 * vm[2];
+      const float t01 = j00 * vm[4] + j02 * vm[6];
+      const float t02 = j00 * vm[8] + j02 * vm[10];
+      const float t10 = j11 * vm[1] + j12 * vm[2];
+      const float t11 = j11 * vm[5] + j12 * vm[6];
+      const float t12 = j11 * vm[9] + j12 * vm[10];
+      // S * T^T rows
+      const float s0x = c6[0] * t00 + c6[1] * t01 + c6[2] * t02;
+      const float s0y = c6[1] * t00 + c6[3] * t01 + c6[4] * t02;
+      const float s0z = c6[2] * t00 + c6[4] * t01 + c6[5] * t02;
+      const float s1x = c6[0] * t10 + c6[1] * t11 + c6[2] * t12;
+      const float s1y = c6[1] * t10 + c6[3] * t11 + c6[4] * t12;
+      const float s1z = c6[2] * t10 + c6[4] * t11 + c6[5] * t12;
+      const float a = t00 * s0x + t01 * s0y + t02 * s0z + kLowpass;
+      const float b = t00 * s1x + t01 * s1y + t02 * s1z;
+      const float c = t10 * s1x + t11 * s1y + t12 * s1z + kLowpass;
+      const float det = a * c - b * b;
+      if (det != 0.0f) {
+        const float inv = 1.0f / det;
+        const float mid = 0.5f * (a + c);
+        const float lam = mid + sqrtf(fmaxf(kLambdaFloor, mid * mid - det));
+        const int rad = static_cast<int>(ceilf(3.0f * sqrtf(lam)));
+        int x0, x1, y0, y1;
+        tile_rect(px, py, rad, gx, gy, x0, x1, y0, y1);
+        const uint32_t nt = static_cast<uint32_t>((x1 - x0) * (y1 - y0));
+        if (nt > 0) {
+          radius = rad;
+          ntiles = nt;
+          float r, gcol, bcol;
+          if (colors != nullptr) {
+            r = colors[gi * 3 + 0];
+            gcol = colors[gi * 3 + 1];
+            bcol = colors[gi * 3 + 2];
+          } else {
+            float dx = mx - campos[v * 3 + 0], dy = my - campos[v * 3 + 1],
+                  dz = mz - campos[v * 3 + 2];
+            const float il = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
+            dx *= il; dy *= il; dz *= il;
+            float basis[16];
+            basis[0] = SH_C0;
+            if (n_sh > 1) {
+              basis[1] = -SH_C1 * dy; basis[2] = SH_C1 * dz; basis[3] = -SH_C1 * dx;
+            }
+            if (n_sh > 4) {
+              const float xx = dx * dx, yy = dy * dy, zz = dz * dz;
+              const float xy_ = dx * dy, yz = dy * dz, xz = dx * dz;
+              basis[4] = SH_C2[0] * xy_;
+              basis[5] = SH_C2[1] * yz;
+              basis[6] = SH_C2[2] * (2.0f * zz - xx - yy);
+              basis[7] = SH_C2[3] * xz;
+              basis[8] = SH_C2[4] * (xx - yy);
+              if (n_sh > 9) {
+                basis[9] = SH_C3[0] * dy * (3.0f * xx - yy);
+                basis[10] = SH_C3[1] * xy_ * dz;
+                basis[11] = SH_C3[2] * dy * (4.0f * zz - xx - yy);
+                basis[12] = SH_C3[3] * dz * (2.0f * zz - 3.0f * xx - 3.0f * yy);
+                basis[13] = SH_C3[4] * dx * (4.0f * zz - xx - yy);
+                basis[14] = SH_C3[5] * dz * (xx - yy);
+                basis[15] = SH_C3[6] * dx * (xx - 3.0f * yy);
+              }
+            }
+            r = 0.f; gcol = 0.f; bcol = 0.f;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+              if (k < n_sh) {
+                r += basis[k] * my_sh[k * sh_cs + 0 * sh_ch];
+                gcol += basis[k] * my_sh[k * sh_cs + 1 * sh_ch];
+                bcol += basis[k] * my_sh[k * sh_cs + 2 * sh_ch];
+              }
+            }
+            r = fmaxf(r + 0.5f, 0.0f);
+            gcol = fmaxf(gcol + 0.5f, 0.0f);
+            bcol = fmaxf(bcol + 0.5f, 0.0f);
+          }
+          xy[o] = make_float2(px, py);
+          conic_o[o] = make_float4(c * inv, -b * inv, a * inv, op);
+          rgbd[o] = make_float4(r, gcol, bcol, tz);
+        }
+      }
+    }
+    tiles[o] = ntiles;
+    radii[o] = radius;
+  }
+}
+
+// ------------------------------------------------------------------ binning
+__global__ void emit_pairs_kernel(size_t VG, int G, int H, int W, const float2* __restrict__ xy,
+                                  const float4* __restrict__ rgbd, const int32_t* __restrict__ radii,
+                                  const uint32_t* __restrict__ offsets, uint64_t* __restrict__ keys,
+                                  uint32_t* __restrict__ vals, int64_t max_pairs) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= VG) return;
+  const int rad = radii[i];
+  if (rad <= 0) return;
+  const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
+  const uint32_t v = static_cast<uint32_t>(i / G);
+  uint32_t off = (i == 0) ? 0u : offsets[i - 1];
+  const float2 p = xy[i];
+  int x0, x1, y0, y1;
+  tile_rect(p.x, p.y, rad, gx, gy, x0, x1, y0, y1);
+  const uint32_t dbits = __float_as_uint(rgbd[i].w);
+  for (int y = y0; y < y1; ++y)
+    for (int x = x0; x < x1; ++x) {
+      if (static_cast<int64_t>(off) < max_pairs) {
+        const uint64_t tile = static_cast<uint64_t>(v) * (gx * gy) + y * gx + x;
+        keys[off] = (tile << 32) | dbits;
+        vals[off] = static_cast<uint32_t>(i);
+      }
+      ++off;
+    }
+}
+
+__global__ void pad_keys_kernel(const uint32_t* __restrict__ offsets, size_t VG,
+                                uint64_t* __restrict__ keys, int64_t max_pairs,
+                                int64_t* __restrict__ num_pairs_out) {
+  const int64_t n = offsets[VG - 1];
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i == 0 && num_pairs_out != nullptr) *num_pairs_out = n;
+  if (i >= n && i < max_pairs) keys[i] = ~0ull;
+}
+
+__global__ void tile_ranges_kernel(const uint64_t* __restrict__ keys, int64_t max_pairs,
+                                   const uint32_t* __restrict__ offsets, size_t VG,
+                                   uint2* __restrict__ ranges) {
+  const int64_t n = min(static_cast<int64_t>(offsets[VG - 1]), max_pairs);
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t t = static_cast<uint32_t>(keys[i] >> 32);
+  if (i == 0) ranges[t].x = 0;
+  else {
+    const uint32_t tp = static_cast<uint32_t>(keys[i - 1] >> 32);
+    if (tp != t) {
+      ranges[tp].y = static_cast<uint32_t>(i);
+      ranges[t].x = static_cast<uint32_t>(i);
+    }
+  }
+  if (i == n - 1) ranges[t].y = static_cast<uint32_t>(n);
+}
+
+// ------------------------------------------------------------------ blend
+__global__ void __launch_bounds__(BLEND_THREADS)
+    blend_kernel(int G, int H, int W, const uint2* __restrict__ ranges,
+                 const uint32_t* __restrict__ vals, const float2* __restrict__ xy,
+                 const float4* __restrict__ conic_o, const float4* __restrict__ rgbd,
+                 const float* __restrict__ bg, float* __restrict__ out_color,
+                 float* __restrict__ out_depth, float* __restrict__ out_alpha,
+                 float* __restrict__ final_T, int32_t* __restrict__ n_contrib,
+                 int32_t* __restrict__ n_touched) {
+  __shared__ uint32_t s_id[BLEND_THREADS];
+  __shared__ float2 s_xy[BLEND_THREADS];
+  __shared__ float4 s_co[BLEND_THREADS];
+  __shared__ float4 s_cd[BLEND_THREADS];
+
+  const int gx = gridDim.x, gy = gridDim.y;
+  const int v = blockIdx.z;
+  const int tile = (v * gy + blockIdx.y) * gx + blockIdx.x;
+  const int px = blockIdx.x * TILE + (threadIdx.x & (TILE - 1));
+  const int py = blockIdx.y * TILE + (threadIdx.x >> 4);
+  const bool inside = px < W && py < H;
+  const float pxf = static_cast<float>(px), pyf = static_cast<float>(py);
+
+  const uint2 range = ranges[tile];
+  const int total = static_cast<int>(range.y - range.x);
+  const int rounds = (total + BLEND_THREADS - 1) / BLEND_THREADS;
+
+  bool done = !inside;
+  float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f, D = 0.f, A = 0.f;
+  int contributor = 0, last_contributor = 0;
+  int todo = total;
+
+  for (int r = 0; r < rounds; ++r, todo -= BLEND_THREADS) {
+    if (__syncthreads_count(done) == BLEND_THREADS) break;
+    const int idx = r * BLEND_THREADS + threadIdx.x;
+    if (idx < total) {
+      const uint32_t id = vals[range.x + idx];
+      s_id[threadIdx.x] = id;
+      s_xy[threadIdx.x] = xy[id];
+      s_co[threadIdx.x] = conic_o[id];
+      s_cd[threadIdx.x] = rgbd[id];
+    }
+    __syncthreads();
+    const int nb = min(BLEND_THREADS, todo);
+    for (int j = 0; j < nb; ++j) {
+      // warp-level early exit: the whole warp leaves the batch once all its pixels are done
+      if (__ballot_sync(0xffffffffu, !done) == 0u) break;
+      bool hit = false;
+      if (!done) {
+        ++contributor;
+        const float2 p = s_xy[j];
+        const float4 co = s_co[j];
+        const float dx = p.x - pxf, dy = p.y - pyf;
+        const float power = -0.5f * (co.x * dx * dx + co.z * dy * dy) - co.y * dx * dy;
+        if (power <= 0.0f) {
+          const float alpha = fminf(kAlphaMax, co.w * __expf(power));
+          if (alpha >= kAlphaMin) {
+            const float test_T = T * (1.0f - alpha);
+            if (test_T < kTStop) {
+              done = true;
+            } else {
+              const float4 cd = s_cd[j];
+              const float w = alpha * T;
+              C0 += cd.x * w; C1 += cd.y * w; C2 += cd.z * w;
+              D += cd.w * w;
+              A += w;
+              hit = T > kNTouchedT;
+              T = test_T;
+              last_contributor = contributor;
+            }
+          }
+        }
+      }
+      if (n_touched != nullptr) {
+        const uint32_t m = __ballot_sync(0xffffffffu, hit);
+        if (m != 0u && (threadIdx.x & 31) == 0) atomicAdd(n_touched + s_id[j], __popc(m));
+      }
+    }
+  }
+  if (inside) {
+    const size_t hw = static_cast<size_t>(H) * W;
+    const size_t pix = static_cast<size_t>(py) * W + px;
+    const float* b = bg + v * 3;
+    out_color[(static_cast<size_t>(v) * 3 + 0) * hw + pix] = C0 + T * b[0];
+    out_color[(static_cast<size_t>(v) * 3 + 1) * hw + pix] = C1 + T * b[1];
+    out_color[(static_cast<size_t>(v) * 3 + 2) * hw + pix] = C2 + T * b[2];
+    if (out_depth) out_depth[static_cast<size_t>(v) * hw + pix] = D;
+    if (out_alpha) out_alpha[static_cast<size_t>(v) * hw + pix] = A;
+    if (final_T) final_T[static_cast<size_t>(v) * hw + pix] = T;
+    if (n_contrib) n_contrib[static_cast<size_t>(v) * hw + pix] = last_contributor;
+  }
+}
+
+int highest_bit(uint64_t x) {
+  int b = 0;
+  while (x) { ++b; x >>= 1; }
+  return b;
+}
+
+}  // namespace
+}  // namespace vs
+
+extern "C" int64_t vs_raster_workspace_bytes(int V, int G, int H, int W, int64_t max_pairs) {
+  if (V <= 0 || G <= 0 || H <= 0 || W <= 0 || max_pairs <= 0) return 0;
+  return static_cast<int64_t>(vs::carve(nullptr, V, G, H, W, max_pairs).total);
+}
+
+extern "C" int vs_raster_forward(const vs_raster_params* p, vs_stream_t stream_) {
+  using namespace vs;
+  VS_REQUIRE(p != nullptr, "vs_raster_forward: null params");
+  VS_REQUIRE(p->V > 0 && p->H > 0 && p->W > 0 && p->G >= 0, "vs_raster_forward: bad sizes");
+  if (p->G > 0) {
+    VS_REQUIRE(p->means3D && p->cov3D && p->opacities,
+               "vs_raster_forward: missing Gaussian inputs");
+    VS_REQUIRE(p->shs != nullptr || p->colors_precomp != nullptr,
+               "vs_raster_forward: provide either shs or colors_precomp");
+    VS_REQUIRE(!(p->shs != nullptr && p->colors_precomp != nullptr),
+               "vs_raster_forward: provide only one of shs / colors_precomp");
+  }
+  VS_REQUIRE(p->viewmatrix && p->projmatrix && p->campos && p->tanfov && p->bg,
+             "vs_raster_forward: missing camera inputs");
+  VS_REQUIRE(p->out_color != nullptr, "vs_raster_forward: out_color is required");
+  VS_REQUIRE(static_cast<int64_t>(p->V) * p->G < (1ll << 31), "vs_raster_forward: V*G too large");
+  cudaStream_t stream = to_stream(stream_);
+  const int gx = ceil_div(p->W, TILE), gy = ceil_div(p->H, TILE);
+  const size_t hw = static_cast<size_t>(p->H) * p->W;
+
+  VS_REQUIRE(p->workspace != nullptr && p->max_pairs > 0, "vs_raster_forward: workspace required");
+  const int Gc = p->G > 0 ? p->G : 1;
+  Workspace ws = carve(p->workspace, p->V, Gc, p->H, p->W, p->max_pairs);
+  if (static_cast<int64_t>(ws.total) > p->workspace_bytes) {
+    set_error("vs_raster_forward: workspace too small (%lld < %lld bytes)",
+              (long long)p->workspace_bytes, (long long)ws.total);
+    return VS_ERR_WORKSPACE;
+  }
+  const size_t VG = static_cast<size_t>(p->V) * p->G;
+  const size_t n_tiles = static_cast<size_t>(p->V) * gx * gy;
+  int32_t* radii = p->radii ? p->radii : ws.radii;
+  VS_CUDA(cudaMemsetAsync(ws.ranges, 0, n_tiles * sizeof(uint2), stream));
+  if (p->n_touched) VS_CUDA(cudaMemsetAsync(p->n_touched, 0, VG * sizeof(int32_t), stream));
+  if (p->num_pairs_out && p->G == 0) VS_CUDA(cudaMemsetAsync(p->num_pairs_out, 0, 8, stream));
+
+  if (p->G > 0) {
+    int sh_cs = p->sh_stride_coef, sh_ch = p->sh_stride_chan;
+    if (sh_cs == 0 && sh_ch == 0) { sh_cs = 3; sh_ch = 1; }  // reference layout (G, M, 3)
+    if (p->shs) {
+      VS_REQUIRE(p->sh_M >= 1 && p->sh_M <= 32, "vs_raster_forward: sh_M out of range");
+      const int deg = p->sh_degree > 3 ? 3 : p->sh_degree;
+      VS_REQUIRE((deg + 1) * (deg + 1) <= p->sh_M,
+                 "vs_raster_forward: sh_degree needs more coefficients than sh_M");
+    }
+    const int threads = 128;
+    dim3 grid(ceil_div(p->G, threads), p->gaussians_shared ? 1 : p->V);
+    const size_t smem = p->shs ? static_cast<size_t>(threads) * 3 * p->sh_M * sizeof(float) : 0;
+    if (smem > 48 * 1024) {
+      VS_CUDA(cudaFuncSetAttribute(preprocess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   static_cast<int>(smem)));
+    }
+    preprocess_kernel<<<grid, threads, smem, stream>>>(
+        p->G, p->V, p->gaussians_shared, p->H, p->W, p->means3D, p->cov3D, p->opacities, p->shs,
+        p->sh_M, sh_cs, sh_ch, p->sh_degree, p->colors_precomp, p->viewmatrix, p->projmatrix,
+        p->campos, p->tanfov, ws.xy, ws.conic_o, ws.rgbd, ws.tiles, radii);
+    VS_LAUNCH_CHECK();
+
+    size_t tmp = ws.cub_bytes;
+    VS_CUDA(cub::DeviceScan::InclusiveSum(ws.cub_tmp, tmp, ws.tiles, ws.offsets,
+                                          static_cast<int>(VG), stream));
+    emit_pairs_kernel<<<static_cast<unsigned>(ceil_div64(VG, 256)), 256, 0, stream>>>(
+        VG, p->G, p->H, p->W, ws.xy, ws.rgbd, radii, ws.offsets, ws.keys_in, ws.vals_in,
+        p->max_pairs);
+    VS_LAUNCH_CHECK();
+    pad_keys_kernel<<<static_cast<unsigned>(ceil_div64(p->max_pairs, 256)), 256, 0, stream>>>(
+        ws.offsets, VG, ws.keys_in, p->max_pairs, p->num_pairs_out);
+    VS_LAUNCH_CHECK();
+    const int end_bit = 32 + highest_bit(n_tiles);  // padded keys (all ones) sort last
+    tmp = ws.cub_bytes;
+    VS_CUDA(cub::DeviceRadixSort::SortPairs(ws.cub_tmp, tmp, ws.keys_in, ws.keys_out, ws.vals_in,
+                                            ws.vals_out, static_cast<int>(p->max_pairs), 0,
+                                            end_bit, stream));
+    tile_ranges_kernel<<<static_cast<unsigned>(ceil_div64(p->max_pairs, 256)), 256, 0, stream>>>(
+        ws.keys_out, p->max_pairs, ws.offsets, VG, ws.ranges);
+    VS_LAUNCH_CHECK();
+  }
+  dim3 bgrid(gx, gy, p->V);
+  blend_kernel<<<bgrid, BLEND_THREADS, 0, stream>>>(
+      p->G, p->H, p->W, ws.ranges, ws.vals_out, ws.xy, ws.conic_o, ws.rgbd, p->bg, p->out_color,
+      p->out_depth, p->out_alpha, p->final_T, p->n_contrib, p->n_touched);
+  VS_LAUNCH_CHECK();
+  (void)hw;
+  return VS_OK;
+}
+
+extern "C" int vs_raster_backward(const vs_raster_bwd_params* p, vs_stream_t stream_) {
+  (void)p; (void)stream_;
+  vs::set_error("vs_raster_backward: not implemented yet");
+  return VS_ERR_UNSUPPORTED;
+}

@@ -1,0 +1,140 @@
+"""Render path of the reference behind its own plugin surface:
+
+* ``render_cuda``            <-> src/model/decoder/cuda_splatting.py:148-239
+* ``get_projection_matrix``  <-> cuda_splatting.py:18-45
+* ``get_fov``                <-> src/geometry/projection.py:247-261
+* ``DecoderSplattingCUDA``   <-> src/model/decoder/decoder_splatting_cuda.py:23-101
+* ``DecoderOutput``          <-> src/model/decoder/decoder.py:18-21
+
+Same names, argument meaning and return shapes; what changes is underneath: the V views of a
+scene are rendered by ONE launch chain from ONE copy of the Gaussians (no per-view ``repeat``,
+no Python loop, no ``.item()`` syncs, SH consumed in the encoder's (3, d_sh) layout).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from math import isqrt
+from typing import Literal, Optional
+
+import torch
+from torch import Tensor, nn
+
+from .rasterizer import rasterize_views
+
+DepthRenderingMode = Literal["depth", "log", "disparity", "relative_disparity"]
+
+
+@dataclass
+class DecoderOutput:
+    color: Optional[Tensor] = None   # (batch, view, 3, H, W)
+    depth: Optional[Tensor] = None   # (batch, view, H, W)
+
+
+@dataclass
+class DecoderSplattingCUDACfg:
+    name: Literal["splatting_cuda"]
+    background_color: list
+    make_scale_invariant: bool
+    use_gsplat: bool = False
+
+
+def get_fov(intrinsics: Tensor) -> Tensor:
+    """(B,3,3) normalised intrinsics -> (B,2) full field of view (x, y) in radians: the angle
+    between the rays through the mid-points of opposite image borders."""
+    inv = torch.linalg.inv(intrinsics)
+
+    def unit_ray(u, v):
+        d = inv @ torch.tensor([u, v, 1.0], dtype=intrinsics.dtype, device=intrinsics.device)
+        return d / d.norm(dim=-1, keepdim=True)
+
+    cx = (unit_ray(0.0, 0.5) * unit_ray(1.0, 0.5)).sum(-1)
+    cy = (unit_ray(0.5, 0.0) * unit_ray(0.5, 1.0)).sum(-1)
+    return torch.stack((cx.acos(), cy.acos()), dim=-1)
+
+
+def get_projection_matrix(near: Tensor, far: Tensor, fov_x: Tensor, fov_y: Tensor) -> Tensor:
+    """Symmetric-frustum projection: x,y -> [-1,1], z -> [0,1], w = z_view (+z forward)."""
+    P = torch.zeros((near.shape[0], 4, 4), dtype=torch.float32, device=near.device)
+    P[:, 0, 0] = 1.0 / (0.5 * fov_x).tan()
+    P[:, 1, 1] = 1.0 / (0.5 * fov_y).tan()
+    P[:, 2, 2] = far / (far - near)
+    P[:, 2, 3] = -(far * near) / (far - near)
+    P[:, 3, 2] = 1.0
+    return P
+
+
+def _cameras(extrinsics, intrinsics, near, far):
+    fov = get_fov(intrinsics)
+    tanfov = (0.5 * fov).tan()
+    proj_t = get_projection_matrix(near, far, fov[:, 0], fov[:, 1]).transpose(1, 2)
+    view_t = torch.linalg.inv(extrinsics).transpose(1, 2)
+    return tanfov, view_t, view_t @ proj_t, extrinsics[:, :3, 3]
+
+
+def _cov6(cov: Tensor) -> Tensor:
+    return torch.stack([cov[..., 0, 0], cov[..., 0, 1], cov[..., 0, 2], cov[..., 1, 1],
+                        cov[..., 1, 2], cov[..., 2, 2]], dim=-1)
+
+
+def render_cuda(extrinsics, intrinsics, near, far, image_shape, background_color, gaussian_means,
+                gaussian_covariances, gaussian_sh_coefficients, gaussian_opacities,
+                scale_invariant: bool = True, cam_rot_delta=None, cam_trans_delta=None,
+                use_sh: bool = True, sh_degree: Optional[int] = None):
+    """``batch`` cameras; Gaussians either per camera (batch, G, ...) or shared (G, ...).
+    ``scale_invariant`` is accepted and has no effect, as in the reference (:170-178)."""
+    assert use_sh or gaussian_sh_coefficients.shape[-1] == 1
+    n = gaussian_sh_coefficients.shape[-1]
+    degree = sh_degree or isqrt(n) - 1
+    h, w = image_shape
+    tanfov, view_t, full_t, campos = _cameras(extrinsics, intrinsics, near, far)
+    if use_sh:
+        shs, cols = gaussian_sh_coefficients, None
+    else:
+        shs, cols = None, gaussian_sh_coefficients[..., 0]
+    color, _radii, depth, _alpha, _nt = rasterize_views(
+        gaussian_means, _cov6(gaussian_covariances), gaussian_opacities, shs=shs,
+        colors_precomp=cols, sh_degree=degree, sh_layout="chan_major", viewmatrix=view_t,
+        projmatrix=full_t, campos=campos, tanfov=tanfov, bg=background_color, H=h, W=w,
+        theta=cam_rot_delta, rho=cam_trans_delta)
+    return color, depth[:, 0]
+
+
+class DecoderSplattingCUDA(nn.Module):
+    """Same constructor / forward contract as the reference decoder plugin."""
+
+    def __init__(self, cfg: DecoderSplattingCUDACfg) -> None:
+        super().__init__()
+        self.cfg = cfg
+        self.make_scale_invariant = cfg.make_scale_invariant
+        self.register_buffer("background_color",
+                             torch.tensor(cfg.background_color, dtype=torch.float32),
+                             persistent=False)
+
+    def forward(self, gaussians, extrinsics, intrinsics, near, far, image_shape,
+                depth_mode: DepthRenderingMode | None = None, cam_rot_delta=None,
+                cam_trans_delta=None, use_sh: bool = True, active_sh_degree: Optional[int] = None,
+                return_dict: bool = True):
+        if self.cfg.use_gsplat:
+            raise NotImplementedError("use_gsplat=True: gsplat is not part of this hot path "
+                                      "(every shipped experiment sets use_gsplat: false)")
+        b, v = extrinsics.shape[:2]
+        means, cov, sh, opac = (gaussians.means, gaussians.covariances, gaussians.harmonics,
+                                gaussians.opacities)
+        if means.ndim > 3:  # (b, t, h, w, ...) -> (b, G, ...)
+            means, cov, sh = means.flatten(1, 3), cov.flatten(1, 3), sh.flatten(1, 3)
+            opac = opac.flatten(1)
+        colors, depths = [], []
+        for i in range(b):   # scenes; the V views of a scene share one launch chain
+            c, d = render_cuda(
+                extrinsics[i], intrinsics[i], near[i], far[i], image_shape,
+                self.background_color[None].expand(v, 3), means[i], cov[i], sh[i], opac[i],
+                scale_invariant=self.make_scale_invariant,
+                cam_rot_delta=None if cam_rot_delta is None else cam_rot_delta[i],
+                cam_trans_delta=None if cam_trans_delta is None else cam_trans_delta[i],
+                use_sh=use_sh, sh_degree=active_sh_degree)
+            colors.append(c)
+            depths.append(d)
+        color, depth = torch.stack(colors), torch.stack(depths)
+        if not return_dict:
+            return color, depth
+        return DecoderOutput(color, depth)

@@ -1,0 +1,240 @@
+"""Tensor-level wrappers of the C-ABI entry points (include/vicasplat_b200.h).
+
+PyTorch is used for device memory and streams only; every function here launches hand-written
+sm_100a kernels on ``torch.cuda.current_stream()`` and never synchronises.  There is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import (AttentionParams, GemmParams, LayerNormParams, VS_ACT_GELU, VS_ACT_NONE,
+                   VS_ACT_RELU, VS_BF16, VS_F16, VS_F32, check, ptr, stream_ptr)
+
+_DT = {torch.float32: VS_F32, torch.bfloat16: VS_BF16, torch.float16: VS_F16}
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("vicasplat_b200 ops need CUDA tensors (there is no CPU fallback)")
+
+
+def gemm(A, W, *, N=None, K=None, a_rows=None, a_groups=1, a_row_stride=None, a_group_stride=0,
+         bias=None, act=VS_ACT_NONE, gate=None, gate_rows=0, first_row_mode=0, res1=None,
+         res2=None, out=None, out_dtype=torch.bfloat16, ldc=None, out2=None, ldc2=None,
+         out_gin=0, out_gout=0, out_off=0, out_rows=None, block_n=0, w_row_stride=None):
+    """C = epilogue(A @ W^T): rows mode of vs_gemm.  A bf16 (rows, K) [or strided groups], W bf16 (N, K)."""
+    _need_cuda(A, W)
+    lib = _lib.load()
+    p = GemmParams()
+    K = K if K is not None else A.shape[-1]
+    N = N if N is not None else W.shape[0]
+    rows = a_rows if a_rows is not None else A.numel() // A.shape[-1]
+    p.A, p.a_mode, p.a_rows, p.a_groups = ptr(A), 0, rows, a_groups
+    p.a_row_stride = a_row_stride if a_row_stride is not None else A.stride(-2)
+    p.a_group_stride = a_group_stride
+    p.W, p.w_row_stride, p.N, p.K = ptr(W), (w_row_stride or W.stride(0)), N, K
+    _fill_epilogue(p, bias, act, gate, gate_rows, first_row_mode, res1, res2)
+    total = rows * a_groups
+    if out is None:
+        n_out = out_rows if out_rows is not None else total
+        out = torch.empty((n_out, N), dtype=out_dtype, device=A.device)
+    p.C, p.c_dtype, p.ldc = ptr(out), _DT[out.dtype], (ldc if ldc is not None else out.stride(-2))
+    if out2 is not None:
+        p.C2, p.ldc2 = ptr(out2), (ldc2 if ldc2 is not None else out2.stride(-2))
+    p.out_gin, p.out_gout, p.out_off, p.block_n = out_gin, out_gout, out_off, block_n
+    check(lib.vs_gemm(C.byref(p), C.c_void_p(stream_ptr())), "vs_gemm")
+    return out
+
+
+def conv_gemm(x_nhwc, Wp, *, kh, kw, pad, N, bias=None, act=VS_ACT_NONE, res1=None, res2=None,
+              out=None, out_dtype=torch.bfloat16, out2=None, block_n=0):
+    """Stride-1 kh x kw convolution on an NHWC bf16 map as an implicit GEMM (conv mode of vs_gemm).
+    Wp: packed weights (N, kh*kw*cin_pad) bf16, tap-major / channel-minor."""
+    _need_cuda(x_nhwc, Wp)
+    lib = _lib.load()
+    n, h, w, cin = x_nhwc.shape
+    p = GemmParams()
+    p.A, p.a_mode = ptr(x_nhwc), 1
+    p.cn, p.ch, p.cw, p.cin, p.kh, p.kw, p.pad = n, h, w, cin, kh, kw, pad
+    p.W, p.w_row_stride, p.N = ptr(Wp), Wp.stride(0), N
+    _fill_epilogue(p, bias, act, None, 0, 0, res1, res2)
+    if out is None:
+        out = torch.empty((n, h, w, N), dtype=out_dtype, device=x_nhwc.device)
+    p.C, p.c_dtype, p.ldc = ptr(out), _DT[out.dtype], out.stride(-2)
+    if out2 is not None:
+        p.C2, p.ldc2 = ptr(out2), out2.stride(-2)
+    p.block_n = block_n
+    check(lib.vs_gemm(C.byref(p), C.c_void_p(stream_ptr())), "vs_gemm(conv)")
+    return out
+
+
+def _fill_epilogue(p, bias, act, gate, gate_rows, first_row_mode, res1, res2):
+    p.bias, p.act = ptr(bias), act
+    if gate is not None:
+        p.gate, p.gate_ld = ptr(gate), gate.stride(-2)
+    p.gate_rows, p.first_row_mode = gate_rows, first_row_mode
+    if res1 is not None:
+        p.res1, p.res_dtype, p.res_ld = ptr(res1), _DT[res1.dtype], res1.stride(-2)
+        if res2 is not None:
+            assert res2.dtype == res1.dtype and res2.stride(-2) == res1.stride(-2)
+            p.res2 = ptr(res2)
+
+
+def layernorm(x, w=None, b=None, *, eps=1e-6, w0=None, b0=None, scale=None, shift=None,
+              rows_per_frame=0, normalize=True, out_bf16=None, out_f32=None, want_bf16=True,
+              want_f32=False):
+    """Row LayerNorm (+ per-frame AdaLN modulate) on fp32 rows; see vs_layernorm in the header."""
+    _need_cuda(x)
+    lib = _lib.load()
+    rows, Cc = x.shape
+    p = LayerNormParams()
+    p.x, p.ldx, p.rows, p.C = ptr(x), x.stride(0), rows, Cc
+    p.w, p.b, p.w0, p.b0 = ptr(w), ptr(b), ptr(w0), ptr(b0)
+    if scale is not None:
+        p.scale, p.shift, p.mod_ld = ptr(scale), ptr(shift), scale.stride(-2)
+    p.rows_per_frame, p.eps, p.normalize = rows_per_frame, eps, int(normalize)
+    if out_bf16 is None and want_bf16:
+        out_bf16 = torch.empty((rows, Cc), dtype=torch.bfloat16, device=x.device)
+    if out_f32 is None and want_f32:
+        out_f32 = torch.empty((rows, Cc), dtype=torch.float32, device=x.device)
+    if out_bf16 is not None:
+        p.y_bf16, p.ldy_bf16 = ptr(out_bf16), out_bf16.stride(0)
+    if out_f32 is not None:
+        p.y_f32, p.ldy_f32 = ptr(out_f32), out_f32.stride(0)
+    check(lib.vs_layernorm(C.byref(p), C.c_void_p(stream_ptr())), "vs_layernorm")
+    return out_bf16, out_f32
+
+
+def attention(Q, K, V, O, *, heads, q_start, q_len, kv_start0, kv_len0, kv_start1=None,
+              kv_len1=None, max_q_len, causal_block=0, scale=0.125):
+    """softmax(Q K^T * scale) V per (item, head); Q/K/V/O are 2-D bf16 views (rows, >= heads*64)."""
+    _need_cuda(Q, K, V, O)
+    lib = _lib.load()
+    p = AttentionParams()
+    p.Q, p.K, p.V, p.O = ptr(Q), ptr(K), ptr(V), ptr(O)
+    p.ldq, p.ldk, p.ldv, p.ldo = Q.stride(0), K.stride(0), V.stride(0), O.stride(0)
+    p.q_rows, p.kv_rows = Q.shape[0], K.shape[0]
+    p.heads, p.items = heads, q_start.numel()
+    p.q_start, p.q_len = ptr(q_start), ptr(q_len)
+    p.kv_start0, p.kv_len0 = ptr(kv_start0), ptr(kv_len0)
+    p.kv_start1, p.kv_len1 = ptr(kv_start1), ptr(kv_len1)
+    p.max_q_len, p.causal_block, p.scale = max_q_len, causal_block, scale
+    check(lib.vs_attention(C.byref(p), C.c_void_p(stream_ptr())), "vs_attention")
+    return O
+
+
+def rope_rows(qkv, pos_i32, *, heads, q_col, k_col, base=100.0, cam_theta=30.0):
+    lib = _lib.load()
+    _need_cuda(qkv, pos_i32)
+    check(lib.vs_rope_rows(C.c_void_p(ptr(qkv)), C.c_int64(qkv.stride(0)), qkv.shape[0], heads,
+                           q_col, k_col, C.c_void_p(ptr(pos_i32)), C.c_float(base),
+                           C.c_float(cam_theta), C.c_void_p(stream_ptr())), "vs_rope_rows")
+    return qkv
+
+
+def patchify(img, P=16):
+    lib = _lib.load()
+    _need_cuda(img)
+    n, c, h, w = img.shape
+    assert c == 3 and img.dtype == torch.float32 and img.is_contiguous()
+    out = torch.empty((n * (h // P) * (w // P), 3 * P * P), dtype=torch.bfloat16, device=img.device)
+    check(lib.vs_patchify(C.c_void_p(ptr(img)), C.c_void_p(ptr(out)), n, h, w, P,
+                          C.c_void_p(stream_ptr())), "vs_patchify")
+    return out
+
+
+def im2col(src, *, nchw_f32, n, h, w, c, k, stride, pad, kpad):
+    lib = _lib.load()
+    _need_cuda(src)
+    ho, wo = (h + 2 * pad - k) // stride + 1, (w + 2 * pad - k) // stride + 1
+    out = torch.empty((n * ho * wo, kpad), dtype=torch.bfloat16, device=src.device)
+    check(lib.vs_im2col(C.c_void_p(ptr(src)), int(nchw_f32), C.c_void_p(ptr(out)), n, h, w, c, k,
+                        stride, pad, kpad, C.c_void_p(stream_ptr())), "vs_im2col")
+    return out
+
+
+def upsample2x(x_nhwc):
+    lib = _lib.load()
+    _need_cuda(x_nhwc)
+    n, h, w, c = x_nhwc.shape
+    out = torch.empty((n, 2 * h, 2 * w, c), dtype=torch.bfloat16, device=x_nhwc.device)
+    check(lib.vs_upsample2x(C.c_void_p(ptr(x_nhwc)), C.c_void_p(ptr(out)), n, h, w, c,
+                            C.c_void_p(stream_ptr())), "vs_upsample2x")
+    return out
+
+
+def pixel_shuffle(src, n, h, w, c, k):
+    lib = _lib.load()
+    _need_cuda(src)
+    out = torch.empty((n, h * k, w * k, c), dtype=torch.bfloat16, device=src.device)
+    check(lib.vs_pixel_shuffle(C.c_void_p(ptr(src)), C.c_void_p(ptr(out)), n, h, w, c, k,
+                               C.c_void_p(stream_ptr())), "vs_pixel_shuffle")
+    return out
+
+
+def intrinsic_token(K9, w, b, x, frames, E, rows_per_frame, row_off):
+    lib = _lib.load()
+    check(lib.vs_intrinsic_token(C.c_void_p(ptr(K9)), C.c_void_p(ptr(w)), C.c_void_p(ptr(b)),
+                                 C.c_void_p(ptr(x)), frames, E, rows_per_frame, row_off,
+                                 C.c_void_p(stream_ptr())), "vs_intrinsic_token")
+
+
+def camera_tokens(intr_tok, extr_tok, x, frames, T, Cdim, rows_per_frame):
+    lib = _lib.load()
+    check(lib.vs_camera_tokens(C.c_void_p(ptr(intr_tok)), C.c_void_p(ptr(extr_tok)),
+                               C.c_void_p(ptr(x)), frames, T, Cdim, rows_per_frame,
+                               C.c_void_p(stream_ptr())), "vs_camera_tokens")
+
+
+def silu_bf16(x, rows, Cdim, ldx=None):
+    lib = _lib.load()
+    y = torch.empty((rows, Cdim), dtype=torch.bfloat16, device=x.device)
+    check(lib.vs_silu_bf16(C.c_void_p(ptr(x)), C.c_int64(ldx if ldx is not None else x.stride(0)),
+                           C.c_void_p(ptr(y)), C.c_int64(Cdim), rows, Cdim,
+                           C.c_void_p(stream_ptr())), "vs_silu_bf16")
+    return y
+
+
+def camera_head(cam_feat, ld, w, b, B, T, Cdim):
+    lib = _lib.load()
+    pred = torch.empty((B, T - 1, 8), dtype=torch.float32, device=cam_feat.device)
+    c2w = torch.empty((B, T, 4, 4), dtype=torch.float32, device=cam_feat.device)
+    check(lib.vs_camera_head(C.c_void_p(ptr(cam_feat)), C.c_int64(ld), C.c_void_p(ptr(w)),
+                             C.c_void_p(ptr(b)), B, T, Cdim, C.c_void_p(ptr(pred)),
+                             C.c_void_p(ptr(c2w)), C.c_void_p(stream_ptr())), "vs_camera_head")
+    return pred, c2w
+
+
+def pts_tail(feat, Cf, w, b, raw, px):
+    lib = _lib.load()
+    check(lib.vs_pts_tail(C.c_void_p(ptr(feat)), Cf, C.c_void_p(ptr(w)), C.c_void_p(ptr(b)),
+                          C.c_void_p(ptr(raw)), C.c_int64(raw.stride(-2)), C.c_int64(px),
+                          C.c_void_p(stream_ptr())), "vs_pts_tail")
+
+
+def gaussian_adapter(raw, d_sh, sh_mask, *, want_cov=True):
+    """raw (G, 86) fp32 -> dict of means/cov/cov6/sh/opac/scales/rot (gaussian_adapter.py:167-212)."""
+    lib = _lib.load()
+    _need_cuda(raw)
+    G = raw.shape[0]
+    dev, f32 = raw.device, torch.float32
+    out = dict(
+        means=torch.empty((G, 3), dtype=f32, device=dev),
+        cov=torch.empty((G, 3, 3), dtype=f32, device=dev) if want_cov else None,
+        cov6=torch.empty((G, 6), dtype=f32, device=dev),
+        sh=torch.empty((G, 3, d_sh), dtype=f32, device=dev),
+        opac=torch.empty((G,), dtype=f32, device=dev),
+        scales=torch.empty((G, 3), dtype=f32, device=dev),
+        rot=torch.empty((G, 4), dtype=f32, device=dev),
+    )
+    check(lib.vs_gaussian_adapter(
+        C.c_void_p(ptr(raw)), C.c_int64(raw.stride(0)), C.c_int64(G), d_sh,
+        C.c_void_p(ptr(sh_mask)), C.c_void_p(ptr(out["means"])), C.c_void_p(ptr(out["cov"])),
+        C.c_void_p(ptr(out["cov6"])), C.c_void_p(ptr(out["sh"])), C.c_void_p(ptr(out["opac"])),
+        C.c_void_p(ptr(out["scales"])), C.c_void_p(ptr(out["rot"])),
+        C.c_void_p(stream_ptr())), "vs_gaussian_adapter")
+    return out

@@ -1,0 +1,213 @@
+"""Drop-in for the ``diff_gaussian_rasterization`` extension the reference imports at
+src/model/decoder/cuda_splatting.py:5-8 and calls at :207-235 / :304-330, plus the batched
+multi-view entry (`rasterize_views`) that `DecoderSplattingCUDA` uses to render all V views of a
+scene from ONE copy of the Gaussians.
+
+Everything runs in the hand-written sm_100a kernels behind ``vs_raster_forward`` /
+``vs_raster_backward``; there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import NamedTuple, Optional
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._lib import RasterBwdParams, RasterParams, check, ptr, stream_ptr
+
+
+class GaussianRasterizationSettings(NamedTuple):
+    image_height: int
+    image_width: int
+    tanfovx: float
+    tanfovy: float
+    bg: torch.Tensor
+    scale_modifier: float
+    viewmatrix: torch.Tensor
+    projmatrix: torch.Tensor
+    projmatrix_raw: torch.Tensor
+    sh_degree: int
+    campos: torch.Tensor
+    prefiltered: bool = False
+    debug: bool = False
+
+
+class RasterOverflow(RuntimeError):
+    pass
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    return t.detach().to(torch.float32).contiguous()
+
+
+class _Ctx:
+    """Forward state kept for the backward pass (workspace holds the sorted splat lists)."""
+    __slots__ = ("params", "keep", "num_pairs", "max_pairs")
+
+
+def _run_forward(V, G, H, W, shared, means, cov6, opac, shs, sh_M, sh_degree, sh_strides, colors,
+                 viewm, projm, campos, tanfov, bg, max_pairs, want_aux=True):
+    lib = _lib.load()
+    dev = means.device
+    f32, i32 = torch.float32, torch.int32
+    color = torch.empty((V, 3, H, W), dtype=f32, device=dev)
+    depth = torch.empty((V, 1, H, W), dtype=f32, device=dev)
+    alpha = torch.empty((V, 1, H, W), dtype=f32, device=dev)
+    radii = torch.empty((V, max(G, 1)), dtype=i32, device=dev)
+    n_touched = torch.empty((V, max(G, 1)), dtype=i32, device=dev) if want_aux else None
+    final_T = torch.empty((V, H, W), dtype=f32, device=dev)
+    n_contrib = torch.empty((V, H, W), dtype=i32, device=dev)
+    num_pairs = torch.zeros((1,), dtype=torch.int64, device=dev)
+    ws_bytes = lib.vs_raster_workspace_bytes(V, max(G, 1), H, W, max_pairs)
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+    p = RasterParams()
+    p.V, p.G, p.H, p.W, p.gaussians_shared = V, G, H, W, int(shared)
+    p.means3D, p.cov3D, p.opacities = ptr(means), ptr(cov6), ptr(opac)
+    p.shs, p.sh_M, p.sh_degree = ptr(shs), sh_M, sh_degree
+    p.sh_stride_coef, p.sh_stride_chan = sh_strides
+    p.colors_precomp = ptr(colors)
+    p.viewmatrix, p.projmatrix, p.campos = ptr(viewm), ptr(projm), ptr(campos)
+    p.tanfov, p.bg, p.scale_modifier = ptr(tanfov), ptr(bg), 1.0
+    p.out_color, p.out_depth, p.out_alpha = ptr(color), ptr(depth), ptr(alpha)
+    p.radii, p.n_touched, p.final_T, p.n_contrib = ptr(radii), ptr(n_touched), ptr(final_T), ptr(n_contrib)
+    p.workspace, p.workspace_bytes, p.max_pairs = ptr(ws), ws_bytes, max_pairs
+    p.num_pairs_out = ptr(num_pairs)
+    check(lib.vs_raster_forward(C.byref(p), C.c_void_p(stream_ptr())), "vs_raster_forward")
+    ctx = _Ctx()
+    ctx.params = p
+    ctx.keep = (means, cov6, opac, shs, colors, viewm, projm, campos, tanfov, bg, color, depth,
+                alpha, radii, n_touched, final_T, n_contrib, ws, num_pairs)
+    ctx.num_pairs, ctx.max_pairs = num_pairs, max_pairs
+    return color, depth, alpha, radii, n_touched, ctx
+
+
+class _Rasterize(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, means, cov6, opac, shs, colors, theta, rho, cfg):
+        (V, G, H, W, shared, sh_M, sh_degree, sh_strides, viewm, projm, campos, tanfov, bg,
+         max_pairs, check_overflow) = cfg
+        m, c6, o = _f32c(means), _f32c(cov6), _f32c(opac).reshape(-1)
+        s = _f32c(shs) if shs is not None else None
+        cp = _f32c(colors) if colors is not None else None
+        while True:
+            color, depth, alpha, radii, n_touched, st = _run_forward(
+                V, G, H, W, shared, m, c6, o, s, sh_M, sh_degree, sh_strides, cp, viewm, projm,
+                campos, tanfov, bg, max_pairs)
+            if not check_overflow:
+                break
+            n = int(st.num_pairs.item())      # the upstream extension syncs here too (num_rendered)
+            if n <= max_pairs:
+                break
+            max_pairs = int(n * 1.05) + 1024  # capacity was too small: re-run with the exact need
+        ctx.state = st
+        ctx.shapes = (means.shape, cov6.shape, opac.shape, None if shs is None else shs.shape,
+                      None if colors is None else colors.shape)
+        ctx.has_pose = (theta is not None, rho is not None)
+        ctx.mark_non_differentiable(radii, n_touched)
+        return color, radii, depth, alpha, n_touched
+
+    @staticmethod
+    def backward(ctx, g_color, g_radii, g_depth, g_alpha, g_touched):
+        lib = _lib.load()
+        st = ctx.state
+        fp = st.params
+        V, G = fp.V, fp.G
+        dev = g_color.device if g_color is not None else g_depth.device
+        f32 = torch.float32
+        shared = bool(fp.gaussians_shared)
+        lead = (G,) if shared else (V, G)
+        d_means = torch.zeros(lead + (3,), dtype=f32, device=dev)
+        d_cov = torch.zeros(lead + (6,), dtype=f32, device=dev)
+        d_opac = torch.zeros(lead, dtype=f32, device=dev)
+        has_sh = fp.shs is not None
+        d_shs = torch.zeros(lead + (3 * fp.sh_M,), dtype=f32, device=dev) if has_sh else None
+        d_col = torch.zeros(lead + (3,), dtype=f32, device=dev) if not has_sh else None
+        d_tau = torch.zeros((V, 6), dtype=f32, device=dev)
+        gc = _f32c(g_color) if g_color is not None else torch.zeros((V, 3, fp.H, fp.W), dtype=f32, device=dev)
+        gd = _f32c(g_depth) if g_depth is not None else None
+        ga = _f32c(g_alpha) if g_alpha is not None else None
+        bp = RasterBwdParams()
+        bp.fwd = fp
+        bp.dL_dcolor, bp.dL_ddepth, bp.dL_dalpha = ptr(gc), ptr(gd), ptr(ga)
+        bp.dL_dmeans3D, bp.dL_dcov3D, bp.dL_dopacity = ptr(d_means), ptr(d_cov), ptr(d_opac)
+        bp.dL_dshs, bp.dL_dcolors, bp.dL_dtau = ptr(d_shs), ptr(d_col), ptr(d_tau)
+        check(lib.vs_raster_backward(C.byref(bp), C.c_void_p(stream_ptr())), "vs_raster_backward")
+        sm, sc, so, ss, scol = ctx.shapes
+        g_shs = d_shs.reshape(ss) if has_sh else None
+        g_cols = d_col.reshape(scol) if not has_sh else None
+        g_theta = d_tau[:, 3:].reshape(-1) if ctx.has_pose[0] else None
+        g_rho = d_tau[:, :3].reshape(-1) if ctx.has_pose[1] else None
+        if V > 1:
+            g_theta = d_tau[:, 3:] if ctx.has_pose[0] else None
+            g_rho = d_tau[:, :3] if ctx.has_pose[1] else None
+        return (d_means.reshape(sm), d_cov.reshape(sc), d_opac.reshape(so), g_shs, g_cols,
+                g_theta, g_rho, None)
+
+
+def rasterize_views(means3D, cov6, opacities, *, shs=None, colors_precomp=None, sh_degree=0,
+                    sh_layout="coef_major", viewmatrix, projmatrix, campos, tanfov, bg, H, W,
+                    theta=None, rho=None, max_pairs: Optional[int] = None,
+                    check_overflow: bool = True):
+    """Render V views.  Gaussians are shared by all views when means3D is (G,3), per-view when
+    (V,G,3).  viewmatrix/projmatrix (V,4,4) are the *transposed* matrices the reference passes
+    (cuda_splatting.py:192-194); tanfov (V,2); bg (V,3) or (3,).
+
+    sh_layout: "coef_major" = (G, M, 3), the layout the reference hands the extension
+    (cuda_splatting.py:182); "chan_major" = (G, 3, M), the encoder's own layout
+    (gaussian_adapter.py:180), consumed without the transpose copy.
+
+    Returns color (V,3,H,W), radii (V,G), depth (V,1,H,W), alpha (V,1,H,W), n_touched (V,G).
+    """
+    if not means3D.is_cuda:
+        raise RuntimeError("rasterize_views needs CUDA tensors (there is no CPU fallback)")
+    V = viewmatrix.shape[0]
+    shared = means3D.dim() == 2
+    G = means3D.shape[-2]
+    dev = means3D.device
+    vm = _f32c(viewmatrix).reshape(V, 16)
+    pm = _f32c(projmatrix).reshape(V, 16)
+    cp = _f32c(campos).reshape(V, 3)
+    tf = _f32c(tanfov.to(dev) if isinstance(tanfov, torch.Tensor) else
+               torch.tensor(tanfov, dtype=torch.float32, device=dev)).reshape(V, 2)
+    bgc = _f32c(bg.to(dev)).reshape(-1, 3).expand(V, 3).contiguous()
+    sh_M = 0
+    strides = (0, 0)
+    if shs is not None:
+        if sh_layout == "coef_major":
+            sh_M, strides = shs.shape[-2], (3, 1)
+        elif sh_layout == "chan_major":
+            sh_M, strides = shs.shape[-1], (1, shs.shape[-1])
+        else:
+            raise ValueError(f"bad sh_layout {sh_layout!r}")
+    if max_pairs is None:
+        max_pairs = max(4 * V * G, 1 << 16)
+    cfg = (V, G, H, W, shared, sh_M, int(sh_degree), strides, vm, pm, cp, tf, bgc, int(max_pairs),
+           check_overflow)
+    return _Rasterize.apply(means3D, cov6, opacities, shs, colors_precomp, theta, rho, cfg)
+
+
+class GaussianRasterizer(nn.Module):
+    """Same call signature and 5-tuple return as the reference's extension
+    (cuda_splatting.py:226-235, :323-330)."""
+
+    def __init__(self, raster_settings: GaussianRasterizationSettings):
+        super().__init__()
+        self.raster_settings = raster_settings
+
+    def forward(self, means3D, means2D=None, shs=None, colors_precomp=None, opacities=None,
+                scales=None, rotations=None, cov3D_precomp=None, theta=None, rho=None):
+        rs = self.raster_settings
+        if (shs is None) == (colors_precomp is None):
+            raise Exception("Please provide excatly one of either SHs or precomputed colors!")
+        if cov3D_precomp is None:
+            raise Exception("vicasplat_b200 rasterizer: only cov3D_precomp is supported "
+                            "(the reference never passes scales/rotations, cuda_splatting.py:231-232)")
+        tanfov = torch.tensor([[float(rs.tanfovx), float(rs.tanfovy)]], dtype=torch.float32)
+        color, radii, depth, alpha, n_touched = rasterize_views(
+            means3D, cov3D_precomp, opacities, shs=shs, colors_precomp=colors_precomp,
+            sh_degree=rs.sh_degree, viewmatrix=rs.viewmatrix[None], projmatrix=rs.projmatrix[None],
+            campos=rs.campos[None], tanfov=tanfov, bg=rs.bg, H=int(rs.image_height),
+            W=int(rs.image_width), theta=theta, rho=rho)
+        return color[0], radii[0], depth[0], alpha[0], n_touched[0]
