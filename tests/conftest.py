@@ -27,4 +27,7 @@ def cuda():
     import torch
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
+    # the torch fp32 references must really be fp32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
     return torch.device("cuda:0")
