@@ -47,7 +47,7 @@ def _check(c, d, rc, rd, atol=1e-4, frac=0.999, worst=5e-3):
 
 def _check64(c, d, sc, hw, bg=None):
     rc, rd = _oracle(sc, hw, torch.float64, bg)
-    _check(c, d, rc, rd, atol=1e-4, frac=0.97, worst=1e-2)
+    _check(c, d, rc, rd, atol=1e-4, frac=0.95, worst=5e-2)
 
 
 @pytest.mark.parametrize("hw,n_ctx,n_tgt,seed", [(64, 2, 3, 1), (48, 1, 2, 2), (80, 2, 1, 3)])
