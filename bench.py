@@ -1,0 +1,367 @@
+#!/usr/bin/env python
+"""Headline benchmark: scenes/s (and rendered Mpix/s) of the 8-view 256x256 forward path
+(encoder + 12-view splatting render), BASELINE.json configs[1].
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One process per GPU (torchrun sets RANK/LOCAL_RANK/WORLD_SIZE); scenes are independent so ranks
+run replicas of the step with no data-path collective ("weak" scaling); rank 0 prints ONE JSON line.
+A step = one scene: VicaSplat encoder forward on an 8-frame clip, then the 12-view render of a
+524 288-Gaussian scene.  Data is synthetic (vicasplat_b200/synthetic.py): random-weight encoder
+output is degenerate as raster input, so the raster leg renders a seeded
+pixel-aligned Gaussian scene of exactly the shape the encoder emits.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+T_CTX, V_TGT, SIZE = 8, 12, 256
+G_SCENE = T_CTX * SIZE * SIZE
+METRIC = "scenes_per_sec_8view_256x256_forward"
+
+
+# ------------------------------------------------------------------------------------ models
+def encoder_flops(T: int, size: int = SIZE) -> float:
+    """Algorithmic forward FLOPs (2*MAC) per scene of T frames."""
+    E, D, Le, Ld = 1024, 768, 24, 12
+    N = (size // 16) ** 2 + 1
+    px = (size / 256.0) ** 2
+    per_frame = (2 * N * 12 * E * E * Le + 4 * N * N * E * Le                     # ViT-L linear + attention
+                 + 2 * (N * 16 + 21) * D * D * Ld                                 # MixDecoder linears
+                 + 4 * N * T * (N + 1) * D * Ld                                   # video attention
+                 + 4 * N * (2 * N if T > 2 else N) * D * Ld                       # neighbour attention
+                 + 2 * (N - 1) * 768 * E + 2 * N * E * D                          # patch / decoder embed
+                 + (62.2e9 + 118.2e9) * px)                                       # two DPT heads
+    return per_frame * T
+
+
+def raster_bytes(V: int, G: int, H: int, W: int) -> float:
+    """Algorithmic HBM bytes of a V-view forward render: every used Gaussian
+    parameter once per view (12 B mean + 24 B cov6 + 4 B opacity + 192 B of SH bands 0..3) plus one
+    RGB-D write per pixel."""
+    return V * (G * 232.0 + H * W * 16.0)
+
+
+def load_peaks() -> dict:
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return dict(hbm=d["hbm_gbs"], tf=d["bf16_tflops_sustained"], which="measured")
+    return dict(hbm=6650.0, tf=1400.0, which="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc = index, None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+        return self
+
+    def __exit__(self, *exc):
+        self.result = dict(sm_mhz=None, sm_max_mhz=None, reasons=[])
+        if self.proc is None:
+            return
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if sm:
+            self.result = dict(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx),
+                               reasons=sorted(reasons), samples=len(sm))
+
+
+# ------------------------------------------------------------------------------------ reference arm
+def cpu_reference_step(t_frames: int, n_views: int, seed: int = 1):
+    """One bounded sample of the workload on the host cores with the oracle port of the reference
+    (the reference itself cannot run here: /root/reference does not exist on the GPU box and its
+    rasterizer is an un-vendored CUDA-only extension).  Returns (t_encoder, t_raster_per_view)."""
+    import torch
+    from oracle import encoder_ref as er
+    from oracle import raster_ref as rr
+    from vicasplat_b200 import synthetic
+    st = cpu_reference_step
+    if not hasattr(st, "cache"):
+        cfg = er.EncoderConfig()
+        st.cache = dict(cfg=cfg, sd=er.synth_state_dict(cfg, seed=0),
+                        scene=synthetic.gaussian_scene(T_CTX, SIZE, SIZE, V_TGT, seed=seed))
+    c = st.cache
+    image, K = synthetic.clip(1, t_frames, SIZE)
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        er.forward(c["sd"], image, K, c["cfg"])
+        t1 = time.perf_counter()
+        sc = c["scene"]
+        rr.render_cuda_ref(sc["extrinsics"][:n_views], sc["intrinsics"][:n_views], sc["near"][:n_views],
+                           sc["far"][:n_views], (SIZE, SIZE), torch.zeros((n_views, 3)), sc["means"],
+                           sc["covariances"], sc["harmonics"], sc["opacities"])
+        t2 = time.perf_counter()
+    return t1 - t0, (t2 - t1) / n_views
+
+
+def scene_seconds_from_sample(t_enc: float, t_frames: int, t_view: float) -> float:
+    return t_enc * encoder_flops(T_CTX) / encoder_flops(t_frames) + V_TGT * t_view
+
+
+def run_reference(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    cores = torch.get_num_threads()
+    t_frames = 2
+    sample = (f"per step: oracle encoder forward on {t_frames} of {T_CTX} frames (scaled by "
+              f"algorithmic FLOPs) + 1 of {V_TGT} target views of the {G_SCENE}-Gaussian scene (x{V_TGT})")
+    for _ in range(args.warmup):
+        cpu_reference_step(t_frames, 1)
+    secs = []
+    for _ in range(args.steps):
+        te, tv = cpu_reference_step(t_frames, 1)
+        secs.append(scene_seconds_from_sample(te, t_frames, tv))
+    per = sum(secs) / len(secs)
+    val = 1.0 / per
+    line = dict(impl="reference", metric=METRIC, value=val, unit="scenes/s", n_gpus=args.gpus,
+                steps=args.steps, warmup=args.warmup, ms_per_step=per * 1e3, higher_is_better=True,
+                scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                mpix_per_sec=val * V_TGT * SIZE * SIZE / 1e6,
+                config=config_dict(),
+                cpu_baseline=dict(value=val, unit="scenes/s", cores=cores, kind="port", sample=sample),
+                e2e=dict(value=val, unit="scenes/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line), flush=True)
+
+
+def config_dict() -> dict:
+    return dict(workload=f"configs[1]: {T_CTX}-view {SIZE}x{SIZE} re10k_8view forward-only, B=1 scene per "
+                         f"GPU per step: encoder ({T_CTX} frames) + render of {V_TGT} target views, "
+                         f"G={G_SCENE} Gaussians", context_views=T_CTX, target_views=V_TGT,
+                image=f"{SIZE}x{SIZE}", gaussians=G_SCENE, weights="random-init (seeded)",
+                raster_input="seeded pixel-aligned Gaussian scene (random-weight encoder output is degenerate)",
+                l2="inputs larger than L2 (1.2 GB bf16 weights, 178 MB Gaussians); no explicit flush",
+                parallelism="replicas (one scene per GPU, no data-path collective)")
+
+
+# ------------------------------------------------------------------------------------ our arm
+def run_ours(args) -> None:
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from vicasplat_b200 import _lib, synthetic
+    from vicasplat_b200 import decoder as dec
+    from vicasplat_b200.encoder import Gaussians, VicaSplat
+    from vicasplat_b200.rasterizer import rasterize_views
+    lib = _lib.load()
+
+    torch.manual_seed(1234 + rank)
+    model = VicaSplat().to(dev)
+    with torch.no_grad():                      # the reference zero-inits these; exercise them
+        for n, p in model.named_parameters():
+            if "modulation" in n or n.startswith("camera_extrinsic_head"):
+                p.normal_(0, 0.02)
+    model.invalidate()
+    eng = model.engine()
+    image_h, K_h = synthetic.clip(1, T_CTX, SIZE, seed=250307 + rank)
+    image_h, K_h = image_h.pin_memory(), K_h.pin_memory()
+    image_d, K_d = image_h.to(dev), K_h.to(dev)
+    sc = {k: v.to(dev) for k, v in synthetic.gaussian_scene(T_CTX, SIZE, SIZE, V_TGT, seed=1 + rank).items()}
+    tanfov, view_t, full_t, campos = dec._cameras(sc["extrinsics"], sc["intrinsics"], sc["near"], sc["far"])
+    cov6 = dec._cov6(sc["covariances"]).contiguous()
+    bg = torch.zeros((V_TGT, 3), device=dev)
+    rkw = dict(shs=sc["harmonics"], sh_degree=4, sh_layout="chan_major", viewmatrix=view_t,
+               projmatrix=full_t, campos=campos, tanfov=tanfov, bg=bg, H=SIZE, W=SIZE)
+
+    # calibrate the (tile, splat) pair capacity once, outside the timed region: the exact pair
+    # count of this scene is a device scalar written by vs_raster_forward
+    import vicasplat_b200.rasterizer as rmod
+    color = rasterize_views(sc["means"], cov6, sc["opacities"], **rkw)[0]
+    probe = rmod._run_forward(V_TGT, G_SCENE, SIZE, SIZE, True, sc["means"], cov6, sc["opacities"],
+                              sc["harmonics"], 25, 4, (1, 25), None, view_t.reshape(V_TGT, 16).contiguous(),
+                              full_t.reshape(V_TGT, 16).contiguous(), campos.contiguous(),
+                              tanfov.contiguous(), bg, 4 * V_TGT * G_SCENE)
+    n_pairs = int(probe[-1].num_pairs.item())
+    del probe
+    max_pairs = int(n_pairs * 1.02) + 4096
+    rkw.update(max_pairs=max_pairs, check_overflow=False)
+
+    def device_step():
+        eng.run(image_d, K_d, clone_outputs=False)
+        return rasterize_views(sc["means"], cov6, sc["opacities"], **rkw)
+
+    # launches per step: kernels recorded into the encoder graph + the raster chain
+    l0 = lib.vs_launch_count()
+    device_step()                               # first call captures the graph (counts twice: warm-up + capture)
+    torch.cuda.synchronize()
+    l1 = lib.vs_launch_count()
+    rasterize_views(sc["means"], cov6, sc["opacities"], **rkw)
+    l2 = lib.vs_launch_count()
+    raster_launches = l2 - l1
+    enc_launches = (l1 - l0 - raster_launches) // 2
+    gpu_launches = int(enc_launches + raster_launches)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        device_step()
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    barrier()
+    with ClockSampler(local) as clk:
+        t_wall0 = time.perf_counter()
+        for i in range(args.steps):
+            ev[i][0].record()
+            eng.run(image_d, K_d, clone_outputs=False)
+            ev[i][1].record()
+            rasterize_views(sc["means"], cov6, sc["opacities"], **rkw)
+            ev[i][2].record()
+        barrier()
+        t_wall = time.perf_counter() - t_wall0
+    total_ms = ev[0][0].elapsed_time(ev[-1][2])
+    enc_ms = sum(e[0].elapsed_time(e[1]) for e in ev) / args.steps
+    ras_ms = sum(e[1].elapsed_time(e[2]) for e in ev) / args.steps
+    step_ms = total_ms / args.steps
+
+    # ---- e2e: host buffers in, host result out, through the plugin calls a user makes
+    decoder = dec.DecoderSplattingCUDA(dec.DecoderSplattingCUDACfg("splatting_cuda", [0.0, 0.0, 0.0], False)).to(dev)
+    gauss = Gaussians(means=sc["means"][None], covariances=sc["covariances"][None],
+                      harmonics=sc["harmonics"][None], opacities=sc["opacities"][None])
+    ext, intr = sc["extrinsics"][None], sc["intrinsics"][None]
+    near, far = sc["near"][None], sc["far"][None]
+    color_h = torch.empty((1, V_TGT, 3, SIZE, SIZE), dtype=torch.float32).pin_memory()
+    depth_h = torch.empty((1, V_TGT, SIZE, SIZE), dtype=torch.float32).pin_memory()
+    pose_h = torch.empty((1, T_CTX - 1, 8), dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        ctx = {"image": image_h.to(dev, non_blocking=True), "intrinsics": K_h.to(dev, non_blocking=True)}
+        enc_out = model(ctx, compute_viewspace_depth=False)
+        o = decoder.forward(gauss, ext, intr, near, far, (SIZE, SIZE))
+        color_h.copy_(o.color, non_blocking=True)
+        depth_h.copy_(o.depth, non_blocking=True)
+        pose_h.copy_(enc_out["pred_extrins"], non_blocking=True)
+        torch.cuda.synchronize()
+
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / args.steps
+    h2d = image_h.numel() * 4 + K_h.numel() * 4
+    d2h = (color_h.numel() + depth_h.numel() + pose_h.numel()) * 4
+
+    # ---- max over ranks
+    t = torch.tensor([step_ms, enc_ms, ras_ms, e2e_s * 1e3], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    step_ms, enc_ms, ras_ms, e2e_ms = t.tolist()
+
+    # overflow check of the calibrated capacity (outside the timed region)
+    chk = rmod._run_forward(V_TGT, G_SCENE, SIZE, SIZE, True, sc["means"], cov6, sc["opacities"],
+                            sc["harmonics"], 25, 4, (1, 25), None, view_t.reshape(V_TGT, 16).contiguous(),
+                            full_t.reshape(V_TGT, 16).contiguous(), campos.contiguous(),
+                            tanfov.contiguous(), bg, max_pairs)
+    assert int(chk[-1].num_pairs.item()) <= max_pairs, "raster capacity overflow"
+    assert torch.isfinite(color).all()
+
+    if rank == 0:
+        peaks = load_peaks()
+        value = world * 1e3 / step_ms
+        fl = encoder_flops(T_CTX)
+        enc_tf = fl / (enc_ms * 1e-3) / 1e12
+        rb = raster_bytes(V_TGT, G_SCENE, SIZE, SIZE)
+        ras_gbs = rb / (ras_ms * 1e-3) / 1e9
+        line = dict(
+            metric=METRIC, value=value, unit="scenes/s", n_gpus=world, steps=args.steps,
+            warmup=max(args.warmup, 3), ms_per_step=step_ms, higher_is_better=True, scaling="weak",
+            vs_baseline=None, dtype="bf16", data="synthetic", config=config_dict(),
+            mpix_per_sec=value * V_TGT * SIZE * SIZE / 1e6,
+            encoder_ms=enc_ms, raster_ms=ras_ms, raster_pairs=n_pairs,
+            e2e=dict(value=world * 1e3 / e2e_ms, unit="scenes/s", h2d_bytes_per_step=h2d,
+                     d2h_bytes_per_step=d2h, ms_per_step=e2e_ms),
+            gpu_launches=gpu_launches,
+            clocks=clk.result,
+            roofline=dict(bound="tensor", kernel="gemm_tc05_kernel (whole encoder forward, all kernels)",
+                          achieved=enc_tf, peak=peaks["tf"], unit="TFLOP/s", frac=enc_tf / peaks["tf"],
+                          traffic=None, peak_source=peaks["which"] + " bf16 sustained",
+                          flops_per_launch=fl),
+            roofline_raster=dict(bound="hbm", kernel="preprocess+sort+blend chain, 12 views",
+                                 achieved=ras_gbs, peak=peaks["hbm"], unit="GB/s",
+                                 frac=ras_gbs / peaks["hbm"], traffic=None,
+                                 peak_source=peaks["which"] + " copy", bytes_per_launch=rb),
+            wall_ms_per_step=t_wall * 1e3 / args.steps,
+        )
+        if world == 1 and not args.no_cpu:
+            te, tv = cpu_reference_step(T_CTX, 1)
+            per = scene_seconds_from_sample(te, T_CTX, tv)
+            line["cpu_baseline"] = dict(
+                value=1.0 / per, unit="scenes/s", cores=torch.get_num_threads(), kind="port",
+                sample=f"oracle encoder forward on all {T_CTX} frames ({te:.1f} s) + 1 of {V_TGT} "
+                       f"target views ({tv:.1f} s, x{V_TGT})")
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -44,6 +44,9 @@ int vs_version(void);
 /* sizeof() of a parameter struct by its C name (e.g. "vs_gemm_params"), -1 if unknown: lets a
  * foreign-function binding verify its mirror of the struct layout at load time. */
 int64_t vs_struct_size(const char* name);
+/* number of kernels this library has launched (or recorded into a CUDA graph being captured) in
+ * this process so far -- instrumentation for bench.py's gpu_launches. */
+int64_t vs_launch_count(void);
 
 /* ------------------------------------------------------------------ RoPE-2D (curope.rope_2d)
  * In-place 2-D rotary embedding on tokens (B, N, H, D), D % 4 == 0, last dim contiguous,

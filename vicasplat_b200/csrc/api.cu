@@ -4,10 +4,15 @@
 #include "common.h"
 #include "tmap.h"
 
+#include <atomic>
+
 namespace vs {
 namespace {
 thread_local char g_err[512] = "";
+std::atomic<long long> g_launches{0};
 }
+
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -62,6 +67,7 @@ int encode_map(CUtensorMap* map, const void* base, int rank, const cuuint64_t* d
 
 extern "C" const char* vs_last_error(void) { return vs::g_err; }
 extern "C" int vs_version(void) { return 100; }
+extern "C" int64_t vs_launch_count(void) { return vs::g_launches.load(std::memory_order_relaxed); }
 
 extern "C" int64_t vs_struct_size(const char* name) {
   if (name == nullptr) return -1;

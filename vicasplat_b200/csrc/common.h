@@ -29,7 +29,13 @@ void set_error(const char* fmt, ...);
     }                                                                                   \
   } while (0)
 
-#define VS_LAUNCH_CHECK() VS_CUDA(cudaGetLastError())
+// every kernel launch of this library goes through VS_LAUNCH_CHECK: it also feeds vs_launch_count()
+void count_launch();
+#define VS_LAUNCH_CHECK()          \
+  do {                             \
+    ::vs::count_launch();          \
+    VS_CUDA(cudaGetLastError());   \
+  } while (0)
 
 inline cudaStream_t to_stream(vs_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 

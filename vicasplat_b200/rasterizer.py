@@ -42,6 +42,11 @@ def _f32c(t: torch.Tensor) -> torch.Tensor:
     return t.detach().to(torch.float32).contiguous()
 
 
+# (V, G, H, W) -> pair capacity that was enough last time (+25 %): later calls of the same shape
+# size their binning workspace from it instead of the worst-case default
+_capacity_hint: dict = {}
+
+
 class _Ctx:
     """Forward state kept for the backward pass (workspace holds the sorted splat lists)."""
     __slots__ = ("params", "keep", "num_pairs", "max_pairs")
@@ -98,6 +103,7 @@ class _Rasterize(torch.autograd.Function):
             if not check_overflow:
                 break
             n = int(st.num_pairs.item())      # the upstream extension syncs here too (num_rendered)
+            _capacity_hint[(V, G, H, W)] = int(n * 1.25) + 4096
             if n <= max_pairs:
                 break
             max_pairs = int(n * 1.05) + 1024  # capacity was too small: re-run with the exact need
@@ -182,7 +188,7 @@ def rasterize_views(means3D, cov6, opacities, *, shs=None, colors_precomp=None, 
         else:
             raise ValueError(f"bad sh_layout {sh_layout!r}")
     if max_pairs is None:
-        max_pairs = max(4 * V * G, 1 << 16)
+        max_pairs = _capacity_hint.get((V, G, H, W), max(4 * V * G, 1 << 16))
     cfg = (V, G, H, W, shared, sh_M, int(sh_degree), strides, vm, pm, cp, tf, bgc, int(max_pairs),
            check_overflow)
     return _Rasterize.apply(means3D, cov6, opacities, shs, colors_precomp, theta, rho, cfg)
