@@ -167,10 +167,11 @@ def run_reference(args) -> None:
     print(json.dumps(line), flush=True)
 
 
-def config_dict() -> dict:
-    return dict(workload=f"configs[1]: {T_CTX}-view {SIZE}x{SIZE} re10k_8view forward-only, B=1 scene per "
-                         f"GPU per step: encoder ({T_CTX} frames) + render of {V_TGT} target views, "
-                         f"G={G_SCENE} Gaussians", context_views=T_CTX, target_views=V_TGT,
+def config_dict(nb: int = 1) -> dict:
+    return dict(workload=f"configs[1]: {T_CTX}-view {SIZE}x{SIZE} re10k_8view forward-only, {nb} scene(s) per "
+                         f"GPU per step: encoder ({T_CTX} frames/scene) + render of {V_TGT} target views/scene, "
+                         f"G={G_SCENE} Gaussians/scene", scenes_per_step_per_gpu=nb, context_views=T_CTX,
+                target_views=V_TGT,
                 image=f"{SIZE}x{SIZE}", gaussians=G_SCENE, weights="random-init (seeded)",
                 raster_input="seeded pixel-aligned Gaussian scene (random-weight encoder output is degenerate)",
                 l2="inputs larger than L2 (1.2 GB bf16 weights, 178 MB Gaussians); no explicit flush",
@@ -204,7 +205,8 @@ def run_ours(args) -> None:
                 p.normal_(0, 0.02)
     model.invalidate()
     eng = model.engine()
-    image_h, K_h = synthetic.clip(1, T_CTX, SIZE, seed=250307 + rank)
+    NB = args.batch
+    image_h, K_h = synthetic.clip(NB, T_CTX, SIZE, seed=250307 + rank)
     image_h, K_h = image_h.pin_memory(), K_h.pin_memory()
     image_d, K_d = image_h.to(dev), K_h.to(dev)
     sc = {k: v.to(dev) for k, v in synthetic.gaussian_scene(T_CTX, SIZE, SIZE, V_TGT, seed=1 + rank).items()}
@@ -227,16 +229,21 @@ def run_ours(args) -> None:
     max_pairs = int(n_pairs * 1.02) + 4096
     rkw.update(max_pairs=max_pairs, check_overflow=False)
 
+    def raster_batch():
+        for _ in range(NB):           # scenes of the batch: one launch chain (all 12 views) each
+            out = rasterize_views(sc["means"], cov6, sc["opacities"], **rkw)
+        return out
+
     def device_step():
         eng.run(image_d, K_d, clone_outputs=False)
-        return rasterize_views(sc["means"], cov6, sc["opacities"], **rkw)
+        return raster_batch()
 
     # launches per step: kernels recorded into the encoder graph + the raster chain
     l0 = lib.vs_launch_count()
     device_step()                               # first call captures the graph (counts twice: warm-up + capture)
     torch.cuda.synchronize()
     l1 = lib.vs_launch_count()
-    rasterize_views(sc["means"], cov6, sc["opacities"], **rkw)
+    raster_batch()
     l2 = lib.vs_launch_count()
     raster_launches = l2 - l1
     enc_launches = (l1 - l0 - raster_launches) // 2
@@ -257,7 +264,7 @@ def run_ours(args) -> None:
             ev[i][0].record()
             eng.run(image_d, K_d, clone_outputs=False)
             ev[i][1].record()
-            rasterize_views(sc["means"], cov6, sc["opacities"], **rkw)
+            raster_batch()
             ev[i][2].record()
         barrier()
         t_wall = time.perf_counter() - t_wall0
@@ -268,13 +275,14 @@ def run_ours(args) -> None:
 
     # ---- e2e: host buffers in, host result out, through the plugin calls a user makes
     decoder = dec.DecoderSplattingCUDA(dec.DecoderSplattingCUDACfg("splatting_cuda", [0.0, 0.0, 0.0], False)).to(dev)
-    gauss = Gaussians(means=sc["means"][None], covariances=sc["covariances"][None],
-                      harmonics=sc["harmonics"][None], opacities=sc["opacities"][None])
-    ext, intr = sc["extrinsics"][None], sc["intrinsics"][None]
-    near, far = sc["near"][None], sc["far"][None]
-    color_h = torch.empty((1, V_TGT, 3, SIZE, SIZE), dtype=torch.float32).pin_memory()
-    depth_h = torch.empty((1, V_TGT, SIZE, SIZE), dtype=torch.float32).pin_memory()
-    pose_h = torch.empty((1, T_CTX - 1, 8), dtype=torch.float32).pin_memory()
+    rep = lambda t: t[None].expand(NB, *t.shape)
+    gauss = Gaussians(means=rep(sc["means"]), covariances=rep(sc["covariances"]),
+                      harmonics=rep(sc["harmonics"]), opacities=rep(sc["opacities"]))
+    ext, intr = rep(sc["extrinsics"]), rep(sc["intrinsics"])
+    near, far = rep(sc["near"]), rep(sc["far"])
+    color_h = torch.empty((NB, V_TGT, 3, SIZE, SIZE), dtype=torch.float32).pin_memory()
+    depth_h = torch.empty((NB, V_TGT, SIZE, SIZE), dtype=torch.float32).pin_memory()
+    pose_h = torch.empty((NB, T_CTX - 1, 8), dtype=torch.float32).pin_memory()
 
     def e2e_step():
         ctx = {"image": image_h.to(dev, non_blocking=True), "intrinsics": K_h.to(dev, non_blocking=True)}
@@ -312,18 +320,18 @@ def run_ours(args) -> None:
 
     if rank == 0:
         peaks = load_peaks()
-        value = world * 1e3 / step_ms
-        fl = encoder_flops(T_CTX)
+        value = world * NB * 1e3 / step_ms
+        fl = NB * encoder_flops(T_CTX)
         enc_tf = fl / (enc_ms * 1e-3) / 1e12
-        rb = raster_bytes(V_TGT, G_SCENE, SIZE, SIZE)
+        rb = NB * raster_bytes(V_TGT, G_SCENE, SIZE, SIZE)
         ras_gbs = rb / (ras_ms * 1e-3) / 1e9
         line = dict(
             metric=METRIC, value=value, unit="scenes/s", n_gpus=world, steps=args.steps,
             warmup=max(args.warmup, 3), ms_per_step=step_ms, higher_is_better=True, scaling="weak",
-            vs_baseline=None, dtype="bf16", data="synthetic", config=config_dict(),
+            vs_baseline=None, dtype="bf16", data="synthetic", config=config_dict(NB),
             mpix_per_sec=value * V_TGT * SIZE * SIZE / 1e6,
             encoder_ms=enc_ms, raster_ms=ras_ms, raster_pairs=n_pairs,
-            e2e=dict(value=world * 1e3 / e2e_ms, unit="scenes/s", h2d_bytes_per_step=h2d,
+            e2e=dict(value=world * NB * 1e3 / e2e_ms, unit="scenes/s", h2d_bytes_per_step=h2d,
                      d2h_bytes_per_step=d2h, ms_per_step=e2e_ms),
             gpu_launches=gpu_launches,
             clocks=clk.result,
@@ -355,6 +363,7 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=1, help="scenes per step per GPU")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":

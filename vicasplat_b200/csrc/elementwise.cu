@@ -78,31 +78,40 @@ __global__ void rope_rows_kernel(bf16* __restrict__ qkv, long long ld, int rows,
     sincosf(p / powf(base, (d0 + 1) / 16.0f), &s1, &c1);
   }
   bf16* r = qkv + static_cast<long long>(row) * ld;
+  // all loads of a batch of heads are issued before the first store (q/k alias the same buffer,
+  // so the compiler cannot hoist them itself): 8 independent 4-byte loads in flight per lane
+  constexpr int HB = 8;
 #pragma unroll 1
   for (int which = 0; which < 2; ++which) {
     bf16* base_ptr = r + (which == 0 ? q_col : k_col);
-    for (int h = 0; h < H; ++h) {
-      __nv_bfloat162* p2 = reinterpret_cast<__nv_bfloat162*>(base_ptr + h * 64) + lane;
-      const float2 me = __bfloat1622float2(*p2);
-      float2 out;
-      if (cam) {
-        out.x = me.x * c0 - me.y * s0;
-        out.y = me.y * c0 + me.x * s0;
-        // keep the shuffles below convergent
-        (void)__shfl_xor_sync(0xffffffffu, me.x, 8);
-        (void)__shfl_xor_sync(0xffffffffu, me.y, 8);
-      } else {
-        const float ox = __shfl_xor_sync(0xffffffffu, me.x, 8);
-        const float oy = __shfl_xor_sync(0xffffffffu, me.y, 8);
-        if (!upper) {  // me = u, other = v
-          out.x = me.x * c0 - ox * s0;
-          out.y = me.y * c1 - oy * s1;
-        } else {       // me = v, other = u
-          out.x = me.x * c0 + ox * s0;
-          out.y = me.y * c1 + oy * s1;
+#pragma unroll 1
+    for (int h0 = 0; h0 < H; h0 += HB) {
+      float2 me[HB];
+#pragma unroll
+      for (int i = 0; i < HB; ++i)
+        if (h0 + i < H)
+          me[i] = __bfloat1622float2(
+              *(reinterpret_cast<const __nv_bfloat162*>(base_ptr + (h0 + i) * 64) + lane));
+#pragma unroll
+      for (int i = 0; i < HB; ++i) {
+        if (h0 + i < H) {   // warp-uniform
+          float2 out;
+          const float ox = __shfl_xor_sync(0xffffffffu, me[i].x, 8);
+          const float oy = __shfl_xor_sync(0xffffffffu, me[i].y, 8);
+          if (cam) {
+            out.x = me[i].x * c0 - me[i].y * s0;
+            out.y = me[i].y * c0 + me[i].x * s0;
+          } else if (!upper) {  // me = u, other = v
+            out.x = me[i].x * c0 - ox * s0;
+            out.y = me[i].y * c1 - oy * s1;
+          } else {              // me = v, other = u
+            out.x = me[i].x * c0 + ox * s0;
+            out.y = me[i].y * c1 + oy * s1;
+          }
+          *(reinterpret_cast<__nv_bfloat162*>(base_ptr + (h0 + i) * 64) + lane) =
+              __floats2bfloat162_rn(out.x, out.y);
         }
       }
-      *p2 = __floats2bfloat162_rn(out.x, out.y);
     }
   }
 }

@@ -2,16 +2,18 @@
 //
 //   C[m, n] = epilogue( sum_k A[m, k] * W[n, k] )      bf16 x bf16 -> fp32 (TMEM accumulator)
 //
-// One CTA computes one 128 x BN output tile.  Warp roles (192 threads):
-//   warp 0      TMA producer: A tile (128 rows x 64 k) and W tile (BN rows x 64 k) per k-block into
-//               a STAGES-deep ring of 128B-swizzled shared-memory tiles, completion on mbarriers
-//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (4 x K=16 UMMAs per k-block),
-//               tcgen05.commit releases ring slots and finally signals the epilogue
-//   warps 2..5  epilogue: tcgen05.ld 32 lanes x 32 columns -> registers -> shared-memory transpose
-//               -> coalesced bias / activation / AdaLN gate / residual / store
-// The A operand is addressed through a TMA tensor map, which is what makes the same kernel serve
-// nn.Linear on (possibly strided / grouped) token rows and stride-1 kxk convolutions on NHWC maps
-// (one 4-D box per filter tap; out-of-bounds coordinates are zero-filled by TMA = zero padding).
+// Persistent, warp-specialised: one CTA per SM loops over 128 x BN output tiles.
+//   warp 0       TMA producer: A tile (128 rows x 64 k) and W tile (BN rows x 64 k) per k-block into
+//                a STAGES-deep ring (~192 KB in flight) of 128B-swizzled tiles, mbarrier completion
+//   warp 1       TMEM allocator + single-thread tcgen05.mma issuer (4 x K=16 UMMAs per k-block);
+//                tcgen05.commit frees ring slots and hands a finished accumulator to the epilogue
+//   warps 2..    epilogue: thread r owns tile row r (TMEM lane r): tcgen05.ld 32 columns at a time,
+//                bias / activation / AdaLN gate / residual(s) in registers, 16-byte row-wise
+//                loads and stores (every thread touches whole 32-byte sectors of its own row)
+// The accumulator is double buffered in TMEM (2 x BN columns), so the epilogue of tile i overlaps
+// the main loop of tile i+1.  The A operand is addressed through a TMA tensor map, which is what
+// lets the same kernel serve nn.Linear on (strided / grouped) token rows and stride-1 k x k
+// convolutions on NHWC maps (one 4-D box per filter tap; out-of-bounds = zero padding).
 //
 // Replaces in the reference: every nn.Linear in croco/blocks.py:58-130 and backbone_vica.py:57-335
 // and every stride-1 nn.Conv2d in heads/dpt_block.py:79-229,264-459, heads/dpt_gs_head.py:98-157.
@@ -28,10 +30,15 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = one 128-byte swizzle row
 
+enum : int {  // vector-access flags, decided on the host from pointer / stride alignment
+  VEC_BIAS = 1, VEC_GATE = 2, VEC_RES = 4, VEC_C = 8, VEC_C2 = 16
+};
+
 struct GemmDev {
   int mode;
   int N;
   int num_kb;
+  int m_tiles, n_tiles;
   // rows mode
   int a_rows, tiles_per_group;
   // conv mode
@@ -52,49 +59,148 @@ struct GemmDev {
   __nv_bfloat16* C2;
   long long ldc2;
   int out_gin, out_gout, out_off;
+  int vec;
 };
 
 __device__ __forceinline__ float gelu_erf(float x) {
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
 }
 
-template <int BN, int STAGES>
-__global__ void __launch_bounds__(192)
+struct TileCoord {
+  int n0;
+  int grp, r0;          // rows mode
+  int x0, y0, img0;     // conv mode
+};
+
+__device__ __forceinline__ TileCoord tile_coord(const GemmDev& g, int t, int BN) {
+  TileCoord c{};
+  const int nt = t / g.m_tiles;          // m fastest: concurrently running CTAs share W tiles
+  const int mt = t - nt * g.m_tiles;
+  c.n0 = nt * BN;
+  if (g.mode == 0) {
+    c.grp = mt / g.tiles_per_group;
+    c.r0 = (mt - c.grp * g.tiles_per_group) * BM;
+  } else {
+    const int tx = mt % g.tiles_x;
+    const int ty = (mt / g.tiles_x) % g.tiles_y;
+    const int tn = mt / (g.tiles_x * g.tiles_y);
+    c.x0 = tx * g.bw;
+    c.y0 = ty * g.bh;
+    c.img0 = tn * g.bn;
+  }
+  return c;
+}
+
+__device__ __forceinline__ void load32_f32(const float* p, int nv, bool vec, float (&o)[32]) {
+  if (vec && nv == 32) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(p) + i);
+      o[4 * i] = t.x; o[4 * i + 1] = t.y; o[4 * i + 2] = t.z; o[4 * i + 3] = t.w;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) o[i] = i < nv ? __ldg(p + i) : 0.f;
+  }
+}
+
+// plain (coherent) loads: the residual stream may be updated in place by this very kernel
+__device__ __forceinline__ void add32_res(const void* base, int dtype, long long off, int nv,
+                                          bool vec, float (&f)[32]) {
+  if (dtype == VS_F32) {
+    const float* p = static_cast<const float*>(base) + off;
+    if (vec && nv == 32) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 t = *(reinterpret_cast<const float4*>(p) + i);
+        f[4 * i] += t.x; f[4 * i + 1] += t.y; f[4 * i + 2] += t.z; f[4 * i + 3] += t.w;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (i < nv) f[i] += p[i];
+    }
+  } else {
+    const __nv_bfloat16* p = static_cast<const __nv_bfloat16*>(base) + off;
+    if (vec && nv == 32) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint4 t = *(reinterpret_cast<const uint4*>(p) + i);
+        const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[j]));
+          f[8 * i + 2 * j] += v.x;
+          f[8 * i + 2 * j + 1] += v.y;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (i < nv) f[i] += __bfloat162float(p[i]);
+    }
+  }
+}
+
+__device__ __forceinline__ void store32_bf16(__nv_bfloat16* p, int nv, bool vec, const float (&f)[32],
+                                             bool relu) {
+  if (vec && nv == 32) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      uint32_t w[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float a = f[8 * i + 2 * j], b = f[8 * i + 2 * j + 1];
+        if (relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+        const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+        w[j] = *reinterpret_cast<const uint32_t*>(&h);
+      }
+      *(reinterpret_cast<uint4*>(p) + i) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (i < nv) p[i] = __float2bfloat16(relu ? fmaxf(f[i], 0.f) : f[i]);
+  }
+}
+
+__device__ __forceinline__ void store32_f32(float* p, int nv, bool vec, const float (&f)[32]) {
+  if (vec && nv == 32) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      *(reinterpret_cast<float4*>(p) + i) = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (i < nv) p[i] = f[i];
+  }
+}
+
+template <int BN, int STAGES, int EPI_WARPS>
+__global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
     gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA,
                      const __grid_constant__ CUtensorMap tmW, const GemmDev g) {
   constexpr int A_BYTES = BM * 128;
   constexpr int B_BYTES = BN * 128;
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
-  static_assert(4 * 32 * 33 * 4 <= STAGE_BYTES, "epilogue scratch must fit in stage 0");
+  constexpr int TMEM_COLS = 2 * BN;  // two accumulators
+  static_assert(EPI_WARPS == 4 || EPI_WARPS == 8, "epilogue warps");
+  constexpr int NCHUNK = BN / 32;
+  constexpr int CH_PER_WARP = NCHUNK / (EPI_WARPS / 4);
+  static_assert(CH_PER_WARP >= 1, "too many epilogue warps for this tile width");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
   uint64_t* empty = full + STAGES;
-  uint64_t* tmem_full = empty + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  uint64_t* tmem_full = empty + STAGES;   // [2]
+  uint64_t* tmem_empty = tmem_full + 2;   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * BN;
-  const int mt = blockIdx.y;
-
-  // ---- tile coordinates
-  int grp = 0, r0 = 0;           // rows mode
-  int x0 = 0, y0 = 0, img0 = 0;  // conv mode
-  if (g.mode == 0) {
-    grp = mt / g.tiles_per_group;
-    r0 = (mt % g.tiles_per_group) * BM;
-  } else {
-    const int tx = mt % g.tiles_x;
-    const int ty = (mt / g.tiles_x) % g.tiles_y;
-    const int tn = mt / (g.tiles_x * g.tiles_y);
-    x0 = tx * g.bw;
-    y0 = ty * g.bh;
-    img0 = tn * g.bn;
-  }
+  const int total_tiles = g.m_tiles * g.n_tiles;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -103,7 +209,10 @@ __global__ void __launch_bounds__(192)
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
     }
-    mbar_init(tmem_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], EPI_WARPS);
+    }
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -116,120 +225,148 @@ __global__ void __launch_bounds__(192)
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      for (int kb = 0; kb < g.num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(&empty[s], ph ^ 1);
-        uint8_t* sA = smem + s * STAGE_BYTES;
-        uint8_t* sB = sA + A_BYTES;
-        mbar_expect_tx(&full[s], STAGE_BYTES);
-        if (g.mode == 0) {
-          tma_load_3d(sA, &tmA, &full[s], kb * BK, r0, grp);
-        } else {
-          const int tap = kb / g.cblocks;
-          const int c0 = (kb - tap * g.cblocks) * BK;
-          const int dy = tap / g.kw, dx = tap - dy * g.kw;
-          tma_load_4d(sA, &tmA, &full[s], c0, x0 + dx - g.pad, y0 + dy - g.pad, img0);
+      uint32_t it = 0;  // k-block counter across tiles (ring position)
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const TileCoord tc = tile_coord(g, t, BN);
+        for (int kb = 0; kb < g.num_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&empty[s], ph ^ 1);
+          uint8_t* sA = smem + s * STAGE_BYTES;
+          uint8_t* sB = sA + A_BYTES;
+          mbar_expect_tx(&full[s], STAGE_BYTES);
+          if (g.mode == 0) {
+            tma_load_3d(sA, &tmA, &full[s], kb * BK, tc.r0, tc.grp);
+          } else {
+            const int tap = kb / g.cblocks;
+            const int c0 = (kb - tap * g.cblocks) * BK;
+            const int dy = tap / g.kw, dx = tap - dy * g.kw;
+            tma_load_4d(sA, &tmA, &full[s], c0, tc.x0 + dx - g.pad, tc.y0 + dy - g.pad, tc.img0);
+          }
+          tma_load_2d(sB, &tmW, &full[s], kb * BK, tc.n0);
         }
-        tma_load_2d(sB, &tmW, &full[s], kb * BK, n0);
       }
     }
   } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
-      for (int kb = 0; kb < g.num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(&full[s], ph);
+      uint32_t it = 0, ti = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++ti) {
+        const uint32_t a = ti & 1;
+        mbar_wait(&tmem_empty[a], ((ti >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
-        const uint32_t b_addr = a_addr + A_BYTES;
+        const uint32_t d_tmem = tmem_base + a * BN;
+        for (int kb = 0; kb < g.num_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
+          const uint32_t b_addr = a_addr + A_BYTES;
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k) {
-          umma_bf16_ss(tmem_base, umma_desc_k_sw128(a_addr + k * 32),
-                       umma_desc_k_sw128(b_addr + k * 32), idesc, (kb | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < BK / 16; ++k) {
+            umma_bf16_ss(d_tmem, umma_desc_k_sw128(a_addr + k * 32),
+                         umma_desc_k_sw128(b_addr + k * 32), idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty[s]);  // slot reusable once these MMAs have read it
         }
-        umma_commit(&empty[s]);  // slot reusable once these MMAs have read it
+        umma_commit(&tmem_full[a]);
       }
-      umma_commit(tmem_full);
     }
   } else {
     // ------------------------------------------------------------ epilogue
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
-    float* scratch = reinterpret_cast<float*>(smem) + q * (32 * 33);
-    // row bookkeeping for tile row (q*32 + lane); broadcast by shuffle in the store loop
-    long long my_out = -1;
-    int my_gate = -1;
-    {
-      const int r = q * 32 + lane;
-      bool valid;
-      long long m;
-      if (g.mode == 0) {
-        valid = (r0 + r) < g.a_rows;
-        m = static_cast<long long>(grp) * g.a_rows + r0 + r;
-      } else {
-        const int x = x0 + r % g.bw;
-        const int y = y0 + (r / g.bw) % g.bh;
-        const int im = img0 + r / (g.bw * g.bh);
-        valid = x < g.cw && y < g.ch && im < g.cn;
-        m = (static_cast<long long>(im) * g.ch + y) * g.cw + x;
-      }
-      if (valid) {
-        long long o = m;
-        if (g.out_gin > 0) o = (m / g.out_gin) * g.out_gout + g.out_off + (m % g.out_gin);
-        my_out = o;
-        if (g.gate_rows > 0) {
-          const bool first = (o % g.gate_rows) == 0;
-          if (first && g.first_row_mode == 2) my_out = -1;
-          if (g.gate != nullptr && !(first && g.first_row_mode != 0))
-            my_gate = static_cast<int>(o / g.gate_rows);
-        } else if (g.gate != nullptr) {
-          my_gate = 0;
+    const int ew = warp - 2;
+    const int q = warp & 3;            // TMEM lane quarter this warp may access
+    const int half = ew >> 2;          // column half when 8 epilogue warps
+    const int r = q * 32 + lane;       // tile row owned by this thread
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    uint32_t ti = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++ti) {
+      const TileCoord tc = tile_coord(g, t, BN);
+      const uint32_t a = ti & 1;
+      long long my_out = -1;
+      int my_gate = -1;
+      {
+        bool valid;
+        long long m;
+        if (g.mode == 0) {
+          valid = (tc.r0 + r) < g.a_rows;
+          m = static_cast<long long>(tc.grp) * g.a_rows + tc.r0 + r;
+        } else {
+          const int x = tc.x0 + r % g.bw;
+          const int y = tc.y0 + (r / g.bw) % g.bh;
+          const int im = tc.img0 + r / (g.bw * g.bh);
+          valid = x < g.cw && y < g.ch && im < g.cn;
+          m = (static_cast<long long>(im) * g.ch + y) * g.cw + x;
         }
-      }
-    }
-    mbar_wait(tmem_full, 0);
-    tc_fence_after();
-#pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      if (n0 + c * 32 >= g.N) break;
-      uint32_t v[32];
-      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c * 32, v);
-      tmem_ld_wait();
-#pragma unroll
-      for (int j = 0; j < 32; ++j) scratch[lane * 33 + j] = __uint_as_float(v[j]);
-      __syncwarp();
-      const int n = n0 + c * 32 + lane;
-      const bool nvalid = n < g.N;
-      const float bias_v = (g.bias != nullptr && nvalid) ? __ldg(g.bias + n) : 0.0f;
-#pragma unroll 4
-      for (int rr = 0; rr < 32; ++rr) {
-        const long long orow = __shfl_sync(0xffffffffu, my_out, rr);
-        const int grow = __shfl_sync(0xffffffffu, my_gate, rr);
-        if (orow < 0 || !nvalid) continue;
-        float val = scratch[rr * 33 + lane] + bias_v;
-        if (g.act == VS_ACT_GELU) val = gelu_erf(val);
-        else if (g.act == VS_ACT_RELU) val = fmaxf(val, 0.0f);
-        if (grow >= 0) val *= 1.0f + __ldg(g.gate + static_cast<long long>(grow) * g.gate_ld + n);
-        if (g.res1 != nullptr) {
-          const long long ro = orow * g.res_ld + n;
-          if (g.res_dtype == VS_F32) {
-            val += static_cast<const float*>(g.res1)[ro];
-            if (g.res2 != nullptr) val += static_cast<const float*>(g.res2)[ro];
-          } else {
-            val += __bfloat162float(static_cast<const __nv_bfloat16*>(g.res1)[ro]);
-            if (g.res2 != nullptr)
-              val += __bfloat162float(static_cast<const __nv_bfloat16*>(g.res2)[ro]);
+        if (valid) {
+          long long o = m;
+          if (g.out_gin > 0) o = (m / g.out_gin) * g.out_gout + g.out_off + (m % g.out_gin);
+          my_out = o;
+          if (g.gate_rows > 0) {
+            const bool first = (o % g.gate_rows) == 0;
+            if (first && g.first_row_mode == 2) my_out = -1;
+            if (g.gate != nullptr && !(first && g.first_row_mode != 0))
+              my_gate = static_cast<int>(o / g.gate_rows);
+          } else if (g.gate != nullptr) {
+            my_gate = 0;
           }
         }
-        if (g.C != nullptr) {
-          if (g.c_dtype == VS_F32) static_cast<float*>(g.C)[orow * g.ldc + n] = val;
-          else static_cast<__nv_bfloat16*>(g.C)[orow * g.ldc + n] = __float2bfloat16(val);
-        }
-        if (g.C2 != nullptr) g.C2[orow * g.ldc2 + n] = __float2bfloat16(fmaxf(val, 0.0f));
       }
+      mbar_wait(&tmem_full[a], (ti >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int cc = 0; cc < CH_PER_WARP; ++cc) {
+        const int c = half * CH_PER_WARP + cc;
+        const int nb = tc.n0 + c * 32;
+        if (nb >= g.N) break;  // warp-uniform
+        uint32_t v[32];
+        tmem_ld_32x32(t_lane + a * BN + c * 32, v);
+        tmem_ld_wait();
+        if (my_out < 0) continue;
+        const int nv = min(32, g.N - nb);
+        float f[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+        if (g.bias != nullptr) {
+          float b[32];
+          load32_f32(g.bias + nb, nv, g.vec & VEC_BIAS, b);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) f[i] += b[i];
+        }
+        if (g.act == VS_ACT_GELU) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) f[i] = gelu_erf(f[i]);
+        } else if (g.act == VS_ACT_RELU) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
+        }
+        if (my_gate >= 0) {
+          float gt[32];
+          load32_f32(g.gate + static_cast<long long>(my_gate) * g.gate_ld + nb, nv, g.vec & VEC_GATE, gt);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) f[i] *= 1.0f + gt[i];
+        }
+        if (g.res1 != nullptr) {
+          add32_res(g.res1, g.res_dtype, my_out * g.res_ld + nb, nv, g.vec & VEC_RES, f);
+          if (g.res2 != nullptr)
+            add32_res(g.res2, g.res_dtype, my_out * g.res_ld + nb, nv, g.vec & VEC_RES, f);
+        }
+        if (g.C != nullptr) {
+          if (g.c_dtype == VS_F32)
+            store32_f32(static_cast<float*>(g.C) + my_out * g.ldc + nb, nv, g.vec & VEC_C, f);
+          else
+            store32_bf16(static_cast<__nv_bfloat16*>(g.C) + my_out * g.ldc + nb, nv, g.vec & VEC_C, f,
+                         false);
+        }
+        if (g.C2 != nullptr) store32_bf16(g.C2 + my_out * g.ldc2 + nb, nv, g.vec & VEC_C2, f, true);
+      }
+      tc_fence_before();
       __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[a]);
     }
   }
 
@@ -238,21 +375,47 @@ __global__ void __launch_bounds__(192)
   if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-// ------------------------------------------------------------------ host side
-template <int BN, int STAGES>
-int launch(const CUtensorMap& tmA, const CUtensorMap& tmW, const GemmDev& g, int m_tiles,
-           cudaStream_t stream) {
+int num_sms() {
+  static int n = []() {
+    int dev = 0, v = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess)
+      cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    return v;
+  }();
+  return n;
+}
+
+template <int BN, int STAGES, int EPI_WARPS>
+int launch(const CUtensorMap& tmA, const CUtensorMap& tmW, const GemmDev& g, cudaStream_t stream) {
   constexpr int SMEM = STAGES * (BM * 128 + BN * 128) + 1024 /*align*/ + 256 /*barriers*/;
+  static_assert(SMEM <= 227 * 1024, "shared memory budget");
   static bool configured = false;  // attribute is per-function, set once per process
   if (!configured) {
-    VS_CUDA(cudaFuncSetAttribute(gemm_tc05_kernel<BN, STAGES>,
+    VS_CUDA(cudaFuncSetAttribute(gemm_tc05_kernel<BN, STAGES, EPI_WARPS>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     configured = true;
   }
-  dim3 grid(ceil_div(g.N, BN), m_tiles);
-  gemm_tc05_kernel<BN, STAGES><<<grid, 192, SMEM, stream>>>(tmA, tmW, g);
+  const int total = g.m_tiles * g.n_tiles;
+  const int grid = total < num_sms() ? total : num_sms();
+  gemm_tc05_kernel<BN, STAGES, EPI_WARPS>
+      <<<grid, 64 + 32 * EPI_WARPS, SMEM, stream>>>(tmA, tmW, g);
   VS_LAUNCH_CHECK();
   return VS_OK;
+}
+
+inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// cycles of one persistent CTA for tile width bn: waves x k-blocks x max(tensor pipe, L2 feed)
+double tile_cost(int bn, int m_tiles, int N, int num_kb) {
+  const int n_tiles = ceil_div(N, bn);
+  const long long tiles = static_cast<long long>(m_tiles) * n_tiles;
+  const int sms = num_sms();
+  const double waves = static_cast<double>((tiles + sms - 1) / sms);
+  const double active = tiles < sms ? static_cast<double>(tiles) : static_cast<double>(sms);
+  const double mma = 2.0 * bn;                                   // 4 UMMAs of 128 x bn x 16
+  const double l2 = active * (BM + bn) * 128.0 / 6300.0;         // chip-wide L2 -> SM feed (B/clk)
+  const double per_kb = mma > l2 ? mma : l2;
+  return waves * (num_kb * per_kb + 1500.0 /*pipeline fill + epilogue tail*/);
 }
 
 }  // namespace
@@ -263,9 +426,7 @@ extern "C" int vs_gemm(const vs_gemm_params* p, vs_stream_t stream_) {
   VS_REQUIRE(p != nullptr, "vs_gemm: null params");
   VS_REQUIRE(p->A && p->W, "vs_gemm: A and W must be non-null");
   VS_REQUIRE(p->N > 0, "vs_gemm: N must be positive");
-  VS_REQUIRE((reinterpret_cast<uintptr_t>(p->A) & 15) == 0 &&
-                 (reinterpret_cast<uintptr_t>(p->W) & 15) == 0,
-             "vs_gemm: A and W must be 16-byte aligned");
+  VS_REQUIRE(al16(p->A) && al16(p->W), "vs_gemm: A and W must be 16-byte aligned");
   VS_REQUIRE(p->w_row_stride % 8 == 0, "vs_gemm: w_row_stride must be a multiple of 8 elements");
   cudaStream_t stream = to_stream(stream_);
 
@@ -294,6 +455,14 @@ extern "C" int vs_gemm(const vs_gemm_params* p, vs_stream_t stream_) {
   VS_REQUIRE(p->c_dtype == VS_F32 || p->c_dtype == VS_BF16, "vs_gemm: c_dtype must be f32/bf16");
   VS_REQUIRE(p->res_dtype == VS_F32 || p->res_dtype == VS_BF16,
              "vs_gemm: res_dtype must be f32/bf16");
+  g.vec = 0;
+  if (p->bias && al16(p->bias)) g.vec |= VEC_BIAS;
+  if (p->gate && al16(p->gate) && p->gate_ld % 4 == 0) g.vec |= VEC_GATE;
+  if (p->res1 && al16(p->res1) && (p->res2 == nullptr || al16(p->res2)) &&
+      p->res_ld % (p->res_dtype == VS_F32 ? 4 : 8) == 0)
+    g.vec |= VEC_RES;
+  if (p->C && al16(p->C) && p->ldc % (p->c_dtype == VS_F32 ? 4 : 8) == 0) g.vec |= VEC_C;
+  if (p->C2 && al16(p->C2) && p->ldc2 % 8 == 0) g.vec |= VEC_C2;
 
   CUtensorMap tmA, tmW;
   int m_tiles = 0;
@@ -353,17 +522,19 @@ extern "C" int vs_gemm(const vs_gemm_params* p, vs_stream_t stream_) {
     return VS_ERR_INVALID;
   }
   g.num_kb = static_cast<int>((ktot + BK - 1) / BK);
+  g.m_tiles = m_tiles;
 
-  // tile width: fill the 148 SMs first, then prefer wide tiles (fewer A re-reads)
   int bn = p->block_n;
   if (bn == 0) {
-    const long long t256 = static_cast<long long>(m_tiles) * ceil_div(p->N, 256);
-    const long long t128 = static_cast<long long>(m_tiles) * ceil_div(p->N, 128);
-    if (p->N >= 256 && t256 >= 2 * 148) bn = 256;       // 1 CTA/SM, two full waves
-    else if (p->N > 64 && t128 >= 148) bn = 128;        // 2 CTAs/SM
-    else bn = 64;
+    double best = 0;
+    for (int cand : {256, 128, 64}) {
+      if (cand > 64 && cand / 2 >= p->N) continue;  // pure padding
+      const double c = tile_cost(cand, m_tiles, p->N, g.num_kb);
+      if (bn == 0 || c < best) { bn = cand; best = c; }
+    }
   }
   VS_REQUIRE(bn == 64 || bn == 128 || bn == 256, "vs_gemm: block_n must be 64, 128 or 256");
+  g.n_tiles = ceil_div(p->N, bn);
   {
     cuuint64_t dims[2] = {static_cast<cuuint64_t>(ktot), static_cast<cuuint64_t>(p->N)};
     cuuint64_t str[1] = {static_cast<cuuint64_t>(p->w_row_stride) * 2};
@@ -372,8 +543,8 @@ extern "C" int vs_gemm(const vs_gemm_params* p, vs_stream_t stream_) {
     if (rc) return rc;
   }
   switch (bn) {
-    case 64: return launch<64, 4>(tmA, tmW, g, m_tiles, stream);
-    case 128: return launch<128, 3>(tmA, tmW, g, m_tiles, stream);
-    default: return launch<256, 4>(tmA, tmW, g, m_tiles, stream);
+    case 64: return launch<64, 8, 4>(tmA, tmW, g, stream);
+    case 128: return launch<128, 6, 4>(tmA, tmW, g, stream);
+    default: return launch<256, 4, 8>(tmA, tmW, g, stream);
   }
 }
