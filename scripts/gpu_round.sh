@@ -13,6 +13,9 @@ bench4)
 launches)
   timeout 900 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv \
     --log-file gpurun_out/launches.csv python scripts/profile_step.py > gpurun_out/prof_step.log 2>&1; tail -2 gpurun_out/prof_step.log;;
+launches4)
+  timeout 900 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv \
+    --log-file gpurun_out/launches_b4.csv python scripts/profile_step.py 4 > gpurun_out/prof_step4.log 2>&1; tail -2 gpurun_out/prof_step4.log;;
 full:*)
   for k in $(echo ${what#full:} | tr ',' ' '); do
     timeout 600 ncu --profile-from-start off --set full --clock-control none --import-source on \

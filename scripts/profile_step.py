@@ -10,6 +10,7 @@ from vicasplat_b200.encoder import VicaSplat, EncoderEngine
 from vicasplat_b200.rasterizer import rasterize_views
 
 T, V, S = 8, 12, 256
+NB = int(sys.argv[1]) if len(sys.argv) > 1 else 1
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
 model = VicaSplat().to(dev)
@@ -18,7 +19,7 @@ with torch.no_grad():
         if "modulation" in n or n.startswith("camera_extrinsic_head"):
             p.normal_(0, 0.02)
 eng = EncoderEngine(model, use_graph=False)
-image, K = synthetic.clip(1, T, S)
+image, K = synthetic.clip(NB, T, S)
 image, K = image.to(dev), K.to(dev)
 sc = {k: v.to(dev) for k, v in synthetic.gaussian_scene(T, S, S, V, seed=1).items()}
 tanfov, view_t, full_t, campos = dec._cameras(sc["extrinsics"], sc["intrinsics"], sc["near"], sc["far"])

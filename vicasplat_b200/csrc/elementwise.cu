@@ -213,31 +213,61 @@ __global__ void patchify_kernel(const float* __restrict__ img, bf16* __restrict_
   out[i] = __float2bfloat16(v);
 }
 
+// one thread = 8 consecutive output columns (one 16-byte store); for an NHWC source whose channel
+// count is a multiple of 8 those are 8 contiguous channels of one tap (one 16-byte load)
 __global__ void im2col_kernel(const void* __restrict__ src, int nchw_f32, bf16* __restrict__ out,
                               int n, int h, int w, int c, int k, int stride, int pad, int kpad,
                               int ho, int wo) {
-  const long long total = static_cast<long long>(n) * ho * wo * kpad;
+  const int k8 = kpad / 8;
+  const long long total = static_cast<long long>(n) * ho * wo * k8;
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= total) return;
-  const long long row = i / kpad;
-  const int col = static_cast<int>(i - row * kpad);
-  float v = 0.f;
-  if (col < k * k * c) {
-    const int tap = col / c, ch = col - tap * c;
-    const int dy = tap / k, dx = tap - dy * k;
-    const int im = static_cast<int>(row / (ho * wo));
-    const int r = static_cast<int>(row - static_cast<long long>(im) * ho * wo);
-    const int yo = r / wo, xo = r - yo * wo;
-    const int y = yo * stride + dy - pad, x = xo * stride + dx - pad;
-    if (y >= 0 && y < h && x >= 0 && x < w) {
-      if (nchw_f32)
-        v = static_cast<const float*>(src)[((static_cast<long long>(im) * c + ch) * h + y) * w + x];
-      else
-        v = __bfloat162float(
-            static_cast<const bf16*>(src)[((static_cast<long long>(im) * h + y) * w + x) * c + ch]);
+  const long long row = i / k8;
+  const int col0 = static_cast<int>(i - row * k8) * 8;
+  const int im = static_cast<int>(row / (ho * wo));
+  const int r = static_cast<int>(row - static_cast<long long>(im) * ho * wo);
+  const int yo = r / wo, xo = r - yo * wo;
+  const int kkc = k * k * c;
+  uint4 o = make_uint4(0u, 0u, 0u, 0u);
+  if (!nchw_f32 && (c & 7) == 0) {
+    if (col0 < kkc) {
+      const int tap = col0 / c, ch = col0 - tap * c;
+      const int dy = tap / k, dx = tap - dy * k;
+      const int y = yo * stride + dy - pad, x = xo * stride + dx - pad;
+      if (y >= 0 && y < h && x >= 0 && x < w)
+        o = *reinterpret_cast<const uint4*>(static_cast<const bf16*>(src) +
+                                            ((static_cast<long long>(im) * h + y) * w + x) * c + ch);
     }
+  } else {
+    uint32_t pk[4];
+#pragma unroll
+    for (int e = 0; e < 8; e += 2) {
+      float v2[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int col = col0 + e + u;
+        float v = 0.f;
+        if (col < kkc) {
+          const int tap = col / c, ch = col - tap * c;
+          const int dy = tap / k, dx = tap - dy * k;
+          const int y = yo * stride + dy - pad, x = xo * stride + dx - pad;
+          if (y >= 0 && y < h && x >= 0 && x < w) {
+            if (nchw_f32)
+              v = __ldg(static_cast<const float*>(src) +
+                        ((static_cast<long long>(im) * c + ch) * h + y) * w + x);
+            else
+              v = __bfloat162float(static_cast<const bf16*>(
+                  src)[((static_cast<long long>(im) * h + y) * w + x) * c + ch]);
+          }
+        }
+        v2[u] = v;
+      }
+      const __nv_bfloat162 b2 = __floats2bfloat162_rn(v2[0], v2[1]);
+      pk[e >> 1] = *reinterpret_cast<const uint32_t*>(&b2);
+    }
+    o = make_uint4(pk[0], pk[1], pk[2], pk[3]);
   }
-  out[i] = __float2bfloat16(v);
+  *reinterpret_cast<uint4*>(out + row * kpad + col0) = o;
 }
 
 // bilinear x2 align_corners=True on NHWC bf16; one thread per 8 channels of an output pixel
@@ -552,8 +582,9 @@ extern "C" int vs_im2col(const void* src, int src_nchw_f32, void* out, int n, in
                          int k, int stride, int pad, int kpad, vs_stream_t stream) {
   VS_REQUIRE(src && out, "im2col: null tensor");
   VS_REQUIRE(k > 0 && stride > 0 && kpad >= k * k * c, "im2col: bad geometry");
+  VS_REQUIRE(kpad % 8 == 0, "im2col: kpad must be a multiple of 8");
   const int ho = (h + 2 * pad - k) / stride + 1, wo = (w + 2 * pad - k) / stride + 1;
-  const long long total = static_cast<long long>(n) * ho * wo * kpad;
+  const long long total = static_cast<long long>(n) * ho * wo * (kpad / 8);
   if (total <= 0) return VS_OK;
   im2col_kernel<<<blocks_for(total, 256), 256, 0, to_stream(stream)>>>(
       src, src_nchw_f32, static_cast<bf16*>(out), n, h, w, c, k, stride, pad, kpad, ho, wo);

@@ -324,6 +324,13 @@ __global__ void tile_ranges_kernel(const uint64_t* __restrict__ keys, int64_t ma
 }
 
 // ------------------------------------------------------------------ blend
+// One CTA per 16x16 tile, 8 warps; warp w owns the 8x4-pixel sub-block (w & 1, w >> 1).  The tile's
+// depth-sorted splat list is staged through shared memory in batches of 256 (16-byte gathers of
+// the SoA intermediates).  Per batch every warp first culls: lane l tests splat (32 k + l) against
+// the warp's sub-block with the exact bound of the alpha >= 1/255 test (the axis-aligned box of the
+// ellipse power >= -ln(255 o)), ballots, and then walks only the set bits front to back -- pixels
+// outside that box would have rejected the splat anyway, so the image is bit-identical to
+// evaluating every (pixel, splat) pair.  A warp leaves the list as soon as all its pixels are opaque.
 __global__ void __launch_bounds__(BLEND_THREADS)
     blend_kernel(int G, int H, int W, const uint2* __restrict__ ranges,
                  const uint32_t* __restrict__ vals, const float2* __restrict__ xy,
@@ -333,17 +340,22 @@ __global__ void __launch_bounds__(BLEND_THREADS)
                  float* __restrict__ final_T, int32_t* __restrict__ n_contrib,
                  int32_t* __restrict__ n_touched) {
   __shared__ uint32_t s_id[BLEND_THREADS];
-  __shared__ float2 s_xy[BLEND_THREADS];
+  __shared__ float4 s_xe[BLEND_THREADS];   // centre x, y, half extents ex, ey of the alpha box
   __shared__ float4 s_co[BLEND_THREADS];
   __shared__ float4 s_cd[BLEND_THREADS];
 
   const int gx = gridDim.x, gy = gridDim.y;
   const int v = blockIdx.z;
   const int tile = (v * gy + blockIdx.y) * gx + blockIdx.x;
-  const int px = blockIdx.x * TILE + (threadIdx.x & (TILE - 1));
-  const int py = blockIdx.y * TILE + (threadIdx.x >> 4);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sbx = blockIdx.x * TILE + (warp & 1) * 8, sby = blockIdx.y * TILE + (warp >> 1) * 4;
+  const int px = sbx + (lane & 7);
+  const int py = sby + (lane >> 3);
   const bool inside = px < W && py < H;
   const float pxf = static_cast<float>(px), pyf = static_cast<float>(py);
+  // pixel-centre range of this warp's sub-block
+  const float bx0 = static_cast<float>(sbx), bx1 = static_cast<float>(min(sbx + 7, W - 1));
+  const float by0 = static_cast<float>(sby), by1 = static_cast<float>(min(sby + 3, H - 1));
 
   const uint2 range = ranges[tile];
   const int total = static_cast<int>(range.y - range.x);
@@ -351,53 +363,78 @@ __global__ void __launch_bounds__(BLEND_THREADS)
 
   bool done = !inside;
   float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f, D = 0.f, A = 0.f;
-  int contributor = 0, last_contributor = 0;
-  int todo = total;
+  int last_contributor = 0;
 
-  for (int r = 0; r < rounds; ++r, todo -= BLEND_THREADS) {
+  for (int r = 0; r < rounds; ++r) {
     if (__syncthreads_count(done) == BLEND_THREADS) break;
     const int idx = r * BLEND_THREADS + threadIdx.x;
     if (idx < total) {
       const uint32_t id = vals[range.x + idx];
+      const float2 p = xy[id];
+      const float4 co = conic_o[id];
       s_id[threadIdx.x] = id;
-      s_xy[threadIdx.x] = xy[id];
-      s_co[threadIdx.x] = conic_o[id];
+      s_co[threadIdx.x] = co;
       s_cd[threadIdx.x] = rgbd[id];
+      // alpha >= 1/255  <=>  power >= -tau, tau = ln(255 o): ellipse with half extents
+      // sqrt(2 tau C / det), sqrt(2 tau A / det) (conic = (A, B, C)); 1 % + 0.01 px safety margin
+      const float tau = __logf(255.0f * co.w) * 1.01f + 1e-3f;
+      const float det = co.x * co.z - co.y * co.y;
+      float ex = -1.f, ey = -1.f;
+      if (tau > 0.f) {
+        if (det > 0.f) {
+          ex = sqrtf(2.0f * tau * co.z / det) + 0.01f;
+          ey = sqrtf(2.0f * tau * co.x / det) + 0.01f;
+        } else {
+          ex = ey = 1e30f;  // degenerate conic: never cull
+        }
+      }
+      s_xe[threadIdx.x] = make_float4(p.x, p.y, ex, ey);
     }
     __syncthreads();
-    const int nb = min(BLEND_THREADS, todo);
-    for (int j = 0; j < nb; ++j) {
-      // warp-level early exit: the whole warp leaves the batch once all its pixels are done
-      if (__ballot_sync(0xffffffffu, !done) == 0u) break;
-      bool hit = false;
-      if (!done) {
-        ++contributor;
-        const float2 p = s_xy[j];
-        const float4 co = s_co[j];
-        const float dx = p.x - pxf, dy = p.y - pyf;
-        const float power = -0.5f * (co.x * dx * dx + co.z * dy * dy) - co.y * dx * dy;
-        if (power <= 0.0f) {
-          const float alpha = fminf(kAlphaMax, co.w * __expf(power));
-          if (alpha >= kAlphaMin) {
-            const float test_T = T * (1.0f - alpha);
-            if (test_T < kTStop) {
-              done = true;
-            } else {
-              const float4 cd = s_cd[j];
-              const float w = alpha * T;
-              C0 += cd.x * w; C1 += cd.y * w; C2 += cd.z * w;
-              D += cd.w * w;
-              A += w;
-              hit = T > kNTouchedT;
-              T = test_T;
-              last_contributor = contributor;
+    const int nb = min(BLEND_THREADS, total - r * BLEND_THREADS);
+    for (int base = 0; base < nb; base += 32) {
+      if (__all_sync(0xffffffffu, done)) break;
+      bool near_me = false;
+      if (base + lane < nb) {
+        const float4 xe = s_xe[base + lane];
+        const float ddx = fmaxf(fmaxf(bx0 - xe.x, xe.x - bx1), 0.f);
+        const float ddy = fmaxf(fmaxf(by0 - xe.y, xe.y - by1), 0.f);
+        near_me = ddx <= xe.z && ddy <= xe.w;
+      }
+      uint32_t todo = __ballot_sync(0xffffffffu, near_me);
+      while (todo != 0u) {
+        const int j = base + __ffs(todo) - 1;
+        todo &= todo - 1;
+        bool hit = false;
+        if (!done) {
+          const float4 xe = s_xe[j];
+          const float4 co = s_co[j];
+          const float dx = xe.x - pxf, dy = xe.y - pyf;
+          const float power = -0.5f * (co.x * dx * dx + co.z * dy * dy) - co.y * dx * dy;
+          if (power <= 0.0f) {
+            const float alpha = fminf(kAlphaMax, co.w * __expf(power));
+            if (alpha >= kAlphaMin) {
+              const float test_T = T * (1.0f - alpha);
+              if (test_T < kTStop) {
+                done = true;
+              } else {
+                const float4 cd = s_cd[j];
+                const float w = alpha * T;
+                C0 += cd.x * w; C1 += cd.y * w; C2 += cd.z * w;
+                D += cd.w * w;
+                A += w;
+                hit = T > kNTouchedT;
+                T = test_T;
+                last_contributor = r * BLEND_THREADS + j + 1;
+              }
             }
           }
         }
-      }
-      if (n_touched != nullptr) {
-        const uint32_t m = __ballot_sync(0xffffffffu, hit);
-        if (m != 0u && (threadIdx.x & 31) == 0) atomicAdd(n_touched + s_id[j], __popc(m));
+        if (n_touched != nullptr) {
+          const uint32_t m = __ballot_sync(0xffffffffu, hit);
+          if (m != 0u && lane == 0) atomicAdd(n_touched + s_id[j], __popc(m));
+        }
+        if (__all_sync(0xffffffffu, done)) break;
       }
     }
   }
