@@ -70,7 +70,14 @@ int vs_rope_rows(void* qkv, int64_t ld, int rows, int H, int q_col, int k_col, c
  *   group stride a_group_stride, in elements); logical row m = g * a_rows + r.
  * a_mode 1 (conv): A is NHWC bf16 [cn, ch, cw, cin]; stride-1 kh x kw convolution with zero
  *   padding `pad`; logical row m = (n * ch + y) * cw + x; W is [N, kh*kw*cin_pad] with
- *   cin_pad = round_up(cin, 64) (tap-major, channel-minor).
+ *   cin_pad = round_up(cin, 64) (tap-major, channel-minor).  The output map is always ch x cw.
+ *   conv_in_h > 0: the input map has conv_in_h rows (a "valid" convolution in y: pad rows are
+ *   stored, e.g. conv_in_h = ch + kh - 1 with pad = 0).  conv_stride_{x,y,n} > 0 override the
+ *   dense NHWC element strides of the input view -- overlapping views are allowed (stride_x <
+ *   cin turns cin into a sliding window over pixels: the 7x7 stem of dpt_gs_head.py:113-118 is run
+ *   as kh = 7, kw = 1 over windows of 8 pixels x 8 padded channels).
+ *   res_up2 != 0: res1 is an NHWC bf16 map at HALF resolution [cn, ch/2, cw/2, N] that is
+ *   bilinearly upsampled x2 (align_corners=True, dpt_block.py:214-216) on the fly.
  * Output row mapping: out_row = (m / out_gin) * out_gout + out_off + (m % out_gin).
  */
 typedef struct vs_gemm_params {
@@ -79,6 +86,8 @@ typedef struct vs_gemm_params {
   int32_t a_rows, a_groups;
   int64_t a_row_stride, a_group_stride;
   int32_t cn, ch, cw, cin, kh, kw, pad;
+  int32_t conv_in_h;
+  int64_t conv_stride_x, conv_stride_y, conv_stride_n;
   const void* W;
   int64_t w_row_stride;
   int32_t N, K; /* K ignored in conv mode */
@@ -91,6 +100,7 @@ typedef struct vs_gemm_params {
   const void* res1;
   const void* res2;
   int32_t res_dtype;
+  int32_t res_up2;
   int64_t res_ld;
   void* C;
   int32_t c_dtype;
@@ -144,6 +154,7 @@ typedef struct vs_attention_params {
   int32_t heads, items;
   const int32_t *q_start, *q_len, *kv_start0, *kv_len0, *kv_start1, *kv_len1; /* device arrays */
   int32_t max_q_len;
+  int32_t max_kv_len;   /* upper bound of kv_len0 + kv_len1 over the items (0 = unknown) */
   int32_t causal_block;
   float scale;
 } vs_attention_params;
@@ -172,6 +183,9 @@ int vs_intrinsic_token(const float* K9, const float* w, const float* b, float* x
  * intr_tok (+ extr_tok when f % T != 0). */
 int vs_camera_tokens(const float* intr_tok, const float* extr_tok, float* x, int frames, int T,
                      int C, int rows_per_frame, vs_stream_t stream);
+/* fp32 NCHW image [n,3,h,w] -> bf16 NHWC with 8 channels (3 used) and a zero border of `pad`
+ * rows above/below and `pad` / (8 - pad) columns left/right: [n, h + 2*pad, w + 8, 8]. */
+int vs_image_nhwc8(const float* img, void* out, int n, int h, int w, int pad, vs_stream_t stream);
 /* SiLU on fp32 rows -> bf16 (AdaLNModulation.nonlinear, backbone_vica.py:210-212) */
 int vs_silu_bf16(const float* x, int64_t ldx, void* y, int64_t ldy, int rows, int C,
                  vs_stream_t stream);
@@ -185,12 +199,17 @@ int vs_camera_head(const float* cam_feat, int64_t ld, const float* w, const floa
  * postprocess xyz = x/|x| * expm1(|x|) (heads/postprocess.py:42-61) -> raw[px, raw_ld] cols 0..2 */
 int vs_pts_tail(const void* feat, int Cf, const float* w, const float* b, float* raw, int64_t raw_ld,
                 int64_t px, vs_stream_t stream);
-/* MyGaussianAdapter.forward (gaussian_adapter.py:167-212) on raw [G, 86] fp32:
- * means (G,3), covariances (G,3,3), harmonics (G,3,d_sh) masked, opacities (G), scales (G,3),
- * rotations (G,4); also the rasterizer-ready packed cov6 (G,6) (triu order xx,xy,xz,yy,yz,zz). */
-int vs_gaussian_adapter(const float* raw, int64_t raw_ld, int64_t G, int d_sh, const float* sh_mask,
-                        float* means, float* cov, float* cov6, float* sh, float* opac,
-                        float* scales, float* rot, vs_stream_t stream);
+/* MyGaussianAdapter.forward (gaussian_adapter.py:167-212).  Input rows (fp32, leading dimension
+ * src_ld) hold the head outputs: xyz at columns [center_col, +3), the 8 + 3*d_sh Gaussian parameters
+ * (opacity | scale 3 | quaternion xyzw 4 | SH (xyz d_sh)) at [param_col, ...).  The reference's
+ * contiguous raw_gaussians layout is (src_ld = 11 + 3*d_sh, center_col = 0, param_col = 3).
+ * Outputs (any may be NULL): raw_out (G, 11 + 3*d_sh) in the reference layout, means (G,3),
+ * covariances (G,3,3), packed cov6 (G,6) (triu order xx,xy,xz,yy,yz,zz), harmonics (G,3,d_sh)
+ * masked, opacities (G), scales (G,3), rotations (G,4). */
+int vs_gaussian_adapter(const float* src, int64_t src_ld, int center_col, int param_col, int64_t G,
+                        int d_sh, const float* sh_mask, float* raw_out, float* means, float* cov,
+                        float* cov6, float* sh, float* opac, float* scales, float* rot,
+                        vs_stream_t stream);
 
 /* ------------------------------------------------------------------ Gaussian rasterizer
  * Tile-based EWA splatting of G Gaussians into V views (diff_gaussian_rasterization semantics,

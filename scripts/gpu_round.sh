@@ -16,6 +16,9 @@ launches)
 launches4)
   timeout 900 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv \
     --log-file gpurun_out/launches_b4.csv python scripts/profile_step.py 4 > gpurun_out/prof_step4.log 2>&1; tail -2 gpurun_out/prof_step4.log;;
+gemm4)
+  timeout 600 ncu --profile-from-start off --set full --clock-control none --import-source on \
+    -k regex:gemm_tc05 -s 1 -c 4 -f -o gpurun_out/prof_gemm_b4 python scripts/profile_step.py 4 > gpurun_out/prof_gemm_b4.log 2>&1;;
 full:*)
   for k in $(echo ${what#full:} | tr ',' ' '); do
     timeout 600 ncu --profile-from-start off --set full --clock-control none --import-source on \

@@ -119,6 +119,31 @@ def test_gemm_conv(cuda, lib, n, h, w, cin, cout, k):
     assert _rel(out, ref + res.float()) < 2e-5
 
 
+def test_conv7_stem_as_overlapping_view_with_upsampled_residual(cuda, lib):
+    """dpt_gs_head.py:113-118,148-150: relu(conv7x7(img)) + bilinear_x2(path_1), no im2col buffer."""
+    from vicasplat_b200 import ops, _lib
+    g = torch.Generator().manual_seed(21)
+    n, H, W, Cout = 3, 32, 48, 256
+    img = torch.randn((n, 3, H, W), generator=g).to(cuda)
+    w7 = (torch.randn((Cout, 3, 7, 7), generator=g) / 12.0).to(cuda)
+    bias = torch.randn((Cout,), generator=g).to(cuda)
+    p1 = _bf(torch.randn((n, H // 2, W // 2, Cout), generator=g)).to(cuda)
+    wp = torch.zeros((Cout, 7, 8, 8), device=cuda)
+    wp[:, :, :7, :3] = w7.permute(0, 2, 3, 1)
+    img8 = ops.image_nhwc8(img, pad=3)
+    assert img8.shape == (n, H + 6, W + 8, 8)
+    assert (img8[:, :3] == 0).all() and (img8[:, :, :3] == 0).all() and (img8[..., 3:] == 0).all()
+    out = ops.conv_gemm(img8, _bf(wp.reshape(Cout, -1)), kh=7, kw=1, pad=0, N=Cout, bias=bias,
+                        act=_lib.VS_ACT_RELU, res1=p1, res_up2=True, out_dtype=torch.float32,
+                        view=(n, H, W, 64, H + 6, 8, (W + 8) * 8, (H + 6) * (W + 8) * 8))
+    conv = F.conv2d(_bf(img).float(), _bf(w7).float(), bias, padding=3).relu()
+    up = F.interpolate(p1.float().permute(0, 3, 1, 2), scale_factor=2, mode="bilinear",
+                       align_corners=True)
+    ref = (conv + _bf(up).float()).permute(0, 2, 3, 1)
+    assert _rel(out, ref) < 1e-3
+    assert (out - ref).abs().max() < 0.05     # bf16 rounding of the upsampled map may flip by 1 ulp
+
+
 # ------------------------------------------------------------------------------------ LayerNorm
 @pytest.mark.parametrize("C", [768, 1024, 256])
 def test_layernorm_plain_and_modulated(cuda, lib, C):
@@ -185,6 +210,14 @@ def test_attention_encoder_style(cuda, lib):
     t = qkv.view(Fr, N, 3, H, 64).permute(2, 0, 3, 1, 4)
     ref = _attn_ref(t[0], t[1], t[2]).transpose(1, 2).reshape(Fr * N, H * 64)
     assert _rel(O, ref) < 1e-2
+    # same call with the key bound given: the 257th row goes through the CUDA-core tail kernel
+    O2 = torch.zeros_like(O)
+    ops.attention(qkv[:, :H * 64], qkv[:, H * 64:2 * H * 64], qkv[:, 2 * H * 64:], O2, heads=H,
+                  q_start=st, q_len=ln, kv_start0=st, kv_len0=ln, max_q_len=N, max_kv_len=N,
+                  scale=0.125)
+    assert _rel(O2, ref) < 1e-2
+    tail = torch.arange(Fr, device=cuda) * N + N - 1
+    assert _rel(O2[tail], ref[tail]) < 1e-2
 
 
 def test_attention_video_with_camera_mask(cuda, lib):
@@ -232,7 +265,7 @@ def test_attention_two_segments(cuda, lib):
                   q_start=(fr * rpf + 1).to(**i32), q_len=torch.full((T,), N, **i32),
                   kv_start0=(prev * rpf + 1).to(**i32), kv_len0=torch.full((T,), N, **i32),
                   kv_start1=(nxt * rpf + 1).to(**i32), kv_len1=(two * N).to(**i32),
-                  max_q_len=N, scale=0.125)
+                  max_q_len=N, max_kv_len=2 * N, scale=0.125)
     qh = q.view(T, rpf, H, 64)[:, 1:].permute(0, 2, 1, 3)
     kh = k.view(T, rpf, H, 64)[:, 1:].permute(0, 2, 1, 3)
     vh = v.view(T, rpf, H, 64)[:, 1:].permute(0, 2, 1, 3)
@@ -340,3 +373,12 @@ def test_pts_tail_and_gaussian_adapter(cuda, lib):
     assert (out["cov"] - ref["covariances"]).abs().max() < 1e-9 + 1e-5 * ref["covariances"].abs().max()
     iu = torch.triu_indices(3, 3)
     assert torch.equal(out["cov6"], out["cov"][:, iu[0], iu[1]])
+    # padded head-output layout (parameters at column 0, xyz at 84) + reference-layout raw output
+    gsp = torch.full((px, 96), float("nan"), device=cuda)
+    gsp[:, :83], gsp[:, 84:87] = raw[:, 3:], raw[:, :3]
+    raw_out = torch.zeros_like(raw)
+    out2 = ops.gaussian_adapter(gsp, cfg.d_sh, er.sh_mask(cfg, cuda), center_col=84, param_col=0,
+                                raw_out=raw_out)
+    assert torch.equal(raw_out, raw)
+    for k in out:
+        assert torch.equal(out[k], out2[k]), k

@@ -23,11 +23,12 @@ class GemmParams(C.Structure):
         ("A", _vp), ("a_mode", _i32), ("a_rows", _i32), ("a_groups", _i32),
         ("a_row_stride", _i64), ("a_group_stride", _i64),
         ("cn", _i32), ("ch", _i32), ("cw", _i32), ("cin", _i32), ("kh", _i32), ("kw", _i32),
-        ("pad", _i32),
+        ("pad", _i32), ("conv_in_h", _i32),
+        ("conv_stride_x", _i64), ("conv_stride_y", _i64), ("conv_stride_n", _i64),
         ("W", _vp), ("w_row_stride", _i64), ("N", _i32), ("K", _i32),
         ("bias", _vp), ("act", _i32),
         ("gate", _vp), ("gate_ld", _i64), ("gate_rows", _i32), ("first_row_mode", _i32),
-        ("res1", _vp), ("res2", _vp), ("res_dtype", _i32), ("res_ld", _i64),
+        ("res1", _vp), ("res2", _vp), ("res_dtype", _i32), ("res_up2", _i32), ("res_ld", _i64),
         ("C", _vp), ("c_dtype", _i32), ("ldc", _i64),
         ("C2", _vp), ("ldc2", _i64),
         ("out_gin", _i32), ("out_gout", _i32), ("out_off", _i32), ("block_n", _i32),
@@ -51,7 +52,7 @@ class AttentionParams(C.Structure):
         ("q_rows", _i32), ("kv_rows", _i32), ("heads", _i32), ("items", _i32),
         ("q_start", _vp), ("q_len", _vp), ("kv_start0", _vp), ("kv_len0", _vp),
         ("kv_start1", _vp), ("kv_len1", _vp),
-        ("max_q_len", _i32), ("causal_block", _i32), ("scale", _f32),
+        ("max_q_len", _i32), ("max_kv_len", _i32), ("causal_block", _i32), ("scale", _f32),
     ]
 
 

@@ -38,13 +38,20 @@ struct AttnDev {
   const int *q_start, *q_len, *kv_start0, *kv_len0, *kv_start1, *kv_len1;
   int causal_block;
   float scale_log2;
+  int tail;  // the last `tail` query rows of every item are left to attention_tail_kernel
 };
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 __global__ void __launch_bounds__(192, 2)
     attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, const AttnDev a) {
   const int item = blockIdx.z, head = blockIdx.y, qt = blockIdx.x;
-  const int q_len = a.q_len[item];
+  const int q_len = max(a.q_len[item] - a.tail, 0);
   if (qt * QT >= q_len) return;  // uniform for the CTA, before any barrier / allocation
   const int q_row0 = a.q_start[item] + qt * QT;
   const int s0 = a.kv_start0[item], l0 = a.kv_len0[item];
@@ -123,8 +130,10 @@ __global__ void __launch_bounds__(192, 2)
         mbar_wait(v_full, ph);
         mbar_wait(p_full, ph);
         tc_fence_after();
-#pragma unroll
-        for (int k = 0; k < KT / 16; ++k)
+        const int seg_left = j < n0 ? l0 - j * KT : l1 - (j - n0) * KT;
+        const int ksteps = (min(seg_left, KT) + 15) >> 4;   // keys beyond the segment: P is not even written
+#pragma unroll 1
+        for (int k = 0; k < ksteps; ++k)
           umma_bf16_ss(tmem_base + 128,
                        umma_desc_k_sw128(p_addr + (k >> 2) * TILE_BYTES + (k & 3) * 32),
                        umma_desc_mn_sw128(v_addr + k * 2048), idesc_o, k != 0 ? 1u : 0u);
@@ -155,10 +164,12 @@ __global__ void __launch_bounds__(192, 2)
       const int nvalid = min(min(seg_left, KT), lim - row0);  // keys [0, nvalid) of this tile count
       mbar_wait(s_full, ph);
       tc_fence_after();
+      const int nseg = min(seg_left, KT);
+      const int nchunks = (nseg + 31) >> 5;          // CTA-uniform; P is written up to 32 * nchunks
       // ---- pass 1: row maximum
       float mx = -INFINITY;
 #pragma unroll 1
-      for (int c = 0; c < KT / 32; ++c) {
+      for (int c = 0; c < nchunks; ++c) {
         uint32_t v[32];
         tmem_ld_32x32(t_lane + c * 32, v);
         tmem_ld_wait();
@@ -176,20 +187,31 @@ __global__ void __launch_bounds__(192, 2)
       // ---- pass 2: probabilities -> bf16 P tile (K-major, 128B swizzle), row sum
       float rs = 0.f;
 #pragma unroll 1
-      for (int c = 0; c < KT / 32; ++c) {
+      for (int c = 0; c < nchunks; ++c) {
         uint32_t v[32];
         tmem_ld_32x32(t_lane + c * 32, v);
         tmem_ld_wait();
         uint32_t pk[16];
+        if (nvalid >= (c + 1) * 32) {
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float p0 = exp2f(__uint_as_float(v[i]) * a.scale_log2 - m_use);
-          float p1 = exp2f(__uint_as_float(v[i + 1]) * a.scale_log2 - m_use);
-          if (c * 32 + i >= nvalid) p0 = 0.f;
-          if (c * 32 + i + 1 >= nvalid) p1 = 0.f;
-          rs += p0 + p1;
-          const __nv_bfloat162 b2 = __floats2bfloat162_rn(p0, p1);
-          pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&b2);
+          for (int i = 0; i < 32; i += 2) {
+            const float p0 = ex2_approx(__uint_as_float(v[i]) * a.scale_log2 - m_use);
+            const float p1 = ex2_approx(__uint_as_float(v[i + 1]) * a.scale_log2 - m_use);
+            rs += p0 + p1;
+            const __nv_bfloat162 b2 = __floats2bfloat162_rn(p0, p1);
+            pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&b2);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            float p0 = ex2_approx(__uint_as_float(v[i]) * a.scale_log2 - m_use);
+            float p1 = ex2_approx(__uint_as_float(v[i + 1]) * a.scale_log2 - m_use);
+            if (c * 32 + i >= nvalid) p0 = 0.f;
+            if (c * 32 + i + 1 >= nvalid) p1 = 0.f;
+            rs += p0 + p1;
+            const __nv_bfloat162 b2 = __floats2bfloat162_rn(p0, p1);
+            pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&b2);
+          }
         }
         // columns [c*32, c*32+32) = k-block (c>>1), 16-byte chunks (c&1)*4 .. +3 of the 128-B row
         uint8_t* blk = p_row + (c >> 1) * TILE_BYTES;
@@ -203,7 +225,7 @@ __global__ void __launch_bounds__(192, 2)
       fence_proxy_async();
       tc_fence_before();
       mbar_arrive(p_full);
-      const float alpha = exp2f(m - m_use);  // m == -inf -> 0
+      const float alpha = ex2_approx(m - m_use);  // m == -inf -> 0
       l = l * alpha + rs;
       m = m_new;
       // ---- fold O' = P V into the accumulator
@@ -239,6 +261,119 @@ __global__ void __launch_bounds__(192, 2)
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ------------------------------------------------------------------ tail rows
+// The per-frame token count of this model is 2 x 128 + 1 (256 patches + the intrinsic token): a
+// third 128-row query tile for ONE row would add 50 % more CTAs.  Such 1..4-row remainders are done
+// on the CUDA cores instead: one 256-thread block per (item, head, row).
+//   phase 1  thread t scores keys t, t+256, ... (one 128-byte K row per load), scores -> smem
+//   phase 2  block max / sum of exp2
+//   phase 3  thread (part, d) accumulates sum_j p_j V[j][d] over every 4th key, partials -> smem
+constexpr int TAIL_MAX_ROWS = 4;
+constexpr int TAIL_MAX_KEYS = 2048;
+
+__device__ __forceinline__ float block_reduce(float v, float* red, bool is_max) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) {
+    const float o = __shfl_xor_sync(0xffffffffu, v, s);
+    v = is_max ? fmaxf(v, o) : v + o;
+  }
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float r = red[0];
+#pragma unroll
+  for (int i = 1; i < 8; ++i) r = is_max ? fmaxf(r, red[i]) : r + red[i];
+  return r;
+}
+
+__global__ void __launch_bounds__(256)
+    attention_tail_kernel(const __nv_bfloat16* __restrict__ Q, const __nv_bfloat16* __restrict__ K,
+                          const __nv_bfloat16* __restrict__ V, long long ldq, long long ldk,
+                          long long ldv, int heads, const AttnDev a) {
+  __shared__ float s_q[64];
+  __shared__ float s_p[TAIL_MAX_KEYS];
+  __shared__ float s_red[8];
+  __shared__ float s_o[32][64];
+  const int t = blockIdx.x % a.tail;
+  const int head = (blockIdx.x / a.tail) % heads;
+  const int item = blockIdx.x / (a.tail * heads);
+  const int rin = a.q_len[item] - a.tail + t;
+  if (rin < 0) return;
+  const int grow = a.q_start[item] + rin;
+  int lim = 0x7fffffff;
+  if (a.causal_block > 0 && (grow % a.causal_block) == 0)
+    lim = (grow / a.causal_block + 1) * a.causal_block;
+  const int s0 = a.kv_start0[item], l0 = a.kv_len0[item];
+  const int s1 = a.kv_start1 ? a.kv_start1[item] : 0, l1 = a.kv_len1 ? a.kv_len1[item] : 0;
+  const int nk = min(l0 + l1, TAIL_MAX_KEYS);
+  if (threadIdx.x < 64)
+    s_q[threadIdx.x] = __bfloat162float(Q[static_cast<long long>(grow) * ldq + head * HD + threadIdx.x]) *
+                       a.scale_log2;
+  __syncthreads();
+  float mx = -INFINITY;
+  for (int j = threadIdx.x; j < nk; j += 256) {
+    const int krow = j < l0 ? s0 + j : s1 + (j - l0);
+    float s = -INFINITY;
+    if (krow < lim) {
+      const uint4* kp = reinterpret_cast<const uint4*>(K + static_cast<long long>(krow) * ldk + head * HD);
+      uint4 kv[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) kv[i] = __ldg(kp + i);
+      s = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const uint32_t w[4] = {kv[i].x, kv[i].y, kv[i].z, kv[i].w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[u]));
+          s = fmaf(s_q[8 * i + 2 * u], f.x, s);
+          s = fmaf(s_q[8 * i + 2 * u + 1], f.y, s);
+        }
+      }
+    }
+    s_p[j] = s;
+    mx = fmaxf(mx, s);
+  }
+  mx = block_reduce(mx, s_red, true);
+  const float m_use = mx == -INFINITY ? 0.f : mx;
+  float sum = 0.f;
+  for (int j = threadIdx.x; j < nk; j += 256) {
+    const float p = ex2_approx(s_p[j] - m_use);
+    s_p[j] = p;
+    sum += p;
+  }
+  sum = block_reduce(sum, s_red, false);   // also orders the s_p writes before phase 3
+  // phase 3: thread = (part of 32, 8 output dims): one 16-byte V load per key, keys part, part+32, ..
+  const int d8 = (threadIdx.x & 7) * 8, part = threadIdx.x >> 3;
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+#pragma unroll 4
+  for (int j = part; j < nk; j += 32) {
+    const int krow = j < l0 ? s0 + j : s1 + (j - l0);
+    const uint4 t4 = __ldg(reinterpret_cast<const uint4*>(V + static_cast<long long>(krow) * ldv + head * HD + d8));
+    const uint32_t w[4] = {t4.x, t4.y, t4.z, t4.w};
+    const float p = s_p[j];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[u]));
+      acc[2 * u] = fmaf(p, f.x, acc[2 * u]);
+      acc[2 * u + 1] = fmaf(p, f.y, acc[2 * u + 1]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s_o[part][d8 + i] = acc[i];
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    float o = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) o += s_o[i][threadIdx.x];
+    a.O[static_cast<long long>(grow) * a.ldo + head * HD + threadIdx.x] =
+        __float2bfloat16(sum > 0.f ? o / sum : 0.f);
+  }
 }
 
 int make_map(CUtensorMap* map, const void* base, int heads, int rows, long long ld) {
@@ -285,14 +420,27 @@ extern "C" int vs_attention(const vs_attention_params* p, vs_stream_t stream_) {
   a.kv_len1 = p->kv_len1;
   a.causal_block = p->causal_block;
   a.scale_log2 = p->scale * 1.4426950408889634f;
+  const int rem = p->max_q_len % QT;
+  a.tail = (rem > 0 && rem <= TAIL_MAX_ROWS && p->max_kv_len > 0 && p->max_kv_len <= TAIL_MAX_KEYS)
+               ? rem : 0;
   static bool configured = false;
   if (!configured) {
     VS_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  SMEM_BYTES));
     configured = true;
   }
-  dim3 grid(ceil_div(p->max_q_len, QT), p->heads, p->items);
-  attention_kernel<<<grid, 192, SMEM_BYTES, to_stream(stream_)>>>(tmQ, tmK, tmV, a);
-  VS_LAUNCH_CHECK();
+  const int main_rows = p->max_q_len - a.tail;
+  if (main_rows > 0) {
+    dim3 grid(ceil_div(main_rows, QT), p->heads, p->items);
+    attention_kernel<<<grid, 192, SMEM_BYTES, to_stream(stream_)>>>(tmQ, tmK, tmV, a);
+    VS_LAUNCH_CHECK();
+  }
+  if (a.tail > 0) {
+    attention_tail_kernel<<<static_cast<unsigned>(p->items * p->heads * a.tail), 256, 0,
+                            to_stream(stream_)>>>(
+        static_cast<const __nv_bfloat16*>(p->Q), static_cast<const __nv_bfloat16*>(p->K),
+        static_cast<const __nv_bfloat16*>(p->V), p->ldq, p->ldk, p->ldv, p->heads, a);
+    VS_LAUNCH_CHECK();
+  }
   return VS_OK;
 }

@@ -214,19 +214,18 @@ __global__ void patchify_kernel(const float* __restrict__ img, bf16* __restrict_
 }
 
 // one thread = 8 consecutive output columns (one 16-byte store); for an NHWC source whose channel
-// count is a multiple of 8 those are 8 contiguous channels of one tap (one 16-byte load)
+// count is a multiple of 8 those are 8 contiguous channels of one tap (one 16-byte load).
+// grid = (segments of an output row of pixels, output y, image).
 __global__ void im2col_kernel(const void* __restrict__ src, int nchw_f32, bf16* __restrict__ out,
                               int n, int h, int w, int c, int k, int stride, int pad, int kpad,
                               int ho, int wo) {
-  const int k8 = kpad / 8;
-  const long long total = static_cast<long long>(n) * ho * wo * k8;
-  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const long long row = i / k8;
-  const int col0 = static_cast<int>(i - row * k8) * 8;
-  const int im = static_cast<int>(row / (ho * wo));
-  const int r = static_cast<int>(row - static_cast<long long>(im) * ho * wo);
-  const int yo = r / wo, xo = r - yo * wo;
+  const unsigned k8 = kpad / 8;
+  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<unsigned>(wo) * k8) return;
+  const int xo = idx / k8;
+  const int col0 = (idx - xo * k8) * 8;
+  const int yo = blockIdx.y, im = blockIdx.z;
+  const size_t row = (static_cast<size_t>(im) * ho + yo) * wo + xo;
   const int kkc = k * k * c;
   uint4 o = make_uint4(0u, 0u, 0u, 0u);
   if (!nchw_f32 && (c & 7) == 0) {
@@ -235,8 +234,8 @@ __global__ void im2col_kernel(const void* __restrict__ src, int nchw_f32, bf16* 
       const int dy = tap / k, dx = tap - dy * k;
       const int y = yo * stride + dy - pad, x = xo * stride + dx - pad;
       if (y >= 0 && y < h && x >= 0 && x < w)
-        o = *reinterpret_cast<const uint4*>(static_cast<const bf16*>(src) +
-                                            ((static_cast<long long>(im) * h + y) * w + x) * c + ch);
+        o = __ldg(reinterpret_cast<const uint4*>(static_cast<const bf16*>(src) +
+                                                 ((static_cast<size_t>(im) * h + y) * w + x) * c + ch));
     }
   } else {
     uint32_t pk[4];
@@ -254,10 +253,10 @@ __global__ void im2col_kernel(const void* __restrict__ src, int nchw_f32, bf16* 
           if (y >= 0 && y < h && x >= 0 && x < w) {
             if (nchw_f32)
               v = __ldg(static_cast<const float*>(src) +
-                        ((static_cast<long long>(im) * c + ch) * h + y) * w + x);
+                        ((static_cast<size_t>(im) * c + ch) * h + y) * w + x);
             else
               v = __bfloat162float(static_cast<const bf16*>(
-                  src)[((static_cast<long long>(im) * h + y) * w + x) * c + ch]);
+                  src)[((static_cast<size_t>(im) * h + y) * w + x) * c + ch]);
           }
         }
         v2[u] = v;
@@ -270,19 +269,16 @@ __global__ void im2col_kernel(const void* __restrict__ src, int nchw_f32, bf16* 
   *reinterpret_cast<uint4*>(out + row * kpad + col0) = o;
 }
 
-// bilinear x2 align_corners=True on NHWC bf16; one thread per 8 channels of an output pixel
+// bilinear x2 align_corners=True on NHWC bf16; one thread per 8 channels of an output pixel;
+// grid = (segments of an output row, output row, image): no 64-bit index arithmetic
 __global__ void upsample2x_kernel(const bf16* __restrict__ src, bf16* __restrict__ dst, int n,
                                   int h, int w, int c) {
-  const int c8 = c / 8;
+  const unsigned c8 = c / 8;
   const int ho = 2 * h, wo = 2 * w;
-  const long long total = static_cast<long long>(n) * ho * wo * c8;
-  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const int cc = static_cast<int>(i % c8);
-  long long r = i / c8;
-  const int xo = static_cast<int>(r % wo); r /= wo;
-  const int yo = static_cast<int>(r % ho);
-  const int im = static_cast<int>(r / ho);
+  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<unsigned>(wo) * c8) return;
+  const int xo = idx / c8, cc = idx - xo * c8;
+  const int yo = blockIdx.y, im = blockIdx.z;
   const float sy = ho > 1 ? static_cast<float>(h - 1) / (ho - 1) : 0.f;
   const float sx = wo > 1 ? static_cast<float>(w - 1) / (wo - 1) : 0.f;
   const float fy = yo * sy, fx = xo * sx;
@@ -290,9 +286,9 @@ __global__ void upsample2x_kernel(const bf16* __restrict__ src, bf16* __restrict
   const int y1 = min(y0 + 1, h - 1), x1 = min(x0 + 1, w - 1);
   const float ly = fy - y0, lx = fx - x0;
   const float w00 = (1 - ly) * (1 - lx), w01 = (1 - ly) * lx, w10 = ly * (1 - lx), w11 = ly * lx;
+  const bf16* base = src + static_cast<size_t>(im) * h * w * c + cc * 8;
   auto ld = [&](int y, int x) {
-    return *reinterpret_cast<const uint4*>(src + ((static_cast<long long>(im) * h + y) * w + x) * c +
-                                           cc * 8);
+    return __ldg(reinterpret_cast<const uint4*>(base + (static_cast<size_t>(y) * w + x) * c));
   };
   const uint4 a = ld(y0, x0), b = ld(y0, x1), cq = ld(y1, x0), d = ld(y1, x1);
   uint4 o;
@@ -309,8 +305,7 @@ __global__ void upsample2x_kernel(const bf16* __restrict__ src, bf16* __restrict
                               w00 * fa.y + w01 * fb.y + w10 * fc.y + w11 * fd.y);
     po[j] = *reinterpret_cast<const uint32_t*>(&r2);
   }
-  *reinterpret_cast<uint4*>(dst + ((static_cast<long long>(im) * ho + yo) * wo + xo) * c + cc * 8) =
-      o;
+  *reinterpret_cast<uint4*>(dst + ((static_cast<size_t>(im) * ho + yo) * wo + xo) * c + cc * 8) = o;
 }
 
 __global__ void pixel_shuffle_kernel(const bf16* __restrict__ src, bf16* __restrict__ dst, int n,
@@ -331,6 +326,26 @@ __global__ void pixel_shuffle_kernel(const bf16* __restrict__ src, bf16* __restr
                                                   (dy * k + dx) * c + cc * 8);
   *reinterpret_cast<uint4*>(dst + ((static_cast<long long>(im) * ho + yo) * wo + xo) * c + cc * 8) =
       v;
+}
+
+// thread per padded pixel: 16-byte store of (r, g, b, 0, 0, 0, 0, 0) or zeros on the border
+__global__ void image_nhwc8_kernel(const float* __restrict__ img, bf16* __restrict__ out, int h,
+                                   int w, int pad) {
+  const int wp = w + 8;
+  const int xp = blockIdx.x * blockDim.x + threadIdx.x;
+  if (xp >= wp) return;
+  const int yp = blockIdx.y, im = blockIdx.z;
+  const int x = xp - pad, y = yp - pad;
+  uint4 o = make_uint4(0u, 0u, 0u, 0u);
+  if (x >= 0 && x < w && y >= 0 && y < h) {
+    const size_t hw = static_cast<size_t>(h) * w;
+    const float* p = img + static_cast<size_t>(im) * 3 * hw + static_cast<size_t>(y) * w + x;
+    const __nv_bfloat162 rg = __floats2bfloat162_rn(__ldg(p), __ldg(p + hw));
+    const __nv_bfloat162 b0 = __floats2bfloat162_rn(__ldg(p + 2 * hw), 0.f);
+    o.x = *reinterpret_cast<const uint32_t*>(&rg);
+    o.y = *reinterpret_cast<const uint32_t*>(&b0);
+  }
+  *reinterpret_cast<uint4*>(out + ((static_cast<size_t>(im) * (h + 2 * pad) + yp) * wp + xp) * 8) = o;
 }
 
 __global__ void intrinsic_token_kernel(const float* __restrict__ K9, const float* __restrict__ w,
@@ -412,44 +427,57 @@ __global__ void camera_head_kernel(const float* __restrict__ feat, long long ld,
   }
 }
 
-// one warp per pixel: 3 dot products over Cf channels, then the exp-depth postprocess
-__global__ void pts_tail_kernel(const bf16* __restrict__ feat, int Cf, const float* __restrict__ w,
-                                const float* __restrict__ b, float* __restrict__ raw,
-                                long long raw_ld, long long px) {
-  const long long pix = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
+// thread per pixel: the pixel's Cf-channel row is read with 16-byte loads (whole sectors per
+// thread), the 3 x Cf weights are broadcast from shared memory; then the exp-depth postprocess
+__global__ void __launch_bounds__(128)
+    pts_tail_kernel(const bf16* __restrict__ feat, int Cf, const float* __restrict__ w,
+                    const float* __restrict__ b, float* __restrict__ raw, long long raw_ld,
+                    long long px) {
+  extern __shared__ float s_w[];   // [3][Cf]
+  for (int i = threadIdx.x; i < 3 * Cf; i += blockDim.x) s_w[i] = w[i];
+  __syncthreads();
+  const long long pix = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (pix >= px) return;
-  const bf16* f = feat + pix * Cf;
+  const uint4* f = reinterpret_cast<const uint4*>(feat + pix * Cf);
   float a0 = 0.f, a1 = 0.f, a2 = 0.f;
-  for (int c = lane * 2; c < Cf; c += 64) {
-    const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(f + c));
-    a0 += v.x * w[c] + v.y * w[c + 1];
-    a1 += v.x * w[Cf + c] + v.y * w[Cf + c + 1];
-    a2 += v.x * w[2 * Cf + c] + v.y * w[2 * Cf + c + 1];
-  }
+#pragma unroll 4
+  for (int c8 = 0; c8 < Cf / 8; ++c8) {
+    const uint4 t = __ldg(f + c8);
+    const uint32_t u[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
-  for (int s = 16; s > 0; s >>= 1) {
-    a0 += __shfl_xor_sync(0xffffffffu, a0, s);
-    a1 += __shfl_xor_sync(0xffffffffu, a1, s);
-    a2 += __shfl_xor_sync(0xffffffffu, a2, s);
+    for (int j = 0; j < 4; ++j) {
+      const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u[j]));
+      const int c = c8 * 8 + 2 * j;
+      a0 = fmaf(v.x, s_w[c], fmaf(v.y, s_w[c + 1], a0));
+      a1 = fmaf(v.x, s_w[Cf + c], fmaf(v.y, s_w[Cf + c + 1], a1));
+      a2 = fmaf(v.x, s_w[2 * Cf + c], fmaf(v.y, s_w[2 * Cf + c + 1], a2));
+    }
   }
-  if (lane == 0) {
-    a0 += b[0]; a1 += b[1]; a2 += b[2];
-    const float d = sqrtf(a0 * a0 + a1 * a1 + a2 * a2);
-    const float sc = expm1f(d) / fmaxf(d, 1e-8f);
-    float* o = raw + pix * raw_ld;
-    o[0] = a0 * sc; o[1] = a1 * sc; o[2] = a2 * sc;
-  }
+  a0 += b[0]; a1 += b[1]; a2 += b[2];
+  const float d = sqrtf(a0 * a0 + a1 * a1 + a2 * a2);
+  const float sc = expm1f(d) / fmaxf(d, 1e-8f);
+  float* o = raw + pix * raw_ld;
+  o[0] = a0 * sc; o[1] = a1 * sc; o[2] = a2 * sc;
 }
 
 // Gaussian adapter, part 1: per-Gaussian scalars (thread per Gaussian)
-__global__ void adapter_params_kernel(const float* __restrict__ raw, long long raw_ld, long long G,
+__global__ void adapter_params_kernel(const float* __restrict__ src, long long src_ld,
+                                      int center_col, int param_col, long long G, int raw_w,
+                                      float* __restrict__ raw_out,
                                       float* __restrict__ means, float* __restrict__ cov,
                                       float* __restrict__ cov6, float* __restrict__ opac,
                                       float* __restrict__ scales, float* __restrict__ rot) {
   const long long g = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (g >= G) return;
-  const float* r = raw + g * raw_ld;
+  float r[11];   // the reference's raw layout: xyz | opacity | scale(3) | quaternion xyzw(4)
+#pragma unroll
+  for (int i = 0; i < 3; ++i) r[i] = src[g * src_ld + center_col + i];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) r[3 + i] = src[g * src_ld + param_col + i];
+  if (raw_out) {
+#pragma unroll
+    for (int i = 0; i < 11; ++i) raw_out[g * raw_w + i] = r[i];
+  }
   if (means) { means[g * 3] = r[0]; means[g * 3 + 1] = r[1]; means[g * 3 + 2] = r[2]; }
   const float o = 1.0f / (1.0f + expf(-r[3]));
   if (opac) opac[g] = o;
@@ -491,16 +519,23 @@ __global__ void adapter_params_kernel(const float* __restrict__ raw, long long r
   }
 }
 
-// Gaussian adapter, part 2: SH = raw[..., 11:] * sh_mask, flat and fully coalesced
-__global__ void adapter_sh_kernel(const float* __restrict__ raw, long long raw_ld, long long G,
-                                  int d_sh, const float* __restrict__ mask,
-                                  float* __restrict__ sh) {
-  const long long per = 3ll * d_sh;
-  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= G * per) return;
-  const long long g = i / per;
-  const int j = static_cast<int>(i - g * per);
-  sh[i] = raw[g * raw_ld + 11 + j] * mask[j % d_sh];
+// Gaussian adapter, part 2: SH = raw[..., 11:] * sh_mask; a block covers 64 Gaussians, flat and
+// coalesced over their 64 * 3 * d_sh outputs, 32-bit index arithmetic
+__global__ void adapter_sh_kernel(const float* __restrict__ src, long long src_ld, int param_col,
+                                  long long G, int d_sh, const float* __restrict__ mask,
+                                  float* __restrict__ sh, float* __restrict__ raw_out, int raw_w) {
+  const unsigned per = 3u * d_sh;
+  const long long g0 = static_cast<long long>(blockIdx.x) * 64;
+  const unsigned cnt = static_cast<unsigned>(min(64ll, G - g0)) * per;
+  const float* rbase = src + g0 * src_ld + param_col + 8;
+  float* obase = sh ? sh + g0 * per : nullptr;
+  float* wbase = raw_out ? raw_out + g0 * raw_w + 11 : nullptr;
+  for (unsigned i = threadIdx.x; i < cnt; i += blockDim.x) {
+    const unsigned g = i / per, j = i - g * per;
+    const float v = rbase[g * src_ld + j];
+    if (obase) obase[i] = v * __ldg(mask + (j % d_sh));
+    if (wbase) wbase[g * raw_w + j] = v;
+  }
 }
 
 inline unsigned blocks_for(long long n, int threads) {
@@ -584,9 +619,10 @@ extern "C" int vs_im2col(const void* src, int src_nchw_f32, void* out, int n, in
   VS_REQUIRE(k > 0 && stride > 0 && kpad >= k * k * c, "im2col: bad geometry");
   VS_REQUIRE(kpad % 8 == 0, "im2col: kpad must be a multiple of 8");
   const int ho = (h + 2 * pad - k) / stride + 1, wo = (w + 2 * pad - k) / stride + 1;
-  const long long total = static_cast<long long>(n) * ho * wo * (kpad / 8);
-  if (total <= 0) return VS_OK;
-  im2col_kernel<<<blocks_for(total, 256), 256, 0, to_stream(stream)>>>(
+  if (static_cast<long long>(n) * ho * wo <= 0) return VS_OK;
+  VS_REQUIRE(ho <= 65535 && n <= 65535, "im2col: map too large for the launch grid");
+  dim3 grid(blocks_for(static_cast<long long>(wo) * (kpad / 8), 256), ho, n);
+  im2col_kernel<<<grid, 256, 0, to_stream(stream)>>>(
       src, src_nchw_f32, static_cast<bf16*>(out), n, h, w, c, k, stride, pad, kpad, ho, wo);
   VS_LAUNCH_CHECK();
   return VS_OK;
@@ -596,9 +632,10 @@ extern "C" int vs_upsample2x(const void* src, void* dst, int n, int h, int w, in
                              vs_stream_t stream) {
   VS_REQUIRE(src && dst, "upsample2x: null tensor");
   VS_REQUIRE(c % 8 == 0, "upsample2x: channels must be a multiple of 8");
-  const long long total = static_cast<long long>(n) * 4 * h * w * (c / 8);
-  if (total == 0) return VS_OK;
-  upsample2x_kernel<<<blocks_for(total, 256), 256, 0, to_stream(stream)>>>(
+  if (static_cast<long long>(n) * h * w == 0) return VS_OK;
+  VS_REQUIRE(2 * h <= 65535 && n <= 65535, "upsample2x: map too large for the launch grid");
+  dim3 grid(blocks_for(static_cast<long long>(2 * w) * (c / 8), 256), 2 * h, n);
+  upsample2x_kernel<<<grid, 256, 0, to_stream(stream)>>>(
       static_cast<const bf16*>(src), static_cast<bf16*>(dst), n, h, w, c);
   VS_LAUNCH_CHECK();
   return VS_OK;
@@ -612,6 +649,17 @@ extern "C" int vs_pixel_shuffle(const void* src, void* dst, int n, int h, int w,
   if (total == 0) return VS_OK;
   pixel_shuffle_kernel<<<blocks_for(total, 256), 256, 0, to_stream(stream)>>>(
       static_cast<const bf16*>(src), static_cast<bf16*>(dst), n, h, w, c, k);
+  VS_LAUNCH_CHECK();
+  return VS_OK;
+}
+
+extern "C" int vs_image_nhwc8(const float* img, void* out, int n, int h, int w, int pad,
+                              vs_stream_t stream) {
+  VS_REQUIRE(img && out, "image_nhwc8: null tensor");
+  VS_REQUIRE(pad >= 0 && pad <= 8 && h + 2 * pad <= 65535 && n <= 65535, "image_nhwc8: bad geometry");
+  if (n * h * w == 0) return VS_OK;
+  dim3 grid(blocks_for(w + 8, 128), h + 2 * pad, n);
+  image_nhwc8_kernel<<<grid, 128, 0, to_stream(stream)>>>(img, static_cast<bf16*>(out), h, w, pad);
   VS_LAUNCH_CHECK();
   return VS_OK;
 }
@@ -662,26 +710,30 @@ extern "C" int vs_pts_tail(const void* feat, int Cf, const float* w, const float
   VS_REQUIRE(feat && w && b && raw, "pts_tail: null tensor");
   VS_REQUIRE(Cf % 64 == 0, "pts_tail: Cf must be a multiple of 64");
   if (px == 0) return VS_OK;
-  pts_tail_kernel<<<blocks_for(px * 32, 256), 256, 0, to_stream(stream)>>>(
+  VS_REQUIRE(Cf <= 1024, "pts_tail: Cf too large");
+  pts_tail_kernel<<<blocks_for(px, 128), 128, 3 * Cf * sizeof(float), to_stream(stream)>>>(
       static_cast<const bf16*>(feat), Cf, w, b, raw, raw_ld, px);
   VS_LAUNCH_CHECK();
   return VS_OK;
 }
 
-extern "C" int vs_gaussian_adapter(const float* raw, int64_t raw_ld, int64_t G, int d_sh,
-                                   const float* sh_mask, float* means, float* cov, float* cov6,
-                                   float* sh, float* opac, float* scales, float* rot,
-                                   vs_stream_t stream) {
-  VS_REQUIRE(raw, "gaussian_adapter: null input");
-  VS_REQUIRE(raw_ld >= 11 + 3 * d_sh, "gaussian_adapter: raw_ld too small");
+extern "C" int vs_gaussian_adapter(const float* src, int64_t src_ld, int center_col, int param_col,
+                                   int64_t G, int d_sh, const float* sh_mask, float* raw_out,
+                                   float* means, float* cov, float* cov6, float* sh, float* opac,
+                                   float* scales, float* rot, vs_stream_t stream) {
+  VS_REQUIRE(src, "gaussian_adapter: null input");
+  VS_REQUIRE(center_col >= 0 && param_col >= 0 && src_ld >= center_col + 3 &&
+                 src_ld >= param_col + 8 + 3 * d_sh,
+             "gaussian_adapter: src_ld too small for the column layout");
   if (G == 0) return VS_OK;
+  const int raw_w = 11 + 3 * d_sh;
   adapter_params_kernel<<<blocks_for(G, 256), 256, 0, to_stream(stream)>>>(
-      raw, raw_ld, G, means, cov, cov6, opac, scales, rot);
+      src, src_ld, center_col, param_col, G, raw_w, raw_out, means, cov, cov6, opac, scales, rot);
   VS_LAUNCH_CHECK();
-  if (sh != nullptr) {
-    VS_REQUIRE(sh_mask != nullptr, "gaussian_adapter: sh_mask required");
-    adapter_sh_kernel<<<blocks_for(G * 3 * d_sh, 256), 256, 0, to_stream(stream)>>>(
-        raw, raw_ld, G, d_sh, sh_mask, sh);
+  if (sh != nullptr || raw_out != nullptr) {
+    VS_REQUIRE(sh == nullptr || sh_mask != nullptr, "gaussian_adapter: sh_mask required");
+    adapter_sh_kernel<<<blocks_for(G, 64), 256, 0, to_stream(stream)>>>(
+        src, src_ld, param_col, G, d_sh, sh_mask, sh, raw_out, raw_w);
     VS_LAUNCH_CHECK();
   }
   return VS_OK;

@@ -11,7 +11,12 @@
 //                bias / activation / AdaLN gate / residual(s) in registers, 16-byte row-wise
 //                loads and stores (every thread touches whole 32-byte sectors of its own row)
 // The accumulator is double buffered in TMEM (2 x BN columns), so the epilogue of tile i overlaps
-// the main loop of tile i+1.  The A operand is addressed through a TMA tensor map, which is what
+// the main loop of tile i+1.  With CL == 2 the two CTAs of a cluster form a CTA pair
+// (tcgen05 cta_group::2) on a 256 x BN tile: each CTA loads its own 128 rows of A and HALF of the
+// W tile, the leader issues one M = 256 UMMA that reads both shared memories and writes both
+// TMEMs.  A single-CTA 128 x 256 tile ingests 48 KB per 512 MMA cycles per SM -- more than the
+// L2 -> SM port sustains (measured ~45 B/clk/SM, tensor pipe 45-55 % busy); the pair needs 32 KB and
+// fits two more ring stages.  The A operand is addressed through a TMA tensor map, which is what
 // lets the same kernel serve nn.Linear on (strided / grouped) token rows and stride-1 k x k
 // convolutions on NHWC maps (one 4-D box per filter tap; out-of-bounds = zero padding).
 //
@@ -40,7 +45,7 @@ struct GemmDev {
   int num_kb;
   int m_tiles, n_tiles;
   // rows mode
-  int a_rows, tiles_per_group;
+  int a_rows, a_groups, tiles_per_group;
   // conv mode
   int cn, ch, cw, bw, bh, bn, tiles_x, tiles_y, cblocks, kw, pad;
   // epilogue
@@ -52,6 +57,7 @@ struct GemmDev {
   const void* res1;
   const void* res2;
   int res_dtype;
+  int res_up2;
   long long res_ld;
   void* C;
   int c_dtype;
@@ -62,8 +68,20 @@ struct GemmDev {
   int vec;
 };
 
+// exact-erf GELU (nn.GELU default, croco/blocks.py:60) with erf from Abramowitz-Stegun 7.1.26
+// (|err| <= 1.5e-7, far below the bf16 rounding of the result): 2 MUFU + ~12 FMA-pipe instructions
+// instead of erff's ~30 -- the GELU epilogue otherwise out-lasts the K = 1024 main loop.
 __device__ __forceinline__ float gelu_erf(float x) {
-  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
+  const float z = fabsf(x) * 0.70710678118654752f;
+  float t, e;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * z * z));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float erf_abs = fmaf(-p * t, e, 1.0f);
+  return 0.5f * x * (1.0f + copysignf(erf_abs, x));
 }
 
 struct TileCoord {
@@ -72,10 +90,14 @@ struct TileCoord {
   int x0, y0, img0;     // conv mode
 };
 
-__device__ __forceinline__ TileCoord tile_coord(const GemmDev& g, int t, int BN) {
+// work unit u of a cluster -> tile of CTA `rank`: units enumerate (n tile, group of CL m tiles),
+// m fastest so that concurrently running clusters share W tiles.  mt may be >= m_tiles for the
+// last group when m_tiles is odd: such a tile loads zeros and stores nothing.
+__device__ __forceinline__ TileCoord tile_coord(const GemmDev& g, int u, int rank, int CL, int BN) {
   TileCoord c{};
-  const int nt = t / g.m_tiles;          // m fastest: concurrently running CTAs share W tiles
-  const int mt = t - nt * g.m_tiles;
+  const int m_groups = (g.m_tiles + CL - 1) / CL;
+  const int nt = u / m_groups;
+  const int mt = (u - nt * m_groups) * CL + rank;
   c.n0 = nt * BN;
   if (g.mode == 0) {
     c.grp = mt / g.tiles_per_group;
@@ -142,6 +164,38 @@ __device__ __forceinline__ void add32_res(const void* base, int dtype, long long
   }
 }
 
+// += bilinear x2 (align_corners=True) sample of a half-resolution NHWC bf16 map at output pixel
+// (x, y) of image im, channels [nb, nb+32)
+__device__ __forceinline__ void add32_res_up2(const __nv_bfloat16* base, long long ld, int im, int x,
+                                              int y, int ch, int cw, int nb, int nv, bool vec,
+                                              float (&f)[32]) {
+  const int h = ch >> 1, w = cw >> 1;
+  const float sy = ch > 1 ? static_cast<float>(h - 1) / (ch - 1) : 0.f;
+  const float sx = cw > 1 ? static_cast<float>(w - 1) / (cw - 1) : 0.f;
+  const float fy = y * sy, fx = x * sx;
+  const int y0 = static_cast<int>(fy), x0 = static_cast<int>(fx);
+  const int y1 = min(y0 + 1, h - 1), x1 = min(x0 + 1, w - 1);
+  const float ly = fy - y0, lx = fx - x0;
+  const float wt[4] = {(1 - ly) * (1 - lx), (1 - ly) * lx, ly * (1 - lx), ly * lx};
+  const int ys[4] = {y0, y0, y1, y1}, xs[4] = {x0, x1, x0, x1};
+  float acc[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    float tmp[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) tmp[i] = 0.f;
+    add32_res(base, VS_BF16, ((static_cast<long long>(im) * h + ys[t]) * w + xs[t]) * ld + nb, nv, vec,
+              tmp);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) acc[i] = fmaf(wt[t], tmp[i], acc[i]);
+  }
+  // the stand-alone kernel rounds the upsampled map to bf16 before it is consumed: do the same
+#pragma unroll
+  for (int i = 0; i < 32; ++i) f[i] += __bfloat162float(__float2bfloat16(acc[i]));
+}
+
 __device__ __forceinline__ void store32_bf16(__nv_bfloat16* p, int nv, bool vec, const float (&f)[32],
                                              bool relu) {
   if (vec && nv == 32) {
@@ -176,12 +230,12 @@ __device__ __forceinline__ void store32_f32(float* p, int nv, bool vec, const fl
   }
 }
 
-template <int BN, int STAGES, int EPI_WARPS>
+template <int BN, int STAGES, int EPI_WARPS, int CL>
 __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
     gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA,
                      const __grid_constant__ CUtensorMap tmW, const GemmDev g) {
   constexpr int A_BYTES = BM * 128;
-  constexpr int B_BYTES = BN * 128;
+  constexpr int B_BYTES = (BN / CL) * 128;   // a CTA pair splits the W tile
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   constexpr int TMEM_COLS = 2 * BN;  // two accumulators
   static_assert(EPI_WARPS == 4 || EPI_WARPS == 8, "epilogue warps");
@@ -200,7 +254,10 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int total_tiles = g.m_tiles * g.n_tiles;
+  const int rank = CL > 1 ? static_cast<int>(cluster_ctarank()) : 0;
+  const int total_units = ((g.m_tiles + CL - 1) / CL) * g.n_tiles;
+  const int unit0 = blockIdx.x / CL, unit_step = gridDim.x / CL;
+  constexpr uint16_t PAIR_MASK = 3;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -211,16 +268,22 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], EPI_WARPS);
+      mbar_init(&tmem_empty[i], EPI_WARPS * CL);   // pair: both CTAs' epilogues report to the leader
     }
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, TMEM_COLS);
-    tmem_relinquish();
+    if (CL == 1) {
+      tmem_alloc(tmem_slot, TMEM_COLS);
+      tmem_relinquish();
+    } else {
+      tmem_alloc_pair(tmem_slot, TMEM_COLS);
+      tmem_relinquish_pair();
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();   // peer barriers are initialised before anything targets them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -228,33 +291,48 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
       uint32_t it = 0;  // k-block counter across tiles (ring position)
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const TileCoord tc = tile_coord(g, t, BN);
+      for (int u = unit0; u < total_units; u += unit_step) {
+        const TileCoord tc = tile_coord(g, u, rank, CL, BN);
         for (int kb = 0; kb < g.num_kb; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(&empty[s], ph ^ 1);
           uint8_t* sA = smem + s * STAGE_BYTES;
           uint8_t* sB = sA + A_BYTES;
-          mbar_expect_tx(&full[s], STAGE_BYTES);
-          if (g.mode == 0) {
-            tma_load_3d(sA, &tmA, &full[s], kb * BK, tc.r0, tc.grp);
+          if (CL == 1) {
+            mbar_expect_tx(&full[s], STAGE_BYTES);
+            if (g.mode == 0) {
+              tma_load_3d(sA, &tmA, &full[s], kb * BK, tc.r0, tc.grp);
+            } else {
+              const int tap = kb / g.cblocks;
+              const int c0 = (kb - tap * g.cblocks) * BK;
+              const int dy = tap / g.kw, dx = tap - dy * g.kw;
+              tma_load_4d(sA, &tmA, &full[s], c0, tc.x0 + dx - g.pad, tc.y0 + dy - g.pad, tc.img0);
+            }
+            tma_load_2d(sB, &tmW, &full[s], kb * BK, tc.n0);
           } else {
-            const int tap = kb / g.cblocks;
-            const int c0 = (kb - tap * g.cblocks) * BK;
-            const int dy = tap / g.kw, dx = tap - dy * g.kw;
-            tma_load_4d(sA, &tmA, &full[s], c0, tc.x0 + dx - g.pad, tc.y0 + dy - g.pad, tc.img0);
+            // both CTAs' bytes are counted on the leader's barrier (its MMA thread waits there)
+            if (rank == 0) mbar_expect_tx(&full[s], 2 * STAGE_BYTES);
+            if (g.mode == 0) {
+              tma_load_3d_pair(sA, &tmA, &full[s], kb * BK, tc.r0, tc.grp);
+            } else {
+              const int tap = kb / g.cblocks;
+              const int c0 = (kb - tap * g.cblocks) * BK;
+              const int dy = tap / g.kw, dx = tap - dy * g.kw;
+              tma_load_4d_pair(sA, &tmA, &full[s], c0, tc.x0 + dx - g.pad, tc.y0 + dy - g.pad,
+                               tc.img0);
+            }
+            tma_load_2d_pair(sB, &tmW, &full[s], kb * BK, tc.n0 + rank * (BN / CL));
           }
-          tma_load_2d(sB, &tmW, &full[s], kb * BK, tc.n0);
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+    // ------------------------------------------------------------ MMA issuer (pair: leader only)
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM * CL, BN);
       uint32_t it = 0, ti = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++ti) {
+      for (int u = unit0; u < total_units; u += unit_step, ++ti) {
         const uint32_t a = ti & 1;
         mbar_wait(&tmem_empty[a], ((ti >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
         tc_fence_after();
@@ -268,12 +346,19 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
           const uint32_t b_addr = a_addr + A_BYTES;
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
-            umma_bf16_ss(d_tmem, umma_desc_k_sw128(a_addr + k * 32),
-                         umma_desc_k_sw128(b_addr + k * 32), idesc, (kb | k) != 0 ? 1u : 0u);
+            if (CL == 1)
+              umma_bf16_ss(d_tmem, umma_desc_k_sw128(a_addr + k * 32),
+                           umma_desc_k_sw128(b_addr + k * 32), idesc, (kb | k) != 0 ? 1u : 0u);
+            else
+              umma_bf16_ss_pair(d_tmem, umma_desc_k_sw128(a_addr + k * 32),
+                                umma_desc_k_sw128(b_addr + k * 32), idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&empty[s]);  // slot reusable once these MMAs have read it
+          // slot reusable (in both CTAs of a pair) once these MMAs have read it
+          if (CL == 1) umma_commit(&empty[s]);
+          else umma_commit_pair(&empty[s], PAIR_MASK);
         }
-        umma_commit(&tmem_full[a]);
+        if (CL == 1) umma_commit(&tmem_full[a]);
+        else umma_commit_pair(&tmem_full[a], PAIR_MASK);
       }
     }
   } else {
@@ -284,16 +369,17 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
     const int r = q * 32 + lane;       // tile row owned by this thread
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     uint32_t ti = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++ti) {
-      const TileCoord tc = tile_coord(g, t, BN);
+    for (int u = unit0; u < total_units; u += unit_step, ++ti) {
+      const TileCoord tc = tile_coord(g, u, rank, CL, BN);
       const uint32_t a = ti & 1;
       long long my_out = -1;
       int my_gate = -1;
+      int pix_x = 0, pix_y = 0, pix_im = 0;
       {
         bool valid;
         long long m;
         if (g.mode == 0) {
-          valid = (tc.r0 + r) < g.a_rows;
+          valid = (tc.r0 + r) < g.a_rows && tc.grp < g.a_groups;
           m = static_cast<long long>(tc.grp) * g.a_rows + tc.r0 + r;
         } else {
           const int x = tc.x0 + r % g.bw;
@@ -301,6 +387,7 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
           const int im = tc.img0 + r / (g.bw * g.bh);
           valid = x < g.cw && y < g.ch && im < g.cn;
           m = (static_cast<long long>(im) * g.ch + y) * g.cw + x;
+          pix_x = x; pix_y = y; pix_im = im;
         }
         if (valid) {
           long long o = m;
@@ -350,7 +437,10 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
 #pragma unroll
           for (int i = 0; i < 32; ++i) f[i] *= 1.0f + gt[i];
         }
-        if (g.res1 != nullptr) {
+        if (g.res1 != nullptr && g.res_up2) {
+          add32_res_up2(static_cast<const __nv_bfloat16*>(g.res1), g.res_ld, pix_im, pix_x, pix_y,
+                        g.ch, g.cw, nb, nv, g.vec & VEC_RES, f);
+        } else if (g.res1 != nullptr) {
           add32_res(g.res1, g.res_dtype, my_out * g.res_ld + nb, nv, g.vec & VEC_RES, f);
           if (g.res2 != nullptr)
             add32_res(g.res2, g.res_dtype, my_out * g.res_ld + nb, nv, g.vec & VEC_RES, f);
@@ -366,13 +456,20 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[a]);
+      if (lane == 0) {
+        if (CL == 1 || rank == 0) mbar_arrive(&tmem_empty[a]);
+        else mbar_arrive_cluster(&tmem_empty[a], 0);
+      }
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+  if (CL > 1) cluster_sync_all();   // no remote arrive / pair MMA may target a CTA that has exited
+  if (warp == 1) {
+    if (CL == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+    else tmem_dealloc_pair(tmem_base, TMEM_COLS);
+  }
 }
 
 int num_sms() {
@@ -385,21 +482,32 @@ int num_sms() {
   return n;
 }
 
-template <int BN, int STAGES, int EPI_WARPS>
+template <int BN, int STAGES, int EPI_WARPS, int CL>
 int launch(const CUtensorMap& tmA, const CUtensorMap& tmW, const GemmDev& g, cudaStream_t stream) {
-  constexpr int SMEM = STAGES * (BM * 128 + BN * 128) + 1024 /*align*/ + 256 /*barriers*/;
+  constexpr int SMEM = STAGES * (BM * 128 + (BN / CL) * 128) + 1024 /*align*/ + 256 /*barriers*/;
   static_assert(SMEM <= 227 * 1024, "shared memory budget");
+  auto kernel = gemm_tc05_kernel<BN, STAGES, EPI_WARPS, CL>;
   static bool configured = false;  // attribute is per-function, set once per process
   if (!configured) {
-    VS_CUDA(cudaFuncSetAttribute(gemm_tc05_kernel<BN, STAGES, EPI_WARPS>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    VS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     configured = true;
   }
-  const int total = g.m_tiles * g.n_tiles;
-  const int grid = total < num_sms() ? total : num_sms();
-  gemm_tc05_kernel<BN, STAGES, EPI_WARPS>
-      <<<grid, 64 + 32 * EPI_WARPS, SMEM, stream>>>(tmA, tmW, g);
-  VS_LAUNCH_CHECK();
+  const int units = ceil_div(g.m_tiles, CL) * g.n_tiles;
+  const int slots = num_sms() / CL;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(static_cast<unsigned>((units < slots ? units : slots) * CL));
+  cfg.blockDim = dim3(64 + 32 * EPI_WARPS);
+  cfg.dynamicSmemBytes = SMEM;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  VS_CUDA(cudaLaunchKernelEx(&cfg, kernel, tmA, tmW, g));
+  count_launch();
   return VS_OK;
 }
 
@@ -413,7 +521,8 @@ double tile_cost(int bn, int m_tiles, int N, int num_kb) {
   const double waves = static_cast<double>((tiles + sms - 1) / sms);
   const double active = tiles < sms ? static_cast<double>(tiles) : static_cast<double>(sms);
   const double mma = 2.0 * bn;                                   // 4 UMMAs of 128 x bn x 16
-  const double l2 = active * (BM + bn) * 128.0 / 6300.0;         // chip-wide L2 -> SM feed (B/clk)
+  const double wshare = (bn >= 128 && m_tiles >= 2) ? 0.5 : 1.0;  // a CTA pair splits the W tile
+  const double l2 = active * (BM + wshare * bn) * 128.0 / 6300.0;  // chip-wide L2 -> SM feed (B/clk)
   const double per_kb = mma > l2 ? mma : l2;
   return waves * (num_kb * per_kb + 1500.0 /*pipeline fill + epilogue tail*/);
 }
@@ -442,7 +551,11 @@ extern "C" int vs_gemm(const vs_gemm_params* p, vs_stream_t stream_) {
   g.res1 = p->res1;
   g.res2 = p->res2;
   g.res_dtype = p->res_dtype;
+  g.res_up2 = p->res_up2;
   g.res_ld = p->res_ld;
+  VS_REQUIRE(!p->res_up2 || (p->a_mode == 1 && p->res1 && p->res_dtype == VS_BF16 && !p->res2 &&
+                             p->ch % 2 == 0 && p->cw % 2 == 0),
+             "vs_gemm: res_up2 needs conv mode, one bf16 residual map and even output sizes");
   g.C = p->C;
   g.c_dtype = p->c_dtype;
   g.ldc = p->ldc;
@@ -473,6 +586,7 @@ extern "C" int vs_gemm(const vs_gemm_params* p, vs_stream_t stream_) {
     VS_REQUIRE(p->a_groups == 1 || p->a_group_stride % 8 == 0,
                "vs_gemm: a_group_stride must be a multiple of 8");
     g.a_rows = p->a_rows;
+    g.a_groups = p->a_groups;
     g.tiles_per_group = ceil_div(p->a_rows, BM);
     m_tiles = g.tiles_per_group * p->a_groups;
     ktot = p->K;
@@ -508,11 +622,16 @@ extern "C" int vs_gemm(const vs_gemm_params* p, vs_stream_t stream_) {
     m_tiles = g.tiles_x * g.tiles_y * ceil_div(p->cn, bn);
     g.cblocks = ceil_div(p->cin, BK);
     ktot = static_cast<long long>(p->kh) * p->kw * g.cblocks * BK;
+    const long long in_h = p->conv_in_h > 0 ? p->conv_in_h : p->ch;
+    const long long sx = p->conv_stride_x > 0 ? p->conv_stride_x : p->cin;
+    const long long sy = p->conv_stride_y > 0 ? p->conv_stride_y : sx * p->cw;
+    const long long sn = p->conv_stride_n > 0 ? p->conv_stride_n : sy * in_h;
+    VS_REQUIRE(sx % 8 == 0 && sy % 8 == 0 && sn % 8 == 0,
+               "vs_gemm: conv strides must be multiples of 8 elements");
     cuuint64_t dims[4] = {static_cast<cuuint64_t>(p->cin), static_cast<cuuint64_t>(p->cw),
-                          static_cast<cuuint64_t>(p->ch), static_cast<cuuint64_t>(p->cn)};
-    cuuint64_t str[3] = {static_cast<cuuint64_t>(p->cin) * 2,
-                         static_cast<cuuint64_t>(p->cin) * p->cw * 2,
-                         static_cast<cuuint64_t>(p->cin) * p->cw * p->ch * 2};
+                          static_cast<cuuint64_t>(in_h), static_cast<cuuint64_t>(p->cn)};
+    cuuint64_t str[3] = {static_cast<cuuint64_t>(sx) * 2, static_cast<cuuint64_t>(sy) * 2,
+                         static_cast<cuuint64_t>(sn) * 2};
     cuuint32_t box[4] = {BK, static_cast<cuuint32_t>(bw), static_cast<cuuint32_t>(bh),
                          static_cast<cuuint32_t>(bn)};
     int rc = encode_map(&tmA, p->A, 4, dims, str, box);
@@ -535,16 +654,22 @@ extern "C" int vs_gemm(const vs_gemm_params* p, vs_stream_t stream_) {
   }
   VS_REQUIRE(bn == 64 || bn == 128 || bn == 256, "vs_gemm: block_n must be 64, 128 or 256");
   g.n_tiles = ceil_div(p->N, bn);
+  // vertically adjacent tiles are computed by a CTA pair that splits the W tile (see header)
+  const int cl = (bn >= 128 && m_tiles >= 2) ? 2 : 1;
   {
     cuuint64_t dims[2] = {static_cast<cuuint64_t>(ktot), static_cast<cuuint64_t>(p->N)};
     cuuint64_t str[1] = {static_cast<cuuint64_t>(p->w_row_stride) * 2};
-    cuuint32_t box[2] = {BK, static_cast<cuuint32_t>(bn)};
+    cuuint32_t box[2] = {BK, static_cast<cuuint32_t>(bn / cl)};
     int rc = encode_map(&tmW, p->W, 2, dims, str, box);
     if (rc) return rc;
   }
   switch (bn) {
-    case 64: return launch<64, 8, 4>(tmA, tmW, g, stream);
-    case 128: return launch<128, 6, 4>(tmA, tmW, g, stream);
-    default: return launch<256, 4, 8>(tmA, tmW, g, stream);
+    case 64: return launch<64, 8, 4, 1>(tmA, tmW, g, stream);
+    case 128:
+      return cl == 2 ? launch<128, 8, 4, 2>(tmA, tmW, g, stream)
+                     : launch<128, 6, 4, 1>(tmA, tmW, g, stream);
+    default:
+      return cl == 2 ? launch<256, 6, 8, 2>(tmA, tmW, g, stream)
+                     : launch<256, 4, 8, 1>(tmA, tmW, g, stream);
   }
 }

@@ -372,10 +372,12 @@ class EncoderEngine:
                 w[k + ".head.4.w"] = sd[k + ".head.4.weight"].flatten(1).to(F32).contiguous()
             else:
                 w[k + ".head.4"] = _bf(sd[k + ".head.4.weight"].flatten(1))
+                # 7x7 stem as kh = 7, kw = 1 over windows of 8 pixels x 8 (zero-padded) channels:
+                # K index = dy * 64 + dx * 8 + c
                 w7 = sd[k + ".input_merger.0.weight"]                        # [256,3,7,7]
-                p = torch.zeros((w7.shape[0], 192), dtype=F32, device=w7.device)
-                p[:, :147] = w7.permute(0, 2, 3, 1).reshape(w7.shape[0], -1)
-                w[k + ".merger"] = _bf(p)
+                p = torch.zeros((w7.shape[0], 7, 8, 8), dtype=F32, device=w7.device)
+                p[:, :, :7, :3] = w7.permute(0, 2, 3, 1)
+                w[k + ".merger"] = _bf(p.reshape(w7.shape[0], -1))
 
     # ---- per-shape plan: buffers + item tables
     def _plan(self, B, T, H, W) -> dict:
@@ -439,6 +441,8 @@ class EncoderEngine:
         pl["pred"] = None
         # outputs
         pl["raw"] = z(Fr * H * W, 3 + self.m.raw_gs_dim, dt=F32)
+        # head outputs, 16-byte aligned rows: 83 Gaussian parameters at columns 0.., xyz at 84..86
+        pl["gsp"] = z(Fr * H * W, 96, dt=F32)
         self._plans[key] = pl
         return pl
 
@@ -459,7 +463,7 @@ class EncoderEngine:
             ops.rope_rows(qkv, pl["pos_enc"], heads=H, q_col=0, k_col=E, base=100.0)
             ops.attention(qkv[:, :E], qkv[:, E:2 * E], qkv[:, 2 * E:], pl["att_enc"], heads=H,
                           q_start=pl["enc_start"], q_len=pl["enc_len"], kv_start0=pl["enc_start"],
-                          kv_len0=pl["enc_len"], max_q_len=N, scale=0.125)
+                          kv_len0=pl["enc_len"], max_q_len=N, max_kv_len=N, scale=0.125)
             ops.gemm(pl["att_enc"], w[k + ".attn.proj"], bias=w[k + ".attn.proj.bias"], res1=x, out=x)
             ops.layernorm(x, w[k + ".norm2.weight"], w[k + ".norm2.bias"], out_bf16=pl["h_enc"])
             ops.gemm(pl["h_enc"], w[k + ".mlp.fc1"], bias=w[k + ".mlp.fc1.bias"], act=VS_ACT_GELU,
@@ -497,7 +501,8 @@ class EncoderEngine:
             ops.rope_rows(qkv, pl["pos_dec"], heads=H, q_col=0, k_col=D, base=100.0, cam_theta=theta)
             ops.attention(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], pl["att_dec"], heads=H,
                           q_start=pl["vid_start"], q_len=pl["vid_len"], kv_start0=pl["vid_start"],
-                          kv_len0=pl["vid_len"], max_q_len=T * rpf, causal_block=rpf, scale=0.125)
+                          kv_len0=pl["vid_len"], max_q_len=T * rpf, max_kv_len=T * rpf,
+                          causal_block=rpf, scale=0.125)
             ops.gemm(pl["att_dec"], w[k + ".attn.proj"], bias=w[k + ".attn.proj.bias"],
                      gate=m1[:, 2 * D:], gate_rows=rpf, first_row_mode=1, res1=x, out=x)
             # --- neighbour cross attention (image rows only)
@@ -513,7 +518,7 @@ class EncoderEngine:
             ops.attention(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], pl["att_dec"], heads=H,
                           q_start=pl["nb_q"], q_len=pl["nb_len"], kv_start0=pl["nb_k0"],
                           kv_len0=pl["nb_len"], kv_start1=pl["nb_k1"], kv_len1=pl["nb_len1"],
-                          max_q_len=N, scale=0.125)
+                          max_q_len=N, max_kv_len=2 * N, scale=0.125)
             ops.gemm(pl["att_dec"], w[k + ".cross_attn.proj"], bias=w[k + ".cross_attn.proj.bias"],
                      gate=m2[:, 2 * D:3 * D], gate_rows=rpf, first_row_mode=2, res1=x, out=x)
             # --- MLPs
@@ -604,28 +609,29 @@ class EncoderEngine:
     def _heads(self, pl, taps, gs=True):
         w = self.w
         Fr, H, W = pl["Fr"], pl["H"], pl["W"]
-        raw = pl["raw"]
+        gsp = pl["gsp"]
         # --- Gaussian centres: 'regression' head + exp-depth postprocess
         k = "downstream_head1.dpt"
         p1 = self._trunk(pl, "downstream_head1", taps)
         y = self._conv(p1, k + ".head.0", N=FEAT // 2, bias=w[k + ".head.0.bias"])
         y = self._conv(ops.upsample2x(y), k + ".head.2", N=FEAT // 2, bias=w[k + ".head.2.bias"],
                        act=VS_ACT_RELU)
-        ops.pts_tail(y, FEAT // 2, w[k + ".head.4.w"], w[k + ".head.4.bias"], raw, Fr * H * W)
+        ops.pts_tail(y, FEAT // 2, w[k + ".head.4.w"], w[k + ".head.4.bias"], gsp[:, 84:], Fr * H * W)
         if not gs:
             return
         # --- Gaussian parameters: trunk x2 + relu(conv7x7(image)) -> conv3x3 + ReLU -> 1x1
         k = "gaussian_param_head.dpt"
-        p1 = ops.upsample2x(self._trunk(pl, "gaussian_param_head", taps))
-        cols = ops.im2col(pl["image"], nchw_f32=True, n=Fr, h=H, w=W, c=3, k=7, stride=1, pad=3, kpad=192)
-        merged = ops.gemm(cols, w[k + ".merger"], bias=w[k + ".input_merger.0.bias"], act=VS_ACT_RELU,
-                          res1=p1.view(-1, FEAT))
-        del cols
-        y = self._conv(merged.view(Fr, H, W, FEAT), k + ".head.0", act=VS_ACT_RELU)
-        ops.gemm(y.view(-1, FEAT), w[k + ".head.4"], bias=w[k + ".head.4.bias"], out=raw[:, 3:],
-                 ldc=raw.stride(0))
-        if taps is not None:
-            taps["raw"] = raw.clone()
+        p1 = self._trunk(pl, "gaussian_param_head", taps)                  # (Fr, H/2, W/2, 256)
+        img8 = ops.image_nhwc8(pl["image"], pad=3)                        # (Fr, H+6, W+8, 8)
+        # relu(conv7x7(image)) + bilinear_x2(p1): the image is addressed through an overlapping TMA
+        # view (no im2col buffer), the upsampling happens in the epilogue (no full-res copy of p1)
+        merged = ops.conv_gemm(img8, w[k + ".merger"], kh=7, kw=1, pad=0, N=FEAT,
+                               bias=w[k + ".input_merger.0.bias"], act=VS_ACT_RELU, res1=p1,
+                               res_up2=True,
+                               view=(Fr, H, W, 64, H + 6, 8, (W + 8) * 8, (H + 6) * (W + 8) * 8))
+        y = self._conv(merged, k + ".head.0", act=VS_ACT_RELU)
+        ops.gemm(y.view(-1, FEAT), w[k + ".head.4"], bias=w[k + ".head.4.bias"], out=gsp,
+                 N=self.m.raw_gs_dim)
 
     def _forward(self, pl, heads=True, gs=True, taps=None):
         self._encoder(pl, taps)
@@ -633,7 +639,10 @@ class EncoderEngine:
         if heads:
             self._heads(pl, taps, gs)
             if gs:
-                pl["gauss"] = ops.gaussian_adapter(pl["raw"], self.m.d_sh, self.m.sh_mask.to(self.dev))
+                pl["gauss"] = ops.gaussian_adapter(pl["gsp"], self.m.d_sh, self.m.sh_mask.to(self.dev),
+                                                   center_col=84, param_col=0, raw_out=pl["raw"])
+            else:   # distill: only the centres are produced
+                pl["raw"][:, :3].copy_(pl["gsp"][:, 84:87])
 
     # ---- public
     @torch.no_grad()

@@ -51,17 +51,24 @@ def gemm(A, W, *, N=None, K=None, a_rows=None, a_groups=1, a_row_stride=None, a_
 
 
 def conv_gemm(x_nhwc, Wp, *, kh, kw, pad, N, bias=None, act=VS_ACT_NONE, res1=None, res2=None,
-              out=None, out_dtype=torch.bfloat16, out2=None, block_n=0):
+              out=None, out_dtype=torch.bfloat16, out2=None, block_n=0, res_up2=False, view=None):
     """Stride-1 kh x kw convolution on an NHWC bf16 map as an implicit GEMM (conv mode of vs_gemm).
-    Wp: packed weights (N, kh*kw*cin_pad) bf16, tap-major / channel-minor."""
+    Wp: packed weights (N, kh*kw*cin_pad) bf16, tap-major / channel-minor.
+    view = (n, out_h, out_w, cin, in_h, stride_x, stride_y, stride_n): explicit (possibly
+    overlapping) input view instead of the dense NHWC shape of x_nhwc.
+    res_up2: res1 is a half-resolution NHWC map, bilinearly upsampled x2 in the epilogue."""
     _need_cuda(x_nhwc, Wp)
     lib = _lib.load()
-    n, h, w, cin = x_nhwc.shape
     p = GemmParams()
+    if view is None:
+        n, h, w, cin = x_nhwc.shape
+    else:
+        n, h, w, cin, p.conv_in_h, p.conv_stride_x, p.conv_stride_y, p.conv_stride_n = view
     p.A, p.a_mode = ptr(x_nhwc), 1
     p.cn, p.ch, p.cw, p.cin, p.kh, p.kw, p.pad = n, h, w, cin, kh, kw, pad
     p.W, p.w_row_stride, p.N = ptr(Wp), Wp.stride(0), N
     _fill_epilogue(p, bias, act, None, 0, 0, res1, res2)
+    p.res_up2 = int(res_up2)
     if out is None:
         out = torch.empty((n, h, w, N), dtype=out_dtype, device=x_nhwc.device)
     p.C, p.c_dtype, p.ldc = ptr(out), _DT[out.dtype], out.stride(-2)
@@ -110,7 +117,7 @@ def layernorm(x, w=None, b=None, *, eps=1e-6, w0=None, b0=None, scale=None, shif
 
 
 def attention(Q, K, V, O, *, heads, q_start, q_len, kv_start0, kv_len0, kv_start1=None,
-              kv_len1=None, max_q_len, causal_block=0, scale=0.125):
+              kv_len1=None, max_q_len, max_kv_len=0, causal_block=0, scale=0.125):
     """softmax(Q K^T * scale) V per (item, head); Q/K/V/O are 2-D bf16 views (rows, >= heads*64)."""
     _need_cuda(Q, K, V, O)
     lib = _lib.load()
@@ -122,7 +129,7 @@ def attention(Q, K, V, O, *, heads, q_start, q_len, kv_start0, kv_len0, kv_start
     p.q_start, p.q_len = ptr(q_start), ptr(q_len)
     p.kv_start0, p.kv_len0 = ptr(kv_start0), ptr(kv_len0)
     p.kv_start1, p.kv_len1 = ptr(kv_start1), ptr(kv_len1)
-    p.max_q_len, p.causal_block, p.scale = max_q_len, causal_block, scale
+    p.max_q_len, p.max_kv_len, p.causal_block, p.scale = max_q_len, max_kv_len, causal_block, scale
     check(lib.vs_attention(C.byref(p), C.c_void_p(stream_ptr())), "vs_attention")
     return O
 
@@ -154,6 +161,18 @@ def im2col(src, *, nchw_f32, n, h, w, c, k, stride, pad, kpad):
     out = torch.empty((n * ho * wo, kpad), dtype=torch.bfloat16, device=src.device)
     check(lib.vs_im2col(C.c_void_p(ptr(src)), int(nchw_f32), C.c_void_p(ptr(out)), n, h, w, c, k,
                         stride, pad, kpad, C.c_void_p(stream_ptr())), "vs_im2col")
+    return out
+
+
+def image_nhwc8(img, pad=3):
+    """fp32 NCHW (n,3,h,w) -> zero-bordered bf16 (n, h+2*pad, w+8, 8) for the 7x7 stem."""
+    lib = _lib.load()
+    _need_cuda(img)
+    n, c, h, w = img.shape
+    assert c == 3 and img.dtype == torch.float32 and img.is_contiguous()
+    out = torch.empty((n, h + 2 * pad, w + 8, 8), dtype=torch.bfloat16, device=img.device)
+    check(lib.vs_image_nhwc8(C.c_void_p(ptr(img)), C.c_void_p(ptr(out)), n, h, w, pad,
+                             C.c_void_p(stream_ptr())), "vs_image_nhwc8")
     return out
 
 
@@ -216,12 +235,13 @@ def pts_tail(feat, Cf, w, b, raw, px):
                           C.c_void_p(stream_ptr())), "vs_pts_tail")
 
 
-def gaussian_adapter(raw, d_sh, sh_mask, *, want_cov=True):
-    """raw (G, 86) fp32 -> dict of means/cov/cov6/sh/opac/scales/rot (gaussian_adapter.py:167-212)."""
+def gaussian_adapter(src, d_sh, sh_mask, *, center_col=0, param_col=3, want_cov=True, raw_out=None):
+    """src (G, ld) fp32 head outputs -> dict of means/cov/cov6/sh/opac/scales/rot
+    (gaussian_adapter.py:167-212); optionally also writes the reference-layout raw (G, 86)."""
     lib = _lib.load()
-    _need_cuda(raw)
-    G = raw.shape[0]
-    dev, f32 = raw.device, torch.float32
+    _need_cuda(src)
+    G = src.shape[0]
+    dev, f32 = src.device, torch.float32
     out = dict(
         means=torch.empty((G, 3), dtype=f32, device=dev),
         cov=torch.empty((G, 3, 3), dtype=f32, device=dev) if want_cov else None,
@@ -232,9 +252,9 @@ def gaussian_adapter(raw, d_sh, sh_mask, *, want_cov=True):
         rot=torch.empty((G, 4), dtype=f32, device=dev),
     )
     check(lib.vs_gaussian_adapter(
-        C.c_void_p(ptr(raw)), C.c_int64(raw.stride(0)), C.c_int64(G), d_sh,
-        C.c_void_p(ptr(sh_mask)), C.c_void_p(ptr(out["means"])), C.c_void_p(ptr(out["cov"])),
-        C.c_void_p(ptr(out["cov6"])), C.c_void_p(ptr(out["sh"])), C.c_void_p(ptr(out["opac"])),
-        C.c_void_p(ptr(out["scales"])), C.c_void_p(ptr(out["rot"])),
+        C.c_void_p(ptr(src)), C.c_int64(src.stride(0)), center_col, param_col, C.c_int64(G), d_sh,
+        C.c_void_p(ptr(sh_mask)), C.c_void_p(ptr(raw_out)), C.c_void_p(ptr(out["means"])),
+        C.c_void_p(ptr(out["cov"])), C.c_void_p(ptr(out["cov6"])), C.c_void_p(ptr(out["sh"])),
+        C.c_void_p(ptr(out["opac"])), C.c_void_p(ptr(out["scales"])), C.c_void_p(ptr(out["rot"])),
         C.c_void_p(stream_ptr())), "vs_gaussian_adapter")
     return out
