@@ -263,7 +263,9 @@ typedef struct vs_raster_bwd_params {
   float* dL_dopacity;        /* (G) */
   float* dL_dshs;            /* (G,M,3) */
   float* dL_dcolors;         /* (G,3) when colors_precomp */
-  float* dL_dtau;            /* (V,6): rho (3) then theta (3) */
+  float* dL_dtau;            /* (V,6): rho (3) then theta (3), accumulated (caller zeroes); or NULL */
+  void* bwd_workspace;       /* scratch: V*G*10 floats (per-view screen-space partials) */
+  int64_t bwd_workspace_bytes;
 } vs_raster_bwd_params;
 int vs_raster_backward(const vs_raster_bwd_params* p, vs_stream_t stream);
 

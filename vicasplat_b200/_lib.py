@@ -76,6 +76,7 @@ class RasterBwdParams(C.Structure):
         ("dL_dcolor", _vp), ("dL_ddepth", _vp), ("dL_dalpha", _vp),
         ("dL_dmeans3D", _vp), ("dL_dcov3D", _vp), ("dL_dopacity", _vp), ("dL_dshs", _vp),
         ("dL_dcolors", _vp), ("dL_dtau", _vp),
+        ("bwd_workspace", _vp), ("bwd_workspace_bytes", _i64),
     ]
 
 

@@ -550,10 +550,10 @@ using namespace vs;
 extern "C" int vs_rope_2d(void* tokens, int dtype, int B, int N, int H, int D, int64_t stride_b,
                           int64_t stride_n, const int64_t* positions, float base, float fwd,
                           vs_stream_t stream) {
-  VS_REQUIRE(tokens && positions, "rope_2d: null tensor");
   VS_REQUIRE(D % 4 == 0, "token dim must be multiple of 4");  // kernels.cu:94
   VS_REQUIRE(B >= 0 && N >= 0 && H >= 0, "rope_2d: negative size");
   if (B * N == 0 || H == 0) return VS_OK;
+  VS_REQUIRE(tokens && positions, "rope_2d: null tensor");
   const int threads = 256;
   const unsigned blocks = blocks_for(static_cast<long long>(B) * N * 32, threads);
   cudaStream_t s = to_stream(stream);

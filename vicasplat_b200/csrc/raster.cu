@@ -452,6 +452,386 @@ __global__ void __launch_bounds__(BLEND_THREADS)
   }
 }
 
+// ------------------------------------------------------------------ backward: blend
+// Per-(view, Gaussian) gradient slots accumulated by the blend backward pass (SoA, stride VG)
+enum { GA_X = 0, GA_Y, GA_CA, GA_CB, GA_CC, GA_OP, GA_R, GA_G, GA_B, GA_D, GA_COUNT };
+
+// Same tile / sub-block / ballot-culling structure as the forward kernel, walked back to front.
+// Each pixel replays only the splats in front of its last contributor (n_contrib), rebuilding
+// T_before = T_after / (1 - alpha); the per-splat partials of the 8x4 pixels of a warp are reduced
+// with shuffles and leave the warp as ONE atomicAdd per quantity.
+__global__ void __launch_bounds__(BLEND_THREADS)
+    blend_backward_kernel(int H, int W, const uint2* __restrict__ ranges,
+                          const uint32_t* __restrict__ vals, const float2* __restrict__ xy,
+                          const float4* __restrict__ conic_o, const float4* __restrict__ rgbd,
+                          const float* __restrict__ bg, const float* __restrict__ final_T,
+                          const int32_t* __restrict__ n_contrib, const float* __restrict__ dL_dcolor,
+                          const float* __restrict__ dL_ddepth, const float* __restrict__ dL_dalpha,
+                          float* __restrict__ gacc, size_t VG) {
+  __shared__ uint32_t s_id[BLEND_THREADS];
+  __shared__ float4 s_xe[BLEND_THREADS];
+  __shared__ float4 s_co[BLEND_THREADS];
+  __shared__ float4 s_cd[BLEND_THREADS];
+
+  const int gx = gridDim.x, gy = gridDim.y;
+  const int v = blockIdx.z;
+  const int tile = (v * gy + blockIdx.y) * gx + blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sbx = blockIdx.x * TILE + (warp & 1) * 8, sby = blockIdx.y * TILE + (warp >> 1) * 4;
+  const int px = sbx + (lane & 7), py = sby + (lane >> 3);
+  const bool inside = px < W && py < H;
+  const float pxf = static_cast<float>(px), pyf = static_cast<float>(py);
+  const float bx0 = static_cast<float>(sbx), bx1 = static_cast<float>(min(sbx + 7, W - 1));
+  const float by0 = static_cast<float>(sby), by1 = static_cast<float>(min(sby + 3, H - 1));
+  const size_t hw = static_cast<size_t>(H) * W;
+  const size_t pix = static_cast<size_t>(py) * W + px;
+
+  float dpix[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+  float T_final = 1.f;
+  int last = 0;
+  if (inside) {
+    T_final = final_T[static_cast<size_t>(v) * hw + pix];
+    last = n_contrib[static_cast<size_t>(v) * hw + pix];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) dpix[c] = dL_dcolor[(static_cast<size_t>(v) * 3 + c) * hw + pix];
+    if (dL_ddepth) dpix[3] = dL_ddepth[static_cast<size_t>(v) * hw + pix];
+    if (dL_dalpha) dpix[4] = dL_dalpha[static_cast<size_t>(v) * hw + pix];
+  }
+  const float bg_dot = bg[v * 3] * dpix[0] + bg[v * 3 + 1] * dpix[1] + bg[v * 3 + 2] * dpix[2];
+  float T = T_final, last_alpha = 0.f;
+  float last_val[5] = {0.f, 0.f, 0.f, 0.f, 0.f}, accum[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+
+  const uint2 range = ranges[tile];
+  const int total = static_cast<int>(range.y - range.x);
+  const int rounds = (total + BLEND_THREADS - 1) / BLEND_THREADS;
+  for (int r = rounds - 1; r >= 0; --r) {
+    __syncthreads();
+    const int idx = r * BLEND_THREADS + threadIdx.x;
+    if (idx < total) {
+      const uint32_t id = vals[range.x + idx];
+      const float2 p = xy[id];
+      const float4 co = conic_o[id];
+      s_id[threadIdx.x] = id;
+      s_co[threadIdx.x] = co;
+      s_cd[threadIdx.x] = rgbd[id];
+      const float tau = __logf(255.0f * co.w) * 1.01f + 1e-3f;
+      const float det = co.x * co.z - co.y * co.y;
+      float ex = -1.f, ey = -1.f;
+      if (tau > 0.f) {
+        if (det > 0.f) {
+          ex = sqrtf(2.0f * tau * co.z / det) + 0.01f;
+          ey = sqrtf(2.0f * tau * co.x / det) + 0.01f;
+        } else {
+          ex = ey = 1e30f;
+        }
+      }
+      s_xe[threadIdx.x] = make_float4(p.x, p.y, ex, ey);
+    }
+    __syncthreads();
+    const int nb = min(BLEND_THREADS, total - r * BLEND_THREADS);
+    for (int base = ((nb - 1) >> 5) << 5; base >= 0; base -= 32) {
+      bool near_me = false;
+      if (base + lane < nb) {
+        const float4 xe = s_xe[base + lane];
+        const float ddx = fmaxf(fmaxf(bx0 - xe.x, xe.x - bx1), 0.f);
+        const float ddy = fmaxf(fmaxf(by0 - xe.y, xe.y - by1), 0.f);
+        near_me = ddx <= xe.z && ddy <= xe.w;
+      }
+      uint32_t todo = __ballot_sync(0xffffffffu, near_me);
+      while (todo != 0u) {
+        const int bit = 31 - __clz(todo);   // back to front
+        todo &= ~(1u << bit);
+        const int j = base + bit;
+        const int listidx = r * BLEND_THREADS + j;
+        float g[GA_COUNT];
+#pragma unroll
+        for (int k = 0; k < GA_COUNT; ++k) g[k] = 0.f;
+        bool contrib = false;
+        if (listidx < last) {
+          const float4 xe = s_xe[j];
+          const float4 co = s_co[j];
+          const float dx = xe.x - pxf, dy = xe.y - pyf;
+          const float power = -0.5f * (co.x * dx * dx + co.z * dy * dy) - co.y * dx * dy;
+          if (power <= 0.0f) {
+            const float Gv = __expf(power);
+            const float a_raw = co.w * Gv;
+            const float alpha = fminf(kAlphaMax, a_raw);
+            if (alpha >= kAlphaMin) {
+              contrib = true;
+              const float4 cd = s_cd[j];
+              T = T / (1.0f - alpha);
+              const float wgt = alpha * T;
+              const float val[5] = {cd.x, cd.y, cd.z, cd.w, 1.0f};
+              float dLa = 0.f;
+#pragma unroll
+              for (int c = 0; c < 5; ++c) {
+                accum[c] = last_alpha * last_val[c] + (1.0f - last_alpha) * accum[c];
+                last_val[c] = val[c];
+                dLa += (val[c] - accum[c]) * dpix[c];
+              }
+              g[GA_R] = wgt * dpix[0]; g[GA_G] = wgt * dpix[1]; g[GA_B] = wgt * dpix[2];
+              g[GA_D] = wgt * dpix[3];
+              dLa *= T;
+              last_alpha = alpha;
+              dLa += (-T_final / (1.0f - alpha)) * bg_dot;
+              const float dLraw = a_raw <= kAlphaMax ? dLa : 0.f;   // d min(0.99, x)
+              const float dLdG = co.w * dLraw * Gv;                   // includes dG/dpower = G
+              g[GA_OP] = Gv * dLraw;
+              g[GA_X] = dLdG * (-(co.x * dx + co.y * dy));
+              g[GA_Y] = dLdG * (-(co.z * dy + co.y * dx));
+              g[GA_CA] = dLdG * (-0.5f * dx * dx);
+              g[GA_CB] = dLdG * (-dx * dy);
+              g[GA_CC] = dLdG * (-0.5f * dy * dy);
+            }
+          }
+        }
+        if (__ballot_sync(0xffffffffu, contrib) != 0u) {
+#pragma unroll
+          for (int k = 0; k < GA_COUNT; ++k) {
+            float x = g[k];
+#pragma unroll
+            for (int s = 16; s > 0; s >>= 1) x += __shfl_xor_sync(0xffffffffu, x, s);
+            g[k] = x;
+          }
+          if (lane == 0) {
+            const size_t id = s_id[j];
+#pragma unroll
+            for (int k = 0; k < GA_COUNT; ++k) atomicAdd(gacc + k * VG + id, g[k]);
+          }
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ backward: per Gaussian
+__device__ __forceinline__ float block_sum(float v, float* red) {
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = 0.f;
+  for (int i = 0; i < static_cast<int>(blockDim.x >> 5); ++i) r += red[i];
+  return r;
+}
+
+// One thread per Gaussian, looping over the views that share it: turns the screen-space partials
+// of the blend pass into gradients of means3D / cov6 / opacity / SH (or colours) and, reduced over
+// the block, of the camera twist tau = (rho, theta) of the left perturbation W2C <- exp(tau) W2C
+// (src/misc/cam_utils.py:123-142).  Assumes projmatrix = viewmatrix o standard perspective with
+// the given tan(fov), which is how cuda_splatting.py:187-194 builds it.
+__global__ void __launch_bounds__(128)
+    preprocess_backward_kernel(int G, int V, int shared_set, int H, int W,
+                               const float* __restrict__ means, const float* __restrict__ cov6,
+                               const float* __restrict__ shs, int M, int sh_cs, int sh_ch,
+                               int degree, int has_colors, const float* __restrict__ viewm,
+                               const float* __restrict__ campos, const float* __restrict__ tanfov,
+                               const int32_t* __restrict__ radii, const float4* __restrict__ rgbd,
+                               const float* __restrict__ gacc, size_t VG,
+                               float* __restrict__ d_means, float* __restrict__ d_cov,
+                               float* __restrict__ d_opac, float* __restrict__ d_shs,
+                               float* __restrict__ d_colors, float* __restrict__ d_tau) {
+  __shared__ float red[4];
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = g < G;
+  const int v_begin = shared_set ? 0 : blockIdx.y;
+  const int v_end = shared_set ? V : blockIdx.y + 1;
+  const size_t gi = (shared_set ? 0 : static_cast<size_t>(blockIdx.y) * G) + (live ? g : 0);
+  const int n_sh = shs ? (degree >= 3 ? 16 : (degree + 1) * (degree + 1)) : 0;
+
+  float mx = 0.f, my = 0.f, mz = 0.f, c6[6] = {0, 0, 0, 0, 0, 0};
+  if (live) {
+    mx = means[gi * 3]; my = means[gi * 3 + 1]; mz = means[gi * 3 + 2];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) c6[i] = cov6[gi * 6 + i];
+  }
+  float dmean[3] = {0.f, 0.f, 0.f}, dcov[6] = {0, 0, 0, 0, 0, 0}, dop = 0.f, dcol[3] = {0, 0, 0};
+  float dsh[48];
+#pragma unroll
+  for (int i = 0; i < 48; ++i) dsh[i] = 0.f;
+  const float* my_sh = shs ? shs + gi * 3 * M : nullptr;
+
+  for (int v = v_begin; v < v_end; ++v) {
+    const float* vm = viewm + v * 16;
+    float dtau[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const size_t o = static_cast<size_t>(v) * G + (live ? g : 0);
+    if (live && radii[o] > 0) {
+      const float gX = gacc[GA_X * VG + o], gY = gacc[GA_Y * VG + o];
+      const float gA = gacc[GA_CA * VG + o], gB = gacc[GA_CB * VG + o], gC = gacc[GA_CC * VG + o];
+      dop += gacc[GA_OP * VG + o];
+      float gr[3] = {gacc[GA_R * VG + o], gacc[GA_G * VG + o], gacc[GA_B * VG + o]};
+      const float gD = gacc[GA_D * VG + o];
+      const float4 cd = rgbd[o];
+      // ---- forward recomputation
+      const float tx = vm[0] * mx + vm[4] * my + vm[8] * mz + vm[12];
+      const float ty = vm[1] * mx + vm[5] * my + vm[9] * mz + vm[13];
+      const float tz = vm[2] * mx + vm[6] * my + vm[10] * mz + vm[14];
+      const float tanx = tanfov[v * 2], tany = tanfov[v * 2 + 1];
+      const float fx = W / (2.0f * tanx), fy = H / (2.0f * tany);
+      const float limx = kFovClamp * tanx, limy = kFovClamp * tany;
+      const float rx = tx / tz, ry = ty / tz;
+      const bool clx = rx < -limx || rx > limx, cly = ry < -limy || ry > limy;
+      const float txc = fminf(limx, fmaxf(-limx, rx)) * tz;
+      const float tyc = fminf(limy, fmaxf(-limy, ry)) * tz;
+      const float itz = 1.0f / tz, itz2 = itz * itz;
+      const float j00 = fx * itz, j02 = -fx * txc * itz2, j11 = fy * itz, j12 = -fy * tyc * itz2;
+      const float T0[3] = {j00 * vm[0] + j02 * vm[2], j00 * vm[4] + j02 * vm[6], j00 * vm[8] + j02 * vm[10]};
+      const float T1[3] = {j11 * vm[1] + j12 * vm[2], j11 * vm[5] + j12 * vm[6], j11 * vm[9] + j12 * vm[10]};
+      const float S[3][3] = {{c6[0], c6[1], c6[2]}, {c6[1], c6[3], c6[4]}, {c6[2], c6[4], c6[5]}};
+      float ST0[3], ST1[3];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        ST0[i] = S[i][0] * T0[0] + S[i][1] * T0[1] + S[i][2] * T0[2];
+        ST1[i] = S[i][0] * T1[0] + S[i][1] * T1[1] + S[i][2] * T1[2];
+      }
+      const float a = T0[0] * ST0[0] + T0[1] * ST0[1] + T0[2] * ST0[2] + kLowpass;
+      const float b = T0[0] * ST1[0] + T0[1] * ST1[1] + T0[2] * ST1[2];
+      const float c = T1[0] * ST1[0] + T1[1] * ST1[1] + T1[2] * ST1[2] + kLowpass;
+      const float det = a * c - b * b;
+      const float id = 1.0f / det, id2 = id * id;
+      // ---- conic (c, -b, a) / det  ->  a, b, c
+      const float dLa = gA * (-c * c * id2) + gB * (b * c * id2) + gC * (id - a * c * id2);
+      const float dLc = gA * (id - a * c * id2) + gB * (a * b * id2) + gC * (-a * a * id2);
+      const float dLb = gA * (2.f * b * c * id2) + gB * (-id - 2.f * b * b * id2) + gC * (2.f * a * b * id2);
+      // ---- cov2D = T S T^T -> S (6 unique entries) and T
+      dcov[0] += dLa * T0[0] * T0[0] + dLb * T0[0] * T1[0] + dLc * T1[0] * T1[0];
+      dcov[3] += dLa * T0[1] * T0[1] + dLb * T0[1] * T1[1] + dLc * T1[1] * T1[1];
+      dcov[5] += dLa * T0[2] * T0[2] + dLb * T0[2] * T1[2] + dLc * T1[2] * T1[2];
+      dcov[1] += 2.f * dLa * T0[0] * T0[1] + dLb * (T0[0] * T1[1] + T0[1] * T1[0]) + 2.f * dLc * T1[0] * T1[1];
+      dcov[2] += 2.f * dLa * T0[0] * T0[2] + dLb * (T0[0] * T1[2] + T0[2] * T1[0]) + 2.f * dLc * T1[0] * T1[2];
+      dcov[4] += 2.f * dLa * T0[1] * T0[2] + dLb * (T0[1] * T1[2] + T0[2] * T1[1]) + 2.f * dLc * T1[1] * T1[2];
+      float dT0[3], dT1[3];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        dT0[i] = 2.f * dLa * ST0[i] + dLb * ST1[i];
+        dT1[i] = 2.f * dLc * ST1[i] + dLb * ST0[i];
+      }
+      // ---- T = J Wrot (Wrot[r][i] = vm[i*4 + r])
+      const float W0[3] = {vm[0], vm[4], vm[8]}, W1[3] = {vm[1], vm[5], vm[9]}, W2[3] = {vm[2], vm[6], vm[10]};
+      const float dj00 = dT0[0] * W0[0] + dT0[1] * W0[1] + dT0[2] * W0[2];
+      const float dj02 = dT0[0] * W2[0] + dT0[1] * W2[1] + dT0[2] * W2[2];
+      const float dj11 = dT1[0] * W1[0] + dT1[1] * W1[1] + dT1[2] * W1[2];
+      const float dj12 = dT1[0] * W2[0] + dT1[1] * W2[1] + dT1[2] * W2[2];
+      float dW0[3], dW1[3], dW2[3];   // gradient w.r.t. the rows of Wrot (for the pose)
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        dW0[i] = dT0[i] * j00;
+        dW1[i] = dT1[i] * j11;
+        dW2[i] = dT0[i] * j02 + dT1[i] * j12;
+      }
+      // ---- J(t) with the frustum clamp, depth, and the projected centre
+      float dt[3];
+      dt[0] = dj02 * (-fx * itz2) * (clx ? 0.f : 1.f);
+      dt[1] = dj12 * (-fy * itz2) * (cly ? 0.f : 1.f);
+      dt[2] = dj00 * (-fx * itz2) + dj11 * (-fy * itz2) +
+              dj02 * (2.f * fx * txc * itz2 * itz - (clx ? fx * itz2 * (txc * itz) : 0.f)) +
+              dj12 * (2.f * fy * tyc * itz2 * itz - (cly ? fy * itz2 * (tyc * itz) : 0.f)) + gD;
+      const float pw = 1.0f / (tz + kWEps);
+      const float hx = tx / tanx, hy = ty / tany;
+      const float sxp = gX * 0.5f * W, syp = gY * 0.5f * H;
+      dt[0] += sxp * pw / tanx;
+      dt[1] += syp * pw / tany;
+      dt[2] += -(sxp * hx + syp * hy) * pw * pw;
+      // ---- colour: SH (bands 0..3) of dir = normalize(p - campos), clamped at 0
+      float dcam[3] = {0.f, 0.f, 0.f};
+      if (has_colors) {
+        dcol[0] += gr[0]; dcol[1] += gr[1]; dcol[2] += gr[2];
+      } else if (my_sh != nullptr) {
+        if (cd.x <= 0.f) gr[0] = 0.f;
+        if (cd.y <= 0.f) gr[1] = 0.f;
+        if (cd.z <= 0.f) gr[2] = 0.f;
+        float ux = mx - campos[v * 3], uy = my - campos[v * 3 + 1], uz = mz - campos[v * 3 + 2];
+        const float il = 1.0f / sqrtf(ux * ux + uy * uy + uz * uz);
+        const float x = ux * il, y = uy * il, z = uz * il;
+        const float xx = x * x, yy = y * y, zz = z * z, xy_ = x * y, yz = y * z, xz = x * z;
+        float bas[16], bdx[16], bdy[16], bdz[16];
+        bas[0] = SH_C0; bdx[0] = bdy[0] = bdz[0] = 0.f;
+        bas[1] = -SH_C1 * y; bdx[1] = 0.f; bdy[1] = -SH_C1; bdz[1] = 0.f;
+        bas[2] = SH_C1 * z; bdx[2] = 0.f; bdy[2] = 0.f; bdz[2] = SH_C1;
+        bas[3] = -SH_C1 * x; bdx[3] = -SH_C1; bdy[3] = 0.f; bdz[3] = 0.f;
+        bas[4] = SH_C2[0] * xy_; bdx[4] = SH_C2[0] * y; bdy[4] = SH_C2[0] * x; bdz[4] = 0.f;
+        bas[5] = SH_C2[1] * yz; bdx[5] = 0.f; bdy[5] = SH_C2[1] * z; bdz[5] = SH_C2[1] * y;
+        bas[6] = SH_C2[2] * (2.f * zz - xx - yy);
+        bdx[6] = SH_C2[2] * -2.f * x; bdy[6] = SH_C2[2] * -2.f * y; bdz[6] = SH_C2[2] * 4.f * z;
+        bas[7] = SH_C2[3] * xz; bdx[7] = SH_C2[3] * z; bdy[7] = 0.f; bdz[7] = SH_C2[3] * x;
+        bas[8] = SH_C2[4] * (xx - yy); bdx[8] = SH_C2[4] * 2.f * x; bdy[8] = SH_C2[4] * -2.f * y; bdz[8] = 0.f;
+        bas[9] = SH_C3[0] * y * (3.f * xx - yy);
+        bdx[9] = SH_C3[0] * 6.f * xy_; bdy[9] = SH_C3[0] * (3.f * xx - 3.f * yy); bdz[9] = 0.f;
+        bas[10] = SH_C3[1] * xy_ * z; bdx[10] = SH_C3[1] * yz; bdy[10] = SH_C3[1] * xz; bdz[10] = SH_C3[1] * xy_;
+        bas[11] = SH_C3[2] * y * (4.f * zz - xx - yy);
+        bdx[11] = SH_C3[2] * -2.f * xy_; bdy[11] = SH_C3[2] * (4.f * zz - xx - 3.f * yy); bdz[11] = SH_C3[2] * 8.f * yz;
+        bas[12] = SH_C3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy);
+        bdx[12] = SH_C3[3] * -6.f * xz; bdy[12] = SH_C3[3] * -6.f * yz; bdz[12] = SH_C3[3] * (6.f * zz - 3.f * xx - 3.f * yy);
+        bas[13] = SH_C3[4] * x * (4.f * zz - xx - yy);
+        bdx[13] = SH_C3[4] * (4.f * zz - 3.f * xx - yy); bdy[13] = SH_C3[4] * -2.f * xy_; bdz[13] = SH_C3[4] * 8.f * xz;
+        bas[14] = SH_C3[5] * z * (xx - yy);
+        bdx[14] = SH_C3[5] * 2.f * xz; bdy[14] = SH_C3[5] * -2.f * yz; bdz[14] = SH_C3[5] * (xx - yy);
+        bas[15] = SH_C3[6] * x * (xx - 3.f * yy);
+        bdx[15] = SH_C3[6] * (3.f * xx - 3.f * yy); bdy[15] = SH_C3[6] * -6.f * xy_; bdz[15] = 0.f;
+        float ddx = 0.f, ddy = 0.f, ddz = 0.f;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          if (k < n_sh) {
+            float wsum = 0.f;
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+              dsh[k * 3 + ch] += bas[k] * gr[ch];
+              wsum += gr[ch] * my_sh[k * sh_cs + ch * sh_ch];
+            }
+            ddx += wsum * bdx[k]; ddy += wsum * bdy[k]; ddz += wsum * bdz[k];
+          }
+        }
+        // through the normalisation
+        const float dot = ddx * x + ddy * y + ddz * z;
+        const float dux = (ddx - x * dot) * il, duy = (ddy - y * dot) * il, duz = (ddz - z * dot) * il;
+        dmean[0] += dux; dmean[1] += duy; dmean[2] += duz;
+        dcam[0] = -dux; dcam[1] = -duy; dcam[2] = -duz;
+      }
+      // ---- t = Wrot p + tw  ->  p
+      dmean[0] += W0[0] * dt[0] + W1[0] * dt[1] + W2[0] * dt[2];
+      dmean[1] += W0[1] * dt[0] + W1[1] * dt[1] + W2[1] * dt[2];
+      dmean[2] += W0[2] * dt[0] + W1[2] * dt[1] + W2[2] * dt[2];
+      // ---- camera twist at tau = 0: t' = t + rho + theta x t ; Wrot' = (I + [theta]x) Wrot ;
+      //      campos' = campos - Wrot^T rho
+      dtau[0] = dt[0] - (W0[0] * dcam[0] + W0[1] * dcam[1] + W0[2] * dcam[2]);
+      dtau[1] = dt[1] - (W1[0] * dcam[0] + W1[1] * dcam[1] + W1[2] * dcam[2]);
+      dtau[2] = dt[2] - (W2[0] * dcam[0] + W2[1] * dcam[1] + W2[2] * dcam[2]);
+      float th[3] = {ty * dt[2] - tz * dt[1], tz * dt[0] - tx * dt[2], tx * dt[1] - ty * dt[0]};
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {   // column i of Wrot crossed with column i of dL/dWrot
+        const float wx = W0[i], wy = W1[i], wz = W2[i];
+        const float gx_ = dW0[i], gy_ = dW1[i], gz_ = dW2[i];
+        th[0] += wy * gz_ - wz * gy_;
+        th[1] += wz * gx_ - wx * gz_;
+        th[2] += wx * gy_ - wy * gx_;
+      }
+      dtau[3] = th[0]; dtau[4] = th[1]; dtau[5] = th[2];
+    }
+    if (d_tau != nullptr) {
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        const float s = block_sum(dtau[k], red);
+        if (threadIdx.x == 0 && s != 0.f) atomicAdd(d_tau + v * 6 + k, s);
+      }
+    }
+  }
+  if (!live) return;
+  d_means[gi * 3] += dmean[0]; d_means[gi * 3 + 1] += dmean[1]; d_means[gi * 3 + 2] += dmean[2];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) d_cov[gi * 6 + i] += dcov[i];
+  d_opac[gi] += dop;
+  if (has_colors && d_colors != nullptr) {
+    d_colors[gi * 3] += dcol[0]; d_colors[gi * 3 + 1] += dcol[1]; d_colors[gi * 3 + 2] += dcol[2];
+  } else if (d_shs != nullptr) {
+#pragma unroll
+    for (int k = 0; k < 16; ++k)
+      if (k < n_sh)
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) d_shs[gi * 3 * M + k * sh_cs + ch * sh_ch] += dsh[k * 3 + ch];
+  }
+}
+
 int highest_bit(uint64_t x) {
   int b = 0;
   while (x) { ++b; x >>= 1; }
@@ -552,7 +932,39 @@ extern "C" int vs_raster_forward(const vs_raster_params* p, vs_stream_t stream_)
 }
 
 extern "C" int vs_raster_backward(const vs_raster_bwd_params* p, vs_stream_t stream_) {
-  (void)p; (void)stream_;
-  vs::set_error("vs_raster_backward: not implemented yet");
-  return VS_ERR_UNSUPPORTED;
+  using namespace vs;
+  VS_REQUIRE(p != nullptr, "vs_raster_backward: null params");
+  const vs_raster_params& f = p->fwd;
+  VS_REQUIRE(f.V > 0 && f.H > 0 && f.W > 0 && f.G >= 0, "vs_raster_backward: bad sizes");
+  if (f.G == 0) return VS_OK;
+  VS_REQUIRE(p->dL_dcolor != nullptr, "vs_raster_backward: dL_dcolor is required");
+  VS_REQUIRE(p->dL_dmeans3D && p->dL_dcov3D && p->dL_dopacity, "vs_raster_backward: missing outputs");
+  VS_REQUIRE(f.final_T && f.n_contrib && f.radii && f.workspace,
+             "vs_raster_backward: forward state (final_T, n_contrib, radii, workspace) is required");
+  VS_REQUIRE(f.shs == nullptr || p->dL_dshs != nullptr, "vs_raster_backward: dL_dshs is required");
+  VS_REQUIRE(f.colors_precomp == nullptr || p->dL_dcolors != nullptr,
+             "vs_raster_backward: dL_dcolors is required");
+  const size_t VG = static_cast<size_t>(f.V) * f.G;
+  VS_REQUIRE(p->bwd_workspace != nullptr &&
+                 p->bwd_workspace_bytes >= static_cast<int64_t>(VG * GA_COUNT * sizeof(float)),
+             "vs_raster_backward: bwd_workspace too small (need V*G*10 floats)");
+  cudaStream_t stream = to_stream(stream_);
+  Workspace ws = carve(f.workspace, f.V, f.G, f.H, f.W, f.max_pairs);
+  float* gacc = static_cast<float*>(p->bwd_workspace);
+  VS_CUDA(cudaMemsetAsync(gacc, 0, VG * GA_COUNT * sizeof(float), stream));
+  const int gx = ceil_div(f.W, TILE), gy = ceil_div(f.H, TILE);
+  dim3 bgrid(gx, gy, f.V);
+  blend_backward_kernel<<<bgrid, BLEND_THREADS, 0, stream>>>(
+      f.H, f.W, ws.ranges, ws.vals_out, ws.xy, ws.conic_o, ws.rgbd, f.bg, f.final_T, f.n_contrib,
+      p->dL_dcolor, p->dL_ddepth, p->dL_dalpha, gacc, VG);
+  VS_LAUNCH_CHECK();
+  int sh_cs = f.sh_stride_coef, sh_ch = f.sh_stride_chan;
+  if (sh_cs == 0 && sh_ch == 0) { sh_cs = 3; sh_ch = 1; }
+  dim3 grid(ceil_div(f.G, 128), f.gaussians_shared ? 1 : f.V);
+  preprocess_backward_kernel<<<grid, 128, 0, stream>>>(
+      f.G, f.V, f.gaussians_shared, f.H, f.W, f.means3D, f.cov3D, f.shs, f.sh_M, sh_cs, sh_ch,
+      f.sh_degree, f.colors_precomp != nullptr, f.viewmatrix, f.campos, f.tanfov, f.radii, ws.rgbd,
+      gacc, VG, p->dL_dmeans3D, p->dL_dcov3D, p->dL_dopacity, p->dL_dshs, p->dL_dcolors, p->dL_dtau);
+  VS_LAUNCH_CHECK();
+  return VS_OK;
 }

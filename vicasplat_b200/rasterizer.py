@@ -111,6 +111,7 @@ class _Rasterize(torch.autograd.Function):
         ctx.shapes = (means.shape, cov6.shape, opac.shape, None if shs is None else shs.shape,
                       None if colors is None else colors.shape)
         ctx.has_pose = (theta is not None, rho is not None)
+        ctx.pose_shapes = (None if theta is None else theta.shape, None if rho is None else rho.shape)
         ctx.mark_non_differentiable(radii, n_touched)
         return color, radii, depth, alpha, n_touched
 
@@ -134,8 +135,10 @@ class _Rasterize(torch.autograd.Function):
         gc = _f32c(g_color) if g_color is not None else torch.zeros((V, 3, fp.H, fp.W), dtype=f32, device=dev)
         gd = _f32c(g_depth) if g_depth is not None else None
         ga = _f32c(g_alpha) if g_alpha is not None else None
+        bws = torch.empty((V * G * 10,), dtype=f32, device=dev)
         bp = RasterBwdParams()
         bp.fwd = fp
+        bp.bwd_workspace, bp.bwd_workspace_bytes = ptr(bws), bws.numel() * 4
         bp.dL_dcolor, bp.dL_ddepth, bp.dL_dalpha = ptr(gc), ptr(gd), ptr(ga)
         bp.dL_dmeans3D, bp.dL_dcov3D, bp.dL_dopacity = ptr(d_means), ptr(d_cov), ptr(d_opac)
         bp.dL_dshs, bp.dL_dcolors, bp.dL_dtau = ptr(d_shs), ptr(d_col), ptr(d_tau)
@@ -143,11 +146,8 @@ class _Rasterize(torch.autograd.Function):
         sm, sc, so, ss, scol = ctx.shapes
         g_shs = d_shs.reshape(ss) if has_sh else None
         g_cols = d_col.reshape(scol) if not has_sh else None
-        g_theta = d_tau[:, 3:].reshape(-1) if ctx.has_pose[0] else None
-        g_rho = d_tau[:, :3].reshape(-1) if ctx.has_pose[1] else None
-        if V > 1:
-            g_theta = d_tau[:, 3:] if ctx.has_pose[0] else None
-            g_rho = d_tau[:, :3] if ctx.has_pose[1] else None
+        g_theta = d_tau[:, 3:].reshape(ctx.pose_shapes[0]) if ctx.has_pose[0] else None
+        g_rho = d_tau[:, :3].reshape(ctx.pose_shapes[1]) if ctx.has_pose[1] else None
         return (d_means.reshape(sm), d_cov.reshape(sc), d_opac.reshape(so), g_shs, g_cols,
                 g_theta, g_rho, None)
 
