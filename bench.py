@@ -182,9 +182,8 @@ def config_dict(nb: int = 1) -> dict:
 def run_ours(args) -> None:
     import torch
     import torch.distributed as dist
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    from vicasplat_b200 import dist_util
+    rank, world, local = dist_util.rank_world()
     assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback)"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -206,10 +205,10 @@ def run_ours(args) -> None:
     model.invalidate()
     eng = model.engine()
     NB = args.batch
-    image_h, K_h = synthetic.clip(NB, T_CTX, SIZE, seed=250307 + rank)
+    image_h, K_h = synthetic.clip(NB, T_CTX, SIZE, seed=dist_util.scene_seed(250307, rank))
     image_h, K_h = image_h.pin_memory(), K_h.pin_memory()
     image_d, K_d = image_h.to(dev), K_h.to(dev)
-    sc = {k: v.to(dev) for k, v in synthetic.gaussian_scene(T_CTX, SIZE, SIZE, V_TGT, seed=1 + rank).items()}
+    sc = {k: v.to(dev) for k, v in synthetic.gaussian_scene(T_CTX, SIZE, SIZE, V_TGT, seed=dist_util.scene_seed(1, rank)).items()}
     tanfov, view_t, full_t, campos = dec._cameras(sc["extrinsics"], sc["intrinsics"], sc["near"], sc["far"])
     cov6 = dec._cov6(sc["covariances"]).contiguous()
     bg = torch.zeros((V_TGT, 3), device=dev)
@@ -305,10 +304,8 @@ def run_ours(args) -> None:
     d2h = (color_h.numel() + depth_h.numel() + pose_h.numel()) * 4
 
     # ---- max over ranks
-    t = torch.tensor([step_ms, enc_ms, ras_ms, e2e_s * 1e3], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    step_ms, enc_ms, ras_ms, e2e_ms = t.tolist()
+    step_ms, enc_ms, ras_ms, e2e_ms = dist_util.max_over_ranks(
+        [step_ms, enc_ms, ras_ms, e2e_s * 1e3], dev)
 
     # overflow check of the calibrated capacity (outside the timed region)
     chk = rmod._run_forward(V_TGT, G_SCENE, SIZE, SIZE, True, sc["means"], cov6, sc["opacities"],

@@ -20,3 +20,25 @@ def run_smoke():
     ok = (ec <= 1e-4).double().mean().item()
     assert ok > 0.999, f"raster smoke mismatch: {ok}"
     print(f"smoke: raster ok ({ok:.5f} of pixels within 1e-4, max {ec.max():.2e})")
+
+
+    # encoder: a shallow-depth VicaSplat on a 3-frame 64x64 clip against the fp32 oracle restatement
+    from oracle import encoder_ref as er
+    from vicasplat_b200.encoder import VicaSplat, VicaSplatCfg, default_backbone_cfg
+    cfg = er.EncoderConfig(img_size=64, enc_depth=2, dec_depth=10)
+    bb = dict(default_backbone_cfg(), img_size=64, enc_depth=2, dec_depth=10)
+    model = VicaSplat(VicaSplatCfg(backbone=bb)).to(dev)
+    sd = er.synth_state_dict(cfg, seed=0)
+    model.load_state_dict(sd, strict=True)
+    g = torch.Generator().manual_seed(7)
+    image = torch.rand((1, 3, 3, 64, 64), generator=g) * 2 - 1
+    K = torch.tensor([[0.86, 0, 0.5], [0, 0.86, 0.5], [0, 0, 1.0]]).expand(1, 3, 3, 3).clone()
+    out = model({"image": image.to(dev), "intrinsics": K.to(dev)}, compute_viewspace_depth=False)
+    with torch.no_grad():
+        ref = er.forward(sd, image, K, cfg)
+    torch.cuda.synchronize()
+    e_pose = (out["pred_extrins"].cpu() - ref["pred_extrins"]).abs().max().item()
+    a, b = out["raw_gaussians"][..., 3:].cpu(), ref["raw_gaussians"][..., 3:]
+    e_raw = ((a - b).norm() / b.norm()).item()
+    assert e_pose < 2e-2 and e_raw < 3e-2, (e_pose, e_raw)
+    print(f"smoke: encoder ok (pose abs err {e_pose:.2e}, Gaussian-parameter rel-L2 {e_raw:.2e})")

@@ -1,0 +1,65 @@
+"""world_size-2 gloo test of the N>1 plumbing (replicas + max-over-ranks timing) and of the
+reference arm's rank gating."""
+import json
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank),
+                      MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    sys.path.insert(0, str(ROOT))
+    from vicasplat_b200 import dist_util
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    r, w, lr = dist_util.rank_world()
+    ms = [10.0 + 5 * rank, 3.0 - rank]                      # rank 1 slower on [0], faster on [1]
+    red = dist_util.max_over_ranks(ms, "cpu")
+    seeds = [None, None]
+    dist.all_gather_object(seeds, dist_util.scene_seed(100, r))
+    if rank == 0:
+        out.put((r, w, red, seeds, dist_util.aggregate_throughput(4, w, red[0] / 1e3)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_max_reduce_and_seeds():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    r, w, red, seeds, thr = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert (r, w) == (0, 2)
+    assert red == [15.0, 3.0]
+    assert len(set(seeds)) == 2
+    assert abs(thr - 2 * 4 / 0.015) < 1e-6
+
+
+def test_reference_arm_runs_on_rank0_only():
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--gpus", "2",
+                        "--steps", "1", "--warmup", "0"], env=env, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_bench_models_match_survey_figures():
+    sys.path.insert(0, str(ROOT))
+    import bench
+    assert abs(bench.encoder_flops(8) / 1e9 - 3405) < 10          # 3 405 GF/scene at T=8
+    assert abs(bench.encoder_flops(2) / 1e9 - 817) < 5
+    assert abs(bench.raster_bytes(1, 524288, 256, 256) / 1e6 - 122.7) < 0.1   # 122.7 MB / view
+    cfg = bench.config_dict(4)
+    assert "workload" in cfg and cfg["scenes_per_step_per_gpu"] == 4 and "model" not in cfg
+    json.dumps(cfg)

@@ -113,3 +113,31 @@ def test_backward_without_pose_and_with_precomputed_colors(cuda, lib):
     (torch.stack(imgs) * wc.double()).sum().backward()
     assert _rel(cols.grad, rc.grad) < 2e-3
     assert _rel(means.grad, rm.grad) < 2e-3
+
+
+def test_decoder_plugin_forward_backward_with_pose_deltas(cuda, lib):
+    """DecoderSplattingCUDA.forward as ModelWrapper.test_step_align drives it
+    (model_wrapper.py:473-482): batch of scenes, per-view pose deltas, gradients to the deltas."""
+    from vicasplat_b200.decoder import DecoderSplattingCUDA, DecoderSplattingCUDACfg, DecoderOutput
+    from vicasplat_b200.encoder import Gaussians
+    hw, V = 32, 3
+    sc, wc, wd = _setup(hw, 1, V, 13)
+    d = {k: v.to(cuda) for k, v in sc.items()}
+    B = 2
+    rep = lambda t: t[None].expand(B, *t.shape).contiguous()
+    g = Gaussians(means=rep(d["means"]).view(B, 1, hw, hw, 3), covariances=rep(d["covariances"]).view(B, 1, hw, hw, 3, 3),
+                  harmonics=rep(d["harmonics"]).view(B, 1, hw, hw, 3, 25), opacities=rep(d["opacities"]).view(B, 1, hw, hw))
+    dec_ = DecoderSplattingCUDA(DecoderSplattingCUDACfg("splatting_cuda", [0.0, 0.0, 0.0], False)).to(cuda)
+    rot = torch.zeros((B, V, 3), device=cuda, requires_grad=True)
+    trans = torch.zeros((B, V, 3), device=cuda, requires_grad=True)
+    out = dec_.forward(g, rep(d["extrinsics"]), rep(d["intrinsics"]), rep(d["near"]), rep(d["far"]), (hw, hw),
+                       cam_rot_delta=rot, cam_trans_delta=trans)
+    assert isinstance(out, DecoderOutput)
+    assert out.color.shape == (B, V, 3, hw, hw) and out.depth.shape == (B, V, hw, hw)
+    assert torch.equal(out.color[0], out.color[1])
+    (out.color * wc.to(cuda)[None]).sum().backward()
+    ref = _oracle_grads(sc, wc, torch.zeros_like(wd), hw, with_pose=True, dtype=torch.float32)
+    assert _rel(rot.grad[0], ref["theta"]) < 5e-3 and _rel(trans.grad[1], ref["rho"]) < 5e-3
+    c2, d2 = dec_.forward(g, rep(d["extrinsics"]), rep(d["intrinsics"]), rep(d["near"]), rep(d["far"]), (hw, hw),
+                          return_dict=False)
+    assert torch.equal(c2, out.color.detach())
