@@ -7,7 +7,9 @@ case $what in
 tests)
   python -m pytest tests -m gpu -q --timeout 900 2>&1 | tail -25 > gpurun_out/pytest_gpu.txt; cat gpurun_out/pytest_gpu.txt;;
 bench)
-  python bench.py --steps 20 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -3 gpurun_out/bench.err; cat gpurun_out/bench.json;;
+  python bench.py --steps 20 --warmup 3 --batch 1 > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -3 gpurun_out/bench.err; cat gpurun_out/bench.json;;
+bench8)
+  python bench.py --steps 10 --warmup 3 --batch 8 --no-cpu > gpurun_out/bench_b8.json 2> gpurun_out/bench_b8.err; tail -3 gpurun_out/bench_b8.err; cat gpurun_out/bench_b8.json;;
 bench4)
   python bench.py --steps 10 --warmup 3 --batch 4 --no-cpu > gpurun_out/bench_b4.json 2> gpurun_out/bench_b4.err; tail -3 gpurun_out/bench_b4.err; cat gpurun_out/bench_b4.json;;
 launches)
