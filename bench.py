@@ -213,20 +213,18 @@ def run_ours(args) -> None:
     cov6 = dec._cov6(sc["covariances"]).contiguous()
     bg = torch.zeros((V_TGT, 3), device=dev)
     rkw = dict(shs=sc["harmonics"], sh_degree=4, sh_layout="chan_major", viewmatrix=view_t,
-               projmatrix=full_t, campos=campos, tanfov=tanfov, bg=bg, H=SIZE, W=SIZE)
+               projmatrix=full_t, campos=campos, tanfov=tanfov, bg=bg, H=SIZE, W=SIZE,
+               want_n_touched=False)   # render_cuda discards it (cuda_splatting.py:226-239)
 
-    # calibrate the (tile, splat) pair capacity once, outside the timed region: the exact pair
-    # count of this scene is a device scalar written by vs_raster_forward
+    # calibrate the binning capacities once, outside the timed region: a checked call reads the
+    # exact pair count and the largest per-tile count of this scene from device scalars and leaves
+    # them (+25 %) in the rasterizer's per-shape hint, which the unchecked timed calls then use
     import vicasplat_b200.rasterizer as rmod
-    color = rasterize_views(sc["means"], cov6, sc["opacities"], **rkw)[0]
-    probe = rmod._run_forward(V_TGT, G_SCENE, SIZE, SIZE, True, sc["means"], cov6, sc["opacities"],
-                              sc["harmonics"], 25, 4, (1, 25), None, view_t.reshape(V_TGT, 16).contiguous(),
-                              full_t.reshape(V_TGT, 16).contiguous(), campos.contiguous(),
-                              tanfov.contiguous(), bg, 4 * V_TGT * G_SCENE)
-    n_pairs = int(probe[-1].num_pairs.item())
-    del probe
-    max_pairs = int(n_pairs * 1.02) + 4096
-    rkw.update(max_pairs=max_pairs, check_overflow=False)
+    for _ in range(2):
+        color = rasterize_views(sc["means"], cov6, sc["opacities"], **rkw)[0]
+    max_pairs, max_tile = rmod._capacity_hint[(V_TGT, G_SCENE, SIZE, SIZE)]
+    n_pairs = int((max_pairs - 4096) / 1.25)
+    rkw.update(check_overflow=False)
 
     def raster_batch():
         for _ in range(NB):           # scenes of the batch: one launch chain (all 12 views) each
@@ -335,13 +333,11 @@ def run_ours(args) -> None:
     step_ms, enc_ms, ras_ms, e2e_ms, seq_ms = dist_util.max_over_ranks(
         [step_ms, enc_ms, ras_ms, e2e_s * 1e3, seq_ms], dev)
 
-    # overflow check of the calibrated capacity (outside the timed region)
-    chk = rmod._run_forward(V_TGT, G_SCENE, SIZE, SIZE, True, sc["means"], cov6, sc["opacities"],
-                            sc["harmonics"], 25, 4, (1, 25), None, view_t.reshape(V_TGT, 16).contiguous(),
-                            full_t.reshape(V_TGT, 16).contiguous(), campos.contiguous(),
-                            tanfov.contiguous(), bg, max_pairs)
-    assert int(chk[-1].num_pairs.item()) <= max_pairs, "raster capacity overflow"
-    assert torch.isfinite(color).all()
+    # overflow check of the calibrated capacities (outside the timed region): a checked call would
+    # have re-run and changed the hint if either bound had been exceeded
+    chk = rasterize_views(sc["means"], cov6, sc["opacities"], **dict(rkw, check_overflow=True))[0]
+    assert rmod._capacity_hint[(V_TGT, G_SCENE, SIZE, SIZE)] == (max_pairs, max_tile), "raster capacity changed"
+    assert torch.isfinite(chk).all() and torch.equal(chk, color)
 
     if rank == 0:
         peaks = load_peaks()
@@ -356,6 +352,7 @@ def run_ours(args) -> None:
             vs_baseline=None, dtype="bf16", data="synthetic", config=config_dict(NB),
             mpix_per_sec=value * V_TGT * SIZE * SIZE / 1e6,
             encoder_ms=enc_ms, raster_ms=ras_ms, sequential_ms_per_step=seq_ms, raster_pairs=n_pairs,
+            raster_sort=("per-tile shared-memory sort" if max_tile > 0 else "global 64-bit radix sort"),
             schedule=("sequential" if not args.pipelined else
                       "pipelined: render of batch i (stream B, event-dependent on encoder i) overlaps "
                       "encoder of batch i+1 (stream A); encoder_ms / raster_ms are un-overlapped"),

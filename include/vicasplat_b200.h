@@ -248,7 +248,12 @@ typedef struct vs_raster_params {
   void* workspace;
   int64_t workspace_bytes;
   int64_t max_pairs; /* capacity (in (tile,splat) pairs) the workspace was sized for */
-  int64_t* num_pairs_out; /* device scalar: pairs actually produced (for the caller to check) */
+  int64_t* num_pairs_out; /* device int64[2]: [0] pairs actually produced (caller checks it against
+                             max_pairs), [1] largest per-tile count (0 on the global-sort path) */
+  int32_t max_tile_pairs; /* > 0: upper bound of the pairs of any single tile (e.g. from a previous
+                             call on similar data): enables per-tile binning + shared-memory sort
+                             (<= 16384); a tile that exceeds it is left unsorted, which the caller
+                             detects from num_pairs_out[1].  0: global 64-bit radix sort. */
 } vs_raster_params;
 int64_t vs_raster_workspace_bytes(int V, int G, int H, int W, int64_t max_pairs);
 int vs_raster_forward(const vs_raster_params* p, vs_stream_t stream);

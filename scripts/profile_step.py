@@ -25,7 +25,7 @@ sc = {k: v.to(dev) for k, v in synthetic.gaussian_scene(T, S, S, V, seed=1).item
 tanfov, view_t, full_t, campos = dec._cameras(sc["extrinsics"], sc["intrinsics"], sc["near"], sc["far"])
 cov6 = dec._cov6(sc["covariances"]).contiguous()
 kw = dict(shs=sc["harmonics"], sh_degree=4, sh_layout="chan_major", viewmatrix=view_t, projmatrix=full_t,
-          campos=campos, tanfov=tanfov, bg=torch.zeros((V, 3), device=dev), H=S, W=S)
+          campos=campos, tanfov=tanfov, bg=torch.zeros((V, 3), device=dev), H=S, W=S, want_n_touched=False)
 rasterize_views(sc["means"], cov6, sc["opacities"], **kw)          # calibrates the pair capacity hint
 for _ in range(2):
     eng.run(image, K, clone_outputs=False)

@@ -66,7 +66,7 @@ class RasterParams(C.Structure):
         ("out_color", _vp), ("out_depth", _vp), ("out_alpha", _vp), ("radii", _vp),
         ("n_touched", _vp), ("final_T", _vp), ("n_contrib", _vp),
         ("workspace", _vp), ("workspace_bytes", _i64), ("max_pairs", _i64),
-        ("num_pairs_out", _vp),
+        ("num_pairs_out", _vp), ("max_tile_pairs", _i32),
     ]
 
 

@@ -9,6 +9,7 @@
 //   * per-view intermediates are SoA so the blend kernel's gathers are 16-byte vector loads;
 //   * the blend kernel stages 256-splat batches of a tile's list in shared memory, each warp
 //     ballots its done-mask for early exit.
+#include <cub/block/block_radix_sort.cuh>
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
@@ -51,6 +52,8 @@ struct Workspace {
   uint32_t* vals_in;
   uint32_t* vals_out;
   uint2* ranges;     // (V*tiles)
+  uint32_t* tile_counts;  // (V*tiles)  per-tile binning path
+  uint32_t* tile_cursor;  // (V*tiles)
   void* cub_tmp;
   size_t cub_bytes;
   size_t total;
@@ -88,6 +91,8 @@ Workspace carve(void* base, int V, int G, int H, int W, int64_t max_pairs) {
   w.vals_in = static_cast<uint32_t*>(take(static_cast<size_t>(max_pairs) * 4));
   w.vals_out = static_cast<uint32_t*>(take(static_cast<size_t>(max_pairs) * 4));
   w.ranges = static_cast<uint2*>(take(nt * sizeof(uint2)));
+  w.tile_counts = static_cast<uint32_t*>(take(nt * 4));
+  w.tile_cursor = static_cast<uint32_t*>(take(nt * 4));
   w.cub_tmp = take(w.cub_bytes);
   w.total = off;
   return w;
@@ -321,6 +326,185 @@ __global__ void tile_ranges_kernel(const uint64_t* __restrict__ keys, int64_t ma
     }
   }
   if (i == n - 1) ranges[t].y = static_cast<uint32_t>(n);
+}
+
+// ------------------------------------------------------------------ per-tile binning + sort
+// Alternative to the global 64-bit radix sort (6 passes over every pair): pairs are counted per
+// tile, scattered into their tile's segment, and each segment is sorted by ONE CTA in shared
+// memory (cub::BlockRadixSort on (depth bits, Gaussian id): the id makes the order independent of
+// the scatter order and reproduces the stable global sort exactly).  HBM traffic drops from
+// ~12 x 12 B to ~3 x 8 B per pair.  Used when the caller provides max_tile_pairs <= 16384.
+// Pixel-aligned Gaussians of one block land in a handful of tiles: count in shared memory first,
+// then ONE global atomic per touched tile per block (13 M same-address global atomics otherwise).
+// grid = (blocks over g, V); dynamic smem = tiles_per_view counters (0 -> direct global atomics).
+__global__ void tile_count_kernel(int G, int H, int W, const float2* __restrict__ xy,
+                                  const int32_t* __restrict__ radii,
+                                  uint32_t* __restrict__ tile_counts, int use_smem) {
+  extern __shared__ uint32_t s_cnt[];
+  const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
+  const int tpv = gx * gy;
+  const uint32_t v = blockIdx.y;
+  if (use_smem) {
+    for (int i = threadIdx.x; i < tpv; i += blockDim.x) s_cnt[i] = 0u;
+    __syncthreads();
+  }
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < G) {
+    const size_t i = static_cast<size_t>(v) * G + g;
+    const int rad = radii[i];
+    if (rad > 0) {
+      const float2 p = xy[i];
+      int x0, x1, y0, y1;
+      tile_rect(p.x, p.y, rad, gx, gy, x0, x1, y0, y1);
+      for (int y = y0; y < y1; ++y)
+        for (int x = x0; x < x1; ++x) {
+          if (use_smem) atomicAdd(s_cnt + y * gx + x, 1u);
+          else atomicAdd(tile_counts + v * tpv + y * gx + x, 1u);
+        }
+    }
+  }
+  if (use_smem) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < tpv; i += blockDim.x)
+      if (s_cnt[i] != 0u) atomicAdd(tile_counts + v * tpv + i, s_cnt[i]);
+  }
+}
+
+// single CTA: exclusive scan of the tile counts -> ranges (clipped to the capacity), totals
+__global__ void __launch_bounds__(1024)
+    tile_offsets_kernel(const uint32_t* __restrict__ counts, int n_tiles, int64_t max_pairs,
+                        uint2* __restrict__ ranges, uint32_t* __restrict__ cursor,
+                        int64_t* __restrict__ num_pairs_out) {
+  __shared__ unsigned long long s_part[1024];
+  __shared__ unsigned s_max[1024];
+  const int t = threadIdx.x;
+  const int per = (n_tiles + 1023) / 1024;
+  const int b = t * per, e = min(n_tiles, b + per);
+  unsigned long long sum = 0;
+  unsigned mx = 0;
+  for (int i = b; i < e; ++i) { sum += counts[i]; mx = max(mx, counts[i]); }
+  s_part[t] = sum;
+  s_max[t] = mx;
+  __syncthreads();
+  for (int off = 1; off < 1024; off <<= 1) {   // Hillis-Steele inclusive scan / max
+    unsigned long long v = t >= off ? s_part[t - off] : 0ull;
+    unsigned m = t >= off ? s_max[t - off] : 0u;
+    __syncthreads();
+    s_part[t] += v;
+    s_max[t] = max(s_max[t], m);
+    __syncthreads();
+  }
+  unsigned long long run = s_part[t] - sum;   // exclusive prefix of this thread's chunk
+  for (int i = b; i < e; ++i) {
+    const unsigned long long lo = run < static_cast<unsigned long long>(max_pairs) ? run : max_pairs;
+    run += counts[i];
+    const unsigned long long hi = run < static_cast<unsigned long long>(max_pairs) ? run : max_pairs;
+    ranges[i] = make_uint2(static_cast<unsigned>(lo), static_cast<unsigned>(hi));
+    cursor[i] = 0u;
+  }
+  if (t == 1023 && num_pairs_out != nullptr) {
+    num_pairs_out[0] = static_cast<int64_t>(s_part[1023]);
+    num_pairs_out[1] = static_cast<int64_t>(s_max[1023]);
+  }
+}
+
+// Same aggregation for the scatter: the block counts per tile in shared memory, reserves one
+// contiguous chunk per touched tile with a single global atomic, then hands out slots locally.
+__global__ void tile_scatter_kernel(int G, int H, int W, const float2* __restrict__ xy,
+                                    const float4* __restrict__ rgbd,
+                                    const int32_t* __restrict__ radii,
+                                    const uint2* __restrict__ ranges, uint32_t* __restrict__ cursor,
+                                    uint64_t* __restrict__ keys, int id_bits, int use_smem) {
+  extern __shared__ uint32_t s_buf[];   // [tpv] counts -> local cursors, [tpv] chunk bases
+  const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
+  const int tpv = gx * gy;
+  const uint32_t v = blockIdx.y;
+  uint32_t* s_cnt = s_buf;
+  uint32_t* s_base = s_buf + tpv;
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t i = static_cast<size_t>(v) * G + (g < G ? g : 0);
+  int x0 = 0, x1 = 0, y0 = 0, y1 = 0;
+  if (g < G) {
+    const int rad = radii[i];
+    if (rad > 0) {
+      const float2 p = xy[i];
+      tile_rect(p.x, p.y, rad, gx, gy, x0, x1, y0, y1);
+    }
+  }
+  const uint64_t key = (static_cast<uint64_t>(__float_as_uint(g < G ? rgbd[i].w : 0.f)) << id_bits) | i;
+  if (use_smem) {
+    for (int t = threadIdx.x; t < tpv; t += blockDim.x) s_cnt[t] = 0u;
+    __syncthreads();
+    for (int y = y0; y < y1; ++y)
+      for (int x = x0; x < x1; ++x) atomicAdd(s_cnt + y * gx + x, 1u);
+    __syncthreads();
+    for (int t = threadIdx.x; t < tpv; t += blockDim.x) {
+      const uint32_t c = s_cnt[t];
+      s_base[t] = c != 0u ? atomicAdd(cursor + v * tpv + t, c) : 0u;
+      s_cnt[t] = 0u;
+    }
+    __syncthreads();
+  }
+  for (int y = y0; y < y1; ++y)
+    for (int x = x0; x < x1; ++x) {
+      const int t = y * gx + x;
+      const uint2 r = ranges[v * tpv + t];
+      const uint32_t pos = r.x + (use_smem ? s_base[t] + atomicAdd(s_cnt + t, 1u)
+                                           : atomicAdd(cursor + v * tpv + t, 1u));
+      if (pos < r.y) keys[pos] = key;
+    }
+}
+
+constexpr int SORT_THREADS = 512;
+template <int ITEMS, int LOWER>   // owns tiles with LOWER < n <= SORT_THREADS * ITEMS
+__global__ void __launch_bounds__(SORT_THREADS)
+    tile_sort_kernel(const uint2* __restrict__ ranges, const uint64_t* __restrict__ keys,
+                     uint32_t* __restrict__ vals_out, int key_bits, int id_bits, int max_cap) {
+  using Sort = cub::BlockRadixSort<uint64_t, SORT_THREADS, ITEMS, cub::NullType, 5>;
+  extern __shared__ __align__(16) unsigned char sort_smem[];
+  typename Sort::TempStorage& temp = *reinterpret_cast<typename Sort::TempStorage*>(sort_smem);
+  constexpr int CAP = SORT_THREADS * ITEMS;
+  const uint2 r = ranges[blockIdx.x];
+  const int n = static_cast<int>(r.y - r.x);
+  const uint64_t id_mask = (1ull << id_bits) - 1ull;
+  if (n > max_cap) {
+    // larger than the caller's bound: ids are passed through UNSORTED (valid indices, wrong order);
+    // the caller sees num_pairs_out[1] > max_tile_pairs and re-runs on the global-sort path
+    if (LOWER == 0)
+      for (int i = threadIdx.x; i < n; i += SORT_THREADS)
+        vals_out[r.x + i] = static_cast<uint32_t>(keys[r.x + i] & id_mask);
+    return;
+  }
+  if (n <= LOWER || n > CAP) return;   // another instantiation owns this tile (or it is empty)
+  uint64_t k[ITEMS];
+#pragma unroll
+  for (int i = 0; i < ITEMS; ++i) {
+    const int idx = threadIdx.x * ITEMS + i;
+    k[i] = idx < n ? keys[r.x + idx] : ~0ull;
+  }
+  Sort(temp).Sort(k, 0, key_bits);
+#pragma unroll
+  for (int i = 0; i < ITEMS; ++i) {
+    const int idx = threadIdx.x * ITEMS + i;
+    if (idx < n) vals_out[r.x + idx] = static_cast<uint32_t>(k[i] & id_mask);
+  }
+}
+
+template <int ITEMS, int LOWER>
+int launch_tile_sort(const Workspace& ws, int n_tiles, int key_bits, int id_bits, int max_cap,
+                     cudaStream_t stream) {
+  using Sort = cub::BlockRadixSort<uint64_t, SORT_THREADS, ITEMS, cub::NullType, 5>;
+  const int smem = static_cast<int>(sizeof(typename Sort::TempStorage));
+  static bool configured = false;
+  if (!configured) {
+    VS_CUDA(cudaFuncSetAttribute(tile_sort_kernel<ITEMS, LOWER>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  tile_sort_kernel<ITEMS, LOWER><<<n_tiles, SORT_THREADS, smem, stream>>>(
+      ws.ranges, ws.keys_in, ws.vals_out, key_bits, id_bits, max_cap);
+  VS_LAUNCH_CHECK();
+  return VS_OK;
 }
 
 // ------------------------------------------------------------------ blend
@@ -879,7 +1063,7 @@ extern "C" int vs_raster_forward(const vs_raster_params* p, vs_stream_t stream_)
   int32_t* radii = p->radii ? p->radii : ws.radii;
   VS_CUDA(cudaMemsetAsync(ws.ranges, 0, n_tiles * sizeof(uint2), stream));
   if (p->n_touched) VS_CUDA(cudaMemsetAsync(p->n_touched, 0, VG * sizeof(int32_t), stream));
-  if (p->num_pairs_out && p->G == 0) VS_CUDA(cudaMemsetAsync(p->num_pairs_out, 0, 8, stream));
+  if (p->num_pairs_out) VS_CUDA(cudaMemsetAsync(p->num_pairs_out, 0, 16, stream));
 
   if (p->G > 0) {
     int sh_cs = p->sh_stride_coef, sh_ch = p->sh_stride_chan;
@@ -903,6 +1087,42 @@ extern "C" int vs_raster_forward(const vs_raster_params* p, vs_stream_t stream_)
         p->campos, p->tanfov, ws.xy, ws.conic_o, ws.rgbd, ws.tiles, radii);
     VS_LAUNCH_CHECK();
 
+    if (p->max_tile_pairs > 0 && p->max_tile_pairs <= 16384 && n_tiles < (1u << 20)) {
+      // ---- per-tile binning + shared-memory sort
+      VS_CUDA(cudaMemsetAsync(ws.tile_counts, 0, n_tiles * 4, stream));
+      const int tpv = gx * gy;
+      const int use_smem = tpv <= 4096;
+      dim3 cgrid(ceil_div(p->G, 256), p->V);
+      tile_count_kernel<<<cgrid, 256, use_smem ? tpv * 4 : 0, stream>>>(
+          p->G, p->H, p->W, ws.xy, radii, ws.tile_counts, use_smem);
+      VS_LAUNCH_CHECK();
+      tile_offsets_kernel<<<1, 1024, 0, stream>>>(ws.tile_counts, static_cast<int>(n_tiles),
+                                                  p->max_pairs, ws.ranges, ws.tile_cursor,
+                                                  p->num_pairs_out);
+      VS_LAUNCH_CHECK();
+      const int id_bits = highest_bit(VG > 1 ? VG - 1 : 1);
+      tile_scatter_kernel<<<cgrid, 256, use_smem ? tpv * 8 : 0, stream>>>(
+          p->G, p->H, p->W, ws.xy, ws.rgbd, radii, ws.ranges, ws.tile_cursor, ws.keys_in, id_bits,
+          use_smem);
+      VS_LAUNCH_CHECK();
+      const int key_bits = 32 + id_bits, nt = static_cast<int>(n_tiles);
+      const int mt = p->max_tile_pairs;
+      // size classes (capacity = 512 x ITEMS): a tile is sorted at the narrowest class that fits
+      static const int caps[8] = {2048, 3072, 4096, 5120, 6144, 8192, 12288, 16384};
+      int max_cap = 16384;
+      for (int c = 7; c >= 0; --c)
+        if (mt <= caps[c]) max_cap = caps[c];
+      int rc = launch_tile_sort<4, 0>(ws, nt, key_bits, id_bits, max_cap, stream);
+      if (rc == VS_OK && mt > 2048) rc = launch_tile_sort<6, 2048>(ws, nt, key_bits, id_bits, max_cap, stream);
+      if (rc == VS_OK && mt > 3072) rc = launch_tile_sort<8, 3072>(ws, nt, key_bits, id_bits, max_cap, stream);
+      if (rc == VS_OK && mt > 4096) rc = launch_tile_sort<10, 4096>(ws, nt, key_bits, id_bits, max_cap, stream);
+      if (rc == VS_OK && mt > 5120) rc = launch_tile_sort<12, 5120>(ws, nt, key_bits, id_bits, max_cap, stream);
+      if (rc == VS_OK && mt > 6144) rc = launch_tile_sort<16, 6144>(ws, nt, key_bits, id_bits, max_cap, stream);
+      if (rc == VS_OK && mt > 8192) rc = launch_tile_sort<24, 8192>(ws, nt, key_bits, id_bits, max_cap, stream);
+      if (rc == VS_OK && mt > 12288) rc = launch_tile_sort<32, 12288>(ws, nt, key_bits, id_bits, max_cap, stream);
+      if (rc != VS_OK) return rc;
+    } else {
+    // ---- global path: scan, emit (tile | depth) keys, one 64-bit radix sort
     size_t tmp = ws.cub_bytes;
     VS_CUDA(cub::DeviceScan::InclusiveSum(ws.cub_tmp, tmp, ws.tiles, ws.offsets,
                                           static_cast<int>(VG), stream));
@@ -921,6 +1141,7 @@ extern "C" int vs_raster_forward(const vs_raster_params* p, vs_stream_t stream_)
     tile_ranges_kernel<<<static_cast<unsigned>(ceil_div64(p->max_pairs, 256)), 256, 0, stream>>>(
         ws.keys_out, p->max_pairs, ws.offsets, VG, ws.ranges);
     VS_LAUNCH_CHECK();
+    }
   }
   dim3 bgrid(gx, gy, p->V);
   blend_kernel<<<bgrid, BLEND_THREADS, 0, stream>>>(

@@ -95,7 +95,7 @@ def render_cuda(extrinsics, intrinsics, near, far, image_shape, background_color
         gaussian_means, _cov6(gaussian_covariances), gaussian_opacities, shs=shs,
         colors_precomp=cols, sh_degree=degree, sh_layout="chan_major", viewmatrix=view_t,
         projmatrix=full_t, campos=campos, tanfov=tanfov, bg=background_color, H=h, W=w,
-        theta=cam_rot_delta, rho=cam_trans_delta)
+        theta=cam_rot_delta, rho=cam_trans_delta, want_n_touched=False)
     return color, depth[:, 0]
 
 

@@ -42,9 +42,11 @@ def _f32c(t: torch.Tensor) -> torch.Tensor:
     return t.detach().to(torch.float32).contiguous()
 
 
-# (V, G, H, W) -> pair capacity that was enough last time (+25 %): later calls of the same shape
-# size their binning workspace from it instead of the worst-case default
+# (V, G, H, W) -> (pair capacity, per-tile bound) that was enough last time (+25 %): later calls of
+# the same shape size their binning workspace from it instead of the worst-case default, and sort
+# per tile in shared memory (bound <= 16384) instead of one global 64-bit radix sort (bound 0)
 _capacity_hint: dict = {}
+MAX_TILE_SORT = 16384
 
 
 class _Ctx:
@@ -53,7 +55,7 @@ class _Ctx:
 
 
 def _run_forward(V, G, H, W, shared, means, cov6, opac, shs, sh_M, sh_degree, sh_strides, colors,
-                 viewm, projm, campos, tanfov, bg, max_pairs, want_aux=True):
+                 viewm, projm, campos, tanfov, bg, max_pairs, max_tile_pairs=0, want_aux=True):
     lib = _lib.load()
     dev = means.device
     f32, i32 = torch.float32, torch.int32
@@ -64,7 +66,7 @@ def _run_forward(V, G, H, W, shared, means, cov6, opac, shs, sh_M, sh_degree, sh
     n_touched = torch.empty((V, max(G, 1)), dtype=i32, device=dev) if want_aux else None
     final_T = torch.empty((V, H, W), dtype=f32, device=dev)
     n_contrib = torch.empty((V, H, W), dtype=i32, device=dev)
-    num_pairs = torch.zeros((1,), dtype=torch.int64, device=dev)
+    num_pairs = torch.zeros((2,), dtype=torch.int64, device=dev)
     ws_bytes = lib.vs_raster_workspace_bytes(V, max(G, 1), H, W, max_pairs)
     ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
     p = RasterParams()
@@ -79,6 +81,7 @@ def _run_forward(V, G, H, W, shared, means, cov6, opac, shs, sh_M, sh_degree, sh
     p.radii, p.n_touched, p.final_T, p.n_contrib = ptr(radii), ptr(n_touched), ptr(final_T), ptr(n_contrib)
     p.workspace, p.workspace_bytes, p.max_pairs = ptr(ws), ws_bytes, max_pairs
     p.num_pairs_out = ptr(num_pairs)
+    p.max_tile_pairs = int(max_tile_pairs)
     check(lib.vs_raster_forward(C.byref(p), C.c_void_p(stream_ptr())), "vs_raster_forward")
     ctx = _Ctx()
     ctx.params = p
@@ -92,26 +95,35 @@ class _Rasterize(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means, cov6, opac, shs, colors, theta, rho, cfg):
         (V, G, H, W, shared, sh_M, sh_degree, sh_strides, viewm, projm, campos, tanfov, bg,
-         max_pairs, check_overflow) = cfg
+         max_pairs, max_tile, check_overflow, want_aux) = cfg
         m, c6, o = _f32c(means), _f32c(cov6), _f32c(opac).reshape(-1)
         s = _f32c(shs) if shs is not None else None
         cp = _f32c(colors) if colors is not None else None
         while True:
             color, depth, alpha, radii, n_touched, st = _run_forward(
                 V, G, H, W, shared, m, c6, o, s, sh_M, sh_degree, sh_strides, cp, viewm, projm,
-                campos, tanfov, bg, max_pairs)
+                campos, tanfov, bg, max_pairs, max_tile, want_aux)
             if not check_overflow:
                 break
-            n = int(st.num_pairs.item())      # the upstream extension syncs here too (num_rendered)
-            _capacity_hint[(V, G, H, W)] = int(n * 1.25) + 4096
-            if n <= max_pairs:
+            n, tmax = st.num_pairs.tolist()   # the upstream extension syncs here too (num_rendered)
+            ok = n <= max_pairs and (max_tile == 0 or tmax <= max_tile)
+            if max_tile == 0:
+                next_tile = 0 if _capacity_hint.get((V, G, H, W), (0, 1))[1] == 0 else MAX_TILE_SORT
+            else:
+                next_tile = min(MAX_TILE_SORT, int(tmax * 1.25) + 64) if tmax <= MAX_TILE_SORT else 0
+            _capacity_hint[(V, G, H, W)] = (int(n * 1.25) + 4096, next_tile)
+            if ok:
                 break
-            max_pairs = int(n * 1.05) + 1024  # capacity was too small: re-run with the exact need
+            # capacity or per-tile bound was too small: re-run with what this scene needs
+            max_pairs = max(max_pairs, int(n * 1.05) + 1024)
+            max_tile = 0 if tmax > MAX_TILE_SORT else min(MAX_TILE_SORT, int(tmax * 1.05) + 64)
         ctx.state = st
         ctx.shapes = (means.shape, cov6.shape, opac.shape, None if shs is None else shs.shape,
                       None if colors is None else colors.shape)
         ctx.has_pose = (theta is not None, rho is not None)
         ctx.pose_shapes = (None if theta is None else theta.shape, None if rho is None else rho.shape)
+        if n_touched is None:
+            n_touched = radii.new_zeros(())
         ctx.mark_non_differentiable(radii, n_touched)
         return color, radii, depth, alpha, n_touched
 
@@ -155,7 +167,8 @@ class _Rasterize(torch.autograd.Function):
 def rasterize_views(means3D, cov6, opacities, *, shs=None, colors_precomp=None, sh_degree=0,
                     sh_layout="coef_major", viewmatrix, projmatrix, campos, tanfov, bg, H, W,
                     theta=None, rho=None, max_pairs: Optional[int] = None,
-                    check_overflow: bool = True):
+                    max_tile_pairs: Optional[int] = None, check_overflow: bool = True,
+                    want_n_touched: bool = True):
     """Render V views.  Gaussians are shared by all views when means3D is (G,3), per-view when
     (V,G,3).  viewmatrix/projmatrix (V,4,4) are the *transposed* matrices the reference passes
     (cuda_splatting.py:192-194); tanfov (V,2); bg (V,3) or (3,).
@@ -164,7 +177,9 @@ def rasterize_views(means3D, cov6, opacities, *, shs=None, colors_precomp=None, 
     (cuda_splatting.py:182); "chan_major" = (G, 3, M), the encoder's own layout
     (gaussian_adapter.py:180), consumed without the transpose copy.
 
-    Returns color (V,3,H,W), radii (V,G), depth (V,1,H,W), alpha (V,1,H,W), n_touched (V,G).
+    Returns color (V,3,H,W), radii (V,G), depth (V,1,H,W), alpha (V,1,H,W), n_touched (V,G)
+    (a 0-d placeholder when want_n_touched=False: the reference's render_cuda discards it,
+    cuda_splatting.py:226-239, and counting costs one atomic per (warp, splat) hit).
     """
     if not means3D.is_cuda:
         raise RuntimeError("rasterize_views needs CUDA tensors (there is no CPU fallback)")
@@ -187,10 +202,13 @@ def rasterize_views(means3D, cov6, opacities, *, shs=None, colors_precomp=None, 
             sh_M, strides = shs.shape[-1], (1, shs.shape[-1])
         else:
             raise ValueError(f"bad sh_layout {sh_layout!r}")
+    hint = _capacity_hint.get((V, G, H, W), (max(4 * V * G, 1 << 16), MAX_TILE_SORT))
     if max_pairs is None:
-        max_pairs = _capacity_hint.get((V, G, H, W), max(4 * V * G, 1 << 16))
+        max_pairs = hint[0]
+    if max_tile_pairs is None:
+        max_tile_pairs = hint[1]
     cfg = (V, G, H, W, shared, sh_M, int(sh_degree), strides, vm, pm, cp, tf, bgc, int(max_pairs),
-           check_overflow)
+           int(max_tile_pairs), check_overflow, bool(want_n_touched))
     return _Rasterize.apply(means3D, cov6, opacities, shs, colors_precomp, theta, rho, cfg)
 
 
