@@ -6,9 +6,10 @@
 //                 S[128x128] = Q K^T   (both operands K-major, 128B-swizzled, straight from TMA)
 //                 O'[128x64] = P V     (P written by the softmax warps as a K-major swizzled tile,
 //                                       V consumed as an MN-major operand: no transpose anywhere)
-//   warps 2..5  softmax: thread r owns query row r (TMEM lane r): two passes over S in TMEM (row
-//               max, then exp2 / row sum / bf16 P -> shared memory), then folds the fresh O' tile
-//               into its fp32 register accumulator with the running-max correction.
+//   warps 2..9  softmax: two threads share query row r (TMEM lane r), each owning half of the key
+//               columns and half of the output columns: two passes over S in TMEM (row max, then
+//               exp2 / row sum / bf16 P -> shared memory), then the fresh O' tile is folded into the
+//               fp32 register accumulator with the running-max correction.
 // The exponentials (MUFU) bound this kernel at hd = 64, not the tensor pipe, so S is single
 // buffered and two CTAs per SM interleave their softmax and MMA phases.
 //
@@ -29,7 +30,8 @@ constexpr int QT = 128;   // queries per CTA
 constexpr int KT = 128;   // keys per step
 constexpr int HD = 64;
 constexpr int TILE_BYTES = 128 * 128;  // 128 rows x 128 B
-constexpr int SMEM_BYTES = 5 * TILE_BYTES /*Q,K,V,P(2)*/ + 1024 /*align*/ + 128 /*barriers*/;
+constexpr int SMEM_BYTES = 5 * TILE_BYTES /*Q,K,V,P(2)*/ + 1024 /*align*/ + 128 /*barriers*/ + 2048 /*row max*/;
+constexpr int ATT_THREADS = 64 + 8 * 32;
 constexpr int TMEM_COLS = 256;  // S: [0,128)  O': [128,192)
 
 struct AttnDev {
@@ -47,7 +49,7 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
-__global__ void __launch_bounds__(192, 2)
+__global__ void __launch_bounds__(ATT_THREADS, 2)
     attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, const AttnDev a) {
   const int item = blockIdx.z, head = blockIdx.y, qt = blockIdx.x;
@@ -70,6 +72,7 @@ __global__ void __launch_bounds__(192, 2)
   uint64_t *q_full = bars, *k_full = bars + 1, *k_empty = bars + 2, *v_full = bars + 3,
            *v_empty = bars + 4, *s_full = bars + 5, *p_full = bars + 6, *o_full = bars + 7;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  float* s_mx = reinterpret_cast<float*>(bars + 10);   // [2 tiles][2 halves][128 rows]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
@@ -82,7 +85,7 @@ __global__ void __launch_bounds__(192, 2)
     mbar_init(v_full, 1);
     mbar_init(v_empty, 1);
     mbar_init(s_full, 1);
-    mbar_init(p_full, 128);
+    mbar_init(p_full, 256);
     mbar_init(o_full, 1);
     fence_mbar_init();
   }
@@ -142,7 +145,13 @@ __global__ void __launch_bounds__(192, 2)
       }
     }
   } else {
+    // 8 softmax warps: warps (w, w+4) share TMEM lane quarter q = w & 3, i.e. the same 32 query
+    // rows; `half` owns key columns [64 half, 64 half + 64) of every S tile (= k-block `half` of
+    // the P tile) and output columns [32 half, 32 half + 32).  Per thread that is half the
+    // dependent chain of a full row, and 16 instead of 8 warps per SM hide the TMEM / MUFU /
+    // mbarrier latencies.  The two halves agree on the row maximum through shared memory.
     const int q = warp & 3;  // TMEM lane quarter of this warp
+    const int half = (warp - 2) >> 2;
     const int r = q * 32 + lane;
     const int grow = q_row0 + r;  // absolute query row
     const bool row_valid = (qt * QT + r) < q_len;
@@ -151,10 +160,10 @@ __global__ void __launch_bounds__(192, 2)
       lim = (grow / a.causal_block + 1) * a.causal_block;
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     float m = -INFINITY, l = 0.f;
-    float o[HD];
+    float o[HD / 2];
 #pragma unroll
-    for (int i = 0; i < HD; ++i) o[i] = 0.f;
-    uint8_t* p_row = sP + r * 128;
+    for (int i = 0; i < HD / 2; ++i) o[i] = 0.f;
+    uint8_t* p_row = sP + half * TILE_BYTES + r * 128;
     const int sw = r & 7;
 
     for (int j = 0; j < nt; ++j) {
@@ -162,32 +171,42 @@ __global__ void __launch_bounds__(192, 2)
       const int row0 = j < n0 ? s0 + j * KT : s1 + (j - n0) * KT;
       const int seg_left = j < n0 ? l0 - j * KT : l1 - (j - n0) * KT;
       const int nvalid = min(min(seg_left, KT), lim - row0);  // keys [0, nvalid) of this tile count
+      const int nseg = min(seg_left, KT);
+      const int nchunks = (nseg + 31) >> 5;   // CTA-uniform; P is written up to 32 * nchunks
+      const int c_lo = half * 2, c_hi = min(c_lo + 2, nchunks);   // my chunks of 32 columns
       mbar_wait(s_full, ph);
       tc_fence_after();
-      const int nseg = min(seg_left, KT);
-      const int nchunks = (nseg + 31) >> 5;          // CTA-uniform; P is written up to 32 * nchunks
-      // ---- pass 1: row maximum
-      float mx = -INFINITY;
+      // ---- pass 1: maximum over my columns (4 independent chains), exchanged with the other half
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll 1
-      for (int c = 0; c < nchunks; ++c) {
+      for (int c = c_lo; c < c_hi; ++c) {
         uint32_t v[32];
         tmem_ld_32x32(t_lane + c * 32, v);
         tmem_ld_wait();
         if (nvalid >= (c + 1) * 32) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+          for (int i = 0; i < 32; i += 4) {
+            mx0 = fmaxf(mx0, __uint_as_float(v[i]));
+            mx1 = fmaxf(mx1, __uint_as_float(v[i + 1]));
+            mx2 = fmaxf(mx2, __uint_as_float(v[i + 2]));
+            mx3 = fmaxf(mx3, __uint_as_float(v[i + 3]));
+          }
         } else {
 #pragma unroll
           for (int i = 0; i < 32; ++i)
-            if (c * 32 + i < nvalid) mx = fmaxf(mx, __uint_as_float(v[i]));
+            if (c * 32 + i < nvalid) mx0 = fmaxf(mx0, __uint_as_float(v[i]));
         }
       }
+      float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+      s_mx[(j & 1) * 256 + half * 128 + r] = mx;
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");   // the two warps of this quarter
+      mx = fmaxf(mx, s_mx[(j & 1) * 256 + (half ^ 1) * 128 + r]);
       const float m_new = fmaxf(m, mx * a.scale_log2);
       const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
-      // ---- pass 2: probabilities -> bf16 P tile (K-major, 128B swizzle), row sum
-      float rs = 0.f;
+      // ---- pass 2: probabilities -> bf16 P tile (K-major, 128B swizzle), partial row sum
+      float rs0 = 0.f, rs1 = 0.f;
 #pragma unroll 1
-      for (int c = 0; c < nchunks; ++c) {
+      for (int c = c_lo; c < c_hi; ++c) {
         uint32_t v[32];
         tmem_ld_32x32(t_lane + c * 32, v);
         tmem_ld_wait();
@@ -197,7 +216,8 @@ __global__ void __launch_bounds__(192, 2)
           for (int i = 0; i < 32; i += 2) {
             const float p0 = ex2_approx(__uint_as_float(v[i]) * a.scale_log2 - m_use);
             const float p1 = ex2_approx(__uint_as_float(v[i + 1]) * a.scale_log2 - m_use);
-            rs += p0 + p1;
+            rs0 += p0;
+            rs1 += p1;
             const __nv_bfloat162 b2 = __floats2bfloat162_rn(p0, p1);
             pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&b2);
           }
@@ -208,44 +228,49 @@ __global__ void __launch_bounds__(192, 2)
             float p1 = ex2_approx(__uint_as_float(v[i + 1]) * a.scale_log2 - m_use);
             if (c * 32 + i >= nvalid) p0 = 0.f;
             if (c * 32 + i + 1 >= nvalid) p1 = 0.f;
-            rs += p0 + p1;
+            rs0 += p0;
+            rs1 += p1;
             const __nv_bfloat162 b2 = __floats2bfloat162_rn(p0, p1);
             pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&b2);
           }
         }
-        // columns [c*32, c*32+32) = k-block (c>>1), 16-byte chunks (c&1)*4 .. +3 of the 128-B row
-        uint8_t* blk = p_row + (c >> 1) * TILE_BYTES;
+        // columns [c*32, c*32+32): 16-byte chunks (c&1)*4 .. +3 of my k-block's 128-B row
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
           const int chunk = ((c & 1) * 4 + ch) ^ sw;
-          *reinterpret_cast<uint4*>(blk + chunk * 16) =
+          *reinterpret_cast<uint4*>(p_row + chunk * 16) =
               make_uint4(pk[ch * 4], pk[ch * 4 + 1], pk[ch * 4 + 2], pk[ch * 4 + 3]);
         }
       }
+      // a chunk that exists in the tile but belongs to nobody's valid range must still be zero:
+      // the PV MMA reads whole 16-key steps up to ceil(nseg / 16)
       fence_proxy_async();
       tc_fence_before();
       mbar_arrive(p_full);
       const float alpha = ex2_approx(m - m_use);  // m == -inf -> 0
-      l = l * alpha + rs;
+      l = l * alpha + (rs0 + rs1);
       m = m_new;
-      // ---- fold O' = P V into the accumulator
+      // ---- fold my 32 columns of O' = P V into the accumulator
       mbar_wait(o_full, ph);
       tc_fence_after();
-#pragma unroll
-      for (int c = 0; c < HD / 32; ++c) {
+      {
         uint32_t v[32];
-        tmem_ld_32x32(t_lane + 128 + c * 32, v);
+        tmem_ld_32x32(t_lane + 128 + half * 32, v);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) o[c * 32 + i] = o[c * 32 + i] * alpha + __uint_as_float(v[i]);
+        for (int i = 0; i < 32; ++i) o[i] = o[i] * alpha + __uint_as_float(v[i]);
       }
       tc_fence_before();
     }
+    // total row sum = my half + the other half's
+    s_mx[half * 128 + r] = l;
+    asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+    l += s_mx[(half ^ 1) * 128 + r];
     if (row_valid) {
       const float inv = l > 0.f ? 1.0f / l : 0.f;
-      __nv_bfloat16* dst = a.O + static_cast<long long>(grow) * a.ldo + head * HD;
+      __nv_bfloat16* dst = a.O + static_cast<long long>(grow) * a.ldo + head * HD + half * 32;
 #pragma unroll
-      for (int ch = 0; ch < HD / 8; ++ch) {
+      for (int ch = 0; ch < 4; ++ch) {
         uint32_t w[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -432,7 +457,7 @@ extern "C" int vs_attention(const vs_attention_params* p, vs_stream_t stream_) {
   const int main_rows = p->max_q_len - a.tail;
   if (main_rows > 0) {
     dim3 grid(ceil_div(main_rows, QT), p->heads, p->items);
-    attention_kernel<<<grid, 192, SMEM_BYTES, to_stream(stream_)>>>(tmQ, tmK, tmV, a);
+    attention_kernel<<<grid, ATT_THREADS, SMEM_BYTES, to_stream(stream_)>>>(tmQ, tmK, tmV, a);
     VS_LAUNCH_CHECK();
   }
   if (a.tail > 0) {
