@@ -1,9 +1,9 @@
 // Flash-style attention for head_dim 64 on tcgen05 (sm_100a).
 //
-// One CTA = one (item, head, 128-query tile).  Warp roles (192 threads):
-//   warp 0      TMA producer: Q tile once, then one K tile and one V tile (128 rows x 64) per step
+// One CTA = one (item, head, 128-query tile).  Warp roles (320 threads):
+//   warp 0      TMA producer: Q tile once, then K and V tiles (64 keys x 64) through 3-deep rings
 //   warp 1      TMEM allocator + single-thread tcgen05.mma issuer:
-//                 S[128x128] = Q K^T   (both operands K-major, 128B-swizzled, straight from TMA)
+//                 S[128x64] = Q K^T    (both operands K-major, 128B-swizzled, straight from TMA)
 //                 O'[128x64] = P V     (P written by the softmax warps as a K-major swizzled tile,
 //                                       V consumed as an MN-major operand: no transpose anywhere)
 //   warps 2..9  softmax: two threads share query row r (TMEM lane r), each owning half of the key
@@ -27,12 +27,16 @@ namespace vs {
 namespace {
 
 constexpr int QT = 128;   // queries per CTA
-constexpr int KT = 128;   // keys per step
+constexpr int KT = 64;    // keys per step
 constexpr int HD = 64;
-constexpr int TILE_BYTES = 128 * 128;  // 128 rows x 128 B
-constexpr int SMEM_BYTES = 5 * TILE_BYTES /*Q,K,V,P(2)*/ + 1024 /*align*/ + 128 /*barriers*/ + 2048 /*row max*/;
+constexpr int KV_STAGES = 3;                 // K and V tiles in flight: TMA latency (~1.5 us) is
+                                             // what paced the single-buffered version
+constexpr int TILE_BYTES = 128 * 128;        // Q / P tile: 128 rows x 128 B
+constexpr int KV_BYTES = KT * 128;           // K / V tile: 64 rows x 128 B
+constexpr int SMEM_BYTES = 3 * TILE_BYTES /*Q, P x2*/ + 2 * KV_STAGES * KV_BYTES + 1024 /*align*/ +
+                           256 /*barriers*/ + 2048 /*row max*/;
 constexpr int ATT_THREADS = 64 + 8 * 32;
-constexpr int TMEM_COLS = 256;  // S: [0,128)  O': [128,192)
+constexpr int TMEM_COLS = 256;  // S[2]: [0,128)  O'[2]: [128,256)
 
 struct AttnDev {
   __nv_bfloat16* O;
@@ -65,14 +69,16 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
   uint8_t* smem = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* sQ = smem;
-  uint8_t* sK = smem + TILE_BYTES;
-  uint8_t* sV = smem + 2 * TILE_BYTES;
-  uint8_t* sP = smem + 3 * TILE_BYTES;  // two 64-wide k-blocks
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 5 * TILE_BYTES);
-  uint64_t *q_full = bars, *k_full = bars + 1, *k_empty = bars + 2, *v_full = bars + 3,
-           *v_empty = bars + 4, *s_full = bars + 5, *p_full = bars + 6, *o_full = bars + 7;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
-  float* s_mx = reinterpret_cast<float*>(bars + 10);   // [2 tiles][2 halves][128 rows]
+  uint8_t* sP = smem + TILE_BYTES;                       // two P tiles (one 64-wide k-block each)
+  uint8_t* sK = smem + 3 * TILE_BYTES;                   // ring of KV_STAGES tiles
+  uint8_t* sV = sK + KV_STAGES * KV_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + KV_STAGES * KV_BYTES);
+  uint64_t *q_full = bars, *s_full = bars + 1 /*[2]*/, *p_full = bars + 3 /*[2]*/,
+           *o_full = bars + 5 /*[2]*/;
+  uint64_t *k_full = bars + 8, *k_empty = k_full + KV_STAGES, *v_full = k_empty + KV_STAGES,
+           *v_empty = v_full + KV_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(v_empty + KV_STAGES);
+  float* s_mx = reinterpret_cast<float*>(bars + 32);   // [2 tiles][2 halves][128 rows]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
@@ -80,13 +86,17 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
     mbar_init(q_full, 1);
-    mbar_init(k_full, 1);
-    mbar_init(k_empty, 1);
-    mbar_init(v_full, 1);
-    mbar_init(v_empty, 1);
-    mbar_init(s_full, 1);
-    mbar_init(p_full, 256);
-    mbar_init(o_full, 1);
+    for (int i = 0; i < KV_STAGES; ++i) {
+      mbar_init(k_full + i, 1);
+      mbar_init(k_empty + i, 1);
+      mbar_init(v_full + i, 1);
+      mbar_init(v_empty + i, 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(s_full + i, 1);
+      mbar_init(p_full + i, 256);
+      mbar_init(o_full + i, 1);
+    }
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -97,59 +107,79 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // TMEM columns: S[b] at b*64, O'[b] at 128 + b*64 (b = tile parity)
 
   if (warp == 0) {
     if (lane == 0) {
       mbar_expect_tx(q_full, TILE_BYTES);
       tma_load_2d(sQ, &tmQ, q_full, head * HD, q_row0);
-      for (int j = 0; j < nt; ++j) {
+      for (int j = 0, st = 0, ph = 0; j < nt; ++j) {
         const int row = j < n0 ? s0 + j * KT : s1 + (j - n0) * KT;
-        const uint32_t ph = j & 1;
-        mbar_wait(k_empty, ph ^ 1);
-        mbar_expect_tx(k_full, TILE_BYTES);
-        tma_load_2d(sK, &tmK, k_full, head * HD, row);
-        mbar_wait(v_empty, ph ^ 1);
-        mbar_expect_tx(v_full, TILE_BYTES);
-        tma_load_2d(sV, &tmV, v_full, head * HD, row);
+        mbar_wait(k_empty + st, ph ^ 1);
+        mbar_expect_tx(k_full + st, KV_BYTES);
+        tma_load_2d(sK + st * KV_BYTES, &tmK, k_full + st, head * HD, row);
+        mbar_wait(v_empty + st, ph ^ 1);
+        mbar_expect_tx(v_full + st, KV_BYTES);
+        tma_load_2d(sV + st * KV_BYTES, &tmV, v_full + st, head * HD, row);
+        if (++st == KV_STAGES) { st = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
+    // Software pipeline: S(j+1) = Q K(j+1)^T is issued BEFORE waiting for the probabilities of tile
+    // j, so the tensor core works on the next scores while the softmax warps are busy; S, P and O'
+    // are double buffered by tile parity.  Buffer reuse is ordered by the p_full waits below:
+    // every softmax thread arrives on p_full[j&1] only after it has read S(j), and (deferred
+    // accumulation) after it has read O'(j-2) and seen o_full of MMA2(j-2), which also frees P(j-2).
     if (lane == 0) {
       constexpr uint32_t idesc_s = umma_idesc_bf16(QT, KT, 0);
       constexpr uint32_t idesc_o = umma_idesc_bf16(QT, HD, 1);
       const uint32_t q_addr = smem_u32(sQ), k_addr = smem_u32(sK), v_addr = smem_u32(sV),
                      p_addr = smem_u32(sP);
-      mbar_wait(q_full, 0);
-      for (int j = 0; j < nt; ++j) {
-        const uint32_t ph = j & 1;
-        mbar_wait(k_full, ph);
-        tc_fence_after();
+      auto issue_s = [&](int j, int st) {
 #pragma unroll
         for (int k = 0; k < HD / 16; ++k)
-          umma_bf16_ss(tmem_base, umma_desc_k_sw128(q_addr + k * 32),
-                       umma_desc_k_sw128(k_addr + k * 32), idesc_s, k != 0 ? 1u : 0u);
-        umma_commit(k_empty);
-        umma_commit(s_full);
-        mbar_wait(v_full, ph);
-        mbar_wait(p_full, ph);
+          umma_bf16_ss(tmem_base + (j & 1) * KT, umma_desc_k_sw128(q_addr + k * 32),
+                       umma_desc_k_sw128(k_addr + st * KV_BYTES + k * 32), idesc_s, k != 0 ? 1u : 0u);
+        umma_commit(k_empty + st);
+        umma_commit(s_full + (j & 1));
+      };
+      mbar_wait(q_full, 0);
+      int st_k = 0, ph_k = 0;   // ring position of the next K tile to consume
+      if (nt > 0) {
+        mbar_wait(k_full + st_k, ph_k);
+        tc_fence_after();
+        issue_s(0, st_k);
+        if (++st_k == KV_STAGES) { st_k = 0; ph_k ^= 1; }
+      }
+      for (int j = 0, st_v = 0, ph_v = 0; j < nt; ++j) {
+        if (j + 1 < nt) {
+          mbar_wait(k_full + st_k, ph_k);
+          tc_fence_after();
+          issue_s(j + 1, st_k);
+          if (++st_k == KV_STAGES) { st_k = 0; ph_k ^= 1; }
+        }
+        mbar_wait(v_full + st_v, ph_v);
+        mbar_wait(p_full + (j & 1), (j >> 1) & 1);
         tc_fence_after();
         const int seg_left = j < n0 ? l0 - j * KT : l1 - (j - n0) * KT;
         const int ksteps = (min(seg_left, KT) + 15) >> 4;   // keys beyond the segment: P is not even written
 #pragma unroll 1
         for (int k = 0; k < ksteps; ++k)
-          umma_bf16_ss(tmem_base + 128,
-                       umma_desc_k_sw128(p_addr + (k >> 2) * TILE_BYTES + (k & 3) * 32),
-                       umma_desc_mn_sw128(v_addr + k * 2048), idesc_o, k != 0 ? 1u : 0u);
-        umma_commit(v_empty);
-        umma_commit(o_full);
+          umma_bf16_ss(tmem_base + 2 * KT + (j & 1) * HD,
+                       umma_desc_k_sw128(p_addr + (j & 1) * TILE_BYTES + k * 32),
+                       umma_desc_mn_sw128(v_addr + st_v * KV_BYTES + k * 2048), idesc_o,
+                       k != 0 ? 1u : 0u);
+        umma_commit(v_empty + st_v);
+        umma_commit(o_full + (j & 1));
+        if (++st_v == KV_STAGES) { st_v = 0; ph_v ^= 1; }
       }
     }
   } else {
     // 8 softmax warps: warps (w, w+4) share TMEM lane quarter q = w & 3, i.e. the same 32 query
-    // rows; `half` owns key columns [64 half, 64 half + 64) of every S tile (= k-block `half` of
-    // the P tile) and output columns [32 half, 32 half + 32).  Per thread that is half the
-    // dependent chain of a full row, and 16 instead of 8 warps per SM hide the TMEM / MUFU /
-    // mbarrier latencies.  The two halves agree on the row maximum through shared memory.
+    // rows; `half` owns key columns [32 half, 32 half + 32) of every 64-key S tile and output
+    // columns [32 half, 32 half + 32).  The two halves agree on the row maximum through shared
+    // memory.  The accumulation of O'(j) is deferred until after the probabilities of tile j+1 have
+    // been handed to the tensor core, so it never sits between two MMAs.
     const int q = warp & 3;  // TMEM lane quarter of this warp
     const int half = (warp - 2) >> 2;
     const int r = q * 32 + lane;
@@ -159,31 +189,39 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
     if (a.causal_block > 0 && (grow % a.causal_block) == 0)
       lim = (grow / a.causal_block + 1) * a.causal_block;
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    float m = -INFINITY, l = 0.f;
+    float m = -INFINITY, l = 0.f, alpha_prev = 0.f;
     float o[HD / 2];
 #pragma unroll
     for (int i = 0; i < HD / 2; ++i) o[i] = 0.f;
-    uint8_t* p_row = sP + half * TILE_BYTES + r * 128;
     const int sw = r & 7;
 
+    auto fold = [&](int j) {   // o = o * alpha(j) + O'(j)[my 32 columns]
+      mbar_wait(o_full + (j & 1), (j >> 1) & 1);
+      tc_fence_after();
+      uint32_t v[32];
+      tmem_ld_32x32(t_lane + 2 * KT + (j & 1) * HD + half * 32, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) o[i] = o[i] * alpha_prev + __uint_as_float(v[i]);
+      tc_fence_before();
+    };
+
     for (int j = 0; j < nt; ++j) {
-      const uint32_t ph = j & 1;
       const int row0 = j < n0 ? s0 + j * KT : s1 + (j - n0) * KT;
       const int seg_left = j < n0 ? l0 - j * KT : l1 - (j - n0) * KT;
       const int nvalid = min(min(seg_left, KT), lim - row0);  // keys [0, nvalid) of this tile count
       const int nseg = min(seg_left, KT);
-      const int nchunks = (nseg + 31) >> 5;   // CTA-uniform; P is written up to 32 * nchunks
-      const int c_lo = half * 2, c_hi = min(c_lo + 2, nchunks);   // my chunks of 32 columns
-      mbar_wait(s_full, ph);
+      const bool mine = half * 32 < nseg;      // my 32-column chunk exists in this tile
+      const int my_valid = nvalid - half * 32;  // valid columns of my chunk (may be <= 0 or >= 32)
+      mbar_wait(s_full + (j & 1), (j >> 1) & 1);
       tc_fence_after();
-      // ---- pass 1: maximum over my columns (4 independent chains), exchanged with the other half
-      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-#pragma unroll 1
-      for (int c = c_lo; c < c_hi; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(t_lane + c * 32, v);
+      uint32_t v[32];
+      float mx = -INFINITY;
+      if (mine) {   // warp-uniform
+        tmem_ld_32x32(t_lane + (j & 1) * KT + half * 32, v);
         tmem_ld_wait();
-        if (nvalid >= (c + 1) * 32) {
+        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+        if (my_valid >= 32) {
 #pragma unroll
           for (int i = 0; i < 32; i += 4) {
             mx0 = fmaxf(mx0, __uint_as_float(v[i]));
@@ -194,24 +232,19 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
         } else {
 #pragma unroll
           for (int i = 0; i < 32; ++i)
-            if (c * 32 + i < nvalid) mx0 = fmaxf(mx0, __uint_as_float(v[i]));
+            if (i < my_valid) mx0 = fmaxf(mx0, __uint_as_float(v[i]));
         }
+        mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
       }
-      float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
       s_mx[(j & 1) * 256 + half * 128 + r] = mx;
       asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");   // the two warps of this quarter
       mx = fmaxf(mx, s_mx[(j & 1) * 256 + (half ^ 1) * 128 + r]);
       const float m_new = fmaxf(m, mx * a.scale_log2);
       const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
-      // ---- pass 2: probabilities -> bf16 P tile (K-major, 128B swizzle), partial row sum
       float rs0 = 0.f, rs1 = 0.f;
-#pragma unroll 1
-      for (int c = c_lo; c < c_hi; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(t_lane + c * 32, v);
-        tmem_ld_wait();
+      if (mine) {
         uint32_t pk[16];
-        if (nvalid >= (c + 1) * 32) {
+        if (my_valid >= 32) {
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
             const float p0 = ex2_approx(__uint_as_float(v[i]) * a.scale_log2 - m_use);
@@ -226,42 +259,33 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
           for (int i = 0; i < 32; i += 2) {
             float p0 = ex2_approx(__uint_as_float(v[i]) * a.scale_log2 - m_use);
             float p1 = ex2_approx(__uint_as_float(v[i + 1]) * a.scale_log2 - m_use);
-            if (c * 32 + i >= nvalid) p0 = 0.f;
-            if (c * 32 + i + 1 >= nvalid) p1 = 0.f;
+            if (i >= my_valid) p0 = 0.f;
+            if (i + 1 >= my_valid) p1 = 0.f;
             rs0 += p0;
             rs1 += p1;
             const __nv_bfloat162 b2 = __floats2bfloat162_rn(p0, p1);
             pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&b2);
           }
         }
-        // columns [c*32, c*32+32): 16-byte chunks (c&1)*4 .. +3 of my k-block's 128-B row
+        // my 32 columns = 16-byte chunks half*4 .. +3 of the row in P tile (j & 1)
+        uint8_t* p_row = sP + (j & 1) * TILE_BYTES + r * 128;
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
-          const int chunk = ((c & 1) * 4 + ch) ^ sw;
+          const int chunk = (half * 4 + ch) ^ sw;
           *reinterpret_cast<uint4*>(p_row + chunk * 16) =
               make_uint4(pk[ch * 4], pk[ch * 4 + 1], pk[ch * 4 + 2], pk[ch * 4 + 3]);
         }
       }
-      // a chunk that exists in the tile but belongs to nobody's valid range must still be zero:
-      // the PV MMA reads whole 16-key steps up to ceil(nseg / 16)
       fence_proxy_async();
       tc_fence_before();
-      mbar_arrive(p_full);
+      mbar_arrive(p_full + (j & 1));
       const float alpha = ex2_approx(m - m_use);  // m == -inf -> 0
       l = l * alpha + (rs0 + rs1);
       m = m_new;
-      // ---- fold my 32 columns of O' = P V into the accumulator
-      mbar_wait(o_full, ph);
-      tc_fence_after();
-      {
-        uint32_t v[32];
-        tmem_ld_32x32(t_lane + 128 + half * 32, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o[i] = o[i] * alpha + __uint_as_float(v[i]);
-      }
-      tc_fence_before();
+      if (j > 0) fold(j - 1);   // uses alpha_prev = alpha(j-1)
+      alpha_prev = alpha;
     }
+    if (nt > 0) fold(nt - 1);
     // total row sum = my half + the other half's
     s_mx[half * 128 + r] = l;
     asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
@@ -401,10 +425,10 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-int make_map(CUtensorMap* map, const void* base, int heads, int rows, long long ld) {
+int make_map(CUtensorMap* map, const void* base, int heads, int rows, long long ld, int box_rows) {
   cuuint64_t dims[2] = {static_cast<cuuint64_t>(heads) * HD, static_cast<cuuint64_t>(rows)};
   cuuint64_t str[1] = {static_cast<cuuint64_t>(ld) * 2};
-  cuuint32_t box[2] = {HD, 128};
+  cuuint32_t box[2] = {HD, static_cast<cuuint32_t>(box_rows)};
   return encode_map(map, base, 2, dims, str, box);
 }
 
@@ -428,11 +452,11 @@ extern "C" int vs_attention(const vs_attention_params* p, vs_stream_t stream_) {
   VS_REQUIRE(p->q_rows > 0 && p->kv_rows > 0, "vs_attention: q_rows / kv_rows must be positive");
   if (p->items == 0 || p->max_q_len == 0) return VS_OK;
   CUtensorMap tmQ, tmK, tmV;
-  int rc = make_map(&tmQ, p->Q, p->heads, p->q_rows, p->ldq);
+  int rc = make_map(&tmQ, p->Q, p->heads, p->q_rows, p->ldq, QT);
   if (rc) return rc;
-  rc = make_map(&tmK, p->K, p->heads, p->kv_rows, p->ldk);
+  rc = make_map(&tmK, p->K, p->heads, p->kv_rows, p->ldk, KT);
   if (rc) return rc;
-  rc = make_map(&tmV, p->V, p->heads, p->kv_rows, p->ldv);
+  rc = make_map(&tmV, p->V, p->heads, p->kv_rows, p->ldv, KT);
   if (rc) return rc;
   AttnDev a{};
   a.O = static_cast<__nv_bfloat16*>(p->O);
