@@ -18,6 +18,9 @@ launches)
 launches4)
   timeout 900 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv \
     --log-file gpurun_out/launches_b4.csv python scripts/profile_step.py 4 > gpurun_out/prof_step4.log 2>&1; tail -2 gpurun_out/prof_step4.log;;
+traffic)
+  timeout 1200 ncu --profile-from-start off --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv \
+    --log-file gpurun_out/traffic.csv python scripts/profile_step.py 1 > gpurun_out/prof_traffic.log 2>&1; tail -2 gpurun_out/prof_traffic.log;;
 gemm4)
   timeout 600 ncu --profile-from-start off --set full --clock-control none --import-source on \
     -k regex:gemm_tc05 -s 1 -c 4 -f -o gpurun_out/prof_gemm_b4 python scripts/profile_step.py 4 > gpurun_out/prof_gemm_b4.log 2>&1;;

@@ -15,6 +15,32 @@ from ._lib import (AttentionParams, GemmParams, LayerNormParams, VS_ACT_GELU, VS
 
 _DT = {torch.float32: VS_F32, torch.bfloat16: VS_BF16, torch.float16: VS_F16}
 
+# Optional per-kernel-family timing (bench.py's roofline leg): when TIMERS is a dict, every wrapper
+# brackets its launch with CUDA events on the launching stream; `family_ms()` sums them afterwards.
+TIMERS = None
+
+
+class _timed:
+    def __init__(self, family):
+        self.family = family
+
+    def __enter__(self):
+        if TIMERS is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if TIMERS is not None:
+            self.e1.record()
+            TIMERS.setdefault(self.family, []).append((self.e0, self.e1))
+
+
+def family_ms(timers) -> dict:
+    torch.cuda.synchronize()
+    return {k: sum(a.elapsed_time(b) for a, b in v) for k, v in timers.items()}
+
 
 def _need_cuda(*ts):
     for t in ts:
@@ -46,7 +72,8 @@ def gemm(A, W, *, N=None, K=None, a_rows=None, a_groups=1, a_row_stride=None, a_
     if out2 is not None:
         p.C2, p.ldc2 = ptr(out2), (ldc2 if ldc2 is not None else out2.stride(-2))
     p.out_gin, p.out_gout, p.out_off, p.block_n = out_gin, out_gout, out_off, block_n
-    check(lib.vs_gemm(C.byref(p), C.c_void_p(stream_ptr())), "vs_gemm")
+    with _timed("gemm"):
+        check(lib.vs_gemm(C.byref(p), C.c_void_p(stream_ptr())), "vs_gemm")
     return out
 
 
@@ -75,7 +102,8 @@ def conv_gemm(x_nhwc, Wp, *, kh, kw, pad, N, bias=None, act=VS_ACT_NONE, res1=No
     if out2 is not None:
         p.C2, p.ldc2 = ptr(out2), out2.stride(-2)
     p.block_n = block_n
-    check(lib.vs_gemm(C.byref(p), C.c_void_p(stream_ptr())), "vs_gemm(conv)")
+    with _timed("gemm"):
+        check(lib.vs_gemm(C.byref(p), C.c_void_p(stream_ptr())), "vs_gemm(conv)")
     return out
 
 
@@ -112,7 +140,8 @@ def layernorm(x, w=None, b=None, *, eps=1e-6, w0=None, b0=None, scale=None, shif
         p.y_bf16, p.ldy_bf16 = ptr(out_bf16), out_bf16.stride(0)
     if out_f32 is not None:
         p.y_f32, p.ldy_f32 = ptr(out_f32), out_f32.stride(0)
-    check(lib.vs_layernorm(C.byref(p), C.c_void_p(stream_ptr())), "vs_layernorm")
+    with _timed("layernorm"):
+        check(lib.vs_layernorm(C.byref(p), C.c_void_p(stream_ptr())), "vs_layernorm")
     return out_bf16, out_f32
 
 
@@ -130,7 +159,8 @@ def attention(Q, K, V, O, *, heads, q_start, q_len, kv_start0, kv_len0, kv_start
     p.kv_start0, p.kv_len0 = ptr(kv_start0), ptr(kv_len0)
     p.kv_start1, p.kv_len1 = ptr(kv_start1), ptr(kv_len1)
     p.max_q_len, p.max_kv_len, p.causal_block, p.scale = max_q_len, max_kv_len, causal_block, scale
-    check(lib.vs_attention(C.byref(p), C.c_void_p(stream_ptr())), "vs_attention")
+    with _timed("attention"):
+        check(lib.vs_attention(C.byref(p), C.c_void_p(stream_ptr())), "vs_attention")
     return O
 
 
