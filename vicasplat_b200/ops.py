@@ -21,8 +21,8 @@ TIMERS = None
 
 
 class _timed:
-    def __init__(self, family):
-        self.family = family
+    def __init__(self, family, meta=None):
+        self.family, self.meta = family, meta
 
     def __enter__(self):
         if TIMERS is not None:
@@ -34,12 +34,12 @@ class _timed:
     def __exit__(self, *exc):
         if TIMERS is not None:
             self.e1.record()
-            TIMERS.setdefault(self.family, []).append((self.e0, self.e1))
+            TIMERS.setdefault(self.family, []).append((self.e0, self.e1, self.meta))
 
 
 def family_ms(timers) -> dict:
     torch.cuda.synchronize()
-    return {k: sum(a.elapsed_time(b) for a, b in v) for k, v in timers.items()}
+    return {k: sum(e[0].elapsed_time(e[1]) for e in v) for k, v in timers.items()}
 
 
 def _need_cuda(*ts):
@@ -72,7 +72,7 @@ def gemm(A, W, *, N=None, K=None, a_rows=None, a_groups=1, a_row_stride=None, a_
     if out2 is not None:
         p.C2, p.ldc2 = ptr(out2), (ldc2 if ldc2 is not None else out2.stride(-2))
     p.out_gin, p.out_gout, p.out_off, p.block_n = out_gin, out_gout, out_off, block_n
-    with _timed("gemm"):
+    with _timed("gemm", ("lin", total, N, K, act, res1 is not None, out.dtype == torch.float32)):
         check(lib.vs_gemm(C.byref(p), C.c_void_p(stream_ptr())), "vs_gemm")
     return out
 
@@ -102,7 +102,8 @@ def conv_gemm(x_nhwc, Wp, *, kh, kw, pad, N, bias=None, act=VS_ACT_NONE, res1=No
     if out2 is not None:
         p.C2, p.ldc2 = ptr(out2), out2.stride(-2)
     p.block_n = block_n
-    with _timed("gemm"):
+    with _timed("gemm", (f"conv{kh}x{kw}", n * h * w, N, kh * kw * ((cin + 63) // 64 * 64), act,
+                         res1 is not None, out.dtype == torch.float32)):
         check(lib.vs_gemm(C.byref(p), C.c_void_p(stream_ptr())), "vs_gemm(conv)")
     return out
 
@@ -167,9 +168,10 @@ def attention(Q, K, V, O, *, heads, q_start, q_len, kv_start0, kv_len0, kv_start
 def rope_rows(qkv, pos_i32, *, heads, q_col, k_col, base=100.0, cam_theta=30.0):
     lib = _lib.load()
     _need_cuda(qkv, pos_i32)
-    check(lib.vs_rope_rows(C.c_void_p(ptr(qkv)), C.c_int64(qkv.stride(0)), qkv.shape[0], heads,
-                           q_col, k_col, C.c_void_p(ptr(pos_i32)), C.c_float(base),
-                           C.c_float(cam_theta), C.c_void_p(stream_ptr())), "vs_rope_rows")
+    with _timed("rope_rows"):
+        check(lib.vs_rope_rows(C.c_void_p(ptr(qkv)), C.c_int64(qkv.stride(0)), qkv.shape[0], heads,
+                               q_col, k_col, C.c_void_p(ptr(pos_i32)), C.c_float(base),
+                               C.c_float(cam_theta), C.c_void_p(stream_ptr())), "vs_rope_rows")
     return qkv
 
 
@@ -211,8 +213,9 @@ def upsample2x(x_nhwc):
     _need_cuda(x_nhwc)
     n, h, w, c = x_nhwc.shape
     out = torch.empty((n, 2 * h, 2 * w, c), dtype=torch.bfloat16, device=x_nhwc.device)
-    check(lib.vs_upsample2x(C.c_void_p(ptr(x_nhwc)), C.c_void_p(ptr(out)), n, h, w, c,
-                            C.c_void_p(stream_ptr())), "vs_upsample2x")
+    with _timed("upsample2x"):
+        check(lib.vs_upsample2x(C.c_void_p(ptr(x_nhwc)), C.c_void_p(ptr(out)), n, h, w, c,
+                                C.c_void_p(stream_ptr())), "vs_upsample2x")
     return out
 
 
