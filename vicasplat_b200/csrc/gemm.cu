@@ -66,6 +66,9 @@ struct GemmDev {
   long long ldc2;
   int out_gin, out_gout, out_off;
   int vec;
+  int fast;      // every present C / C2 / residual pointer allows aligned 4-column segments
+  int res_kind;  // 0 none, 1 fp32, 2 bf16, 3 bilinear-x2 bf16
+  float up_sx, up_sy;  // res_up2: source step per output pixel (align_corners=True)
 };
 
 // exact-erf GELU (nn.GELU default, croco/blocks.py:60) with erf from Abramowitz-Stegun 7.1.26
@@ -126,49 +129,42 @@ __device__ __forceinline__ void load32_f32(const float* p, int nv, bool vec, flo
   }
 }
 
+// ---- 4-column segment helpers of the transposed epilogue (one lane = 4 consecutive columns of a row)
 // plain (coherent) loads: the residual stream may be updated in place by this very kernel
-__device__ __forceinline__ void add32_res(const void* base, int dtype, long long off, int nv,
-                                          bool vec, float (&f)[32]) {
+__device__ __forceinline__ void add4_res(const void* base, int dtype, long long off, int nv, bool vec,
+                                         float4& f) {
   if (dtype == VS_F32) {
     const float* p = static_cast<const float*>(base) + off;
-    if (vec && nv == 32) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float4 t = *(reinterpret_cast<const float4*>(p) + i);
-        f[4 * i] += t.x; f[4 * i + 1] += t.y; f[4 * i + 2] += t.z; f[4 * i + 3] += t.w;
-      }
+    if (vec && nv == 4) {
+      const float4 t = *reinterpret_cast<const float4*>(p);
+      f.x += t.x; f.y += t.y; f.z += t.z; f.w += t.w;
     } else {
-#pragma unroll
-      for (int i = 0; i < 32; ++i)
-        if (i < nv) f[i] += p[i];
+      if (nv > 0) f.x += p[0];
+      if (nv > 1) f.y += p[1];
+      if (nv > 2) f.z += p[2];
+      if (nv > 3) f.w += p[3];
     }
   } else {
     const __nv_bfloat16* p = static_cast<const __nv_bfloat16*>(base) + off;
-    if (vec && nv == 32) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const uint4 t = *(reinterpret_cast<const uint4*>(p) + i);
-        const uint32_t w[4] = {t.x, t.y, t.z, t.w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[j]));
-          f[8 * i + 2 * j] += v.x;
-          f[8 * i + 2 * j + 1] += v.y;
-        }
-      }
+    if (vec && nv == 4) {
+      const uint2 t = *reinterpret_cast<const uint2*>(p);
+      const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.x));
+      const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.y));
+      f.x += a.x; f.y += a.y; f.z += b.x; f.w += b.y;
     } else {
-#pragma unroll
-      for (int i = 0; i < 32; ++i)
-        if (i < nv) f[i] += __bfloat162float(p[i]);
+      if (nv > 0) f.x += __bfloat162float(p[0]);
+      if (nv > 1) f.y += __bfloat162float(p[1]);
+      if (nv > 2) f.z += __bfloat162float(p[2]);
+      if (nv > 3) f.w += __bfloat162float(p[3]);
     }
   }
 }
 
 // += bilinear x2 (align_corners=True) sample of a half-resolution NHWC bf16 map at output pixel
-// (x, y) of image im, channels [nb, nb+32)
-__device__ __forceinline__ void add32_res_up2(const __nv_bfloat16* base, long long ld, int im, int x,
-                                              int y, int ch, int cw, int nb, int nv, bool vec,
-                                              float (&f)[32]) {
+// (x, y) of image im, channels [col, col+4)
+__device__ __forceinline__ void add4_res_up2(const __nv_bfloat16* base, long long ld, int im, int x,
+                                             int y, int ch, int cw, int col, int nv, bool vec,
+                                             float4& f) {
   const int h = ch >> 1, w = cw >> 1;
   const float sy = ch > 1 ? static_cast<float>(h - 1) / (ch - 1) : 0.f;
   const float sx = cw > 1 ? static_cast<float>(w - 1) / (cw - 1) : 0.f;
@@ -178,55 +174,162 @@ __device__ __forceinline__ void add32_res_up2(const __nv_bfloat16* base, long lo
   const float ly = fy - y0, lx = fx - x0;
   const float wt[4] = {(1 - ly) * (1 - lx), (1 - ly) * lx, ly * (1 - lx), ly * lx};
   const int ys[4] = {y0, y0, y1, y1}, xs[4] = {x0, x1, x0, x1};
-  float acc[32];
-#pragma unroll
-  for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
   for (int t = 0; t < 4; ++t) {
-    float tmp[32];
-#pragma unroll
-    for (int i = 0; i < 32; ++i) tmp[i] = 0.f;
-    add32_res(base, VS_BF16, ((static_cast<long long>(im) * h + ys[t]) * w + xs[t]) * ld + nb, nv, vec,
-              tmp);
-#pragma unroll
-    for (int i = 0; i < 32; ++i) acc[i] = fmaf(wt[t], tmp[i], acc[i]);
+    float4 tmp = make_float4(0.f, 0.f, 0.f, 0.f);
+    add4_res(base, VS_BF16, ((static_cast<long long>(im) * h + ys[t]) * w + xs[t]) * ld + col, nv, vec,
+             tmp);
+    acc.x = fmaf(wt[t], tmp.x, acc.x); acc.y = fmaf(wt[t], tmp.y, acc.y);
+    acc.z = fmaf(wt[t], tmp.z, acc.z); acc.w = fmaf(wt[t], tmp.w, acc.w);
   }
   // the stand-alone kernel rounds the upsampled map to bf16 before it is consumed: do the same
-#pragma unroll
-  for (int i = 0; i < 32; ++i) f[i] += __bfloat162float(__float2bfloat16(acc[i]));
+  f.x += __bfloat162float(__float2bfloat16(acc.x)); f.y += __bfloat162float(__float2bfloat16(acc.y));
+  f.z += __bfloat162float(__float2bfloat16(acc.z)); f.w += __bfloat162float(__float2bfloat16(acc.w));
 }
 
-__device__ __forceinline__ void store32_bf16(__nv_bfloat16* p, int nv, bool vec, const float (&f)[32],
-                                             bool relu) {
-  if (vec && nv == 32) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      uint32_t w[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float a = f[8 * i + 2 * j], b = f[8 * i + 2 * j + 1];
-        if (relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
-        const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-        w[j] = *reinterpret_cast<const uint32_t*>(&h);
-      }
-      *(reinterpret_cast<uint4*>(p) + i) = make_uint4(w[0], w[1], w[2], w[3]);
-    }
+__device__ __forceinline__ void store4_bf16(__nv_bfloat16* p, int nv, bool vec, float4 f, bool relu) {
+  if (relu) { f.x = fmaxf(f.x, 0.f); f.y = fmaxf(f.y, 0.f); f.z = fmaxf(f.z, 0.f); f.w = fmaxf(f.w, 0.f); }
+  if (vec && nv == 4) {
+    const __nv_bfloat162 a = __floats2bfloat162_rn(f.x, f.y), b = __floats2bfloat162_rn(f.z, f.w);
+    *reinterpret_cast<uint2*>(p) = make_uint2(*reinterpret_cast<const uint32_t*>(&a),
+                                              *reinterpret_cast<const uint32_t*>(&b));
   } else {
-#pragma unroll
-    for (int i = 0; i < 32; ++i)
-      if (i < nv) p[i] = __float2bfloat16(relu ? fmaxf(f[i], 0.f) : f[i]);
+    if (nv > 0) p[0] = __float2bfloat16(f.x);
+    if (nv > 1) p[1] = __float2bfloat16(f.y);
+    if (nv > 2) p[2] = __float2bfloat16(f.z);
+    if (nv > 3) p[3] = __float2bfloat16(f.w);
   }
 }
 
-__device__ __forceinline__ void store32_f32(float* p, int nv, bool vec, const float (&f)[32]) {
-  if (vec && nv == 32) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-      *(reinterpret_cast<float4*>(p) + i) = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+__device__ __forceinline__ void store4_f32(float* p, int nv, bool vec, const float4 f) {
+  if (vec && nv == 4) {
+    *reinterpret_cast<float4*>(p) = f;
   } else {
+    if (nv > 0) p[0] = f.x;
+    if (nv > 1) p[1] = f.y;
+    if (nv > 2) p[2] = f.z;
+    if (nv > 3) p[3] = f.w;
+  }
+}
+
+__device__ __forceinline__ void add_bf16x4(float4& f, const uint2 t) {
+  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.x));
+  const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.y));
+  f.x += a.x; f.y += a.y; f.z += b.x; f.w += b.y;
+}
+__device__ __forceinline__ void fma_bf16x4(float4& f, const float w, const uint2 t) {
+  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.x));
+  const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.y));
+  f.x = fmaf(w, a.x, f.x); f.y = fmaf(w, a.y, f.y); f.z = fmaf(w, b.x, f.z); f.w = fmaf(w, b.y, f.w);
+}
+
+struct Up2Taps { int x0, x1, y0, y1; float lx, ly; };
+// bilinear x2, align_corners=True: source taps / weights of output pixel (x, y) of a ch x cw map
+__device__ __forceinline__ Up2Taps up2_taps(int x, int y, int ch, int cw, float sx, float sy) {
+  const int h = ch >> 1, w = cw >> 1;
+  const float fy = y * sy, fx = x * sx;
+  Up2Taps t;
+  t.y0 = static_cast<int>(fy); t.x0 = static_cast<int>(fx);
+  t.y1 = min(t.y0 + 1, h - 1); t.x1 = min(t.x0 + 1, w - 1);
+  t.ly = fy - t.y0; t.lx = fx - t.x0;
+  return t;
+}
+
+// all 8 residual segments of one chunk in flight at once (fast path: aligned, full chunk).
+// kind 1: 4 fp32; kind 2: 4 bf16 of res1 in .xy and of res2 (or zeros) in .zw.  Plain (coherent)
+// loads: the residual stream may be updated in place by this very kernel.
+__device__ __forceinline__ void load_res_seg(const GemmDev& g, int rk, const int (&oj)[8], int col,
+                                             uint4 (&r)[8]) {
+  // unconditional loads (rows without output read row 0 and are never stored): a predicated
+  // load would become a branch whose join waits for the data, serialising the 8 requests
+  if (rk == 1) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i)
-      if (i < nv) p[i] = f[i];
+    for (int j = 0; j < 8; ++j)
+      r[j] = *reinterpret_cast<const uint4*>(static_cast<const float*>(g.res1) +
+                                             static_cast<long long>(max(oj[j], 0)) * g.res_ld + col);
+  } else if (rk == 2) {
+    const __nv_bfloat16* r2 = static_cast<const __nv_bfloat16*>(g.res2 != nullptr ? g.res2 : g.res1);
+    const uint32_t keep2 = g.res2 != nullptr ? 0xffffffffu : 0u;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const long long off = static_cast<long long>(max(oj[j], 0)) * g.res_ld + col;
+      const uint2 lo = *reinterpret_cast<const uint2*>(static_cast<const __nv_bfloat16*>(g.res1) + off);
+      const uint2 hi = *reinterpret_cast<const uint2*>(r2 + off);
+      r[j] = make_uint4(lo.x, lo.y, hi.x & keep2, hi.y & keep2);
+    }
+  }
+}
+
+__device__ __forceinline__ void st_shared_f4(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ float4 ld_shared_f4(uint32_t addr) {
+  float4 t;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w) : "r"(addr) : "memory");
+  return t;
+}
+
+// Fast store phase of one 32 x 32 chunk (aligned pointers, full chunk): lane l owns columns
+// [col, col+4) of rows 4j + l/8.  RK = residual kind, CF32 = fp32 output.
+template <int RK, bool CF32>
+__device__ __forceinline__ void epi_store(const GemmDev& g, uint32_t tile_s, int lane, const int (&oj)[8],
+                                          int col, const uint4 (&rb)[8], int pix_x, int pix_y, int pix_im) {
+  const int cs = lane & 7;
+#pragma unroll
+  for (int jh = 0; jh < 8; jh += 4) {
+    uint2 up[RK == 3 ? 4 : 1][4];
+    float lxs[4], lys[4];
+    if (RK == 3) {   // 16 tap loads in flight per half
+      const __nv_bfloat16* base = static_cast<const __nv_bfloat16*>(g.res1) + col;
+      const int h2 = g.ch >> 1, w2 = g.cw >> 1;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int rr = 4 * (jh + j) + (lane >> 3);
+        const int px = __shfl_sync(0xffffffffu, pix_x, rr);
+        const int py = __shfl_sync(0xffffffffu, pix_y, rr);
+        const int pim = __shfl_sync(0xffffffffu, pix_im, rr);
+        const Up2Taps tp = up2_taps(px, py, g.ch, g.cw, g.up_sx, g.up_sy);
+        lxs[j] = tp.lx; lys[j] = tp.ly;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {   // pix_* are clamped to the map: unconditional loads
+          const int yy = (t & 2) ? tp.y1 : tp.y0, xx = (t & 1) ? tp.x1 : tp.x0;
+          up[RK == 3 ? j : 0][t] =
+              *reinterpret_cast<const uint2*>(base + static_cast<long long>((pim * h2 + yy) * w2 + xx) * g.res_ld);
+        }
+      }
+    }
+#pragma unroll
+    for (int j4 = 0; j4 < 4; ++j4) {
+      const int j = jh + j4;
+      const int rr = 4 * j + (lane >> 3);
+      float4 t = ld_shared_f4(tile_s + (rr * 8 + (cs ^ (rr & 7))) * 16);
+      if (RK == 1) {
+        t.x += __uint_as_float(rb[j].x); t.y += __uint_as_float(rb[j].y);
+        t.z += __uint_as_float(rb[j].z); t.w += __uint_as_float(rb[j].w);
+      } else if (RK == 2) {
+        add_bf16x4(t, make_uint2(rb[j].x, rb[j].y));
+        add_bf16x4(t, make_uint2(rb[j].z, rb[j].w));
+      } else if (RK == 3) {
+        const float lx = lxs[j4], ly = lys[j4];
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        fma_bf16x4(acc, (1 - ly) * (1 - lx), up[RK == 3 ? j4 : 0][0]);
+        fma_bf16x4(acc, (1 - ly) * lx, up[RK == 3 ? j4 : 0][1]);
+        fma_bf16x4(acc, ly * (1 - lx), up[RK == 3 ? j4 : 0][2]);
+        fma_bf16x4(acc, ly * lx, up[RK == 3 ? j4 : 0][3]);
+        // the stand-alone kernel rounds the upsampled map to bf16 before it is consumed
+        t.x += __bfloat162float(__float2bfloat16(acc.x)); t.y += __bfloat162float(__float2bfloat16(acc.y));
+        t.z += __bfloat162float(__float2bfloat16(acc.z)); t.w += __bfloat162float(__float2bfloat16(acc.w));
+      }
+      if (oj[j] >= 0) {
+        const long long o = oj[j];
+        if (CF32)
+          *reinterpret_cast<float4*>(static_cast<float*>(g.C) + o * g.ldc + col) = t;
+        else
+          store4_bf16(static_cast<__nv_bfloat16*>(g.C) + o * g.ldc + col, 4, true, t, false);
+        if (g.C2 != nullptr) store4_bf16(g.C2 + o * g.ldc2 + col, 4, true, t, true);
+      }
+    }
   }
 }
 
@@ -251,6 +354,8 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
   uint64_t* tmem_full = empty + STAGES;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;   // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  // per-epilogue-warp 32 x 32 fp32 transposition tile (XOR-swizzled 16-byte slots, no padding)
+  float4* epi_scratch = reinterpret_cast<float4*>(smem + STAGES * STAGE_BYTES + 256);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -368,6 +473,7 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
     const int half = ew >> 2;          // column half when 8 epilogue warps
     const int r = q * 32 + lane;       // tile row owned by this thread
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const uint32_t tile_s = smem_u32(epi_scratch + ew * 256);
     uint32_t ti = 0;
     for (int u = unit0; u < total_units; u += unit_step, ++ti) {
       const TileCoord tc = tile_coord(g, u, rank, CL, BN);
@@ -387,7 +493,7 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
           const int im = tc.img0 + r / (g.bw * g.bh);
           valid = x < g.cw && y < g.ch && im < g.cn;
           m = (static_cast<long long>(im) * g.ch + y) * g.cw + x;
-          pix_x = x; pix_y = y; pix_im = im;
+          pix_x = min(x, g.cw - 1); pix_y = min(y, g.ch - 1); pix_im = min(im, g.cn - 1);
         }
         if (valid) {
           long long o = m;
@@ -403,6 +509,19 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
           }
         }
       }
+      // After the shared-memory exchange lane l holds 4 consecutive columns (cs) of rows 4j + l/8.
+      const int cs = lane & 7;
+      int oj[8];      // output row (fits 31 bits: checked on the host), -1 = nothing to store
+#pragma unroll
+      for (int j = 0; j < 8; ++j) oj[j] = static_cast<int>(__shfl_sync(0xffffffffu, my_out, 4 * j + (lane >> 3)));
+      const int rk = g.res_kind;   // 0 none, 1 f32, 2 bf16 (one or two maps), 3 bilinear-x2 bf16
+      // residual segments are fetched ahead of their use (first chunk: before the accumulator is
+      // even ready; later chunks: before the TMEM read of that chunk)
+      uint4 rb[8];
+      {
+        const int nb0 = tc.n0 + half * CH_PER_WARP * 32;
+        if (g.fast && nb0 + 32 <= g.N) load_res_seg(g, rk, oj, nb0 + 4 * cs, rb);
+      }
       mbar_wait(&tmem_full[a], (ti >> 1) & 1);
       tc_fence_after();
 #pragma unroll 1
@@ -412,9 +531,10 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
         if (nb >= g.N) break;  // warp-uniform
         uint32_t v[32];
         tmem_ld_32x32(t_lane + a * BN + c * 32, v);
-        tmem_ld_wait();
-        if (my_out < 0) continue;
         const int nv = min(32, g.N - nb);
+        const bool fast = g.fast && nv == 32;
+        const int col = nb + 4 * cs;
+        tmem_ld_wait();
         float f[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
@@ -437,22 +557,58 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
 #pragma unroll
           for (int i = 0; i < 32; ++i) f[i] *= 1.0f + gt[i];
         }
-        if (g.res1 != nullptr && g.res_up2) {
-          add32_res_up2(static_cast<const __nv_bfloat16*>(g.res1), g.res_ld, pix_im, pix_x, pix_y,
-                        g.ch, g.cw, nb, nv, g.vec & VEC_RES, f);
-        } else if (g.res1 != nullptr) {
-          add32_res(g.res1, g.res_dtype, my_out * g.res_ld + nb, nv, g.vec & VEC_RES, f);
-          if (g.res2 != nullptr)
-            add32_res(g.res2, g.res_dtype, my_out * g.res_ld + nb, nv, g.vec & VEC_RES, f);
+        // Transpose through shared memory: a thread owns a ROW here (TMEM lane), but row-per-thread
+        // global accesses cost one LSU wavefront per lane; afterwards a warp instruction touches
+        // 4 rows x 128 B.
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          st_shared_f4(tile_s + (lane * 8 + (i ^ (lane & 7))) * 16, f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+        __syncwarp();
+        if (fast) {
+          const bool cf32 = g.c_dtype == VS_F32;
+          switch (rk) {
+            case 0: cf32 ? epi_store<0, true>(g, tile_s, lane, oj, col, rb, 0, 0, 0)
+                         : epi_store<0, false>(g, tile_s, lane, oj, col, rb, 0, 0, 0); break;
+            case 1: cf32 ? epi_store<1, true>(g, tile_s, lane, oj, col, rb, 0, 0, 0)
+                         : epi_store<1, false>(g, tile_s, lane, oj, col, rb, 0, 0, 0); break;
+            case 2: cf32 ? epi_store<2, true>(g, tile_s, lane, oj, col, rb, 0, 0, 0)
+                         : epi_store<2, false>(g, tile_s, lane, oj, col, rb, 0, 0, 0); break;
+            default: cf32 ? epi_store<3, true>(g, tile_s, lane, oj, col, rb, pix_x, pix_y, pix_im)
+                          : epi_store<3, false>(g, tile_s, lane, oj, col, rb, pix_x, pix_y, pix_im); break;
+          }
+        } else {
+          const int nvl = min(4, g.N - col);
+#pragma unroll 1
+          for (int j = 0; j < 8; ++j) {
+            const int rr = 4 * j + (lane >> 3);
+            float4 t = ld_shared_f4(tile_s + (rr * 8 + (cs ^ (rr & 7))) * 16);
+            const long long o = __shfl_sync(0xffffffffu, my_out, rr);
+            int px = 0, py = 0, pim = 0;
+            if (g.res_up2) {
+              px = __shfl_sync(0xffffffffu, pix_x, rr);
+              py = __shfl_sync(0xffffffffu, pix_y, rr);
+              pim = __shfl_sync(0xffffffffu, pix_im, rr);
+            }
+            if (o < 0 || nvl <= 0) continue;
+            if (g.res1 != nullptr && g.res_up2) {
+              add4_res_up2(static_cast<const __nv_bfloat16*>(g.res1), g.res_ld, pim, px, py, g.ch, g.cw,
+                           col, nvl, g.vec & VEC_RES, t);
+            } else if (g.res1 != nullptr) {
+              add4_res(g.res1, g.res_dtype, o * g.res_ld + col, nvl, g.vec & VEC_RES, t);
+              if (g.res2 != nullptr)
+                add4_res(g.res2, g.res_dtype, o * g.res_ld + col, nvl, g.vec & VEC_RES, t);
+            }
+            if (g.C != nullptr) {
+              if (g.c_dtype == VS_F32)
+                store4_f32(static_cast<float*>(g.C) + o * g.ldc + col, nvl, g.vec & VEC_C, t);
+              else
+                store4_bf16(static_cast<__nv_bfloat16*>(g.C) + o * g.ldc + col, nvl, g.vec & VEC_C, t, false);
+            }
+            if (g.C2 != nullptr) store4_bf16(g.C2 + o * g.ldc2 + col, nvl, g.vec & VEC_C2, t, true);
+          }
         }
-        if (g.C != nullptr) {
-          if (g.c_dtype == VS_F32)
-            store32_f32(static_cast<float*>(g.C) + my_out * g.ldc + nb, nv, g.vec & VEC_C, f);
-          else
-            store32_bf16(static_cast<__nv_bfloat16*>(g.C) + my_out * g.ldc + nb, nv, g.vec & VEC_C, f,
-                         false);
-        }
-        if (g.C2 != nullptr) store32_bf16(g.C2 + my_out * g.ldc2 + nb, nv, g.vec & VEC_C2, f, true);
+        __syncwarp();   // the tile is rewritten by the next chunk
+        if (cc + 1 < CH_PER_WARP && g.fast && nb + 64 <= g.N) load_res_seg(g, rk, oj, col + 32, rb);
       }
       tc_fence_before();
       __syncwarp();
@@ -484,7 +640,8 @@ int num_sms() {
 
 template <int BN, int STAGES, int EPI_WARPS, int CL>
 int launch(const CUtensorMap& tmA, const CUtensorMap& tmW, const GemmDev& g, cudaStream_t stream) {
-  constexpr int SMEM = STAGES * (BM * 128 + (BN / CL) * 128) + 1024 /*align*/ + 256 /*barriers*/;
+  constexpr int SMEM = STAGES * (BM * 128 + (BN / CL) * 128) + 1024 /*align*/ + 256 /*barriers*/ +
+                       EPI_WARPS * 4096 /*epilogue transposition tiles*/;
   static_assert(SMEM <= 227 * 1024, "shared memory budget");
   auto kernel = gemm_tc05_kernel<BN, STAGES, EPI_WARPS, CL>;
   static bool configured = false;  // attribute is per-function, set once per process
@@ -576,6 +733,12 @@ extern "C" int vs_gemm(const vs_gemm_params* p, vs_stream_t stream_) {
     g.vec |= VEC_RES;
   if (p->C && al16(p->C) && p->ldc % (p->c_dtype == VS_F32 ? 4 : 8) == 0) g.vec |= VEC_C;
   if (p->C2 && al16(p->C2) && p->ldc2 % 8 == 0) g.vec |= VEC_C2;
+  if (p->res_up2) {
+    g.up_sy = p->ch > 1 ? static_cast<float>(p->ch / 2 - 1) / static_cast<float>(p->ch - 1) : 0.f;
+    g.up_sx = p->cw > 1 ? static_cast<float>(p->cw / 2 - 1) / static_cast<float>(p->cw - 1) : 0.f;
+  }
+  g.res_kind = !p->res1 ? 0 : p->res_up2 ? 3 : p->res_dtype == VS_F32 ? 1 : 2;
+  g.fast = p->C && (g.vec & VEC_C) && (!p->C2 || (g.vec & VEC_C2)) && (!p->res1 || (g.vec & VEC_RES));
 
   CUtensorMap tmA, tmW;
   int m_tiles = 0;
@@ -642,6 +805,8 @@ extern "C" int vs_gemm(const vs_gemm_params* p, vs_stream_t stream_) {
   }
   g.num_kb = static_cast<int>((ktot + BK - 1) / BK);
   g.m_tiles = m_tiles;
+  VS_REQUIRE(static_cast<long long>(m_tiles) * BM * (p->out_gin > 0 ? 2 : 1) < (1ll << 30),
+             "vs_gemm: more than 2^30 output rows");
 
   int bn = p->block_n;
   if (bn == 0) {
