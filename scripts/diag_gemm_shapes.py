@@ -34,7 +34,10 @@ tot = 0.0
 for (fam, meta), (n, ms) in acc.items():
     ms /= REP; n //= REP
     tf = None
-    if meta is not None:
+    if meta is not None and meta[0] == "attn":
+        _, items, heads, ql, kl, cb = meta
+        tf = 4.0 * items * heads * ql * kl * 64 * n / (ms * 1e-3) / 1e12
+    elif meta is not None:
         kind, M, N, Kd = meta[:4]
         tf = 2.0 * M * N * Kd * n / (ms * 1e-3) / 1e12
     rows.append((ms, fam, meta, n, tf))

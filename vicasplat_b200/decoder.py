@@ -38,17 +38,23 @@ class DecoderSplattingCUDACfg:
     use_gsplat: bool = False
 
 
+def _inv(m: Tensor) -> Tensor:
+    """Batched inverse without the host synchronisation of torch.linalg.inv's error check."""
+    return torch.linalg.inv_ex(m, check_errors=False)[0]
+
+
 def get_fov(intrinsics: Tensor) -> Tensor:
     """(B,3,3) normalised intrinsics -> (B,2) full field of view (x, y) in radians: the angle
     between the rays through the mid-points of opposite image borders."""
-    inv = torch.linalg.inv(intrinsics)
+    inv = _inv(intrinsics)
+    # rays through (0, .5), (1, .5), (.5, 0), (.5, 1): columns of inv combined, no host tensors
+    c0, c1, c2 = inv[..., 0], inv[..., 1], inv[..., 2]
 
-    def unit_ray(u, v):
-        d = inv @ torch.tensor([u, v, 1.0], dtype=intrinsics.dtype, device=intrinsics.device)
+    def unit(d):
         return d / d.norm(dim=-1, keepdim=True)
 
-    cx = (unit_ray(0.0, 0.5) * unit_ray(1.0, 0.5)).sum(-1)
-    cy = (unit_ray(0.5, 0.0) * unit_ray(0.5, 1.0)).sum(-1)
+    cx = (unit(0.5 * c1 + c2) * unit(c0 + 0.5 * c1 + c2)).sum(-1)
+    cy = (unit(0.5 * c0 + c2) * unit(0.5 * c0 + c1 + c2)).sum(-1)
     return torch.stack((cx.acos(), cy.acos()), dim=-1)
 
 
@@ -67,7 +73,7 @@ def _cameras(extrinsics, intrinsics, near, far):
     fov = get_fov(intrinsics)
     tanfov = (0.5 * fov).tan()
     proj_t = get_projection_matrix(near, far, fov[:, 0], fov[:, 1]).transpose(1, 2)
-    view_t = torch.linalg.inv(extrinsics).transpose(1, 2)
+    view_t = _inv(extrinsics).transpose(1, 2)
     return tanfov, view_t, view_t @ proj_t, extrinsics[:, :3, 3]
 
 
@@ -113,7 +119,9 @@ class DecoderSplattingCUDA(nn.Module):
     def forward(self, gaussians, extrinsics, intrinsics, near, far, image_shape,
                 depth_mode: DepthRenderingMode | None = None, cam_rot_delta=None,
                 cam_trans_delta=None, use_sh: bool = True, active_sh_degree: Optional[int] = None,
-                return_dict: bool = True):
+                return_dict: bool = True, check_overflow=True):
+        """``check_overflow``: see ``rasterize_views`` ("deferred" keeps this call free of host
+        synchronisation; ScenePipeline verifies the queued counters with the batch's results)."""
         if self.cfg.use_gsplat:
             raise NotImplementedError("use_gsplat=True: gsplat is not part of this hot path "
                                       "(every shipped experiment sets use_gsplat: false)")
@@ -123,17 +131,29 @@ class DecoderSplattingCUDA(nn.Module):
         if means.ndim > 3:  # (b, t, h, w, ...) -> (b, G, ...)
             means, cov, sh = means.flatten(1, 3), cov.flatten(1, 3), sh.flatten(1, 3)
             opac = opac.flatten(1)
+        # camera set-up once for all b*v cameras (a handful of tiny kernels, no host sync), then one
+        # launch chain per scene
+        h, w = image_shape
+        tanfov, view_t, full_t, campos = _cameras(extrinsics.flatten(0, 1), intrinsics.flatten(0, 1),
+                                                  near.flatten(), far.flatten())
+        n = sh.shape[-1]
+        degree = active_sh_degree or isqrt(n) - 1
+        assert use_sh or n == 1
+        cov6 = _cov6(cov)
+        bg = self.background_color[None].expand(v, 3)
         colors, depths = [], []
-        for i in range(b):   # scenes; the V views of a scene share one launch chain
-            c, d = render_cuda(
-                extrinsics[i], intrinsics[i], near[i], far[i], image_shape,
-                self.background_color[None].expand(v, 3), means[i], cov[i], sh[i], opac[i],
-                scale_invariant=self.make_scale_invariant,
-                cam_rot_delta=None if cam_rot_delta is None else cam_rot_delta[i],
-                cam_trans_delta=None if cam_trans_delta is None else cam_trans_delta[i],
-                use_sh=use_sh, sh_degree=active_sh_degree)
+        for i in range(b):
+            sl = slice(i * v, (i + 1) * v)
+            c, _r, d, _a, _n = rasterize_views(
+                means[i], cov6[i], opac[i], shs=sh[i] if use_sh else None,
+                colors_precomp=None if use_sh else sh[i][..., 0], sh_degree=degree,
+                sh_layout="chan_major", viewmatrix=view_t[sl], projmatrix=full_t[sl], campos=campos[sl],
+                tanfov=tanfov[sl], bg=bg, H=h, W=w,
+                theta=None if cam_rot_delta is None else cam_rot_delta[i],
+                rho=None if cam_trans_delta is None else cam_trans_delta[i], want_n_touched=False,
+                check_overflow=check_overflow)
             colors.append(c)
-            depths.append(d)
+            depths.append(d[:, 0])
         color, depth = torch.stack(colors), torch.stack(depths)
         if not return_dict:
             return color, depth

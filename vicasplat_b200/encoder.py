@@ -268,14 +268,19 @@ class VicaSplat(nn.Module):
 
     @torch.no_grad()
     def forward(self, context: dict, global_step: int = 0, visualization_dump: Optional[dict] = None,
-                distill: bool = False, compute_viewspace_depth: bool = True, **kwargs) -> dict:
+                distill: bool = False, compute_viewspace_depth: bool = True,
+                clone_outputs: bool = True, **kwargs) -> dict:
+        """``clone_outputs=False`` returns views of the engine's static output buffers (valid until
+        the next forward on this module): what a consumer on the same stream needs, without the
+        ~3 GB of copies per 8-scene batch."""
         image = context["image"]
         if not image.is_cuda:
             raise RuntimeError("vicasplat_b200.VicaSplat runs on CUDA only (no CPU fallback)")
         intr = context.get("intrinsics", None)
         assert intr is not None, "use_intrinsic_embedding=True needs context['intrinsics']"
         B, T, _, H, W = image.shape
-        out = self.engine().run(image, intr, heads=not distill, gs=not distill)
+        out = self.engine().run(image, intr, heads=not distill, gs=not distill,
+                                clone_outputs=clone_outputs)
         centers = out["raw"][..., :3] if not distill else out["centers"]
         depth = None
         if compute_viewspace_depth:

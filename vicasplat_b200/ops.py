@@ -160,7 +160,7 @@ def attention(Q, K, V, O, *, heads, q_start, q_len, kv_start0, kv_len0, kv_start
     p.kv_start0, p.kv_len0 = ptr(kv_start0), ptr(kv_len0)
     p.kv_start1, p.kv_len1 = ptr(kv_start1), ptr(kv_len1)
     p.max_q_len, p.max_kv_len, p.causal_block, p.scale = max_q_len, max_kv_len, causal_block, scale
-    with _timed("attention"):
+    with _timed("attention", ("attn", p.items, heads, max_q_len, max_kv_len, causal_block)):
         check(lib.vs_attention(C.byref(p), C.c_void_p(stream_ptr())), "vs_attention")
     return O
 

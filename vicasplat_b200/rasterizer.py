@@ -49,6 +49,34 @@ _capacity_hint: dict = {}
 MAX_TILE_SORT = 16384
 
 
+# check_overflow="deferred": the render runs unchecked with the hinted capacities and its device-side
+# counters (pairs, largest tile) are queued here; the caller copies them to the host with the rest
+# of its results and calls `verify_deferred` on them -- no host synchronisation in the render call
+_deferred: list = []
+
+
+def take_deferred() -> list:
+    """[(counters int64[2] device tensor, max_pairs, max_tile, shape key)] since the last call."""
+    out = list(_deferred)
+    _deferred.clear()
+    return out
+
+
+def verify_deferred(counts, records) -> None:
+    """counts: host int64 (n, 2) copies of the queued counters.  Raises RasterOverflow (after
+    raising the per-shape capacity hint, so that a re-submission succeeds) if any render of the
+    batch had more (tile, splat) pairs than its workspace held."""
+    bad = None
+    for (n, tmax), (_t, max_pairs, max_tile, key) in zip(counts.tolist(), records):
+        if n > max_pairs or (max_tile > 0 and tmax > max_tile):
+            next_tile = 0 if tmax > MAX_TILE_SORT else min(MAX_TILE_SORT, int(tmax * 1.25) + 64)
+            _capacity_hint[key] = (max(int(n * 1.25) + 4096, max_pairs), next_tile)
+            bad = (n, tmax, max_pairs, max_tile)
+    if bad is not None:
+        raise RasterOverflow("render exceeded its binning capacity (pairs=%d, largest tile=%d, capacity=%d/%d); "
+                             "the capacity hint has been raised: re-submit the batch" % bad)
+
+
 class _Ctx:
     """Forward state kept for the backward pass (workspace holds the sorted splat lists)."""
     __slots__ = ("params", "keep", "num_pairs", "max_pairs")
@@ -103,6 +131,9 @@ class _Rasterize(torch.autograd.Function):
             color, depth, alpha, radii, n_touched, st = _run_forward(
                 V, G, H, W, shared, m, c6, o, s, sh_M, sh_degree, sh_strides, cp, viewm, projm,
                 campos, tanfov, bg, max_pairs, max_tile, want_aux)
+            if check_overflow == "deferred":
+                _deferred.append((st.num_pairs, max_pairs, max_tile, (V, G, H, W)))
+                break
             if not check_overflow:
                 break
             n, tmax = st.num_pairs.tolist()   # the upstream extension syncs here too (num_rendered)
@@ -167,7 +198,7 @@ class _Rasterize(torch.autograd.Function):
 def rasterize_views(means3D, cov6, opacities, *, shs=None, colors_precomp=None, sh_degree=0,
                     sh_layout="coef_major", viewmatrix, projmatrix, campos, tanfov, bg, H, W,
                     theta=None, rho=None, max_pairs: Optional[int] = None,
-                    max_tile_pairs: Optional[int] = None, check_overflow: bool = True,
+                    max_tile_pairs: Optional[int] = None, check_overflow=True,
                     want_n_touched: bool = True):
     """Render V views.  Gaussians are shared by all views when means3D is (G,3), per-view when
     (V,G,3).  viewmatrix/projmatrix (V,4,4) are the *transposed* matrices the reference passes
@@ -176,6 +207,10 @@ def rasterize_views(means3D, cov6, opacities, *, shs=None, colors_precomp=None, 
     sh_layout: "coef_major" = (G, M, 3), the layout the reference hands the extension
     (cuda_splatting.py:182); "chan_major" = (G, 3, M), the encoder's own layout
     (gaussian_adapter.py:180), consumed without the transpose copy.
+
+    check_overflow: True = read the pair counters back and re-run larger if the workspace was too
+    small (one host sync, like the upstream extension's num_rendered); False = trust the
+    per-shape hint; "deferred" = trust it now, queue the counters for `verify_deferred`.
 
     Returns color (V,3,H,W), radii (V,G), depth (V,1,H,W), alpha (V,1,H,W), n_touched (V,G)
     (a 0-d placeholder when want_n_touched=False: the reference's render_cuda discards it,
