@@ -45,6 +45,14 @@ def encoder_flops(T: int, size: int = SIZE) -> float:
     return per_frame * T
 
 
+def outconv_flops_saved(T: int, size: int = SIZE) -> float:
+    """FLOPs NOT executed per scene: the four 1x1 out_convs of both DPT trunks run before their
+    bilinear x2 (they commute), i.e. on a quarter of the pixels the reference convolves."""
+    g = size // 16
+    px = sum((g * s) ** 2 for s in (1, 2, 4, 8))          # out_conv output pixels per frame, per head
+    return T * 2 * px * 2 * 256 * 256 * 0.75
+
+
 def attention_flops(T: int, size: int = SIZE) -> float:
     """The part of encoder_flops done by the attention kernel (QK^T and PV), per scene."""
     E, D, Le, Ld = 1024, 768, 24, 12
@@ -382,7 +390,7 @@ def run_ours(args) -> None:
         value = world * NB * 1e3 / step_ms
         fl = NB * encoder_flops(T_CTX)
         enc_tf = fl / (enc_ms * 1e-3) / 1e12
-        gemm_fl = NB * (encoder_flops(T_CTX) - attention_flops(T_CTX))
+        gemm_fl = NB * (encoder_flops(T_CTX) - attention_flops(T_CTX) - outconv_flops_saved(T_CTX))   # executed
         gemm_tf = gemm_fl / (gemm_ms * 1e-3) / 1e12
         rb = NB * raster_bytes(V_TGT, G_SCENE, SIZE, SIZE)
         ras_gbs = rb / (ras_ms * 1e-3) / 1e9

@@ -79,6 +79,11 @@ int vs_rope_rows(void* qkv, int64_t ld, int rows, int H, int q_col, int k_col, c
  *   res_up2 != 0: res1 is an NHWC bf16 map at HALF resolution [cn, ch/2, cw/2, N] that is
  *   bilinearly upsampled x2 (align_corners=True, dpt_block.py:214-216) on the fly.
  * Output row mapping: out_row = (m / out_gin) * out_gout + out_off + (m % out_gin).
+ * rope_pos != NULL: the rotary embedding of vs_rope_rows is applied to the fp32 accumulator (after
+ *   bias) of the q columns [rope_q_col, rope_q_col + 64*rope_heads) and the k columns
+ *   [rope_k_col, ...) before the store -- same (y, x) / camera-row convention, positions indexed
+ *   by OUTPUT row; both column offsets must be multiples of 64 (replaces the separate in-place
+ *   pass over the packed qkv buffer that the reference's cuRoPE2D makes, curope2d.py:12-44).
  */
 typedef struct vs_gemm_params {
   const void* A;
@@ -109,6 +114,9 @@ typedef struct vs_gemm_params {
   int64_t ldc2;
   int32_t out_gin, out_gout, out_off; /* out_gin == 0: identity mapping */
   int32_t block_n;                    /* 0 = choose; else 64, 128 or 256 */
+  const int32_t* rope_pos;            /* (out_rows, 2) int32 or NULL */
+  int32_t rope_q_col, rope_k_col, rope_heads;
+  float rope_base, rope_cam_theta;
 } vs_gemm_params;
 
 int vs_gemm(const vs_gemm_params* p, vs_stream_t stream);

@@ -191,6 +191,38 @@ def test_rope_rows_image_and_camera(cuda, lib):
     assert torch.equal(qkv.view(T, N + 1, 3, H, 64)[:, :, 2].float(), ref[:, :, 2])  # v untouched
 
 
+def test_gemm_with_fused_rope_matches_oracle_rope(cuda, lib):
+    """qkv projection with the rotary embedding applied in the epilogue (vs_gemm_params.rope_pos)
+    against fp32 GEMM + the oracle's rope2d / interleaved camera rope (croco/blocks.py:101-103,
+    rope_utils.py:297-305)."""
+    from vicasplat_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    T, N, H, K = 3, 17, 12, 256
+    rows = T * (N + 1)
+    A = _bf(torch.randn((rows, K), generator=g)).to(cuda)
+    W = _bf(torch.randn((3 * H * 64, K), generator=g) / math.sqrt(K)).to(cuda)
+    bias = torch.randn((3 * H * 64,), generator=g).to(cuda)
+    pos = er.positions(T, 4, 4, True)
+    pos_rows = torch.zeros((T, N + 1, 2), dtype=torch.int32)
+    pos_rows[:, 1:] = pos.to(torch.int32)
+    for t in range(T):
+        pos_rows[t, 0, 0] = -1 - t
+    pos_rows = pos_rows.view(rows, 2).to(cuda).contiguous()
+    ref = (A.float() @ W.float().t() + bias).view(T, N + 1, 3, H, 64).clone()
+    for which in (0, 1):
+        img = ref[:, 1:, which].permute(0, 2, 1, 3)
+        ref[:, 1:, which] = er.rope2d(img, pos.to(cuda), 100.0).permute(0, 2, 1, 3)
+        cam = ref[:, 0, which].permute(1, 0, 2)[None]
+        ref[:, 0, which] = er.rope1d_interleaved(cam, torch.arange(T, device=cuda), 30.0)[0].permute(1, 0, 2)
+    for dt, tol in ((torch.float32, 2e-5), (torch.bfloat16, 4e-3)):
+        out = torch.empty((rows, 3 * H * 64), dtype=dt, device=cuda)
+        ops.gemm(A, W, bias=bias, out=out, rope=(pos_rows, 0, H * 64, H, 100.0, 30.0))
+        assert _rel(out, ref.view(rows, -1)) < tol, (dt, _rel(out, ref.view(rows, -1)))
+    plain = ops.gemm(A, W, bias=bias, out_dtype=torch.float32)
+    assert torch.equal(out.view(T, N + 1, 3, H, 64)[:, :, 2].float(),
+                       plain.view(T, N + 1, 3, H, 64)[:, :, 2].to(torch.bfloat16).float())   # v untouched
+
+
 # ------------------------------------------------------------------------------------ attention
 def _attn_ref(q, k, v, mask=None):
     return er.sdpa(q.float(), k.float(), v.float(), mask)

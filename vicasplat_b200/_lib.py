@@ -32,6 +32,8 @@ class GemmParams(C.Structure):
         ("C", _vp), ("c_dtype", _i32), ("ldc", _i64),
         ("C2", _vp), ("ldc2", _i64),
         ("out_gin", _i32), ("out_gout", _i32), ("out_off", _i32), ("block_n", _i32),
+        ("rope_pos", _vp), ("rope_q_col", _i32), ("rope_k_col", _i32), ("rope_heads", _i32),
+        ("rope_base", _f32), ("rope_cam_theta", _f32),
     ]
 
 

@@ -23,6 +23,8 @@
 // Replaces in the reference: every nn.Linear in croco/blocks.py:58-130 and backbone_vica.py:57-335
 // and every stride-1 nn.Conv2d in heads/dpt_block.py:79-229,264-459, heads/dpt_gs_head.py:98-157.
 #include <cuda.h>
+
+#include <cmath>
 #include <cuda_bf16.h>
 
 #include "common.h"
@@ -69,6 +71,11 @@ struct GemmDev {
   int fast;      // every present C / C2 / residual pointer allows aligned 4-column segments
   int res_kind;  // 0 none, 1 fp32, 2 bf16, 3 bilinear-x2 bf16
   float up_sx, up_sy;  // res_up2: source step per output pixel (align_corners=True)
+  // rotary embedding of the q / k column blocks (nullptr = none); inverse frequencies live in the
+  // kernel parameter (constant) bank
+  const int* rope_pos;
+  int rope_q0, rope_k0, rope_cols;
+  float rope_if_img[16], rope_if_cam[32];
 };
 
 // exact-erf GELU (nn.GELU default, croco/blocks.py:60) with erf from Abramowitz-Stegun 7.1.26
@@ -509,6 +516,11 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
           }
         }
       }
+      int rp_y = 0, rp_x = 0;
+      if (g.rope_pos != nullptr && my_out >= 0) {
+        const int2 pp = __ldg(reinterpret_cast<const int2*>(g.rope_pos) + my_out);
+        rp_y = pp.x; rp_x = pp.y;
+      }
       // After the shared-memory exchange lane l holds 4 consecutive columns (cs) of rows 4j + l/8.
       const int cs = lane & 7;
       int oj[8];      // output row (fits 31 bits: checked on the host), -1 = nothing to store
@@ -543,6 +555,33 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
           load32_f32(g.bias + nb, nv, g.vec & VEC_BIAS, b);
 #pragma unroll
           for (int i = 0; i < 32; ++i) f[i] += b[i];
+        }
+        if (g.rope_pos != nullptr &&
+            (static_cast<unsigned>(nb - g.rope_q0) < static_cast<unsigned>(g.rope_cols) ||
+             static_cast<unsigned>(nb - g.rope_k0) < static_cast<unsigned>(g.rope_cols))) {
+          // this chunk is one 32-wide half of a head: y block (even) or x block (odd)
+          const int hb = (nb >> 5) & 1;
+          if (rp_y >= 0) {   // image token: pairs (d, d + 16), angle = pos * base^(-d/16)
+            const float pos = static_cast<float>(hb ? rp_x : rp_y);
+#pragma unroll
+            for (int d = 0; d < 16; ++d) {
+              float sn, cs_;
+              __sincosf(pos * g.rope_if_img[d], &sn, &cs_);
+              const float u = f[d], w = f[d + 16];
+              f[d] = u * cs_ - w * sn;
+              f[d + 16] = w * cs_ + u * sn;
+            }
+          } else {           // camera token: interleaved pairs, frame index t = -1 - y
+            const float t = static_cast<float>(-1 - rp_y);
+#pragma unroll
+            for (int l = 0; l < 16; ++l) {
+              float sn, cs_;
+              __sincosf(t * (hb ? g.rope_if_cam[16 + l] : g.rope_if_cam[l]), &sn, &cs_);
+              const float u = f[2 * l], w = f[2 * l + 1];
+              f[2 * l] = u * cs_ - w * sn;
+              f[2 * l + 1] = w * cs_ + u * sn;
+            }
+          }
         }
         if (g.act == VS_ACT_GELU) {
 #pragma unroll
@@ -736,6 +775,21 @@ extern "C" int vs_gemm(const vs_gemm_params* p, vs_stream_t stream_) {
   if (p->res_up2) {
     g.up_sy = p->ch > 1 ? static_cast<float>(p->ch / 2 - 1) / static_cast<float>(p->ch - 1) : 0.f;
     g.up_sx = p->cw > 1 ? static_cast<float>(p->cw / 2 - 1) / static_cast<float>(p->cw - 1) : 0.f;
+  }
+  g.rope_pos = p->rope_pos;
+  if (p->rope_pos != nullptr) {
+    VS_REQUIRE(p->rope_heads > 0 && p->rope_q_col % 64 == 0 && p->rope_k_col % 64 == 0 &&
+                   p->rope_q_col >= 0 && p->rope_k_col >= 0,
+               "vs_gemm: rope column offsets must be non-negative multiples of 64");
+    VS_REQUIRE(p->rope_base > 0.f && p->rope_cam_theta > 0.f, "vs_gemm: rope bases must be positive");
+    VS_REQUIRE(p->act == VS_ACT_NONE && p->gate == nullptr, "vs_gemm: rope goes with a plain epilogue");
+    g.rope_q0 = p->rope_q_col;
+    g.rope_k0 = p->rope_k_col;
+    g.rope_cols = p->rope_heads * 64;
+    for (int d = 0; d < 16; ++d)
+      g.rope_if_img[d] = static_cast<float>(1.0 / pow(static_cast<double>(p->rope_base), d / 16.0));
+    for (int l = 0; l < 32; ++l)
+      g.rope_if_cam[l] = static_cast<float>(1.0 / pow(static_cast<double>(p->rope_cam_theta), (2 * l) / 64.0));
   }
   g.res_kind = !p->res1 ? 0 : p->res_up2 ? 3 : p->res_dtype == VS_F32 ? 1 : 2;
   g.fast = p->C && (g.vec & VEC_C) && (!p->C2 || (g.vec & VEC_C2)) && (!p->res1 || (g.vec & VEC_RES));

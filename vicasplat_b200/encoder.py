@@ -464,8 +464,9 @@ class EncoderEngine:
         for i in range(bb["enc_depth"]):
             k = f"backbone.enc_blocks.{i}"
             ops.layernorm(x, w[k + ".norm1.weight"], w[k + ".norm1.bias"], out_bf16=pl["h_enc"])
-            qkv = ops.gemm(pl["h_enc"], w[k + ".attn.qkv"], bias=w[k + ".attn.qkv.bias"], out=pl["qkv_enc"])
-            ops.rope_rows(qkv, pl["pos_enc"], heads=H, q_col=0, k_col=E, base=100.0)
+            # RoPE2D of q and k (croco/blocks.py:101-103) is applied in the GEMM epilogue
+            qkv = ops.gemm(pl["h_enc"], w[k + ".attn.qkv"], bias=w[k + ".attn.qkv.bias"], out=pl["qkv_enc"],
+                           rope=(pl["pos_enc"], 0, E, H, 100.0, 30.0))
             ops.attention(qkv[:, :E], qkv[:, E:2 * E], qkv[:, 2 * E:], pl["att_enc"], heads=H,
                           q_start=pl["enc_start"], q_len=pl["enc_len"], kv_start0=pl["enc_start"],
                           kv_len0=pl["enc_len"], max_q_len=N, max_kv_len=N, scale=0.125)
@@ -502,8 +503,8 @@ class EncoderEngine:
             ops.layernorm(x, w[k + ".norm1.weight"], w[k + ".norm1.bias"],
                           w0=w[k + ".cam_norm1.weight"], b0=w[k + ".cam_norm1.bias"],
                           scale=m1[:, :D], shift=m1[:, D:2 * D], rows_per_frame=rpf, out_bf16=pl["h_dec"])
-            qkv = ops.gemm(pl["h_dec"], w[k + ".attn.qkv"], bias=w[k + ".attn.qkv.bias"], out=pl["qkv_dec"])
-            ops.rope_rows(qkv, pl["pos_dec"], heads=H, q_col=0, k_col=D, base=100.0, cam_theta=theta)
+            qkv = ops.gemm(pl["h_dec"], w[k + ".attn.qkv"], bias=w[k + ".attn.qkv.bias"], out=pl["qkv_dec"],
+                           rope=(pl["pos_dec"], 0, D, H, 100.0, theta))
             ops.attention(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], pl["att_dec"], heads=H,
                           q_start=pl["vid_start"], q_len=pl["vid_len"], kv_start0=pl["vid_start"],
                           kv_len0=pl["vid_len"], max_q_len=T * rpf, max_kv_len=T * rpf,
@@ -518,8 +519,8 @@ class EncoderEngine:
             m2 = pl["mod2"]
             ops.layernorm(x, w[k + ".norm2.weight"], w[k + ".norm2.bias"], scale=m2[:, :D],
                           shift=m2[:, D:2 * D], rows_per_frame=rpf, out_bf16=pl["h_dec"])
-            qkv = ops.gemm(pl["h_dec"], w[k + ".cross_qkv"], bias=w[k + ".cross_qkv.bias"], out=pl["qkv_dec"])
-            ops.rope_rows(qkv, pl["pos_dec"], heads=H, q_col=0, k_col=D, base=100.0, cam_theta=theta)
+            qkv = ops.gemm(pl["h_dec"], w[k + ".cross_qkv"], bias=w[k + ".cross_qkv.bias"], out=pl["qkv_dec"],
+                           rope=(pl["pos_dec"], 0, D, H, 100.0, theta))
             ops.attention(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], pl["att_dec"], heads=H,
                           q_start=pl["nb_q"], q_len=pl["nb_len"], kv_start0=pl["nb_k0"],
                           kv_len0=pl["nb_len"], kv_start1=pl["nb_k1"], kv_len1=pl["nb_len1"],
@@ -568,12 +569,13 @@ class EncoderEngine:
         return self._conv(y, f"{rk}.conv2", bias=b("conv2"), res1=x, res2=extra, relu_copy=relu_copy)
 
     def _fusion(self, rk, x, x_relu):
-        """resConfUnit2 -> bilinear x2 -> 1x1 out_conv."""
+        """resConfUnit2 -> bilinear x2 -> 1x1 out_conv (dpt_block.py:196-205).  A 1x1 convolution
+        (+ bias) commutes with bilinear interpolation (the weights of every output pixel sum to 1),
+        so the out_conv runs BEFORE the upsampling, on a quarter of the pixels."""
         y = self._rcu(rk + ".resConfUnit2", x, x_relu)
-        up = ops.upsample2x(y)
-        n, h, w_, c = up.shape
-        out = ops.gemm(up.view(-1, c), self.w[rk + ".out"], bias=self.w[rk + ".out_conv.bias"])
-        return out.view(n, h, w_, FEAT)
+        n, h, w_, c = y.shape
+        out = ops.gemm(y.view(-1, c), self.w[rk + ".out"], bias=self.w[rk + ".out_conv.bias"])
+        return ops.upsample2x(out.view(n, h, w_, FEAT))
 
     def _trunk(self, pl, head, taps):
         w, bb = self.w, self.bb

@@ -51,8 +51,11 @@ def _need_cuda(*ts):
 def gemm(A, W, *, N=None, K=None, a_rows=None, a_groups=1, a_row_stride=None, a_group_stride=0,
          bias=None, act=VS_ACT_NONE, gate=None, gate_rows=0, first_row_mode=0, res1=None,
          res2=None, out=None, out_dtype=torch.bfloat16, ldc=None, out2=None, ldc2=None,
-         out_gin=0, out_gout=0, out_off=0, out_rows=None, block_n=0, w_row_stride=None):
-    """C = epilogue(A @ W^T): rows mode of vs_gemm.  A bf16 (rows, K) [or strided groups], W bf16 (N, K)."""
+         out_gin=0, out_gout=0, out_off=0, out_rows=None, block_n=0, w_row_stride=None,
+         rope=None):
+    """C = epilogue(A @ W^T): rows mode of vs_gemm.  A bf16 (rows, K) [or strided groups], W bf16 (N, K).
+    rope = (pos_i32 (out_rows, 2), q_col, k_col, heads, base, cam_theta): rotary embedding of the
+    q / k columns applied in the epilogue (see vs_gemm_params.rope_pos)."""
     _need_cuda(A, W)
     lib = _lib.load()
     p = GemmParams()
@@ -72,6 +75,11 @@ def gemm(A, W, *, N=None, K=None, a_rows=None, a_groups=1, a_row_stride=None, a_
     if out2 is not None:
         p.C2, p.ldc2 = ptr(out2), (ldc2 if ldc2 is not None else out2.stride(-2))
     p.out_gin, p.out_gout, p.out_off, p.block_n = out_gin, out_gout, out_off, block_n
+    if rope is not None:
+        pos, p.rope_q_col, p.rope_k_col, p.rope_heads, p.rope_base, p.rope_cam_theta = rope
+        _need_cuda(pos)
+        assert pos.dtype == torch.int32 and pos.is_contiguous()
+        p.rope_pos = ptr(pos)
     with _timed("gemm", ("lin", total, N, K, act, res1 is not None, out.dtype == torch.float32)):
         check(lib.vs_gemm(C.byref(p), C.c_void_p(stream_ptr())), "vs_gemm")
     return out
