@@ -282,6 +282,15 @@ typedef struct vs_raster_bwd_params {
 } vs_raster_bwd_params;
 int vs_raster_backward(const vs_raster_bwd_params* p, vs_stream_t stream);
 
+/* ------------------------------------------------------------------ MSE loss (+ its gradient)
+ * LossMse.forward, src/loss/loss_mse.py:23-31: loss = weight * mean((pred - target)^2), and in the
+ * same pass dL/dpred = (2 * weight / n) * (pred - target) (nullable): the render is read once
+ * instead of three times (sub, square+mean, backward).  Deterministic: per-block partial sums in
+ * `workspace`, reduced in a fixed order by the last block to finish.  loss_out: device float[1]. */
+int64_t vs_mse_workspace_bytes(void);
+int vs_mse_loss(const float* pred, const float* target, int64_t n, float weight, float* loss_out,
+                float* grad_out, void* workspace, vs_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -117,6 +117,7 @@ def load() -> C.CDLL:
     lib.vs_raster_workspace_bytes.restype = _i64
     lib.vs_raster_workspace_bytes.argtypes = [_i32, _i32, _i32, _i32, _i64]
     lib.vs_launch_count.restype = _i64
+    lib.vs_mse_workspace_bytes.restype = _i64
     lib.vs_struct_size.restype = _i64
     lib.vs_struct_size.argtypes = [C.c_char_p]
     for name, cls in STRUCTS.items():

@@ -538,6 +538,72 @@ __global__ void adapter_sh_kernel(const float* __restrict__ src, long long src_l
   }
 }
 
+// ------------------------------------------------------------------ MSE loss + gradient
+constexpr int MSE_BLOCKS = 148 * 8, MSE_THREADS = 256;
+
+__global__ void __launch_bounds__(MSE_THREADS)
+    mse_loss_kernel(const float* __restrict__ pred, const float* __restrict__ target, long long n,
+                    float weight, float* __restrict__ loss_out, float* __restrict__ grad,
+                    float* __restrict__ partial, unsigned int* __restrict__ counter) {
+  const float gs = 2.0f * weight / static_cast<float>(n);
+  float acc = 0.f;
+  const long long n4 = n >> 2;
+  const bool vec = ((reinterpret_cast<uintptr_t>(pred) | reinterpret_cast<uintptr_t>(target) |
+                     reinterpret_cast<uintptr_t>(grad)) & 15) == 0;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  const long long tid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (vec) {
+    for (long long i = tid; i < n4; i += stride) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(pred) + i);
+      const float4 b = __ldg(reinterpret_cast<const float4*>(target) + i);
+      const float4 d = make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w);
+      acc += (d.x * d.x + d.y * d.y) + (d.z * d.z + d.w * d.w);
+      if (grad) reinterpret_cast<float4*>(grad)[i] = make_float4(gs * d.x, gs * d.y, gs * d.z, gs * d.w);
+    }
+    for (long long i = n4 * 4 + tid; i < n; i += stride) {
+      const float d = pred[i] - target[i];
+      acc += d * d;
+      if (grad) grad[i] = gs * d;
+    }
+  } else {
+    for (long long i = tid; i < n; i += stride) {
+      const float d = pred[i] - target[i];
+      acc += d * d;
+      if (grad) grad[i] = gs * d;
+    }
+  }
+  __shared__ float red[MSE_THREADS / 32];
+  __shared__ bool last;
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < MSE_THREADS / 32; ++i) t += red[i];
+    partial[blockIdx.x] = t;
+    __threadfence();
+    last = atomicAdd(counter, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (last) {   // fixed-order final reduction: the result does not depend on block scheduling
+    __threadfence();
+    float t = 0.f;
+    for (int i = threadIdx.x; i < static_cast<int>(gridDim.x); i += MSE_THREADS)
+      t += *(volatile float*)(partial + i);
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) t += __shfl_xor_sync(0xffffffffu, t, s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = t;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float tot = 0.f;
+      for (int i = 0; i < MSE_THREADS / 32; ++i) tot += red[i];
+      *loss_out = weight * tot / static_cast<float>(n);
+      *counter = 0u;   // ready for the next call on this workspace
+    }
+  }
+}
+
 inline unsigned blocks_for(long long n, int threads) {
   return static_cast<unsigned>((n + threads - 1) / threads);
 }
@@ -736,5 +802,22 @@ extern "C" int vs_gaussian_adapter(const float* src, int64_t src_ld, int center_
         src, src_ld, param_col, G, d_sh, sh_mask, sh, raw_out, raw_w);
     VS_LAUNCH_CHECK();
   }
+  return VS_OK;
+}
+
+extern "C" int64_t vs_mse_workspace_bytes(void) { return (vs::MSE_BLOCKS + 4) * sizeof(float); }
+
+extern "C" int vs_mse_loss(const float* pred, const float* target, int64_t n, float weight,
+                           float* loss_out, float* grad_out, void* workspace, vs_stream_t stream) {
+  using namespace vs;
+  VS_REQUIRE(pred && target && loss_out && workspace, "mse_loss: null tensor");
+  VS_REQUIRE(n > 0, "mse_loss: empty input");
+  float* partial = static_cast<float*>(workspace);
+  unsigned int* counter = reinterpret_cast<unsigned int*>(partial + MSE_BLOCKS);
+  const long long want = (n / 4 + MSE_THREADS - 1) / MSE_THREADS;
+  const unsigned blocks = static_cast<unsigned>(want < 1 ? 1 : (want > MSE_BLOCKS ? MSE_BLOCKS : want));
+  mse_loss_kernel<<<blocks, MSE_THREADS, 0, to_stream(stream)>>>(pred, target, n, weight, loss_out,
+                                                               grad_out, partial, counter);
+  VS_LAUNCH_CHECK();
   return VS_OK;
 }

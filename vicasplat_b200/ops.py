@@ -299,3 +299,26 @@ def gaussian_adapter(src, d_sh, sh_mask, *, center_col=0, param_col=3, want_cov=
         C.c_void_p(ptr(out["opac"])), C.c_void_p(ptr(out["scales"])), C.c_void_p(ptr(out["rot"])),
         C.c_void_p(stream_ptr())), "vs_gaussian_adapter")
     return out
+
+
+_mse_ws: dict = {}
+
+
+def mse_loss(pred, target, weight=1.0, want_grad=True):
+    """weight * mean((pred - target)^2) and (optionally) its gradient w.r.t. pred in one pass
+    (vs_mse_loss; LossMse.forward, src/loss/loss_mse.py:23-31).  Returns (loss 0-d, grad | None)."""
+    lib = _lib.load()
+    _need_cuda(pred, target)
+    assert pred.shape == target.shape and pred.dtype == target.dtype == torch.float32
+    pred, target = pred.contiguous(), target.contiguous()
+    key = (pred.device, torch.cuda.current_stream().cuda_stream)
+    if key not in _mse_ws:   # zeroed once: the kernel leaves its completion counter at zero
+        lib.vs_mse_workspace_bytes.restype = C.c_int64
+        _mse_ws[key] = torch.zeros((lib.vs_mse_workspace_bytes(),), dtype=torch.uint8, device=pred.device)
+    loss = torch.empty((), dtype=torch.float32, device=pred.device)
+    grad = torch.empty_like(pred) if want_grad else None
+    with _timed("mse"):
+        check(lib.vs_mse_loss(C.c_void_p(ptr(pred)), C.c_void_p(ptr(target)), C.c_int64(pred.numel()),
+                              C.c_float(weight), C.c_void_p(ptr(loss)), C.c_void_p(ptr(grad)),
+                              C.c_void_p(ptr(_mse_ws[key])), C.c_void_p(stream_ptr())), "vs_mse_loss")
+    return loss, grad
