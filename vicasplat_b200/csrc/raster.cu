@@ -328,6 +328,35 @@ __global__ void tile_ranges_kernel(const uint64_t* __restrict__ keys, int64_t ma
   if (i == n - 1) ranges[t].y = static_cast<uint32_t>(n);
 }
 
+// Half extents of the axis-aligned box around the region where a splat's alpha can reach 1/255:
+// alpha >= 1/255  <=>  power >= -tau, tau = ln(255 o): an ellipse with half extents
+// sqrt(2 tau C / det), sqrt(2 tau A / det) (conic = (A, B, C)); 1 % + 0.01 px safety margin.
+// Negative extents = never visible.  Used by the blend's sub-block culling AND by the per-tile
+// binning (a (splat, tile) pair whose box misses the tile's pixel centres cannot contribute to any
+// pixel of it, so dropping it leaves the image bit-identical and shortens sort and blend lists).
+__device__ __forceinline__ float2 alpha_extent(const float4 co) {
+  const float tau = __logf(255.0f * co.w) * 1.01f + 1e-3f;
+  const float det = co.x * co.z - co.y * co.y;
+  float ex = -1.f, ey = -1.f;
+  if (tau > 0.f) {
+    if (det > 0.f) {
+      ex = sqrtf(2.0f * tau * co.z / det) + 0.01f;
+      ey = sqrtf(2.0f * tau * co.x / det) + 0.01f;
+    } else {
+      ex = ey = 1e30f;  // degenerate conic: never cull
+    }
+  }
+  return make_float2(ex, ey);
+}
+
+__device__ __forceinline__ bool tile_may_hit(float cx, float cy, float2 e, int tx, int ty, int W, int H) {
+  const float bx0 = static_cast<float>(tx * TILE), bx1 = static_cast<float>(min(tx * TILE + TILE - 1, W - 1));
+  const float by0 = static_cast<float>(ty * TILE), by1 = static_cast<float>(min(ty * TILE + TILE - 1, H - 1));
+  const float ddx = fmaxf(fmaxf(bx0 - cx, cx - bx1), 0.f);
+  const float ddy = fmaxf(fmaxf(by0 - cy, cy - by1), 0.f);
+  return ddx <= e.x && ddy <= e.y;
+}
+
 // ------------------------------------------------------------------ per-tile binning + sort
 // Alternative to the global 64-bit radix sort (6 passes over every pair): pairs are counted per
 // tile, scattered into their tile's segment, and each segment is sorted by ONE CTA in shared
@@ -338,6 +367,7 @@ __global__ void tile_ranges_kernel(const uint64_t* __restrict__ keys, int64_t ma
 // then ONE global atomic per touched tile per block (13 M same-address global atomics otherwise).
 // grid = (blocks over g, V); dynamic smem = tiles_per_view counters (0 -> direct global atomics).
 __global__ void tile_count_kernel(int G, int H, int W, const float2* __restrict__ xy,
+                                  const float4* __restrict__ conic_o,
                                   const int32_t* __restrict__ radii,
                                   uint32_t* __restrict__ tile_counts, int use_smem) {
   extern __shared__ uint32_t s_cnt[];
@@ -356,8 +386,10 @@ __global__ void tile_count_kernel(int G, int H, int W, const float2* __restrict_
       const float2 p = xy[i];
       int x0, x1, y0, y1;
       tile_rect(p.x, p.y, rad, gx, gy, x0, x1, y0, y1);
+      const float2 ext = alpha_extent(conic_o[i]);
       for (int y = y0; y < y1; ++y)
         for (int x = x0; x < x1; ++x) {
+          if (!tile_may_hit(p.x, p.y, ext, x, y, W, H)) continue;
           if (use_smem) atomicAdd(s_cnt + y * gx + x, 1u);
           else atomicAdd(tile_counts + v * tpv + y * gx + x, 1u);
         }
@@ -411,6 +443,7 @@ __global__ void __launch_bounds__(1024)
 // Same aggregation for the scatter: the block counts per tile in shared memory, reserves one
 // contiguous chunk per touched tile with a single global atomic, then hands out slots locally.
 __global__ void tile_scatter_kernel(int G, int H, int W, const float2* __restrict__ xy,
+                                    const float4* __restrict__ conic_o,
                                     const float4* __restrict__ rgbd,
                                     const int32_t* __restrict__ radii,
                                     const uint2* __restrict__ ranges, uint32_t* __restrict__ cursor,
@@ -424,11 +457,13 @@ __global__ void tile_scatter_kernel(int G, int H, int W, const float2* __restric
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
   const size_t i = static_cast<size_t>(v) * G + (g < G ? g : 0);
   int x0 = 0, x1 = 0, y0 = 0, y1 = 0;
+  float2 p = make_float2(0.f, 0.f), ext = make_float2(-1.f, -1.f);
   if (g < G) {
     const int rad = radii[i];
     if (rad > 0) {
-      const float2 p = xy[i];
+      p = xy[i];
       tile_rect(p.x, p.y, rad, gx, gy, x0, x1, y0, y1);
+      ext = alpha_extent(conic_o[i]);
     }
   }
   const uint64_t key = (static_cast<uint64_t>(__float_as_uint(g < G ? rgbd[i].w : 0.f)) << id_bits) | i;
@@ -436,7 +471,8 @@ __global__ void tile_scatter_kernel(int G, int H, int W, const float2* __restric
     for (int t = threadIdx.x; t < tpv; t += blockDim.x) s_cnt[t] = 0u;
     __syncthreads();
     for (int y = y0; y < y1; ++y)
-      for (int x = x0; x < x1; ++x) atomicAdd(s_cnt + y * gx + x, 1u);
+      for (int x = x0; x < x1; ++x)
+        if (tile_may_hit(p.x, p.y, ext, x, y, W, H)) atomicAdd(s_cnt + y * gx + x, 1u);
     __syncthreads();
     for (int t = threadIdx.x; t < tpv; t += blockDim.x) {
       const uint32_t c = s_cnt[t];
@@ -447,6 +483,7 @@ __global__ void tile_scatter_kernel(int G, int H, int W, const float2* __restric
   }
   for (int y = y0; y < y1; ++y)
     for (int x = x0; x < x1; ++x) {
+      if (!tile_may_hit(p.x, p.y, ext, x, y, W, H)) continue;
       const int t = y * gx + x;
       const uint2 r = ranges[v * tpv + t];
       const uint32_t pos = r.x + (use_smem ? s_base[t] + atomicAdd(s_cnt + t, 1u)
@@ -515,7 +552,7 @@ int launch_tile_sort(const Workspace& ws, int n_tiles, int key_bits, int id_bits
 // ellipse power >= -ln(255 o)), ballots, and then walks only the set bits front to back -- pixels
 // outside that box would have rejected the splat anyway, so the image is bit-identical to
 // evaluating every (pixel, splat) pair.  A warp leaves the list as soon as all its pixels are opaque.
-__global__ void __launch_bounds__(BLEND_THREADS)
+__global__ void __launch_bounds__(BLEND_THREADS, 6)  /* <= 40 registers: a blend CTA then fits beside a resident 320-thread GEMM CTA */
     blend_kernel(int G, int H, int W, const uint2* __restrict__ ranges,
                  const uint32_t* __restrict__ vals, const float2* __restrict__ xy,
                  const float4* __restrict__ conic_o, const float4* __restrict__ rgbd,
@@ -559,19 +596,8 @@ __global__ void __launch_bounds__(BLEND_THREADS)
       s_id[threadIdx.x] = id;
       s_co[threadIdx.x] = co;
       s_cd[threadIdx.x] = rgbd[id];
-      // alpha >= 1/255  <=>  power >= -tau, tau = ln(255 o): ellipse with half extents
-      // sqrt(2 tau C / det), sqrt(2 tau A / det) (conic = (A, B, C)); 1 % + 0.01 px safety margin
-      const float tau = __logf(255.0f * co.w) * 1.01f + 1e-3f;
-      const float det = co.x * co.z - co.y * co.y;
-      float ex = -1.f, ey = -1.f;
-      if (tau > 0.f) {
-        if (det > 0.f) {
-          ex = sqrtf(2.0f * tau * co.z / det) + 0.01f;
-          ey = sqrtf(2.0f * tau * co.x / det) + 0.01f;
-        } else {
-          ex = ey = 1e30f;  // degenerate conic: never cull
-        }
-      }
+      const float2 ext = alpha_extent(co);
+      const float ex = ext.x, ey = ext.y;
       s_xe[threadIdx.x] = make_float4(p.x, p.y, ex, ey);
     }
     __syncthreads();
@@ -1094,7 +1120,7 @@ extern "C" int vs_raster_forward(const vs_raster_params* p, vs_stream_t stream_)
       const int use_smem = tpv <= 4096;
       dim3 cgrid(ceil_div(p->G, 256), p->V);
       tile_count_kernel<<<cgrid, 256, use_smem ? tpv * 4 : 0, stream>>>(
-          p->G, p->H, p->W, ws.xy, radii, ws.tile_counts, use_smem);
+          p->G, p->H, p->W, ws.xy, ws.conic_o, radii, ws.tile_counts, use_smem);
       VS_LAUNCH_CHECK();
       tile_offsets_kernel<<<1, 1024, 0, stream>>>(ws.tile_counts, static_cast<int>(n_tiles),
                                                   p->max_pairs, ws.ranges, ws.tile_cursor,
@@ -1102,7 +1128,7 @@ extern "C" int vs_raster_forward(const vs_raster_params* p, vs_stream_t stream_)
       VS_LAUNCH_CHECK();
       const int id_bits = highest_bit(VG > 1 ? VG - 1 : 1);
       tile_scatter_kernel<<<cgrid, 256, use_smem ? tpv * 8 : 0, stream>>>(
-          p->G, p->H, p->W, ws.xy, ws.rgbd, radii, ws.ranges, ws.tile_cursor, ws.keys_in, id_bits,
+          p->G, p->H, p->W, ws.xy, ws.conic_o, ws.rgbd, radii, ws.ranges, ws.tile_cursor, ws.keys_in, id_bits,
           use_smem);
       VS_LAUNCH_CHECK();
       const int key_bits = 32 + id_bits, nt = static_cast<int>(n_tiles);
