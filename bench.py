@@ -213,6 +213,10 @@ def run_ours(args) -> None:
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # stdout carries exactly one JSON line: NCCL's own "NCCL version ..." banner (printed to
+        # stdout at NCCL_DEBUG=VERSION) must not precede it
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
 
     from vicasplat_b200 import _lib, synthetic
