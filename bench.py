@@ -189,7 +189,7 @@ def run_reference(args) -> None:
                 config=config_dict(),
                 cpu_baseline=dict(value=val, unit="scenes/s", cores=cores, kind="port", sample=sample),
                 e2e=dict(value=val, unit="scenes/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def config_dict(nb: int = 1) -> dict:
@@ -213,10 +213,6 @@ def run_ours(args) -> None:
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # stdout carries exactly one JSON line: NCCL's own "NCCL version ..." banner (printed to
-        # stdout at NCCL_DEBUG=VERSION) must not precede it
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
 
     from vicasplat_b200 import _lib, synthetic
@@ -441,12 +437,30 @@ def run_ours(args) -> None:
                 value=1.0 / per, unit="scenes/s", cores=torch.get_num_threads(), kind="port",
                 sample=f"oracle encoder forward on all {T_CTX} frames ({te:.1f} s) + 1 of {V_TGT} "
                        f"target views ({tv:.1f} s, x{V_TGT})")
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict) -> None:
+    """The ONE JSON line, written to the process's original stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main() -> None:
+    # stdout carries exactly one JSON line: anything a library prints there (NCCL writes its
+    # "NCCL version ..." banner to stdout when the communicator is created) goes to stderr instead
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
