@@ -291,6 +291,14 @@ int64_t vs_mse_workspace_bytes(void);
 int vs_mse_loss(const float* pred, const float* target, int64_t n, float weight, float* loss_out,
                 float* grad_out, void* workspace, vs_stream_t stream);
 
+/* ------------------------------------------------------------------ test-time pose update
+ * update_pose, src/misc/cam_utils.py:127-148: per camera c2w' = inv(SE3_exp([rho, theta]) * inv(c2w))
+ * with the reference's small-angle branches (|theta| < 1e-5, cam_utils.py:74-108); general 4x4
+ * inverses like the reference's .inverse().  rho, theta: (n,3); c2w, c2w_out: (n,4,4) row-major
+ * (c2w_out may alias c2w).  Replaces a host loop of n SE3_exp calls + two batched inverses. */
+int vs_update_pose(const float* rho, const float* theta, const float* c2w, float* c2w_out, int n,
+                   vs_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -58,6 +58,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
                      const __grid_constant__ CUtensorMap tmV, const AttnDev a) {
   const int item = blockIdx.z, head = blockIdx.y, qt = blockIdx.x;
   const int q_len = max(a.q_len[item] - a.tail, 0);
+  pdl_launch_dependents();       // the projection GEMM behind this kernel may start its prologue
   if (qt * QT >= q_len) return;  // uniform for the CTA, before any barrier / allocation
   const int q_row0 = a.q_start[item] + qt * QT;
   const int s0 = a.kv_start0[item], l0 = a.kv_len0[item];

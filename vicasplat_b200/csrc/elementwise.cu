@@ -6,6 +6,7 @@
 #include <cuda_bf16.h>
 
 #include "common.h"
+#include "ptx.cuh"
 
 namespace vs {
 namespace {
@@ -119,6 +120,7 @@ __global__ void rope_rows_kernel(bf16* __restrict__ qkv, long long ld, int rows,
 // ------------------------------------------------------------------ LayerNorm (+ modulate)
 // One warp per row, row kept in registers (C <= 1024, C % 128 == 0): two-pass mean / variance.
 __global__ void layernorm_kernel(vs_layernorm_params p) {
+  pdl_launch_dependents();   // the GEMM that consumes these rows may start its prologue now
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= p.rows) return;
@@ -604,6 +606,89 @@ __global__ void __launch_bounds__(MSE_THREADS)
   }
 }
 
+// ------------------------------------------------------------------ pose update (one thread per camera)
+__device__ __forceinline__ bool inv4(const float (&m)[16], float (&o)[16]) {
+  // cofactor expansion (adjugate / determinant), as a general 4x4 inverse
+  const float s0 = m[0] * m[5] - m[4] * m[1], s1 = m[0] * m[6] - m[4] * m[2];
+  const float s2 = m[0] * m[7] - m[4] * m[3], s3 = m[1] * m[6] - m[5] * m[2];
+  const float s4 = m[1] * m[7] - m[5] * m[3], s5 = m[2] * m[7] - m[6] * m[3];
+  const float c5 = m[10] * m[15] - m[14] * m[11], c4 = m[9] * m[15] - m[13] * m[11];
+  const float c3 = m[9] * m[14] - m[13] * m[10], c2 = m[8] * m[15] - m[12] * m[11];
+  const float c1 = m[8] * m[14] - m[12] * m[10], c0 = m[8] * m[13] - m[12] * m[9];
+  const float det = s0 * c5 - s1 * c4 + s2 * c3 + s3 * c2 - s4 * c1 + s5 * c0;
+  const float id = 1.0f / det;
+  o[0] = (m[5] * c5 - m[6] * c4 + m[7] * c3) * id;
+  o[1] = (-m[1] * c5 + m[2] * c4 - m[3] * c3) * id;
+  o[2] = (m[13] * s5 - m[14] * s4 + m[15] * s3) * id;
+  o[3] = (-m[9] * s5 + m[10] * s4 - m[11] * s3) * id;
+  o[4] = (-m[4] * c5 + m[6] * c2 - m[7] * c1) * id;
+  o[5] = (m[0] * c5 - m[2] * c2 + m[3] * c1) * id;
+  o[6] = (-m[12] * s5 + m[14] * s2 - m[15] * s1) * id;
+  o[7] = (m[8] * s5 - m[10] * s2 + m[11] * s1) * id;
+  o[8] = (m[4] * c4 - m[5] * c2 + m[7] * c0) * id;
+  o[9] = (-m[0] * c4 + m[1] * c2 - m[3] * c0) * id;
+  o[10] = (m[12] * s4 - m[13] * s2 + m[15] * s0) * id;
+  o[11] = (-m[8] * s4 + m[9] * s2 - m[11] * s0) * id;
+  o[12] = (-m[4] * c3 + m[5] * c1 - m[6] * c0) * id;
+  o[13] = (m[0] * c3 - m[1] * c1 + m[2] * c0) * id;
+  o[14] = (-m[12] * s3 + m[13] * s1 - m[14] * s0) * id;
+  o[15] = (m[8] * s3 - m[9] * s1 + m[10] * s0) * id;
+  return det != 0.f;
+}
+
+__global__ void update_pose_kernel(const float* __restrict__ rho, const float* __restrict__ theta,
+                                   const float* c2w, float* c2w_out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float E[16], w2c[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) E[k] = c2w[i * 16 + k];
+  inv4(E, w2c);
+  const float tx = theta[i * 3], ty = theta[i * 3 + 1], tz = theta[i * 3 + 2];
+  const float rx = rho[i * 3], ry = rho[i * 3 + 1], rz = rho[i * 3 + 2];
+  // W = skew(theta), W2 = W W
+  const float W[9] = {0.f, -tz, ty, tz, 0.f, -tx, -ty, tx, 0.f};
+  float W2[9];
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      W2[r * 3 + c] = W[r * 3] * W[c] + W[r * 3 + 1] * W[3 + c] + W[r * 3 + 2] * W[6 + c];
+  const float angle = sqrtf(tx * tx + ty * ty + tz * tz);
+  float a, b, c_, d;   // R = I + a W + b W2,  V = I + c W + d W2
+  if (angle < 1e-5f) {
+    a = 1.f; b = 0.5f; c_ = 0.5f; d = 1.0f / 6.0f;
+  } else {
+    float sn, cs;
+    sincosf(angle, &sn, &cs);
+    a = sn / angle;
+    b = (1.f - cs) / (angle * angle);
+    c_ = b;
+    d = (angle - sn) / (angle * angle * angle);
+  }
+  float T[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+  float Vm[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    const float I = (k % 4 == 0) ? 1.f : 0.f;
+    T[(k / 3) * 4 + (k % 3)] = I + a * W[k] + b * W2[k];
+    Vm[k] = I + c_ * W[k] + d * W2[k];
+  }
+  T[3] = Vm[0] * rx + Vm[1] * ry + Vm[2] * rz;
+  T[7] = Vm[3] * rx + Vm[4] * ry + Vm[5] * rz;
+  T[11] = Vm[6] * rx + Vm[7] * ry + Vm[8] * rz;
+  float nw[16], out[16];
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      nw[r * 4 + c] = T[r * 4] * w2c[c] + T[r * 4 + 1] * w2c[4 + c] + T[r * 4 + 2] * w2c[8 + c] +
+                      T[r * 4 + 3] * w2c[12 + c];
+  inv4(nw, out);
+#pragma unroll
+  for (int k = 0; k < 16; ++k) c2w_out[i * 16 + k] = out[k];
+}
+
 inline unsigned blocks_for(long long n, int threads) {
   return static_cast<unsigned>((n + threads - 1) / threads);
 }
@@ -818,6 +903,16 @@ extern "C" int vs_mse_loss(const float* pred, const float* target, int64_t n, fl
   const unsigned blocks = static_cast<unsigned>(want < 1 ? 1 : (want > MSE_BLOCKS ? MSE_BLOCKS : want));
   mse_loss_kernel<<<blocks, MSE_THREADS, 0, to_stream(stream)>>>(pred, target, n, weight, loss_out,
                                                                grad_out, partial, counter);
+  VS_LAUNCH_CHECK();
+  return VS_OK;
+}
+
+extern "C" int vs_update_pose(const float* rho, const float* theta, const float* c2w, float* c2w_out,
+                              int n, vs_stream_t stream) {
+  using namespace vs;
+  if (n <= 0) return VS_OK;
+  VS_REQUIRE(rho && theta && c2w && c2w_out, "update_pose: null tensor");
+  update_pose_kernel<<<blocks_for(n, 64), 64, 0, to_stream(stream)>>>(rho, theta, c2w, c2w_out, n);
   VS_LAUNCH_CHECK();
   return VS_OK;
 }

@@ -25,6 +25,7 @@
 #include <cuda.h>
 
 #include <cmath>
+#include <cstdlib>
 #include <cuda_bf16.h>
 
 #include "common.h"
@@ -398,6 +399,10 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
   if (CL > 1) cluster_sync_all();   // peer barriers are initialised before anything targets them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // everything above overlapped the tail of the previous kernel (PDL); global memory is touched
+  // only from here on
+  pdl_launch_dependents();
+  pdl_wait();
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -667,6 +672,14 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
   }
 }
 
+bool pdl_enabled() {   // VS_PDL=0 turns programmatic dependent launch off (A/B measurements)
+  static const bool on = []() {
+    const char* e = getenv("VS_PDL");
+    return e == nullptr || e[0] != '0';
+  }();
+  return on;
+}
+
 int num_sms() {
   static int n = []() {
     int dev = 0, v = 148;
@@ -695,13 +708,15 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmW, const GemmDev& g, cud
   cfg.blockDim = dim3(64 + 32 * EPI_WARPS);
   cfg.dynamicSmemBytes = SMEM;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CL;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   VS_CUDA(cudaLaunchKernelEx(&cfg, kernel, tmA, tmW, g));
   count_launch();
   return VS_OK;

@@ -60,6 +60,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 
 // ---------------------------------------------------------------- TMA
+// Programmatic dependent launch (PDL): `pdl_launch_dependents` lets the NEXT kernel of the stream
+// start its prologue (barrier init, TMEM allocation, descriptor prefetch) while this grid is still
+// running; `pdl_wait` blocks until the PREVIOUS grid has completed and its writes are visible.
+// Both are no-ops for launches without the programmatic-serialization attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
 }
