@@ -160,6 +160,36 @@ def cpu_reference_step(t_frames: int, n_views: int, seed: int = 1):
     return t1 - t0, (t2 - t1) / n_views
 
 
+def torch_eager_gpu_encoder(dev, our_ms_per_scene: float) -> dict:
+    import torch
+    from oracle import encoder_ref as er
+    from vicasplat_b200 import synthetic
+    c = cpu_reference_step.cache
+    tf32 = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = True
+    try:
+        sd = {k: v.to(dev) for k, v in c["sd"].items()}
+        image, K = synthetic.clip(1, T_CTX, SIZE)
+        image, K = image.to(dev), K.to(dev)
+        with torch.no_grad():
+            for _ in range(2):
+                er.forward(sd, image, K, c["cfg"])
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(3):
+                er.forward(sd, image, K, c["cfg"])
+            e1.record()
+            torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 3
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32
+    return dict(encoder_ms_per_scene=ms, ours_encoder_ms_per_scene=our_ms_per_scene,
+                encoder_speedup=ms / our_ms_per_scene,
+                what="oracle port of the encoder (functional torch, fp32 weights, TF32 matmul/conv, eager, "
+                     "1 scene of 8 frames) on this GPU; encoder leg only")
+
+
 def scene_seconds_from_sample(t_enc: float, t_frames: int, t_view: float) -> float:
     return t_enc * encoder_flops(T_CTX) / encoder_flops(t_frames) + V_TGT * t_view
 
@@ -437,6 +467,13 @@ def run_ours(args) -> None:
                 value=1.0 / per, unit="scenes/s", cores=torch.get_num_threads(), kind="port",
                 sample=f"oracle encoder forward on all {T_CTX} frames ({te:.1f} s) + 1 of {V_TGT} "
                        f"target views ({tv:.1f} s, x{V_TGT})")
+            # context for the encoder leg (SURVEY.md §8d "its own PyTorch path"): the same oracle
+            # port in eager PyTorch on THIS GPU with TF32 matmuls/convs, as the reference runs
+            # (backbone_vica.py:9) -- a baseline measurement by the checker, nothing we ship
+            try:
+                line["cpu_baseline"]["torch_eager_gpu"] = torch_eager_gpu_encoder(dev, enc_ms / NB)
+            except Exception as e:   # never let the context measurement break the bench line
+                line["cpu_baseline"]["torch_eager_gpu"] = dict(error=str(e)[:200])
         emit(line)
     if world > 1:
         dist.destroy_process_group()
