@@ -37,6 +37,8 @@ cases = dict(
     fc1=lin(16448, 4096, 1024, act=VS_ACT_GELU),
     qkv=lin(16448, 3072, 1024),
     dproj=lin(16512, 768, 768, res=True),
+    dfc1=lin(16512, 3072, 768, act=VS_ACT_GELU),
+    dqkv=lin(16512, 2304, 768),
     stem=stem(),
 )
 for name, fn in cases.items():

@@ -80,19 +80,59 @@ struct GemmDev {
 };
 
 // exact-erf GELU (nn.GELU default, croco/blocks.py:60) with erf from Abramowitz-Stegun 7.1.26
-// (|err| <= 1.5e-7, far below the bf16 rounding of the result): 2 MUFU + ~12 FMA-pipe instructions
-// instead of erff's ~30 -- the GELU epilogue otherwise out-lasts the K = 1024 main loop.
-__device__ __forceinline__ float gelu_erf(float x) {
-  const float z = fabsf(x) * 0.70710678118654752f;
-  float t, e;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * z * z));
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  const float erf_abs = fmaf(-p * t, e, 1.0f);
-  return 0.5f * x * (1.0f + copysignf(erf_abs, x));
+// (|err| <= 1.5e-7, far below the bf16 rounding of the result): 2 MUFU + ~8 FMA-pipe issue slots per
+// value instead of erff's ~30 -- the GELU epilogue otherwise out-lasts the K = 1024 main loop.
+// ---- packed fp32x2 arithmetic (FFMA2 / FMUL2 on sm_100): one issue slot for two lanes of math.
+// The epilogue is issue-bound (8 warps per SM, long dependent chains), not FMA-pipe bound.
+__device__ __forceinline__ uint64_t pk2(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void upk2(uint64_t v, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
+// exact-erf GELU of two values: same Abramowitz-Stegun 7.1.26 polynomial as gelu_erf, rearranged as
+//   gelu(x) = max(x, 0) - 0.5 |x| * (p(t) t) * exp(-z^2),  z = |x| / sqrt(2), t = 1 / (1 + 0.3275911 z)
+// (erf(z) = 1 - p(t) t exp(-z^2) for z >= 0), evaluated with packed FFMA2 / FMUL2: 20 issue slots per
+// pair instead of 2 x 16.
+__device__ __forceinline__ void gelu_erf2(float& x0, float& x1) {
+  const uint64_t AX = pk2(fabsf(x0), fabsf(x1));
+  const uint64_t Z = mul2(AX, pk2(0.70710678118654752f, 0.70710678118654752f));
+  const uint64_t DEN = fma2(pk2(0.3275911f, 0.3275911f), Z, pk2(1.0f, 1.0f));
+  const uint64_t M = mul2(mul2(Z, Z), pk2(-1.4426950408889634f, -1.4426950408889634f));
+  float d0, d1, m0, m1, t0, t1, e0, e1;
+  upk2(DEN, d0, d1);
+  upk2(M, m0, m1);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(d0));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(d1));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(m0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(m1));
+  const uint64_t T = pk2(t0, t1);
+  uint64_t P = fma2(pk2(1.061405429f, 1.061405429f), T, pk2(-1.453152027f, -1.453152027f));
+  P = fma2(P, T, pk2(1.421413741f, 1.421413741f));
+  P = fma2(P, T, pk2(-0.284496736f, -0.284496736f));
+  P = fma2(P, T, pk2(0.254829592f, 0.254829592f));
+  const uint64_t R = mul2(mul2(P, T), pk2(e0, e1));
+  const uint64_t H = mul2(AX, pk2(-0.5f, -0.5f));
+  const uint64_t O = fma2(H, R, pk2(fmaxf(x0, 0.f), fmaxf(x1, 0.f)));
+  upk2(O, x0, x1);
 }
 
 struct TileCoord {
@@ -559,7 +599,7 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
           float b[32];
           load32_f32(g.bias + nb, nv, g.vec & VEC_BIAS, b);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) f[i] += b[i];
+          for (int i = 0; i < 32; i += 2) upk2(add2(pk2(f[i], f[i + 1]), pk2(b[i], b[i + 1])), f[i], f[i + 1]);
         }
         if (g.rope_pos != nullptr &&
             (static_cast<unsigned>(nb - g.rope_q0) < static_cast<unsigned>(g.rope_cols) ||
@@ -590,7 +630,7 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
         }
         if (g.act == VS_ACT_GELU) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) f[i] = gelu_erf(f[i]);
+          for (int i = 0; i < 32; i += 2) gelu_erf2(f[i], f[i + 1]);
         } else if (g.act == VS_ACT_RELU) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
@@ -599,7 +639,10 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
           float gt[32];
           load32_f32(g.gate + static_cast<long long>(my_gate) * g.gate_ld + nb, nv, g.vec & VEC_GATE, gt);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) f[i] *= 1.0f + gt[i];
+          for (int i = 0; i < 32; i += 2) {   // f * (1 + gate) = f * gate + f
+            const uint64_t F = pk2(f[i], f[i + 1]);
+            upk2(fma2(F, pk2(gt[i], gt[i + 1]), F), f[i], f[i + 1]);
+          }
         }
         // Transpose through shared memory: a thread owns a ROW here (TMEM lane), but row-per-thread
         // global accesses cost one LSU wavefront per lane; afterwards a warp instruction touches
