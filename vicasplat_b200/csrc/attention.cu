@@ -35,7 +35,8 @@ constexpr int TILE_BYTES = 128 * 128;        // Q / P tile: 128 rows x 128 B
 constexpr int KV_BYTES = KT * 128;           // K / V tile: 64 rows x 128 B
 constexpr int SMEM_BYTES = 3 * TILE_BYTES /*Q, P x2*/ + 2 * KV_STAGES * KV_BYTES + 1024 /*align*/ +
                            256 /*barriers*/ + 2048 /*row max*/;
-constexpr int ATT_THREADS = 64 + 8 * 32;
+constexpr int SOFT_WARPS = 4;                // one thread per query row
+constexpr int ATT_THREADS = 64 + SOFT_WARPS * 32;
 constexpr int TMEM_COLS = 256;  // S[2]: [0,128)  O'[2]: [128,256)
 
 struct AttnDev {
@@ -79,7 +80,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
   uint64_t *k_full = bars + 8, *k_empty = k_full + KV_STAGES, *v_full = k_empty + KV_STAGES,
            *v_empty = v_full + KV_STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(v_empty + KV_STAGES);
-  float* s_mx = reinterpret_cast<float*>(bars + 32);   // [2 tiles][2 halves][128 rows]
+
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
@@ -95,7 +96,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(s_full + i, 1);
-      mbar_init(p_full + i, 256);
+      mbar_init(p_full + i, SOFT_WARPS * 32);
       mbar_init(o_full + i, 1);
     }
     fence_mbar_init();
@@ -176,13 +177,12 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
       }
     }
   } else {
-    // 8 softmax warps: warps (w, w+4) share TMEM lane quarter q = w & 3, i.e. the same 32 query
-    // rows; `half` owns key columns [32 half, 32 half + 32) of every 64-key S tile and output
-    // columns [32 half, 32 half + 32).  The two halves agree on the row maximum through shared
-    // memory.  The accumulation of O'(j) is deferred until after the probabilities of tile j+1 have
+    // 4 softmax warps: thread r owns query row r (TMEM lane r) and all 64 key columns of every S
+    // tile, so the row maximum / sum never leave the thread (no shared-memory exchange, no named
+    // barrier between warp pairs) and the per-step bookkeeping is paid once per row instead of
+    // twice.  The accumulation of O'(j) is deferred until after the probabilities of tile j+1 have
     // been handed to the tensor core, so it never sits between two MMAs.
     const int q = warp & 3;  // TMEM lane quarter of this warp
-    const int half = (warp - 2) >> 2;
     const int r = q * 32 + lane;
     const int grow = q_row0 + r;  // absolute query row
     const bool row_valid = (qt * QT + r) < q_len;
@@ -191,19 +191,22 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
       lim = (grow / a.causal_block + 1) * a.causal_block;
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     float m = -INFINITY, l = 0.f, alpha_prev = 0.f;
-    float o[HD / 2];
+    float o[HD];
 #pragma unroll
-    for (int i = 0; i < HD / 2; ++i) o[i] = 0.f;
+    for (int i = 0; i < HD; ++i) o[i] = 0.f;
     const int sw = r & 7;
 
-    auto fold = [&](int j) {   // o = o * alpha(j) + O'(j)[my 32 columns]
+    auto fold = [&](int j) {   // o = o * alpha(j) + O'(j)
       mbar_wait(o_full + (j & 1), (j >> 1) & 1);
       tc_fence_after();
-      uint32_t v[32];
-      tmem_ld_32x32(t_lane + 2 * KT + (j & 1) * HD + half * 32, v);
-      tmem_ld_wait();
 #pragma unroll
-      for (int i = 0; i < 32; ++i) o[i] = o[i] * alpha_prev + __uint_as_float(v[i]);
+      for (int h = 0; h < 2; ++h) {
+        uint32_t v[32];
+        tmem_ld_32x32(t_lane + 2 * KT + (j & 1) * HD + h * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[h * 32 + i] = o[h * 32 + i] * alpha_prev + __uint_as_float(v[i]);
+      }
       tc_fence_before();
     };
 
@@ -212,38 +215,39 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
       const int seg_left = j < n0 ? l0 - j * KT : l1 - (j - n0) * KT;
       const int nvalid = min(min(seg_left, KT), lim - row0);  // keys [0, nvalid) of this tile count
       const int nseg = min(seg_left, KT);
-      const bool mine = half * 32 < nseg;      // my 32-column chunk exists in this tile
-      const int my_valid = nvalid - half * 32;  // valid columns of my chunk (may be <= 0 or >= 32)
+      const bool two = nseg > 32;               // the second 32-column half exists (warp-uniform)
       mbar_wait(s_full + (j & 1), (j >> 1) & 1);
       tc_fence_after();
-      uint32_t v[32];
-      float mx = -INFINITY;
-      if (mine) {   // warp-uniform
-        tmem_ld_32x32(t_lane + (j & 1) * KT + half * 32, v);
-        tmem_ld_wait();
-        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-        if (my_valid >= 32) {
+      uint32_t va[32], vb[32];
+      tmem_ld_32x32(t_lane + (j & 1) * KT, va);
+      if (two) tmem_ld_32x32(t_lane + (j & 1) * KT + 32, vb);
+      tmem_ld_wait();
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+      if (nvalid >= KT) {
 #pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            mx0 = fmaxf(mx0, __uint_as_float(v[i]));
-            mx1 = fmaxf(mx1, __uint_as_float(v[i + 1]));
-            mx2 = fmaxf(mx2, __uint_as_float(v[i + 2]));
-            mx3 = fmaxf(mx3, __uint_as_float(v[i + 3]));
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (i < my_valid) mx0 = fmaxf(mx0, __uint_as_float(v[i]));
+        for (int i = 0; i < 32; i += 4) {
+          mx0 = fmaxf(mx0, fmaxf(__uint_as_float(va[i]), __uint_as_float(vb[i])));
+          mx1 = fmaxf(mx1, fmaxf(__uint_as_float(va[i + 1]), __uint_as_float(vb[i + 1])));
+          mx2 = fmaxf(mx2, fmaxf(__uint_as_float(va[i + 2]), __uint_as_float(vb[i + 2])));
+          mx3 = fmaxf(mx3, fmaxf(__uint_as_float(va[i + 3]), __uint_as_float(vb[i + 3])));
         }
-        mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          if (i < nvalid) mx0 = fmaxf(mx0, __uint_as_float(va[i]));
+          if (two && i + 32 < nvalid) mx1 = fmaxf(mx1, __uint_as_float(vb[i]));
+        }
       }
-      s_mx[(j & 1) * 256 + half * 128 + r] = mx;
-      asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");   // the two warps of this quarter
-      mx = fmaxf(mx, s_mx[(j & 1) * 256 + (half ^ 1) * 128 + r]);
+      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
       const float m_new = fmaxf(m, mx * a.scale_log2);
       const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
       float rs0 = 0.f, rs1 = 0.f;
-      if (mine) {
+      uint8_t* p_row = sP + (j & 1) * TILE_BYTES + r * 128;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        if (h == 1 && !two) break;
+        const uint32_t(&v)[32] = h == 0 ? va : vb;
+        const int my_valid = nvalid - h * 32;
         uint32_t pk[16];
         if (my_valid >= 32) {
 #pragma unroll
@@ -268,11 +272,10 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
             pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&b2);
           }
         }
-        // my 32 columns = 16-byte chunks half*4 .. +3 of the row in P tile (j & 1)
-        uint8_t* p_row = sP + (j & 1) * TILE_BYTES + r * 128;
+        // 32 columns = 16-byte chunks h*4 .. +3 of the row in P tile (j & 1)
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
-          const int chunk = (half * 4 + ch) ^ sw;
+          const int chunk = (h * 4 + ch) ^ sw;
           *reinterpret_cast<uint4*>(p_row + chunk * 16) =
               make_uint4(pk[ch * 4], pk[ch * 4 + 1], pk[ch * 4 + 2], pk[ch * 4 + 3]);
         }
@@ -287,15 +290,11 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
       alpha_prev = alpha;
     }
     if (nt > 0) fold(nt - 1);
-    // total row sum = my half + the other half's
-    s_mx[half * 128 + r] = l;
-    asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
-    l += s_mx[(half ^ 1) * 128 + r];
     if (row_valid) {
       const float inv = l > 0.f ? 1.0f / l : 0.f;
-      __nv_bfloat16* dst = a.O + static_cast<long long>(grow) * a.ldo + head * HD + half * 32;
+      __nv_bfloat16* dst = a.O + static_cast<long long>(grow) * a.ldo + head * HD;
 #pragma unroll
-      for (int ch = 0; ch < 4; ++ch) {
+      for (int ch = 0; ch < 8; ++ch) {
         uint32_t w[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
