@@ -165,12 +165,14 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
         tc_fence_after();
         const int seg_left = j < n0 ? l0 - j * KT : l1 - (j - n0) * KT;
         const int ksteps = (min(seg_left, KT) + 15) >> 4;   // keys beyond the segment: P is not even written
+        // O accumulates in TMEM across the key tiles (the softmax warps rescale it in place on the
+        // rare steps where the running row maximum moved by more than the stale-max threshold)
 #pragma unroll 1
         for (int k = 0; k < ksteps; ++k)
-          umma_bf16_ss(tmem_base + 2 * KT + (j & 1) * HD,
+          umma_bf16_ss(tmem_base + 2 * KT,
                        umma_desc_k_sw128(p_addr + (j & 1) * TILE_BYTES + k * 32),
                        umma_desc_mn_sw128(v_addr + st_v * KV_BYTES + k * 2048), idesc_o,
-                       k != 0 ? 1u : 0u);
+                       (j | k) != 0 ? 1u : 0u);
         umma_commit(v_empty + st_v);
         umma_commit(o_full + (j & 1));
         if (++st_v == KV_STAGES) { st_v = 0; ph_v ^= 1; }
@@ -190,25 +192,13 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
     if (a.causal_block > 0 && (grow % a.causal_block) == 0)
       lim = (grow / a.causal_block + 1) * a.causal_block;
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    float m = -INFINITY, l = 0.f, alpha_prev = 0.f;
-    float o[HD];
-#pragma unroll
-    for (int i = 0; i < HD; ++i) o[i] = 0.f;
+    // m: the (stale) row maximum the exponentials are taken against, in the log2 domain.  It only
+    // follows the true maximum when that has grown by more than STALE (probabilities stay <= 2^8,
+    // harmless for the bf16 P tile and the fp32 sums), so O -- which lives in TMEM and is
+    // accumulated by the tensor core itself -- needs rescaling on very few steps.
+    constexpr float STALE = 8.0f;
+    float m = -INFINITY, l = 0.f;
     const int sw = r & 7;
-
-    auto fold = [&](int j) {   // o = o * alpha(j) + O'(j)
-      mbar_wait(o_full + (j & 1), (j >> 1) & 1);
-      tc_fence_after();
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        uint32_t v[32];
-        tmem_ld_32x32(t_lane + 2 * KT + (j & 1) * HD + h * 32, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o[h * 32 + i] = o[h * 32 + i] * alpha_prev + __uint_as_float(v[i]);
-      }
-      tc_fence_before();
-    };
 
     for (int j = 0; j < nt; ++j) {
       const int row0 = j < n0 ? s0 + j * KT : s1 + (j - n0) * KT;
@@ -238,9 +228,29 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
           if (two && i + 32 < nvalid) mx1 = fmaxf(mx1, __uint_as_float(vb[i]));
         }
       }
-      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-      const float m_new = fmaxf(m, mx * a.scale_log2);
-      const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * a.scale_log2;
+      const bool grow_m = mx > m + STALE || (m == -INFINITY && mx > -INFINITY);
+      if (__any_sync(0xffffffffu, grow_m)) {
+        // rescale this warp's 32 rows of O (and l) by 2^(m - m_new); rows that keep m use 1
+        const float alpha = grow_m ? ex2_approx(m - mx) : 1.0f;   // m == -inf -> 0
+        if (grow_m) m = mx;
+        l *= alpha;
+        if (j > 0) {
+          mbar_wait(o_full + ((j - 1) & 1), ((j - 1) >> 1) & 1);   // PV(j-1) has landed
+          tc_fence_after();
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            uint32_t v[32];
+            tmem_ld_32x32(t_lane + 2 * KT + h * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+            tmem_st_32x32(t_lane + 2 * KT + h * 32, v);
+          }
+          tmem_st_wait();
+        }
+      }
+      const float m_use = (m == -INFINITY) ? 0.f : m;
       float rs0 = 0.f, rs1 = 0.f;
       uint8_t* p_row = sP + (j & 1) * TILE_BYTES + r * 128;
 #pragma unroll
@@ -283,28 +293,39 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
       fence_proxy_async();
       tc_fence_before();
       mbar_arrive(p_full + (j & 1));
-      const float alpha = ex2_approx(m - m_use);  // m == -inf -> 0
-      l = l * alpha + (rs0 + rs1);
-      m = m_new;
-      if (j > 0) fold(j - 1);   // uses alpha_prev = alpha(j-1)
-      alpha_prev = alpha;
+      l += rs0 + rs1;
     }
-    if (nt > 0) fold(nt - 1);
-    if (row_valid) {
-      const float inv = l > 0.f ? 1.0f / l : 0.f;
-      __nv_bfloat16* dst = a.O + static_cast<long long>(grow) * a.ldo + head * HD;
+    if (nt > 0) {
+      mbar_wait(o_full + ((nt - 1) & 1), ((nt - 1) >> 1) & 1);
+      tc_fence_after();
+    }
+    const float inv = l > 0.f ? 1.0f / l : 0.f;
+    __nv_bfloat16* dst = a.O + static_cast<long long>(grow) * a.ldo + head * HD;
 #pragma unroll
-      for (int ch = 0; ch < 8; ++ch) {
-        uint32_t w[4];
+    for (int h = 0; h < 2; ++h) {
+      uint32_t v[32];
+      if (nt > 0) {
+        tmem_ld_32x32(t_lane + 2 * KT + h * 32, v);
+        tmem_ld_wait();
+      } else {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const __nv_bfloat162 b2 =
-              __floats2bfloat162_rn(o[ch * 8 + 2 * i] * inv, o[ch * 8 + 2 * i + 1] * inv);
-          w[i] = *reinterpret_cast<const uint32_t*>(&b2);
+        for (int i = 0; i < 32; ++i) v[i] = 0u;
+      }
+      if (row_valid) {
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          uint32_t w[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const __nv_bfloat162 b2 = __floats2bfloat162_rn(__uint_as_float(v[ch * 8 + 2 * i]) * inv,
+                                                            __uint_as_float(v[ch * 8 + 2 * i + 1]) * inv);
+            w[i] = *reinterpret_cast<const uint32_t*>(&b2);
+          }
+          *reinterpret_cast<uint4*>(dst + h * 32 + ch * 8) = make_uint4(w[0], w[1], w[2], w[3]);
         }
-        *reinterpret_cast<uint4*>(dst + ch * 8) = make_uint4(w[0], w[1], w[2], w[3]);
       }
     }
+    tc_fence_before();
   }
 
   tc_fence_before();
