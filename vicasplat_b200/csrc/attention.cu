@@ -29,15 +29,14 @@ namespace {
 constexpr int QT = 128;   // queries per CTA
 constexpr int KT = 64;    // keys per step
 constexpr int HD = 64;
-constexpr int KV_STAGES = 3;                 // K and V tiles in flight: TMA latency (~1.5 us) is
-                                             // what paced the single-buffered version
+constexpr int KV_STAGES = 2;                 // K and V tiles in flight per CTA (x 3 CTAs per SM)
 constexpr int TILE_BYTES = 128 * 128;        // Q / P tile: 128 rows x 128 B
 constexpr int KV_BYTES = KT * 128;           // K / V tile: 64 rows x 128 B
-constexpr int SMEM_BYTES = 3 * TILE_BYTES /*Q, P x2*/ + 2 * KV_STAGES * KV_BYTES + 1024 /*align*/ +
-                           256 /*barriers*/ + 2048 /*row max*/;
+constexpr int SMEM_BYTES = 2 * TILE_BYTES /*Q, P*/ + 2 * KV_STAGES * KV_BYTES + 1024 /*align*/ +
+                           256 /*barriers*/;   // 65 KB: three CTAs per SM
 constexpr int SOFT_WARPS = 4;                // one thread per query row
 constexpr int ATT_THREADS = 64 + SOFT_WARPS * 32;
-constexpr int TMEM_COLS = 256;  // S[2]: [0,128)  O'[2]: [128,256)
+constexpr int TMEM_COLS = 128;  // S: [0,64)  O: [64,128)  -- 3 CTAs x 128 of the SM's 512 columns
 
 struct AttnDev {
   __nv_bfloat16* O;
@@ -54,7 +53,7 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
-__global__ void __launch_bounds__(ATT_THREADS, 2)
+__global__ void __launch_bounds__(ATT_THREADS, 3)
     attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, const AttnDev a) {
   const int item = blockIdx.z, head = blockIdx.y, qt = blockIdx.x;
@@ -71,12 +70,12 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
   uint8_t* smem = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* sQ = smem;
-  uint8_t* sP = smem + TILE_BYTES;                       // two P tiles (one 64-wide k-block each)
-  uint8_t* sK = smem + 3 * TILE_BYTES;                   // ring of KV_STAGES tiles
+  uint8_t* sP = smem + TILE_BYTES;                       // one P tile (128 rows x 64 keys, bf16)
+  uint8_t* sK = smem + 2 * TILE_BYTES;                   // ring of KV_STAGES tiles
   uint8_t* sV = sK + KV_STAGES * KV_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sV + KV_STAGES * KV_BYTES);
-  uint64_t *q_full = bars, *s_full = bars + 1 /*[2]*/, *p_full = bars + 3 /*[2]*/,
-           *o_full = bars + 5 /*[2]*/;
+  uint64_t *q_full = bars, *s_full = bars + 1, *s_free = bars + 2, *p_full = bars + 3,
+           *o_full = bars + 4;
   uint64_t *k_full = bars + 8, *k_empty = k_full + KV_STAGES, *v_full = k_empty + KV_STAGES,
            *v_empty = v_full + KV_STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(v_empty + KV_STAGES);
@@ -94,11 +93,10 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
       mbar_init(v_full + i, 1);
       mbar_init(v_empty + i, 1);
     }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(s_full + i, 1);
-      mbar_init(p_full + i, SOFT_WARPS * 32);
-      mbar_init(o_full + i, 1);
-    }
+    mbar_init(s_full, 1);
+    mbar_init(s_free, SOFT_WARPS * 32);
+    mbar_init(p_full, SOFT_WARPS * 32);
+    mbar_init(o_full, 1);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -109,7 +107,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  // TMEM columns: S[b] at b*64, O'[b] at 128 + b*64 (b = tile parity)
+  // TMEM columns: S at 0, O at 64
 
   if (warp == 0) {
     if (lane == 0) {
@@ -127,11 +125,11 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
       }
     }
   } else if (warp == 1) {
-    // Software pipeline: S(j+1) = Q K(j+1)^T is issued BEFORE waiting for the probabilities of tile
-    // j, so the tensor core works on the next scores while the softmax warps are busy; S, P and O'
-    // are double buffered by tile parity.  Buffer reuse is ordered by the p_full waits below:
-    // every softmax thread arrives on p_full[j&1] only after it has read S(j), and (deferred
-    // accumulation) after it has read O'(j-2) and seen o_full of MMA2(j-2), which also frees P(j-2).
+    // Software pipeline: S(j+1) = Q K(j+1)^T is issued as soon as the softmax warps have copied
+    // S(j) into registers (s_free), i.e. BEFORE the probabilities of tile j exist, so the tensor
+    // core works on the next scores while the exponentials are computed.  S, P and O are single
+    // buffered (128 TMEM columns and 65 KB of shared memory per CTA -> three CTAs per SM, whose
+    // phases interleave); every barrier completes once per key tile, phase parity = j & 1.
     if (lane == 0) {
       constexpr uint32_t idesc_s = umma_idesc_bf16(QT, KT, 0);
       constexpr uint32_t idesc_o = umma_idesc_bf16(QT, HD, 1);
@@ -140,10 +138,10 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
       auto issue_s = [&](int j, int st) {
 #pragma unroll
         for (int k = 0; k < HD / 16; ++k)
-          umma_bf16_ss(tmem_base + (j & 1) * KT, umma_desc_k_sw128(q_addr + k * 32),
+          umma_bf16_ss(tmem_base, umma_desc_k_sw128(q_addr + k * 32),
                        umma_desc_k_sw128(k_addr + st * KV_BYTES + k * 32), idesc_s, k != 0 ? 1u : 0u);
         umma_commit(k_empty + st);
-        umma_commit(s_full + (j & 1));
+        umma_commit(s_full);
       };
       mbar_wait(q_full, 0);
       int st_k = 0, ph_k = 0;   // ring position of the next K tile to consume
@@ -156,12 +154,13 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
       for (int j = 0, st_v = 0, ph_v = 0; j < nt; ++j) {
         if (j + 1 < nt) {
           mbar_wait(k_full + st_k, ph_k);
+          mbar_wait(s_free, j & 1);          // S(j) is in the softmax warps' registers
           tc_fence_after();
           issue_s(j + 1, st_k);
           if (++st_k == KV_STAGES) { st_k = 0; ph_k ^= 1; }
         }
         mbar_wait(v_full + st_v, ph_v);
-        mbar_wait(p_full + (j & 1), (j >> 1) & 1);
+        mbar_wait(p_full, j & 1);
         tc_fence_after();
         const int seg_left = j < n0 ? l0 - j * KT : l1 - (j - n0) * KT;
         const int ksteps = (min(seg_left, KT) + 15) >> 4;   // keys beyond the segment: P is not even written
@@ -169,12 +168,12 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
         // rare steps where the running row maximum moved by more than the stale-max threshold)
 #pragma unroll 1
         for (int k = 0; k < ksteps; ++k)
-          umma_bf16_ss(tmem_base + 2 * KT,
-                       umma_desc_k_sw128(p_addr + (j & 1) * TILE_BYTES + k * 32),
+          umma_bf16_ss(tmem_base + KT,
+                       umma_desc_k_sw128(p_addr + k * 32),
                        umma_desc_mn_sw128(v_addr + st_v * KV_BYTES + k * 2048), idesc_o,
                        (j | k) != 0 ? 1u : 0u);
         umma_commit(v_empty + st_v);
-        umma_commit(o_full + (j & 1));
+        umma_commit(o_full);
         if (++st_v == KV_STAGES) { st_v = 0; ph_v ^= 1; }
       }
     }
@@ -206,26 +205,30 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
       const int nvalid = min(min(seg_left, KT), lim - row0);  // keys [0, nvalid) of this tile count
       const int nseg = min(seg_left, KT);
       const bool two = nseg > 32;               // the second 32-column half exists (warp-uniform)
-      mbar_wait(s_full + (j & 1), (j >> 1) & 1);
+      mbar_wait(s_full, j & 1);
       tc_fence_after();
-      uint32_t va[32], vb[32];
-      tmem_ld_32x32(t_lane + (j & 1) * KT, va);
-      if (two) tmem_ld_32x32(t_lane + (j & 1) * KT + 32, vb);
-      tmem_ld_wait();
+      // pass 1: row maximum, 32 columns at a time (only 32 score registers are ever live: three
+      // CTAs per SM leave 96 registers per thread)
       float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-      if (nvalid >= KT) {
 #pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          mx0 = fmaxf(mx0, fmaxf(__uint_as_float(va[i]), __uint_as_float(vb[i])));
-          mx1 = fmaxf(mx1, fmaxf(__uint_as_float(va[i + 1]), __uint_as_float(vb[i + 1])));
-          mx2 = fmaxf(mx2, fmaxf(__uint_as_float(va[i + 2]), __uint_as_float(vb[i + 2])));
-          mx3 = fmaxf(mx3, fmaxf(__uint_as_float(va[i + 3]), __uint_as_float(vb[i + 3])));
-        }
-      } else {
+      for (int h = 0; h < 2; ++h) {
+        if (h == 1 && !two) break;
+        uint32_t v[32];
+        tmem_ld_32x32(t_lane + h * 32, v);
+        tmem_ld_wait();
+        const int my_valid = nvalid - h * 32;
+        if (my_valid >= 32) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          if (i < nvalid) mx0 = fmaxf(mx0, __uint_as_float(va[i]));
-          if (two && i + 32 < nvalid) mx1 = fmaxf(mx1, __uint_as_float(vb[i]));
+          for (int i = 0; i < 32; i += 4) {
+            mx0 = fmaxf(mx0, __uint_as_float(v[i]));
+            mx1 = fmaxf(mx1, __uint_as_float(v[i + 1]));
+            mx2 = fmaxf(mx2, __uint_as_float(v[i + 2]));
+            mx3 = fmaxf(mx3, __uint_as_float(v[i + 3]));
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (i < my_valid) mx0 = fmaxf(mx0, __uint_as_float(v[i]));
         }
       }
       const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * a.scale_log2;
@@ -236,27 +239,34 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
         if (grow_m) m = mx;
         l *= alpha;
         if (j > 0) {
-          mbar_wait(o_full + ((j - 1) & 1), ((j - 1) >> 1) & 1);   // PV(j-1) has landed
+          mbar_wait(o_full, (j - 1) & 1);   // PV(j-1) has landed
           tc_fence_after();
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             uint32_t v[32];
-            tmem_ld_32x32(t_lane + 2 * KT + h * 32, v);
+            tmem_ld_32x32(t_lane + KT + h * 32, v);
             tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
-            tmem_st_32x32(t_lane + 2 * KT + h * 32, v);
+            tmem_st_32x32(t_lane + KT + h * 32, v);
           }
           tmem_st_wait();
         }
       }
       const float m_use = (m == -INFINITY) ? 0.f : m;
       float rs0 = 0.f, rs1 = 0.f;
-      uint8_t* p_row = sP + (j & 1) * TILE_BYTES + r * 128;
+      uint8_t* p_row = sP + r * 128;
+      bool p_free = j == 0;              // PV(j-1) must have consumed the P tile before it is rewritten
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         if (h == 1 && !two) break;
-        const uint32_t(&v)[32] = h == 0 ? va : vb;
+        uint32_t v[32];                    // pass 2: the same 32 scores again
+        tmem_ld_32x32(t_lane + h * 32, v);
+        tmem_ld_wait();
+        if (h == 1 || !two) {              // S(j) is not needed any more: the tensor core may
+          tc_fence_before();               // overwrite it with tile j+1
+          mbar_arrive(s_free);
+        }
         const int my_valid = nvalid - h * 32;
         uint32_t pk[16];
         if (my_valid >= 32) {
@@ -282,7 +292,11 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
             pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&b2);
           }
         }
-        // 32 columns = 16-byte chunks h*4 .. +3 of the row in P tile (j & 1)
+        if (!p_free) {
+          mbar_wait(o_full, (j - 1) & 1);
+          p_free = true;
+        }
+        // 32 columns = 16-byte chunks h*4 .. +3 of the row in the P tile
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
           const int chunk = (h * 4 + ch) ^ sw;
@@ -292,11 +306,11 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
       }
       fence_proxy_async();
       tc_fence_before();
-      mbar_arrive(p_full + (j & 1));
+      mbar_arrive(p_full);
       l += rs0 + rs1;
     }
     if (nt > 0) {
-      mbar_wait(o_full + ((nt - 1) & 1), ((nt - 1) >> 1) & 1);
+      mbar_wait(o_full, (nt - 1) & 1);
       tc_fence_after();
     }
     const float inv = l > 0.f ? 1.0f / l : 0.f;
@@ -305,7 +319,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
     for (int h = 0; h < 2; ++h) {
       uint32_t v[32];
       if (nt > 0) {
-        tmem_ld_32x32(t_lane + 2 * KT + h * 32, v);
+        tmem_ld_32x32(t_lane + KT + h * 32, v);
         tmem_ld_wait();
       } else {
 #pragma unroll
