@@ -19,6 +19,7 @@ Launch sequence per stage (reference lines in brackets):
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass, field
 from typing import Dict, Optional
 
@@ -323,6 +324,9 @@ class EncoderEngine:
         self.m = model
         self.bb = model._bb
         self.use_graph = use_graph
+        # K = 448 stem: the bilinear-x2 residual gathered in the GEMM epilogue costs ~4x the main
+        # loop in issue slots; a stand-alone upsample + plain bf16 residual is HBM-bound instead
+        self.fuse_stem_upsample = os.environ.get("VS_FUSE_STEM_UP", "1") == "1"
         self.dev = next(model.parameters()).device
         assert self.dev.type == "cuda", "move the module to CUDA first"
         self.sd = {k: v.detach() for k, v in model.state_dict().items()}
@@ -632,10 +636,16 @@ class EncoderEngine:
         img8 = ops.image_nhwc8(pl["image"], pad=3)                        # (Fr, H+6, W+8, 8)
         # relu(conv7x7(image)) + bilinear_x2(p1): the image is addressed through an overlapping TMA
         # view (no im2col buffer), the upsampling happens in the epilogue (no full-res copy of p1)
-        merged = ops.conv_gemm(img8, w[k + ".merger"], kh=7, kw=1, pad=0, N=FEAT,
-                               bias=w[k + ".input_merger.0.bias"], act=VS_ACT_RELU, res1=p1,
-                               res_up2=True,
-                               view=(Fr, H, W, 64, H + 6, 8, (W + 8) * 8, (H + 6) * (W + 8) * 8))
+        if self.fuse_stem_upsample:
+            merged = ops.conv_gemm(img8, w[k + ".merger"], kh=7, kw=1, pad=0, N=FEAT,
+                                   bias=w[k + ".input_merger.0.bias"], act=VS_ACT_RELU, res1=p1,
+                                   res_up2=True,
+                                   view=(Fr, H, W, 64, H + 6, 8, (W + 8) * 8, (H + 6) * (W + 8) * 8))
+        else:
+            merged = ops.conv_gemm(img8, w[k + ".merger"], kh=7, kw=1, pad=0, N=FEAT,
+                                   bias=w[k + ".input_merger.0.bias"], act=VS_ACT_RELU,
+                                   res1=ops.upsample2x(p1),
+                                   view=(Fr, H, W, 64, H + 6, 8, (W + 8) * 8, (H + 6) * (W + 8) * 8))
         y = self._conv(merged, k + ".head.0", act=VS_ACT_RELU)
         ops.gemm(y.view(-1, FEAT), w[k + ".head.4"], bias=w[k + ".head.4.bias"], out=gsp,
                  N=self.m.raw_gs_dim)
