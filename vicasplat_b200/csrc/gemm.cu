@@ -55,18 +55,18 @@ struct GemmDev {
   const float* bias;
   int act;
   const float* gate;
-  long long gate_ld;
+  int gate_ld;
   int gate_rows, first_row_mode;
   const void* res1;
   const void* res2;
   int res_dtype;
   int res_up2;
-  long long res_ld;
+  int res_ld;
   void* C;
   int c_dtype;
-  long long ldc;
+  int ldc;        // leading dimensions fit 31 bits (checked on the host): row * ld is one IMAD.WIDE
   __nv_bfloat16* C2;
-  long long ldc2;
+  int ldc2;
   int out_gin, out_gout, out_off;
   int vec;
   int fast;      // every present C / C2 / residual pointer allows aligned 4-column segments
@@ -294,16 +294,16 @@ __device__ __forceinline__ void load_res_seg(const GemmDev& g, int rk, const int
   if (rk == 1) {
 #pragma unroll
     for (int j = 0; j < 8; ++j)
-      r[j] = *reinterpret_cast<const uint4*>(static_cast<const float*>(g.res1) +
-                                             static_cast<long long>(max(oj[j], 0)) * g.res_ld + col);
+      r[j] = *reinterpret_cast<const uint4*>(static_cast<const float*>(g.res1) + col +
+                                             static_cast<long long>(max(oj[j], 0)) * g.res_ld);
   } else if (rk == 2) {
     const __nv_bfloat16* r2 = static_cast<const __nv_bfloat16*>(g.res2 != nullptr ? g.res2 : g.res1);
     const uint32_t keep2 = g.res2 != nullptr ? 0xffffffffu : 0u;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const long long off = static_cast<long long>(max(oj[j], 0)) * g.res_ld + col;
-      const uint2 lo = *reinterpret_cast<const uint2*>(static_cast<const __nv_bfloat16*>(g.res1) + off);
-      const uint2 hi = *reinterpret_cast<const uint2*>(r2 + off);
+      const long long off = static_cast<long long>(max(oj[j], 0)) * g.res_ld;
+      const uint2 lo = *reinterpret_cast<const uint2*>(static_cast<const __nv_bfloat16*>(g.res1) + col + off);
+      const uint2 hi = *reinterpret_cast<const uint2*>(r2 + col + off);
       r[j] = make_uint4(lo.x, lo.y, hi.x & keep2, hi.y & keep2);
     }
   }
@@ -321,9 +321,13 @@ __device__ __forceinline__ float4 ld_shared_f4(uint32_t addr) {
 // Fast store phase of one 32 x 32 chunk (aligned pointers, full chunk): lane l owns columns
 // [col, col+4) of rows 4j + l/8.  RK = residual kind, CF32 = fp32 output.
 template <int RK, bool CF32>
-__device__ __forceinline__ void epi_store(const GemmDev& g, uint32_t tile_s, int lane, const int (&oj)[8],
-                                          int col, const uint4 (&rb)[8], int pix_x, int pix_y, int pix_im) {
-  const int cs = lane & 7;
+__device__ __forceinline__ void epi_store(const GemmDev& g, const uint32_t (&lds_base)[2], int lane,
+                                          const int (&oj)[8], int col, const uint4 (&rb)[8], int pix_x,
+                                          int pix_y, int pix_im) {
+  // per chunk: column-adjusted base pointers; per row one 32 x 32 -> 64 multiply-add each
+  float* const cf = static_cast<float*>(g.C) + col;
+  __nv_bfloat16* const cb = static_cast<__nv_bfloat16*>(g.C) + col;
+  __nv_bfloat16* const c2 = g.C2 != nullptr ? g.C2 + col : nullptr;
 #pragma unroll
   for (int jh = 0; jh < 8; jh += 4) {
     uint2 up[RK == 3 ? 4 : 1][4];
@@ -350,8 +354,8 @@ __device__ __forceinline__ void epi_store(const GemmDev& g, uint32_t tile_s, int
 #pragma unroll
     for (int j4 = 0; j4 < 4; ++j4) {
       const int j = jh + j4;
-      const int rr = 4 * j + (lane >> 3);
-      float4 t = ld_shared_f4(tile_s + (rr * 8 + (cs ^ (rr & 7))) * 16);
+      [[maybe_unused]] const int rr = 4 * j + (lane >> 3);
+      float4 t = ld_shared_f4(lds_base[j & 1] + j * 512);
       if (RK == 1) {
         t.x += __uint_as_float(rb[j].x); t.y += __uint_as_float(rb[j].y);
         t.z += __uint_as_float(rb[j].z); t.w += __uint_as_float(rb[j].w);
@@ -370,12 +374,11 @@ __device__ __forceinline__ void epi_store(const GemmDev& g, uint32_t tile_s, int
         t.z += __bfloat162float(__float2bfloat16(acc.z)); t.w += __bfloat162float(__float2bfloat16(acc.w));
       }
       if (oj[j] >= 0) {
-        const long long o = oj[j];
         if (CF32)
-          *reinterpret_cast<float4*>(static_cast<float*>(g.C) + o * g.ldc + col) = t;
+          *reinterpret_cast<float4*>(cf + static_cast<long long>(oj[j]) * g.ldc) = t;
         else
-          store4_bf16(static_cast<__nv_bfloat16*>(g.C) + o * g.ldc + col, 4, true, t, false);
-        if (g.C2 != nullptr) store4_bf16(g.C2 + o * g.ldc2 + col, 4, true, t, true);
+          store4_bf16(cb + static_cast<long long>(oj[j]) * g.ldc, 4, true, t, false);
+        if (c2 != nullptr) store4_bf16(c2 + static_cast<long long>(oj[j]) * g.ldc2, 4, true, t, true);
       }
     }
   }
@@ -525,7 +528,16 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
     const int half = ew >> 2;          // column half when 8 epilogue warps
     const int r = q * 32 + lane;       // tile row owned by this thread
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    const uint32_t tile_s = smem_u32(epi_scratch + ew * 256);
+    const uint32_t tile_s = smem_u32(epi_scratch + ew * 256);   // 4 KB, 256-byte aligned
+    // write side: row = lane, 16-byte slot i ^ (lane & 7)  ->  st_base ^ (i << 4)
+    const uint32_t st_base = (tile_s + lane * 128) | ((lane & 7) << 4);
+    // read side: row 4 j + (lane >> 3), slot (lane & 7) ^ (row & 7); row & 7 only depends on j & 1
+    uint32_t lds_base[2];
+#pragma unroll
+    for (int pj = 0; pj < 2; ++pj) {
+      const int rq = (lane >> 3) + 4 * pj;
+      lds_base[pj] = tile_s + (lane >> 3) * 128 + (((lane & 7) ^ rq) << 4);
+    }
     uint32_t ti = 0;
     for (int u = unit0; u < total_units; u += unit_step, ++ti) {
       const TileCoord tc = tile_coord(g, u, rank, CL, BN);
@@ -649,19 +661,19 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
         // 4 rows x 128 B.
 #pragma unroll
         for (int i = 0; i < 8; ++i)
-          st_shared_f4(tile_s + (lane * 8 + (i ^ (lane & 7))) * 16, f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+          st_shared_f4(st_base ^ (i << 4), f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
         __syncwarp();
         if (fast) {
           const bool cf32 = g.c_dtype == VS_F32;
           switch (rk) {
-            case 0: cf32 ? epi_store<0, true>(g, tile_s, lane, oj, col, rb, 0, 0, 0)
-                         : epi_store<0, false>(g, tile_s, lane, oj, col, rb, 0, 0, 0); break;
-            case 1: cf32 ? epi_store<1, true>(g, tile_s, lane, oj, col, rb, 0, 0, 0)
-                         : epi_store<1, false>(g, tile_s, lane, oj, col, rb, 0, 0, 0); break;
-            case 2: cf32 ? epi_store<2, true>(g, tile_s, lane, oj, col, rb, 0, 0, 0)
-                         : epi_store<2, false>(g, tile_s, lane, oj, col, rb, 0, 0, 0); break;
-            default: cf32 ? epi_store<3, true>(g, tile_s, lane, oj, col, rb, pix_x, pix_y, pix_im)
-                          : epi_store<3, false>(g, tile_s, lane, oj, col, rb, pix_x, pix_y, pix_im); break;
+            case 0: cf32 ? epi_store<0, true>(g, lds_base, lane, oj, col, rb, 0, 0, 0)
+                         : epi_store<0, false>(g, lds_base, lane, oj, col, rb, 0, 0, 0); break;
+            case 1: cf32 ? epi_store<1, true>(g, lds_base, lane, oj, col, rb, 0, 0, 0)
+                         : epi_store<1, false>(g, lds_base, lane, oj, col, rb, 0, 0, 0); break;
+            case 2: cf32 ? epi_store<2, true>(g, lds_base, lane, oj, col, rb, 0, 0, 0)
+                         : epi_store<2, false>(g, lds_base, lane, oj, col, rb, 0, 0, 0); break;
+            default: cf32 ? epi_store<3, true>(g, lds_base, lane, oj, col, rb, pix_x, pix_y, pix_im)
+                          : epi_store<3, false>(g, lds_base, lane, oj, col, rb, pix_x, pix_y, pix_im); break;
           }
         } else {
           const int nvl = min(4, g.N - col);
@@ -799,22 +811,25 @@ extern "C" int vs_gemm(const vs_gemm_params* p, vs_stream_t stream_) {
   g.bias = p->bias;
   g.act = p->act;
   g.gate = p->gate;
-  g.gate_ld = p->gate_ld;
+  g.gate_ld = static_cast<int>(p->gate_ld);
   g.gate_rows = p->gate_rows;
   g.first_row_mode = p->first_row_mode;
   g.res1 = p->res1;
   g.res2 = p->res2;
   g.res_dtype = p->res_dtype;
   g.res_up2 = p->res_up2;
-  g.res_ld = p->res_ld;
+  g.res_ld = static_cast<int>(p->res_ld);
   VS_REQUIRE(!p->res_up2 || (p->a_mode == 1 && p->res1 && p->res_dtype == VS_BF16 && !p->res2 &&
                              p->ch % 2 == 0 && p->cw % 2 == 0),
              "vs_gemm: res_up2 needs conv mode, one bf16 residual map and even output sizes");
   g.C = p->C;
   g.c_dtype = p->c_dtype;
-  g.ldc = p->ldc;
+  VS_REQUIRE(p->ldc >= 0 && p->ldc < (1ll << 31) && p->ldc2 >= 0 && p->ldc2 < (1ll << 31) &&
+                 p->res_ld >= 0 && p->res_ld < (1ll << 31) && p->gate_ld >= 0 && p->gate_ld < (1ll << 31),
+             "vs_gemm: leading dimensions must fit 31 bits");
+  g.ldc = static_cast<int>(p->ldc);
   g.C2 = static_cast<__nv_bfloat16*>(p->C2);
-  g.ldc2 = p->ldc2;
+  g.ldc2 = static_cast<int>(p->ldc2);
   g.out_gin = p->out_gin;
   g.out_gout = p->out_gout;
   g.out_off = p->out_off;
