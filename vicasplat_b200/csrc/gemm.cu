@@ -35,6 +35,13 @@
 namespace vs {
 namespace {
 
+#ifdef VS_EPI_TIMING
+__device__ long long g_epi_stamps[16];
+#define EPI_STAMP(i) do { if (dbg_on) g_epi_stamps[i] = clock64(); } while (0)
+#else
+#define EPI_STAMP(i) do { } while (0)
+#endif
+
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = one 128-byte swizzle row
 
@@ -284,29 +291,40 @@ __device__ __forceinline__ Up2Taps up2_taps(int x, int y, int ch, int cw, float 
   return t;
 }
 
-// all 8 residual segments of one chunk in flight at once (fast path: aligned, full chunk).
-// kind 1: 4 fp32; kind 2: 4 bf16 of res1 in .xy and of res2 (or zeros) in .zw.  Plain (coherent)
-// loads: the residual stream may be updated in place by this very kernel.
-__device__ __forceinline__ void load_res_seg(const GemmDev& g, int rk, const int (&oj)[8], int col,
-                                             uint4 (&r)[8]) {
-  // unconditional loads (rows without output read row 0 and are never stored): a predicated
-  // load would become a branch whose join waits for the data, serialising the 8 requests
+// Residual segments of one chunk, global -> this warp's 4 KB shared buffer with cp.async (lane l,
+// row-group j: 16 bytes at j * 512 + l * 16; kind 1: 4 fp32; kind 2: 4 bf16 of res1 then 4 bf16 of
+// res2 or zeros).  NOT through registers: an outstanding LDG is waited for by the next
+// tcgen05.wait::ld (same scoreboard -- in-kernel stamps showed ~2 000 clk there per chunk), an
+// async copy is not.  Rows without output read row 0 and are never stored.  Plain (coherent)
+// global reads: the residual stream may be updated in place by this very kernel.
+__device__ __forceinline__ void res_async_issue(const GemmDev& g, int rk, const int (&oj)[8], int col,
+                                                uint32_t res_s, int lane) {
+  const uint32_t dst = res_s + lane * 16;
   if (rk == 1) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
-      r[j] = *reinterpret_cast<const uint4*>(static_cast<const float*>(g.res1) + col +
-                                             static_cast<long long>(max(oj[j], 0)) * g.res_ld);
+    for (int j = 0; j < 8; ++j) {
+      const float* src = static_cast<const float*>(g.res1) + col + static_cast<long long>(max(oj[j], 0)) * g.res_ld;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + j * 512), "l"(src) : "memory");
+    }
   } else if (rk == 2) {
     const __nv_bfloat16* r2 = static_cast<const __nv_bfloat16*>(g.res2 != nullptr ? g.res2 : g.res1);
-    const uint32_t keep2 = g.res2 != nullptr ? 0xffffffffu : 0u;
+    const int n2 = g.res2 != nullptr ? 8 : 0;   // src-size 0: the 8 bytes are zero-filled
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const long long off = static_cast<long long>(max(oj[j], 0)) * g.res_ld;
-      const uint2 lo = *reinterpret_cast<const uint2*>(static_cast<const __nv_bfloat16*>(g.res1) + col + off);
-      const uint2 hi = *reinterpret_cast<const uint2*>(r2 + col + off);
-      r[j] = make_uint4(lo.x, lo.y, hi.x & keep2, hi.y & keep2);
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + j * 512),
+                   "l"(static_cast<const __nv_bfloat16*>(g.res1) + col + off) : "memory");
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst + j * 512 + 8),
+                   "l"(r2 + col + off), "r"(n2) : "memory");
     }
   }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void res_async_wait() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ uint4 ld_shared_u4(uint32_t addr) {
+  uint4 t;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(t.x), "=r"(t.y), "=r"(t.z), "=r"(t.w) : "r"(addr));
+  return t;
 }
 
 __device__ __forceinline__ void st_shared_f4(uint32_t addr, float a, float b, float c, float d) {
@@ -314,7 +332,10 @@ __device__ __forceinline__ void st_shared_f4(uint32_t addr, float a, float b, fl
 }
 __device__ __forceinline__ float4 ld_shared_f4(uint32_t addr) {
   float4 t;
-  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w) : "r"(addr) : "memory");
+  // volatile (ordered against the st.shared / __syncwarp around it) but NO memory clobber: the global
+  // stores that consume these values must stay free to be scheduled behind all eight loads --
+  // with the clobber every row was a serial LDS -> STG round trip (~120 clk each, in-kernel stamps)
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w) : "r"(addr));
   return t;
 }
 
@@ -323,7 +344,7 @@ __device__ __forceinline__ float4 ld_shared_f4(uint32_t addr) {
 template <int RK, bool CF32>
 __device__ __forceinline__ void epi_store(const GemmDev& g, const uint32_t (&lds_base)[2], int lane,
                                           const int (&oj)[8], int col, const uint4 (&rb)[8], int pix_x,
-                                          int pix_y, int pix_im) {
+                                          int pix_y, int pix_im, bool all_rows) {
   // per chunk: column-adjusted base pointers; per row one 32 x 32 -> 64 multiply-add each
   float* const cf = static_cast<float*>(g.C) + col;
   __nv_bfloat16* const cb = static_cast<__nv_bfloat16*>(g.C) + col;
@@ -351,10 +372,10 @@ __device__ __forceinline__ void epi_store(const GemmDev& g, const uint32_t (&lds
         }
       }
     }
+    float4 tv[4];
 #pragma unroll
     for (int j4 = 0; j4 < 4; ++j4) {
       const int j = jh + j4;
-      [[maybe_unused]] const int rr = 4 * j + (lane >> 3);
       float4 t = ld_shared_f4(lds_base[j & 1] + j * 512);
       if (RK == 1) {
         t.x += __uint_as_float(rb[j].x); t.y += __uint_as_float(rb[j].y);
@@ -373,12 +394,32 @@ __device__ __forceinline__ void epi_store(const GemmDev& g, const uint32_t (&lds
         t.x += __bfloat162float(__float2bfloat16(acc.x)); t.y += __bfloat162float(__float2bfloat16(acc.y));
         t.z += __bfloat162float(__float2bfloat16(acc.z)); t.w += __bfloat162float(__float2bfloat16(acc.w));
       }
-      if (oj[j] >= 0) {
-        if (CF32)
-          *reinterpret_cast<float4*>(cf + static_cast<long long>(oj[j]) * g.ldc) = t;
-        else
-          store4_bf16(cb + static_cast<long long>(oj[j]) * g.ldc, 4, true, t, false);
-        if (c2 != nullptr) store4_bf16(c2 + static_cast<long long>(oj[j]) * g.ldc2, 4, true, t, true);
+      tv[j4] = t;
+    }
+    // Stores.  A per-row `if (row valid)` compiles to a branch region per row, which serialises
+    // LDS -> STG round trips (~120 clk per row, in-kernel stamps); interior tiles (every row of
+    // the warp valid, warp-uniform flag) therefore take the branch-free path.
+    if (all_rows) {
+#pragma unroll
+      for (int j4 = 0; j4 < 4; ++j4) {
+        const long long o = oj[jh + j4];
+        if (CF32) *reinterpret_cast<float4*>(cf + o * g.ldc) = tv[j4];
+        else store4_bf16(cb + o * g.ldc, 4, true, tv[j4], false);
+      }
+      if (c2 != nullptr) {
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4)
+          store4_bf16(c2 + static_cast<long long>(oj[jh + j4]) * g.ldc2, 4, true, tv[j4], true);
+      }
+    } else {
+#pragma unroll
+      for (int j4 = 0; j4 < 4; ++j4) {
+        const int j = jh + j4;
+        if (oj[j] >= 0) {
+          if (CF32) *reinterpret_cast<float4*>(cf + static_cast<long long>(oj[j]) * g.ldc) = tv[j4];
+          else store4_bf16(cb + static_cast<long long>(oj[j]) * g.ldc, 4, true, tv[j4], false);
+          if (c2 != nullptr) store4_bf16(c2 + static_cast<long long>(oj[j]) * g.ldc2, 4, true, tv[j4], true);
+        }
       }
     }
   }
@@ -407,6 +448,7 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
   // per-epilogue-warp 32 x 32 fp32 transposition tile (XOR-swizzled 16-byte slots, no padding)
   float4* epi_scratch = reinterpret_cast<float4*>(smem + STAGES * STAGE_BYTES + 256);
+  // ... followed by one 4 KB residual staging buffer per epilogue warp (cp.async destination)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -529,6 +571,7 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
     const int r = q * 32 + lane;       // tile row owned by this thread
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const uint32_t tile_s = smem_u32(epi_scratch + ew * 256);   // 4 KB, 256-byte aligned
+    const uint32_t res_s = smem_u32(epi_scratch + (EPI_WARPS + ew) * 256);
     // write side: row = lane, 16-byte slot i ^ (lane & 7)  ->  st_base ^ (i << 4)
     const uint32_t st_base = (tile_s + lane * 128) | ((lane & 7) << 4);
     // read side: row 4 j + (lane >> 3), slot (lane & 7) ^ (row & 7); row & 7 only depends on j & 1
@@ -583,18 +626,29 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
       int oj[8];      // output row (fits 31 bits: checked on the host), -1 = nothing to store
 #pragma unroll
       for (int j = 0; j < 8; ++j) oj[j] = static_cast<int>(__shfl_sync(0xffffffffu, my_out, 4 * j + (lane >> 3)));
+      const bool all_rows = __all_sync(0xffffffffu, my_out >= 0);   // interior tile: no row predicates
       const int rk = g.res_kind;   // 0 none, 1 f32, 2 bf16 (one or two maps), 3 bilinear-x2 bf16
       // residual segments are fetched ahead of their use (first chunk: before the accumulator is
       // even ready; later chunks: before the TMEM read of that chunk)
-      uint4 rb[8];
       {
         const int nb0 = tc.n0 + half * CH_PER_WARP * 32;
-        if (g.fast && nb0 + 32 <= g.N) load_res_seg(g, rk, oj, nb0 + 4 * cs, rb);
+        if (g.fast && (rk == 1 || rk == 2) && nb0 + 32 <= g.N)
+          res_async_issue(g, rk, oj, nb0 + 4 * cs, res_s, lane);
       }
+#ifdef VS_EPI_TIMING
+      const bool dbg_tile = blockIdx.x == 0 && ew == 0 && lane == 0 && ti == 2;
+      bool dbg_on = dbg_tile;
+#endif
+      EPI_STAMP(0);
       mbar_wait(&tmem_full[a], (ti >> 1) & 1);
       tc_fence_after();
+      EPI_STAMP(1);
 #pragma unroll 1
       for (int cc = 0; cc < CH_PER_WARP; ++cc) {
+#ifdef VS_EPI_TIMING
+        dbg_on = dbg_tile && cc == 1;
+#endif
+        EPI_STAMP(2);
         const int c = half * CH_PER_WARP + cc;
         const int nb = tc.n0 + c * 32;
         if (nb >= g.N) break;  // warp-uniform
@@ -604,6 +658,7 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
         const bool fast = g.fast && nv == 32;
         const int col = nb + 4 * cs;
         tmem_ld_wait();
+        EPI_STAMP(3);
         float f[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
@@ -662,18 +717,29 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
 #pragma unroll
         for (int i = 0; i < 8; ++i)
           st_shared_f4(st_base ^ (i << 4), f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+        EPI_STAMP(4);
         __syncwarp();
+        EPI_STAMP(5);
         if (fast) {
+          uint4 rb[8];
+          if (rk == 1 || rk == 2) {
+            res_async_wait();
+#pragma unroll
+            for (int j = 0; j < 8; ++j) rb[j] = ld_shared_u4(res_s + j * 512 + lane * 16);
+            // the buffer is in registers: refill it for the next chunk now, a whole store phase
+            // plus the next chunk's TMEM read / bias / transposition ahead of its use
+            if (cc + 1 < CH_PER_WARP && nb + 64 <= g.N) res_async_issue(g, rk, oj, col + 32, res_s, lane);
+          }
           const bool cf32 = g.c_dtype == VS_F32;
           switch (rk) {
-            case 0: cf32 ? epi_store<0, true>(g, lds_base, lane, oj, col, rb, 0, 0, 0)
-                         : epi_store<0, false>(g, lds_base, lane, oj, col, rb, 0, 0, 0); break;
-            case 1: cf32 ? epi_store<1, true>(g, lds_base, lane, oj, col, rb, 0, 0, 0)
-                         : epi_store<1, false>(g, lds_base, lane, oj, col, rb, 0, 0, 0); break;
-            case 2: cf32 ? epi_store<2, true>(g, lds_base, lane, oj, col, rb, 0, 0, 0)
-                         : epi_store<2, false>(g, lds_base, lane, oj, col, rb, 0, 0, 0); break;
-            default: cf32 ? epi_store<3, true>(g, lds_base, lane, oj, col, rb, pix_x, pix_y, pix_im)
-                          : epi_store<3, false>(g, lds_base, lane, oj, col, rb, pix_x, pix_y, pix_im); break;
+            case 0: cf32 ? epi_store<0, true>(g, lds_base, lane, oj, col, rb, 0, 0, 0, all_rows)
+                         : epi_store<0, false>(g, lds_base, lane, oj, col, rb, 0, 0, 0, all_rows); break;
+            case 1: cf32 ? epi_store<1, true>(g, lds_base, lane, oj, col, rb, 0, 0, 0, all_rows)
+                         : epi_store<1, false>(g, lds_base, lane, oj, col, rb, 0, 0, 0, all_rows); break;
+            case 2: cf32 ? epi_store<2, true>(g, lds_base, lane, oj, col, rb, 0, 0, 0, all_rows)
+                         : epi_store<2, false>(g, lds_base, lane, oj, col, rb, 0, 0, 0, all_rows); break;
+            default: cf32 ? epi_store<3, true>(g, lds_base, lane, oj, col, rb, pix_x, pix_y, pix_im, all_rows)
+                          : epi_store<3, false>(g, lds_base, lane, oj, col, rb, pix_x, pix_y, pix_im, all_rows); break;
           }
         } else {
           const int nvl = min(4, g.N - col);
@@ -706,9 +772,14 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
             if (g.C2 != nullptr) store4_bf16(g.C2 + o * g.ldc2 + col, nvl, g.vec & VEC_C2, t, true);
           }
         }
+        EPI_STAMP(6);
         __syncwarp();   // the tile is rewritten by the next chunk
-        if (cc + 1 < CH_PER_WARP && g.fast && nb + 64 <= g.N) load_res_seg(g, rk, oj, col + 32, rb);
+        EPI_STAMP(7);
       }
+#ifdef VS_EPI_TIMING
+      dbg_on = dbg_tile;
+#endif
+      EPI_STAMP(8);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -748,7 +819,7 @@ int num_sms() {
 template <int BN, int STAGES, int EPI_WARPS, int CL>
 int launch(const CUtensorMap& tmA, const CUtensorMap& tmW, const GemmDev& g, cudaStream_t stream) {
   constexpr int SMEM = STAGES * (BM * 128 + (BN / CL) * 128) + 1024 /*align*/ + 256 /*barriers*/ +
-                       EPI_WARPS * 4096 /*epilogue transposition tiles*/;
+                       2 * EPI_WARPS * 4096 /*epilogue transposition tiles + residual staging*/;
   static_assert(SMEM <= 227 * 1024, "shared memory budget");
   auto kernel = gemm_tc05_kernel<BN, STAGES, EPI_WARPS, CL>;
   static bool configured = false;  // attribute is per-function, set once per process
@@ -961,7 +1032,13 @@ extern "C" int vs_gemm(const vs_gemm_params* p, vs_stream_t stream_) {
       return cl == 2 ? launch<128, 8, 4, 2>(tmA, tmW, g, stream)
                      : launch<128, 6, 4, 1>(tmA, tmW, g, stream);
     default:
-      return cl == 2 ? launch<256, 6, 8, 2>(tmA, tmW, g, stream)
-                     : launch<256, 4, 8, 1>(tmA, tmW, g, stream);
+      return cl == 2 ? launch<256, 5, 8, 2>(tmA, tmW, g, stream)
+                     : launch<256, 3, 8, 1>(tmA, tmW, g, stream);
   }
 }
+
+#ifdef VS_EPI_TIMING
+extern "C" int vs_debug_epi_stamps(long long* out) {
+  return cudaMemcpyFromSymbol(out, vs::g_epi_stamps, sizeof(long long) * 16) == cudaSuccess ? 0 : -1;
+}
+#endif
