@@ -62,7 +62,7 @@ def attention_flops(T: int, size: int = SIZE) -> float:
 
 # DRAM traffic of all GEMM launches of one scene's encoder forward, from the committed ncu capture
 # (profiles/r1_kernel_traffic.txt: sum of dram__bytes_read + dram__bytes_write); None = not captured
-GEMM_DRAM_BYTES_PER_SCENE = 4.93e9      # 1-scene capture; 1.16e9 of it are the bf16 weights
+GEMM_DRAM_BYTES_PER_SCENE = 4.79e9      # 1-scene capture; 1.16e9 of it are the bf16 weights
 GEMM_WEIGHT_BYTES = 1.16e9               # read once per launch whatever the batch
 
 
