@@ -462,82 +462,119 @@ __global__ void __launch_bounds__(128)
   o[0] = a0 * sc; o[1] = a1 * sc; o[2] = a2 * sc;
 }
 
-// Gaussian adapter, part 1: per-Gaussian scalars (thread per Gaussian)
-__global__ void adapter_params_kernel(const float* __restrict__ src, long long src_ld,
-                                      int center_col, int param_col, long long G, int raw_w,
-                                      float* __restrict__ raw_out,
-                                      float* __restrict__ means, float* __restrict__ cov,
-                                      float* __restrict__ cov6, float* __restrict__ opac,
-                                      float* __restrict__ scales, float* __restrict__ rot) {
-  const long long g = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (g >= G) return;
-  float r[11];   // the reference's raw layout: xyz | opacity | scale(3) | quaternion xyzw(4)
-#pragma unroll
-  for (int i = 0; i < 3; ++i) r[i] = src[g * src_ld + center_col + i];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) r[3 + i] = src[g * src_ld + param_col + i];
-  if (raw_out) {
-#pragma unroll
-    for (int i = 0; i < 11; ++i) raw_out[g * raw_w + i] = r[i];
-  }
-  if (means) { means[g * 3] = r[0]; means[g * 3 + 1] = r[1]; means[g * 3 + 2] = r[2]; }
-  const float o = 1.0f / (1.0f + expf(-r[3]));
-  if (opac) opac[g] = o;
-  float s[3];
-#pragma unroll
-  for (int i = 0; i < 3; ++i) {
-    const float x = r[4 + i];
-    const float sp = x > 20.0f ? x : log1pf(expf(x));  // F.softplus (beta 1, threshold 20)
-    s[i] = fminf(0.001f * sp, 0.3f);
-  }
-  float q[4] = {r[7], r[8], r[9], r[10]};
-  const float qn = fmaxf(sqrtf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]), 1e-12f);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) q[i] /= qn;
-  if (scales) { scales[g * 3] = s[0]; scales[g * 3 + 1] = s[1]; scales[g * 3 + 2] = s[2]; }
-  if (rot) { rot[g * 4] = q[0]; rot[g * 4 + 1] = q[1]; rot[g * 4 + 2] = q[2]; rot[g * 4 + 3] = q[3]; }
-  const float i_ = q[0], j_ = q[1], k_ = q[2], rr = q[3];
-  const float two_s = 2.0f / (i_ * i_ + j_ * j_ + k_ * k_ + rr * rr + 1e-8f);
-  const float R[9] = {1 - two_s * (j_ * j_ + k_ * k_), two_s * (i_ * j_ - k_ * rr),
-                      two_s * (i_ * k_ + j_ * rr),     two_s * (i_ * j_ + k_ * rr),
-                      1 - two_s * (i_ * i_ + k_ * k_), two_s * (j_ * k_ - i_ * rr),
-                      two_s * (i_ * k_ - j_ * rr),     two_s * (j_ * k_ + i_ * rr),
-                      1 - two_s * (i_ * i_ + j_ * j_)};
-  const float s2[3] = {s[0] * s[0], s[1] * s[1], s[2] * s[2]};
-  float Cm[9];
-#pragma unroll
-  for (int a = 0; a < 3; ++a)
-#pragma unroll
-    for (int bb = 0; bb < 3; ++bb)
-      Cm[a * 3 + bb] = R[a * 3 + 0] * s2[0] * R[bb * 3 + 0] + R[a * 3 + 1] * s2[1] * R[bb * 3 + 1] +
-                       R[a * 3 + 2] * s2[2] * R[bb * 3 + 2];
-  if (cov) {
-#pragma unroll
-    for (int a = 0; a < 9; ++a) cov[g * 9 + a] = Cm[a];
-  }
-  if (cov6) {
-    cov6[g * 6 + 0] = Cm[0]; cov6[g * 6 + 1] = Cm[1]; cov6[g * 6 + 2] = Cm[2];
-    cov6[g * 6 + 3] = Cm[4]; cov6[g * 6 + 4] = Cm[5]; cov6[g * 6 + 5] = Cm[8];
+// Gaussian adapter (common/gaussian_adapter.py:167-212), one block per 64 Gaussians:
+//   A  the 86 used columns of the 64 head rows (xyz | opacity, scale, quaternion | SH) are staged in
+//      shared memory in the reference's raw layout, with coalesced loads;
+//   B  64 threads turn the 11 scalars of their Gaussian into opacity / scales / rotation / covariance
+//      (into shared memory), while the others already stream out raw (a flat float4 copy of the
+//      staged block) and SH * mask;
+//   C  the per-Gaussian outputs leave as flat, contiguous block writes as well.
+// Every global store of the ~3 GB this writes per 8 scenes is a full-line coalesced access (the
+// thread-per-Gaussian version scattered 4-byte stores at 12..344-byte strides).
+constexpr int AD_G = 64, AD_THREADS = 256;
+
+__device__ __forceinline__ void flat_store(float* __restrict__ dst, const float* s_src, int n, bool vec) {
+  // dst: block-contiguous global range of n floats, s_src: the same range in shared memory
+  if (vec) {
+    for (int i = threadIdx.x; i < (n >> 2); i += AD_THREADS)
+      reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(s_src)[i];
+    for (int i = (n & ~3) + threadIdx.x; i < n; i += AD_THREADS) dst[i] = s_src[i];
+  } else {
+    for (int i = threadIdx.x; i < n; i += AD_THREADS) dst[i] = s_src[i];
   }
 }
 
-// Gaussian adapter, part 2: SH = raw[..., 11:] * sh_mask; a block covers 64 Gaussians, flat and
-// coalesced over their 64 * 3 * d_sh outputs, 32-bit index arithmetic
-__global__ void adapter_sh_kernel(const float* __restrict__ src, long long src_ld, int param_col,
-                                  long long G, int d_sh, const float* __restrict__ mask,
-                                  float* __restrict__ sh, float* __restrict__ raw_out, int raw_w) {
-  const unsigned per = 3u * d_sh;
-  const long long g0 = static_cast<long long>(blockIdx.x) * 64;
-  const unsigned cnt = static_cast<unsigned>(min(64ll, G - g0)) * per;
-  const float* rbase = src + g0 * src_ld + param_col + 8;
-  float* obase = sh ? sh + g0 * per : nullptr;
-  float* wbase = raw_out ? raw_out + g0 * raw_w + 11 : nullptr;
-  for (unsigned i = threadIdx.x; i < cnt; i += blockDim.x) {
-    const unsigned g = i / per, j = i - g * per;
-    const float v = rbase[g * src_ld + j];
-    if (obase) obase[i] = v * __ldg(mask + (j % d_sh));
-    if (wbase) wbase[g * raw_w + j] = v;
+__global__ void __launch_bounds__(AD_THREADS)
+    adapter_kernel(const float* __restrict__ src, long long src_ld, int center_col, int param_col,
+                   long long G, int d_sh, const float* __restrict__ mask, float* __restrict__ raw_out,
+                   float* __restrict__ means, float* __restrict__ cov, float* __restrict__ cov6,
+                   float* __restrict__ sh, float* __restrict__ opac, float* __restrict__ scales,
+                   float* __restrict__ rot) {
+  extern __shared__ __align__(16) float ad_smem[];
+  const int raw_w = 11 + 3 * d_sh;
+  float* s_raw = ad_smem;                       // [64][raw_w]
+  float* s_out = ad_smem + ((AD_G * raw_w + 3) & ~3);   // means 3 | cov 9 | cov6 6 | opac 1 | scales 3 | rot 4
+  float* s_means = s_out, *s_cov = s_means + AD_G * 3, *s_cov6 = s_cov + AD_G * 9,
+        *s_opac = s_cov6 + AD_G * 6, *s_scales = s_opac + AD_G, *s_rot = s_scales + AD_G * 3;
+  const long long g0 = static_cast<long long>(blockIdx.x) * AD_G;
+  const int cnt = static_cast<int>(min(static_cast<long long>(AD_G), G - g0));
+  // ---- A: stage
+  const float* rows = src + g0 * src_ld;
+  for (int i = threadIdx.x; i < cnt * raw_w; i += AD_THREADS) {
+    const int g = i / raw_w, e = i - g * raw_w;
+    s_raw[i] = rows[g * src_ld + (e < 3 ? center_col + e : param_col + e - 3)];
   }
+  __syncthreads();
+  // ---- B: per-Gaussian parameters (threads 0..63)
+  if (threadIdx.x < cnt) {
+    const int g = threadIdx.x;
+    const float* r = s_raw + g * raw_w;   // xyz | opacity | scale(3) | quaternion xyzw(4)
+    s_means[g * 3] = r[0]; s_means[g * 3 + 1] = r[1]; s_means[g * 3 + 2] = r[2];
+    s_opac[g] = 1.0f / (1.0f + expf(-r[3]));
+    float sc[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const float x = r[4 + i];
+      const float sp = x > 20.0f ? x : log1pf(expf(x));  // F.softplus (beta 1, threshold 20)
+      sc[i] = fminf(0.001f * sp, 0.3f);
+      s_scales[g * 3 + i] = sc[i];
+    }
+    float q[4] = {r[7], r[8], r[9], r[10]};
+    const float qn = fmaxf(sqrtf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]), 1e-12f);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { q[i] /= qn; s_rot[g * 4 + i] = q[i]; }
+    const float i_ = q[0], j_ = q[1], k_ = q[2], rr = q[3];
+    const float two_s = 2.0f / (i_ * i_ + j_ * j_ + k_ * k_ + rr * rr + 1e-8f);
+    const float R[9] = {1 - two_s * (j_ * j_ + k_ * k_), two_s * (i_ * j_ - k_ * rr),
+                        two_s * (i_ * k_ + j_ * rr),     two_s * (i_ * j_ + k_ * rr),
+                        1 - two_s * (i_ * i_ + k_ * k_), two_s * (j_ * k_ - i_ * rr),
+                        two_s * (i_ * k_ - j_ * rr),     two_s * (j_ * k_ + i_ * rr),
+                        1 - two_s * (i_ * i_ + j_ * j_)};
+    const float s2[3] = {sc[0] * sc[0], sc[1] * sc[1], sc[2] * sc[2]};
+    float Cm[9];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int bb = 0; bb < 3; ++bb)
+        Cm[a * 3 + bb] = R[a * 3 + 0] * s2[0] * R[bb * 3 + 0] + R[a * 3 + 1] * s2[1] * R[bb * 3 + 1] +
+                         R[a * 3 + 2] * s2[2] * R[bb * 3 + 2];
+#pragma unroll
+    for (int a = 0; a < 9; ++a) s_cov[g * 9 + a] = Cm[a];
+    s_cov6[g * 6 + 0] = Cm[0]; s_cov6[g * 6 + 1] = Cm[1]; s_cov6[g * 6 + 2] = Cm[2];
+    s_cov6[g * 6 + 3] = Cm[4]; s_cov6[g * 6 + 4] = Cm[5]; s_cov6[g * 6 + 5] = Cm[8];
+  }
+  // ---- raw and SH do not depend on B
+  const bool full = cnt == AD_G;   // a full block starts 16-byte aligned in every output (64 rows)
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  if (raw_out) flat_store(raw_out + g0 * raw_w, s_raw, cnt * raw_w, full && al16(raw_out));
+  if (sh) {
+    const int per = 3 * d_sh, n = cnt * per;
+    float* dst = sh + g0 * per;
+    if (full && al16(sh)) {
+      for (int i4 = threadIdx.x; i4 < (n >> 2); i4 += AD_THREADS) {
+        float v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = 4 * i4 + u, g = i / per, j = i - g * per;
+          v[u] = s_raw[g * raw_w + 11 + j] * __ldg(mask + (j % d_sh));
+        }
+        reinterpret_cast<float4*>(dst)[i4] = make_float4(v[0], v[1], v[2], v[3]);
+      }
+    } else {
+      for (int i = threadIdx.x; i < n; i += AD_THREADS) {
+        const int g = i / per, j = i - g * per;
+        dst[i] = s_raw[g * raw_w + 11 + j] * __ldg(mask + (j % d_sh));
+      }
+    }
+  }
+  __syncthreads();
+  // ---- C
+  if (means) flat_store(means + g0 * 3, s_means, cnt * 3, full && al16(means));
+  if (cov) flat_store(cov + g0 * 9, s_cov, cnt * 9, full && al16(cov));
+  if (cov6) flat_store(cov6 + g0 * 6, s_cov6, cnt * 6, full && al16(cov6));
+  if (opac) flat_store(opac + g0, s_opac, cnt, full && al16(opac));
+  if (scales) flat_store(scales + g0 * 3, s_scales, cnt * 3, full && al16(scales));
+  if (rot) flat_store(rot + g0 * 4, s_rot, cnt * 4, full && al16(rot));
 }
 
 // ------------------------------------------------------------------ MSE loss + gradient
@@ -877,16 +914,19 @@ extern "C" int vs_gaussian_adapter(const float* src, int64_t src_ld, int center_
                  src_ld >= param_col + 8 + 3 * d_sh,
              "gaussian_adapter: src_ld too small for the column layout");
   if (G == 0) return VS_OK;
+  VS_REQUIRE(sh == nullptr || sh_mask != nullptr, "gaussian_adapter: sh_mask required");
+  VS_REQUIRE(d_sh >= 0 && d_sh <= 49, "gaussian_adapter: d_sh out of range");
   const int raw_w = 11 + 3 * d_sh;
-  adapter_params_kernel<<<blocks_for(G, 256), 256, 0, to_stream(stream)>>>(
-      src, src_ld, center_col, param_col, G, raw_w, raw_out, means, cov, cov6, opac, scales, rot);
-  VS_LAUNCH_CHECK();
-  if (sh != nullptr || raw_out != nullptr) {
-    VS_REQUIRE(sh == nullptr || sh_mask != nullptr, "gaussian_adapter: sh_mask required");
-    adapter_sh_kernel<<<blocks_for(G, 64), 256, 0, to_stream(stream)>>>(
-        src, src_ld, param_col, G, d_sh, sh_mask, sh, raw_out, raw_w);
-    VS_LAUNCH_CHECK();
+  const size_t smem = (static_cast<size_t>((AD_G * raw_w + 3) & ~3) + AD_G * 26) * sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    VS_CUDA(cudaFuncSetAttribute(adapter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    configured = true;
   }
+  adapter_kernel<<<blocks_for(G, AD_G), AD_THREADS, smem, to_stream(stream)>>>(
+      src, src_ld, center_col, param_col, G, d_sh, sh_mask, raw_out, means, cov, cov6, sh, opac,
+      scales, rot);
+  VS_LAUNCH_CHECK();
   return VS_OK;
 }
 
