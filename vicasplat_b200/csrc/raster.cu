@@ -493,54 +493,154 @@ __global__ void tile_scatter_kernel(int G, int H, int W, const float2* __restric
 }
 
 constexpr int SORT_THREADS = 512;
-template <int ITEMS, int LOWER>   // owns tiles with LOWER < n <= SORT_THREADS * ITEMS
-__global__ void __launch_bounds__(SORT_THREADS)
-    tile_sort_kernel(const uint2* __restrict__ ranges, const uint64_t* __restrict__ keys,
-                     uint32_t* __restrict__ vals_out, int key_bits, int id_bits, int max_cap) {
-  using Sort = cub::BlockRadixSort<uint64_t, SORT_THREADS, ITEMS, cub::NullType, 5>;
-  extern __shared__ __align__(16) unsigned char sort_smem[];
-  typename Sort::TempStorage& temp = *reinterpret_cast<typename Sort::TempStorage*>(sort_smem);
-  constexpr int CAP = SORT_THREADS * ITEMS;
-  const uint2 r = ranges[blockIdx.x];
-  const int n = static_cast<int>(r.y - r.x);
+
+// Sort one tile's pairs by (depth bits, Gaussian id) = the stable global order.
+// Fast path: the 64-bit keys are split into a 32-bit depth key (minus the tile's minimum, so only
+// the bits of the tile's depth RANGE are sorted: ~26 instead of 55 -> 6 radix passes instead of 11)
+// and the id as the carried value.  The radix sort is stable but the scatter order is not, so a
+// tile in which two splats share their depth bits exactly (a few percent of the tiles) is re-sorted
+// on the full key.
+template <int ITEMS>
+__device__ __forceinline__ void sort_tile(unsigned char* smem, const uint2 r, int n,
+                                          const uint64_t* __restrict__ keys,
+                                          uint32_t* __restrict__ vals_out, int key_bits, int id_bits) {
+  using Sort64 = cub::BlockRadixSort<uint64_t, SORT_THREADS, ITEMS, cub::NullType, 5>;
+  using Sort32 = cub::BlockRadixSort<uint32_t, SORT_THREADS, ITEMS, uint32_t, 5>;
+  __shared__ uint32_t s_edge[SORT_THREADS];
+  __shared__ uint32_t s_red[2][SORT_THREADS / 32];
   const uint64_t id_mask = (1ull << id_bits) - 1ull;
-  if (n > max_cap) {
-    // larger than the caller's bound: ids are passed through UNSORTED (valid indices, wrong order);
-    // the caller sees num_pairs_out[1] > max_tile_pairs and re-runs on the global-sort path
-    if (LOWER == 0)
-      for (int i = threadIdx.x; i < n; i += SORT_THREADS)
-        vals_out[r.x + i] = static_cast<uint32_t>(keys[r.x + i] & id_mask);
-    return;
-  }
-  if (n <= LOWER || n > CAP) return;   // another instantiation owns this tile (or it is empty)
-  uint64_t k[ITEMS];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  uint32_t d[ITEMS], id[ITEMS];
+  uint32_t dmin = 0xffffffffu, dmax = 0u;
 #pragma unroll
   for (int i = 0; i < ITEMS; ++i) {
-    const int idx = threadIdx.x * ITEMS + i;
-    k[i] = idx < n ? keys[r.x + idx] : ~0ull;
+    const int idx = tid * ITEMS + i;
+    if (idx < n) {
+      const uint64_t k = keys[r.x + idx];
+      d[i] = static_cast<uint32_t>(k >> id_bits);
+      id[i] = static_cast<uint32_t>(k & id_mask);
+      dmin = min(dmin, d[i]);
+      dmax = max(dmax, d[i]);
+    } else {
+      d[i] = 0xffffffffu;
+      id[i] = 0u;
+    }
   }
-  Sort(temp).Sort(k, 0, key_bits);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    dmin = min(dmin, __shfl_xor_sync(0xffffffffu, dmin, o));
+    dmax = max(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
+  }
+  if (lane == 0) { s_red[0][warp] = dmin; s_red[1][warp] = dmax; }
+  __syncthreads();
+  dmin = s_red[0][0]; dmax = s_red[1][0];
+#pragma unroll
+  for (int w = 1; w < SORT_THREADS / 32; ++w) { dmin = min(dmin, s_red[0][w]); dmax = max(dmax, s_red[1][w]); }
+  const int nbits = 32 - __clz(dmax - dmin);   // 0 when every depth is equal
+#pragma unroll
+  for (int i = 0; i < ITEMS; ++i)
+    if (tid * ITEMS + i < n) d[i] -= dmin;      // padding keeps all ones: stable sort leaves it last
+  Sort32(*reinterpret_cast<typename Sort32::TempStorage*>(smem)).Sort(d, id, 0, nbits);
+  // exact ties among valid neighbours (blocked arrangement: thread t holds elements t*ITEMS ..)
+  s_edge[tid] = d[ITEMS - 1];
+  __syncthreads();
+  bool tie = false;
 #pragma unroll
   for (int i = 0; i < ITEMS; ++i) {
-    const int idx = threadIdx.x * ITEMS + i;
-    if (idx < n) vals_out[r.x + idx] = static_cast<uint32_t>(k[i] & id_mask);
+    const int idx = tid * ITEMS + i;
+    const uint32_t prev = i > 0 ? d[i - 1] : (tid > 0 ? s_edge[tid - 1] : ~d[0]);
+    tie |= idx > 0 && idx < n && d[i] == prev;
+  }
+  if (__syncthreads_or(tie)) {
+    uint64_t k[ITEMS];
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+      const int idx = tid * ITEMS + i;
+      k[i] = idx < n ? keys[r.x + idx] : ~0ull;
+    }
+    Sort64(*reinterpret_cast<typename Sort64::TempStorage*>(smem)).Sort(k, 0, key_bits);
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) id[i] = static_cast<uint32_t>(k[i] & id_mask);
+  }
+#pragma unroll
+  for (int i = 0; i < ITEMS; ++i) {
+    const int idx = tid * ITEMS + i;
+    if (idx < n) vals_out[r.x + idx] = id[i];
   }
 }
 
-template <int ITEMS, int LOWER>
-int launch_tile_sort(const Workspace& ws, int n_tiles, int key_bits, int id_bits, int max_cap,
-                     cudaStream_t stream) {
-  using Sort = cub::BlockRadixSort<uint64_t, SORT_THREADS, ITEMS, cub::NullType, 5>;
-  const int smem = static_cast<int>(sizeof(typename Sort::TempStorage));
+template <int ITEMS>
+constexpr size_t sort_smem_bytes() {
+  using Sort64 = cub::BlockRadixSort<uint64_t, SORT_THREADS, ITEMS, cub::NullType, 5>;
+  using Sort32 = cub::BlockRadixSort<uint32_t, SORT_THREADS, ITEMS, uint32_t, 5>;
+  return sizeof(typename Sort64::TempStorage) > sizeof(typename Sort32::TempStorage)
+             ? sizeof(typename Sort64::TempStorage) : sizeof(typename Sort32::TempStorage);
+}
+
+// tiles of up to 4096 pairs (the common case): one CTA per tile, size class chosen in the kernel --
+// one launch instead of one per class (a class kernel whose CTAs all exit still costs ~35 us of
+// block launches at 3072 tiles)
+__global__ void __launch_bounds__(SORT_THREADS, 2)   // <= 64 registers: two (smem: three) CTAs per SM
+    tile_sort_small_kernel(const uint2* __restrict__ ranges, const uint64_t* __restrict__ keys,
+                           uint32_t* __restrict__ vals_out, int key_bits, int id_bits, int max_cap) {
+  extern __shared__ __align__(16) unsigned char sort_smem[];
+  const uint2 r = ranges[blockIdx.x];
+  const int n = static_cast<int>(r.y - r.x);
+  if (n > max_cap) {
+    // larger than the caller's bound: ids are passed through UNSORTED (valid indices, wrong order);
+    // the caller sees num_pairs_out[1] > max_tile_pairs and re-runs on the global-sort path
+    const uint64_t id_mask = (1ull << id_bits) - 1ull;
+    for (int i = threadIdx.x; i < n; i += SORT_THREADS)
+      vals_out[r.x + i] = static_cast<uint32_t>(keys[r.x + i] & id_mask);
+    return;
+  }
+  if (n == 0 || n > 4096) return;
+  if (n <= 2048) sort_tile<4>(sort_smem, r, n, keys, vals_out, key_bits, id_bits);
+  else if (n <= 3072) sort_tile<6>(sort_smem, r, n, keys, vals_out, key_bits, id_bits);
+  else sort_tile<8>(sort_smem, r, n, keys, vals_out, key_bits, id_bits);
+}
+
+// tiles of 4097 .. 16384 pairs: a persistent grid walks the tile list (nothing to do on most
+// scenes: a sweep over the ranges costs a few microseconds)
+__global__ void __launch_bounds__(SORT_THREADS)
+    tile_sort_large_kernel(const uint2* __restrict__ ranges, int n_tiles,
+                           const uint64_t* __restrict__ keys, uint32_t* __restrict__ vals_out,
+                           int key_bits, int id_bits, int max_cap) {
+  extern __shared__ __align__(16) unsigned char sort_smem[];
+  for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    const uint2 r = ranges[t];
+    const int n = static_cast<int>(r.y - r.x);
+    if (n <= 4096 || n > max_cap) continue;   // block-uniform
+    if (n <= 5120) sort_tile<10>(sort_smem, r, n, keys, vals_out, key_bits, id_bits);
+    else if (n <= 6144) sort_tile<12>(sort_smem, r, n, keys, vals_out, key_bits, id_bits);
+    else if (n <= 8192) sort_tile<16>(sort_smem, r, n, keys, vals_out, key_bits, id_bits);
+    else if (n <= 12288) sort_tile<24>(sort_smem, r, n, keys, vals_out, key_bits, id_bits);
+    else sort_tile<32>(sort_smem, r, n, keys, vals_out, key_bits, id_bits);
+    __syncthreads();   // shared memory is reused by the next tile
+  }
+}
+
+int launch_tile_sorts(const Workspace& ws, int n_tiles, int key_bits, int id_bits, int max_cap,
+                      cudaStream_t stream) {
+  const int smem_small = static_cast<int>(sort_smem_bytes<8>());
+  const int smem_large = static_cast<int>(sort_smem_bytes<32>());
   static bool configured = false;
   if (!configured) {
-    VS_CUDA(cudaFuncSetAttribute(tile_sort_kernel<ITEMS, LOWER>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    VS_CUDA(cudaFuncSetAttribute(tile_sort_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 smem_small));
+    VS_CUDA(cudaFuncSetAttribute(tile_sort_large_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 smem_large));
     configured = true;
   }
-  tile_sort_kernel<ITEMS, LOWER><<<n_tiles, SORT_THREADS, smem, stream>>>(
+  tile_sort_small_kernel<<<n_tiles, SORT_THREADS, smem_small, stream>>>(
       ws.ranges, ws.keys_in, ws.vals_out, key_bits, id_bits, max_cap);
   VS_LAUNCH_CHECK();
+  if (max_cap > 4096) {
+    const int grid = n_tiles < 148 ? n_tiles : 148;
+    tile_sort_large_kernel<<<grid, SORT_THREADS, smem_large, stream>>>(
+        ws.ranges, n_tiles, ws.keys_in, ws.vals_out, key_bits, id_bits, max_cap);
+    VS_LAUNCH_CHECK();
+  }
   return VS_OK;
 }
 
@@ -1138,14 +1238,7 @@ extern "C" int vs_raster_forward(const vs_raster_params* p, vs_stream_t stream_)
       int max_cap = 16384;
       for (int c = 7; c >= 0; --c)
         if (mt <= caps[c]) max_cap = caps[c];
-      int rc = launch_tile_sort<4, 0>(ws, nt, key_bits, id_bits, max_cap, stream);
-      if (rc == VS_OK && mt > 2048) rc = launch_tile_sort<6, 2048>(ws, nt, key_bits, id_bits, max_cap, stream);
-      if (rc == VS_OK && mt > 3072) rc = launch_tile_sort<8, 3072>(ws, nt, key_bits, id_bits, max_cap, stream);
-      if (rc == VS_OK && mt > 4096) rc = launch_tile_sort<10, 4096>(ws, nt, key_bits, id_bits, max_cap, stream);
-      if (rc == VS_OK && mt > 5120) rc = launch_tile_sort<12, 5120>(ws, nt, key_bits, id_bits, max_cap, stream);
-      if (rc == VS_OK && mt > 6144) rc = launch_tile_sort<16, 6144>(ws, nt, key_bits, id_bits, max_cap, stream);
-      if (rc == VS_OK && mt > 8192) rc = launch_tile_sort<24, 8192>(ws, nt, key_bits, id_bits, max_cap, stream);
-      if (rc == VS_OK && mt > 12288) rc = launch_tile_sort<32, 12288>(ws, nt, key_bits, id_bits, max_cap, stream);
+      int rc = launch_tile_sorts(ws, nt, key_bits, id_bits, max_cap, stream);
       if (rc != VS_OK) return rc;
     } else {
     // ---- global path: scan, emit (tile | depth) keys, one 64-bit radix sort

@@ -47,6 +47,7 @@ def _f32c(t: torch.Tensor) -> torch.Tensor:
 # per tile in shared memory (bound <= 16384) instead of one global 64-bit radix sort (bound 0)
 _capacity_hint: dict = {}
 MAX_TILE_SORT = 16384
+SMALL_TILE_SORT = 4096     # tiles up to here are sorted by tile_sort_small_kernel alone
 
 
 # check_overflow="deferred": the render runs unchecked with the hinted capacities and its device-side
@@ -142,6 +143,8 @@ class _Rasterize(torch.autograd.Function):
                 next_tile = 0 if _capacity_hint.get((V, G, H, W), (0, 1))[1] == 0 else MAX_TILE_SORT
             else:
                 next_tile = min(MAX_TILE_SORT, int(tmax * 1.25) + 64) if tmax <= MAX_TILE_SORT else 0
+                if tmax <= SMALL_TILE_SORT < next_tile:
+                    next_tile = SMALL_TILE_SORT   # stay within the one-kernel size classes
             _capacity_hint[(V, G, H, W)] = (int(n * 1.25) + 4096, next_tile)
             if ok:
                 break
