@@ -299,6 +299,40 @@ int vs_mse_loss(const float* pred, const float* target, int64_t n, float weight,
 int vs_update_pose(const float* rho, const float* theta, const float* c2w, float* c2w_out, int n,
                    vs_stream_t stream);
 
+/* ------------------------------------------------------------------ fused AdamW (+ clip + non-finite scan)
+ * One optimizer step over a LIST of fp32 tensors in two launches (the reference steps 847 tensors
+ * one by one: torch.optim.AdamW configured at src/model/model_wrapper.py:884-951, betas (0.9, 0.95),
+ * weight_decay 0.05, two learning-rate groups; Lightning clips the global gradient norm to
+ * gradient_clip_val = 0.5, config/main.yaml:70).
+ *   pass 1  global ||g||_2 (deterministic two-stage sum) and a non-finite flag;
+ *   pass 2  g' = g * min(1, max_grad_norm / (norm + 1e-6))   (max_grad_norm <= 0: no clipping)
+ *           p *= 1 - lr * weight_decay;  m = b1 m + (1 - b1) g';  v = b2 v + (1 - b2) g'^2
+ *           p -= (lr / (1 - b1^t)) * m / (sqrt(v) / sqrt(1 - b2^t) + eps)        (torch.optim.AdamW)
+ *           the whole step is skipped when skip_nonfinite != 0 and a gradient held an inf / nan.
+ * Tensors are described by device tables; work is cut into chunks of VS_ADAMW_CHUNK elements:
+ * chunk c covers elements [chunk_start[c], chunk_start[c] + VS_ADAMW_CHUNK) of tensor chunk_tensor[c]. */
+#define VS_ADAMW_CHUNK 16384
+typedef struct vs_adamw_params {
+  int32_t n_tensors, n_chunks;
+  float* const* params;        /* device array [n_tensors] of device pointers */
+  const float* const* grads;
+  float* const* exp_avg;
+  float* const* exp_avg_sq;
+  const int64_t* sizes;        /* device [n_tensors] */
+  const float* lrs;            /* device [n_tensors]: learning rate of each tensor's group */
+  const int32_t* chunk_tensor; /* device [n_chunks] */
+  const int64_t* chunk_start;  /* device [n_chunks] */
+  float beta1, beta2, eps, weight_decay;
+  int32_t step;                /* t >= 1 */
+  float max_grad_norm;
+  int32_t skip_nonfinite;
+  float* partials;             /* device scratch [n_chunks + 2] floats */
+  uint32_t* counter;           /* device uint32, zero before the first call (left at zero) */
+  float* grad_norm_out;        /* device float[1]: ||g||_2 before clipping */
+  int32_t* found_inf_out;      /* device int32[1] */
+} vs_adamw_params;
+int vs_adamw_step(const vs_adamw_params* p, vs_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

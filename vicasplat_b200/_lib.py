@@ -37,6 +37,17 @@ class GemmParams(C.Structure):
     ]
 
 
+class AdamWParams(C.Structure):
+    _fields_ = [
+        ("n_tensors", _i32), ("n_chunks", _i32),
+        ("params", _vp), ("grads", _vp), ("exp_avg", _vp), ("exp_avg_sq", _vp),
+        ("sizes", _vp), ("lrs", _vp), ("chunk_tensor", _vp), ("chunk_start", _vp),
+        ("beta1", _f32), ("beta2", _f32), ("eps", _f32), ("weight_decay", _f32),
+        ("step", _i32), ("max_grad_norm", _f32), ("skip_nonfinite", _i32),
+        ("partials", _vp), ("counter", _vp), ("grad_norm_out", _vp), ("found_inf_out", _vp),
+    ]
+
+
 class LayerNormParams(C.Structure):
     _fields_ = [
         ("x", _vp), ("ldx", _i64), ("rows", _i32), ("C", _i32),
@@ -88,6 +99,7 @@ STRUCTS = {
     "vs_attention_params": AttentionParams,
     "vs_raster_params": RasterParams,
     "vs_raster_bwd_params": RasterBwdParams,
+    "vs_adamw_params": AdamWParams,
 }
 
 _DECL = re.compile(r"^\s*(?:const\s+char\s*\*|int64_t|int)\s+(vs_\w+)\s*\(", re.M)

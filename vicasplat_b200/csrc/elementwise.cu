@@ -726,6 +726,86 @@ __global__ void update_pose_kernel(const float* __restrict__ rho, const float* _
   for (int k = 0; k < 16; ++k) c2w_out[i * 16 + k] = out[k];
 }
 
+// ------------------------------------------------------------------ fused AdamW
+constexpr int AW_THREADS = 256;
+
+__global__ void __launch_bounds__(AW_THREADS)
+    adamw_norm_kernel(const vs_adamw_params p) {
+  const int c = blockIdx.x;
+  const int t = p.chunk_tensor[c];
+  const long long start = p.chunk_start[c];
+  const long long n = min(static_cast<long long>(VS_ADAMW_CHUNK), p.sizes[t] - start);
+  const float* g = p.grads[t] + start;
+  float acc = 0.f;
+  bool bad = false;
+  for (long long i = threadIdx.x; i < n; i += AW_THREADS) {
+    const float v = g[i];
+    acc = fmaf(v, v, acc);
+    bad |= !isfinite(v);
+  }
+  __shared__ float red[AW_THREADS / 32];
+  __shared__ int s_bad;
+  __shared__ bool last;
+  if (threadIdx.x == 0) s_bad = 0;
+  __syncthreads();
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  if (bad) s_bad = 1;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tot = 0.f;
+    for (int i = 0; i < AW_THREADS / 32; ++i) tot += red[i];
+    p.partials[c] = tot;
+    if (s_bad) atomicExch(p.found_inf_out, 1);
+    __threadfence();
+    last = atomicAdd(p.counter, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (last) {   // fixed-order final reduction (independent of block scheduling)
+    __threadfence();
+    float tsum = 0.f;
+    for (int i = threadIdx.x; i < p.n_chunks; i += AW_THREADS) tsum += *(volatile float*)(p.partials + i);
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) tsum += __shfl_xor_sync(0xffffffffu, tsum, s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = tsum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float tot = 0.f;
+      for (int i = 0; i < AW_THREADS / 32; ++i) tot += red[i];
+      *p.grad_norm_out = sqrtf(tot);
+      *p.counter = 0u;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(AW_THREADS)
+    adamw_update_kernel(const vs_adamw_params p, float bc1, float bc2_sqrt) {
+  if (p.skip_nonfinite && *p.found_inf_out) return;
+  const int c = blockIdx.x;
+  const int t = p.chunk_tensor[c];
+  const long long start = p.chunk_start[c];
+  const long long n = min(static_cast<long long>(VS_ADAMW_CHUNK), p.sizes[t] - start);
+  float* w = p.params[t] + start;
+  const float* g = p.grads[t] + start;
+  float* m = p.exp_avg[t] + start;
+  float* v = p.exp_avg_sq[t] + start;
+  const float lr = p.lrs[t];
+  float clip = 1.0f;
+  if (p.max_grad_norm > 0.f) clip = fminf(1.0f, p.max_grad_norm / (*p.grad_norm_out + 1e-6f));
+  const float decay = 1.0f - lr * p.weight_decay;
+  const float step_size = lr / bc1;
+  for (long long i = threadIdx.x; i < n; i += AW_THREADS) {
+    const float gi = g[i] * clip;
+    const float mi = p.beta1 * m[i] + (1.0f - p.beta1) * gi;
+    const float vi = p.beta2 * v[i] + (1.0f - p.beta2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + p.eps;
+    w[i] = w[i] * decay - step_size * (mi / denom);
+  }
+}
+
 inline unsigned blocks_for(long long n, int threads) {
   return static_cast<unsigned>((n + threads - 1) / threads);
 }
@@ -953,6 +1033,28 @@ extern "C" int vs_update_pose(const float* rho, const float* theta, const float*
   if (n <= 0) return VS_OK;
   VS_REQUIRE(rho && theta && c2w && c2w_out, "update_pose: null tensor");
   update_pose_kernel<<<blocks_for(n, 64), 64, 0, to_stream(stream)>>>(rho, theta, c2w, c2w_out, n);
+  VS_LAUNCH_CHECK();
+  return VS_OK;
+}
+
+extern "C" int vs_adamw_step(const vs_adamw_params* p, vs_stream_t stream) {
+  using namespace vs;
+  VS_REQUIRE(p != nullptr, "adamw_step: null params");
+  if (p->n_tensors <= 0 || p->n_chunks <= 0) return VS_OK;
+  VS_REQUIRE(p->params && p->grads && p->exp_avg && p->exp_avg_sq && p->sizes && p->lrs &&
+                 p->chunk_tensor && p->chunk_start,
+             "adamw_step: null table");
+  VS_REQUIRE(p->partials && p->counter && p->grad_norm_out && p->found_inf_out,
+             "adamw_step: null scratch / output");
+  VS_REQUIRE(p->step >= 1 && p->beta1 >= 0.f && p->beta1 < 1.f && p->beta2 >= 0.f && p->beta2 < 1.f,
+             "adamw_step: bad step / betas");
+  cudaStream_t st = to_stream(stream);
+  VS_CUDA(cudaMemsetAsync(p->found_inf_out, 0, sizeof(int32_t), st));
+  adamw_norm_kernel<<<p->n_chunks, AW_THREADS, 0, st>>>(*p);
+  VS_LAUNCH_CHECK();
+  const float bc1 = 1.0f - powf(p->beta1, static_cast<float>(p->step));
+  const float bc2 = 1.0f - powf(p->beta2, static_cast<float>(p->step));
+  adamw_update_kernel<<<p->n_chunks, AW_THREADS, 0, st>>>(*p, bc1, sqrtf(bc2));
   VS_LAUNCH_CHECK();
   return VS_OK;
 }
