@@ -1,4 +1,6 @@
-"""Debug: in-kernel clock64 stamps of one epilogue chunk (library built with -DVS_EPI_TIMING)."""
+"""Debug: in-kernel clock64 stamps of one GEMM epilogue chunk.  Needs the instrumented library:
+    python -c "import __graft_entry__ as g; g.build_debug_library()"     (nvcc ... -DVS_EPI_TIMING)
+then run this script on the GPU box."""
 import ctypes as C
 import sys
 from pathlib import Path
