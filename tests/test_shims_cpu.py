@@ -38,3 +38,26 @@ def test_rope_shim_rejects_cpu_tensors():
     finally:
         sys.path.remove(str(SHIMS))
         sys.modules.pop("curope", None)
+
+
+def test_deferred_overflow_verification_logic():
+    """rasterizer.verify_deferred: host-side check of the counters a sync-free render queued."""
+    import pytest
+    import torch
+    import vicasplat_b200.rasterizer as r
+    key = (3, 1000, 64, 64)
+    r._capacity_hint.pop(key, None)
+    ok = torch.tensor([[900, 100], [1000, 128]])
+    r.verify_deferred(ok, [(None, 1000, 128, key), (None, 1000, 128, key)])        # within capacity
+    assert key not in r._capacity_hint
+    with pytest.raises(r.RasterOverflow):
+        r.verify_deferred(torch.tensor([[1500, 100]]), [(None, 1000, 128, key)])  # too many pairs
+    pairs, tile = r._capacity_hint[key]
+    assert pairs >= 1500 and tile >= 100
+    with pytest.raises(r.RasterOverflow):
+        r.verify_deferred(torch.tensor([[900, 300]]), [(None, 1000, 128, key)])   # a tile too full
+    assert r._capacity_hint[key][1] >= 300
+    with pytest.raises(r.RasterOverflow):
+        r.verify_deferred(torch.tensor([[900, 50000]]), [(None, 1000, 128, key)]) # beyond the smem sort
+    assert r._capacity_hint[key][1] == 0                                           # -> global sort path
+    r._capacity_hint.pop(key, None)
