@@ -320,6 +320,13 @@ def run_ours(args) -> None:
             ev[i][2].record()
         barrier()
         t_wall = time.perf_counter() - t_wall0
+    if os.environ.get("VS_PROFILE_STEP") == "1":
+        # one extra step between cudaProfilerStart/Stop (outside the timed region) for
+        #   ncu --profile-from-start off --metrics gpu__time_duration.sum ... python bench.py
+        torch.cuda.cudart().cudaProfilerStart()
+        device_step()
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStop()
     seq_ms = ev[0][0].elapsed_time(ev[-1][2]) / args.steps
     enc_ms = sum(e[0].elapsed_time(e[1]) for e in ev) / args.steps
     ras_ms = sum(e[1].elapsed_time(e[2]) for e in ev) / args.steps
