@@ -333,6 +333,55 @@ typedef struct vs_adamw_params {
 } vs_adamw_params;
 int vs_adamw_step(const vs_adamw_params* p, vs_stream_t stream);
 
+/* ------------------------------------------------------------------ encoder training path (backward)
+ * Hand-written backward pass of the ViT block (croco/blocks.py:58-130: the reference gets it from
+ * torch.autograd).  The dense contractions run on vs_gemm:
+ *   dgrad  dX[M,K]  = dY[M,N] W[N,K]      -> vs_gemm(A = dY bf16, W = W^T bf16 [K,N])
+ *   wgrad  dW[N,K] += dY^T[N,M] X[M,K]    -> vs_gemm(A = dY^T bf16 [N,M], W = X^T bf16 [K,M], C = res1 = dW fp32)
+ * and the bandwidth-bound work around them is below. */
+
+/* One pass over a gradient matrix src (rows, cols), f32 or bf16: optionally multiplied elementwise by
+ * gelu'(z) (z = the bf16 pre-activation of an MLP's fc1, croco/blocks.py:60,76), it writes any of
+ *   copy        (rows, cols) bf16 row-major               -- the dgrad A operand
+ *   transposed  (cols, ld_t) bf16, ld_t % 8 == 0 >= rows  -- the wgrad A (or W) operand; pad columns zeroed
+ *   colsum      (cols) f32, ACCUMULATED with atomics      -- the bias gradient (caller zeroes)
+ * cols % 4 == 0; every row start 16-byte (f32) / 8-byte (bf16) aligned. */
+int vs_grad_prep(const void* src, int src_dtype, int64_t ld_src, const void* z, int64_t ld_z, int rows,
+                 int cols, void* copy, int64_t ld_copy, void* transposed, int64_t ld_t, float* colsum,
+                 vs_stream_t stream);
+
+/* Training-mode GELU (exact erf, nn.GELU default): a = gelu(z), bf16 -> bf16; in training the fc1
+ * GEMM stores the pre-activation z (needed by vs_grad_prep) instead of fusing the GELU. */
+int vs_gelu_bf16(const void* z, int64_t ld_z, void* a, int64_t ld_a, int rows, int cols,
+                 vs_stream_t stream);
+
+/* Backward of y = LayerNorm(x) * gamma + beta (eps as given): dx = dres + dLN/dx (dres nullable: the
+ * gradient arriving through the residual connection; dx may alias it), dgamma / dbeta (nullable)
+ * ACCUMULATED with atomics (caller zeroes).  x f32, dy f32 or bf16, C = k*128 <= 1024. */
+typedef struct vs_layernorm_bwd_params {
+  const float* x;
+  int64_t ldx;
+  const void* dy;
+  int32_t dy_dtype;
+  int64_t ldy;
+  const float* gamma;
+  const float* dres;
+  int64_t ldres;
+  float* dx;
+  int64_t lddx;
+  float* dgamma;
+  float* dbeta;
+  int32_t rows, C;
+  float eps;
+} vs_layernorm_bwd_params;
+int vs_layernorm_backward(const vs_layernorm_bwd_params* p, vs_stream_t stream);
+
+/* Backward of vs_rope_rows / of the rope fused into the qkv epilogue: the inverse rotation applied in
+ * place to the q and k columns of the packed bf16 gradient dqkv (cuRoPE2D_func.backward calls
+ * rope_2d with fwd = -1 the same way, curope2d.py:24-29). */
+int vs_rope_rows_backward(void* dqkv, int64_t ld, int rows, int H, int q_col, int k_col,
+                          const int32_t* pos, float base, float cam_theta, vs_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,189 @@
+"""GPU parity of the encoder's training (backward) path -- the ViT block of SURVEY.md §8 E2 -- against
+torch.autograd over the fp32 oracle pieces (oracle/encoder_ref.py), which is how the reference itself
+obtains these gradients.  bf16 operands / fp32 accumulation: tolerances are stated per test."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from oracle import encoder_ref as er
+
+
+def _rel(a, b):
+    return ((a.float() - b.float()).norm() / b.float().norm().clamp_min(1e-12)).item()
+
+
+def _bf(t):
+    return t.to(torch.bfloat16)
+
+
+# ------------------------------------------------------------------------------------ grad_prep
+@pytest.mark.parametrize("rows,cols", [(64, 64), (300, 132), (257, 1024), (2056, 3072), (1, 4), (70, 8)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_grad_prep_copy_transpose_colsum(cuda, lib, rows, cols, dtype):
+    from vicasplat_b200 import ops
+    g = torch.Generator().manual_seed(rows * 7 + cols)
+    src = torch.randn((rows, cols), generator=g).to(dtype).to(cuda)
+    colsum = torch.full((cols,), 0.5, device=cuda)          # accumulated on top of what is there
+    copy, tr = ops.grad_prep(src, colsum=colsum)
+    ref = src.to(torch.bfloat16)
+    assert torch.equal(copy, ref)                             # bit-exact: one bf16 rounding
+    assert tr.shape == (cols, rows) and tr.stride(0) % 8 == 0
+    assert torch.equal(tr, ref.t())
+    base = tr.as_strided((cols, tr.stride(0)), (tr.stride(0), 1))
+    assert torch.count_nonzero(base[:, rows:]) == 0           # pad columns are zeroed
+    want = src.float().sum(0) + 0.5
+    assert torch.allclose(colsum, want, rtol=1e-4, atol=1e-3 * math.sqrt(rows))
+    only_t = ops.grad_prep(src, want_copy=False)[1]
+    assert torch.equal(only_t, ref.t())
+
+
+def test_grad_prep_strided_source_and_gelu_factor(cuda, lib):
+    from vicasplat_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    big = torch.randn((200, 256), generator=g).to(cuda)
+    src = big[:, 64:192]                                      # row stride 256, 128 columns
+    z = _bf(torch.randn((200, 128), generator=g) * 2).to(cuda)
+    colsum = torch.zeros((128,), device=cuda)
+    copy, tr = ops.grad_prep(src, z=z, colsum=colsum)
+    zf = z.float().requires_grad_(True)
+    F.gelu(zf).backward(src)                                  # d/dz of gelu(z) . src
+    ref = zf.grad
+    assert _rel(copy, ref) < 4e-3                             # one bf16 rounding
+    assert torch.equal(tr, copy.t())
+    assert torch.allclose(colsum, ref.sum(0), rtol=1e-3, atol=1e-3)
+
+
+def test_gelu_bf16(cuda, lib):
+    from vicasplat_b200 import ops
+    z = _bf(torch.linspace(-8, 8, 4096 * 8).reshape(8, 4096)).to(cuda)
+    a = ops.gelu_bf16(z)
+    ref = F.gelu(z.float())
+    assert (a.float() - ref).abs().max().item() <= 2 ** -8 * ref.abs().max().item()
+    assert _rel(a, ref) < 3e-3
+
+
+# ------------------------------------------------------------------------------------ LayerNorm
+@pytest.mark.parametrize("rows,C", [(257, 1024), (2056, 768), (9, 128), (5000, 1024)])
+@pytest.mark.parametrize("dy_dtype", [torch.float32, torch.bfloat16])
+def test_layernorm_backward(cuda, lib, rows, C, dy_dtype):
+    from vicasplat_b200 import ops
+    g = torch.Generator().manual_seed(rows + C)
+    x = (torch.randn((rows, C), generator=g) * 1.5 + 0.3).to(cuda)
+    gamma = (1 + 0.2 * torch.randn((C,), generator=g)).to(cuda)
+    beta = (0.1 * torch.randn((C,), generator=g)).to(cuda)
+    dy = torch.randn((rows, C), generator=g).to(dy_dtype).to(cuda)
+    dres = torch.randn((rows, C), generator=g).to(cuda)
+    xr, gr, br = x.clone().requires_grad_(True), gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    F.layer_norm(xr, (C,), gr, br, 1e-6).backward(dy.float())
+    dgamma, dbeta = torch.zeros_like(gamma), torch.zeros_like(beta)
+    dx = ops.layernorm_backward(x, dy, gamma, dres=dres, dgamma=dgamma, dbeta=dbeta, eps=1e-6)
+    assert _rel(dx - dres, xr.grad) < 2e-5
+    assert _rel(dgamma, gr.grad) < 2e-5
+    assert _rel(dbeta, br.grad) < 2e-5
+    # in place on the residual-stream gradient, without parameter gradients
+    buf = dres.clone()
+    ops.layernorm_backward(x, dy, gamma, dres=buf, dx=buf, eps=1e-6)
+    assert torch.allclose(buf, dx, rtol=1e-6, atol=1e-6)
+
+
+# ------------------------------------------------------------------------------------ rope backward
+def test_rope_rows_backward_is_the_transpose(cuda, lib):
+    from vicasplat_b200 import ops
+    from vicasplat_b200.encoder_grad import FrameLayout
+    H, E = 16, 1024
+    lay = FrameLayout.make(2, 16, 16, H, cuda)
+    rows = lay.pos.shape[0]
+    g = torch.Generator().manual_seed(3)
+    a = _bf(torch.randn((rows, 3 * E), generator=g)).to(cuda)
+    b = _bf(torch.randn((rows, 3 * E), generator=g)).to(cuda)
+    Ra = ops.rope_rows(a.clone(), lay.pos, heads=H, q_col=0, k_col=E)
+    Rtb = ops.rope_rows_backward(b.clone(), lay.pos, heads=H, q_col=0, k_col=E)
+    # <R a, b> == <a, R^T b> on the rotated columns; the v columns are untouched by both
+    lhs = (Ra.float() * b.float()).sum().item()
+    rhs = (a.float() * Rtb.float()).sum().item()
+    assert abs(lhs - rhs) <= 2e-3 * (a.float().norm() * b.float().norm()).item()
+    assert torch.equal(Rtb[:, 2 * E:], b[:, 2 * E:])
+    back = ops.rope_rows_backward(Ra.clone(), lay.pos, heads=H, q_col=0, k_col=E)
+    assert _rel(back, a) < 8e-3                               # two bf16 roundings
+    # against the oracle's rope under autograd
+    q = a[:, :E].float().reshape(2, lay.n, H, 64).permute(0, 2, 1, 3).clone().requires_grad_(True)
+    pos = lay.pos.view(2, lay.n, 2).long()
+    er.rope2d(q, pos, 100.0).backward(b[:, :E].float().reshape(2, lay.n, H, 64).permute(0, 2, 1, 3))
+    ref = q.grad.permute(0, 2, 1, 3).reshape(rows, E)
+    assert _rel(Rtb[:, :E], ref) < 6e-3
+
+
+# ------------------------------------------------------------------------------------ linear layer
+@pytest.mark.parametrize("M,K,N", [(2056, 1024, 3072), (514, 768, 768), (2056, 4096, 1024), (300, 128, 64)])
+def test_linear_backward(cuda, lib, M, K, N):
+    from vicasplat_b200 import encoder_grad as eg, ops
+    g = torch.Generator().manual_seed(M + K + N)
+    x = _bf(torch.randn((M, K), generator=g)).to(cuda)
+    W = _bf(torch.randn((N, K), generator=g) / math.sqrt(K)).to(cuda)
+    dy32 = torch.randn((M, N), generator=g).to(cuda)
+    db = torch.zeros((N,), device=cuda)
+    dW = torch.full((N, K), 0.25, device=cuda)               # accumulated in place
+    dy, dy_t = ops.grad_prep(dy32, colsum=db)
+    _, x_t = ops.grad_prep(x, want_copy=False)
+    dx = eg.linear_backward(dy, dy_t, x_t, W.t().contiguous(), dW)
+    dyf = dy.float()                                          # the operands the GEMMs really see
+    assert _rel(dx, dyf @ W.float()) < 2e-5
+    assert _rel(dW - 0.25, dyf.t() @ x.float()) < 2e-5
+    assert _rel(db, dy32.sum(0)) < 1e-4
+    # and against autograd on unrounded gradients: one bf16 rounding of dy
+    xr, Wr = x.float().requires_grad_(True), W.float().requires_grad_(True)
+    F.linear(xr, Wr).backward(dy32)
+    assert _rel(dx, xr.grad) < 5e-3 and _rel(dW - 0.25, Wr.grad) < 5e-3
+
+
+# ------------------------------------------------------------------------------------ MLP half of the block
+def _block_sd(cfg, seed, device):
+    sd = {k: v.to(device) for k, v in er.synth_state_dict(cfg, seed=seed).items()
+          if k.startswith("backbone.enc_blocks.0.")}
+    g = torch.Generator().manual_seed(seed + 1)               # non-trivial LayerNorm parameters and biases
+    for k in sd:
+        if k.endswith("bias"):
+            sd[k] = (0.1 * torch.randn(sd[k].shape, generator=g)).to(device)
+        elif ".norm" in k:
+            sd[k] = (1 + 0.1 * torch.randn(sd[k].shape, generator=g)).to(device)
+    return sd
+
+
+def _cfg():
+    return er.EncoderConfig(enc_depth=1, dec_depth=4)   # only enc_blocks.0 is used
+
+
+def _check_grads(g, sd, names, tol):
+    for name in names:
+        ref = sd["backbone.enc_blocks.0." + name].grad
+        assert ref is not None, name
+        assert _rel(g[name], ref) < tol, (name, _rel(g[name], ref))
+
+
+def test_mlp_half_forward_backward(cuda, lib):
+    from vicasplat_b200 import encoder_grad as eg
+    cfg = _cfg()
+    sd = _block_sd(cfg, 0, cuda)
+    key = "backbone.enc_blocks.0"
+    w = eg.pack_block(sd, key, cuda)
+    g = eg.zero_grads(w)
+    gen = torch.Generator().manual_seed(11)
+    M, E = 2 * 257, cfg.enc_embed_dim
+    x = torch.randn((M, E), generator=gen).to(cuda)
+    dout = torch.randn((M, E), generator=gen).to(cuda)
+    saved = eg.Saved()
+    out = eg.mlp_half_forward(x, w, saved)
+    dx = eg.mlp_half_backward(dout, w, g, saved)
+    for v in sd.values():
+        v.requires_grad_(True)
+    xr = x.clone().requires_grad_(True)
+    ref = xr + er.mlp(sd, key + ".mlp", er.layer_norm(sd, key + ".norm2", xr, cfg.ln_eps))
+    ref.backward(dout)
+    assert _rel(out, ref) < 5e-3
+    assert _rel(dx, xr.grad) < 1e-2
+    _check_grads(g, sd, ["mlp.fc1.weight", "mlp.fc1.bias", "mlp.fc2.weight", "mlp.fc2.bias",
+                         "norm2.weight", "norm2.bias"], 2e-2)

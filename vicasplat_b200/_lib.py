@@ -58,6 +58,14 @@ class LayerNormParams(C.Structure):
     ]
 
 
+class LayerNormBwdParams(C.Structure):
+    _fields_ = [
+        ("x", _vp), ("ldx", _i64), ("dy", _vp), ("dy_dtype", _i32), ("ldy", _i64),
+        ("gamma", _vp), ("dres", _vp), ("ldres", _i64), ("dx", _vp), ("lddx", _i64),
+        ("dgamma", _vp), ("dbeta", _vp), ("rows", _i32), ("C", _i32), ("eps", _f32),
+    ]
+
+
 class AttentionParams(C.Structure):
     _fields_ = [
         ("Q", _vp), ("K", _vp), ("V", _vp), ("O", _vp),
@@ -100,6 +108,7 @@ STRUCTS = {
     "vs_raster_params": RasterParams,
     "vs_raster_bwd_params": RasterBwdParams,
     "vs_adamw_params": AdamWParams,
+    "vs_layernorm_bwd_params": LayerNormBwdParams,
 }
 
 _DECL = re.compile(r"^\s*(?:const\s+char\s*\*|int64_t|int)\s+(vs_\w+)\s*\(", re.M)

@@ -55,7 +55,7 @@ __global__ void rope_2d_kernel(T* __restrict__ tokens, int B, int N, int H, int 
 // lane ^ 8, the camera rope's partner is inside the lane.
 __global__ void rope_rows_kernel(bf16* __restrict__ qkv, long long ld, int rows, int H, int q_col,
                                  int k_col, const int* __restrict__ pos, float base,
-                                 float cam_theta) {
+                                 float cam_theta, float sign) {
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -67,6 +67,7 @@ __global__ void rope_rows_kernel(bf16* __restrict__ qkv, long long ld, int rows,
     const float t = static_cast<float>(-1 - py);
     const float ang = t / powf(cam_theta, (2 * lane) / 64.0f);
     sincosf(ang, &s0, &c0);
+    s0 *= sign;
     c1 = c0; s1 = s0;
   } else {
     const int e0 = 2 * lane;
@@ -77,6 +78,7 @@ __global__ void rope_rows_kernel(bf16* __restrict__ qkv, long long ld, int rows,
     const float p = static_cast<float>(half ? px : py);
     sincosf(p / powf(base, d0 / 16.0f), &s0, &c0);
     sincosf(p / powf(base, (d0 + 1) / 16.0f), &s1, &c1);
+    s0 *= sign; s1 *= sign;   // sign = -1: the inverse rotation = the transpose = the backward pass
   }
   bf16* r = qkv + static_cast<long long>(row) * ld;
   // all loads of a batch of heads are issued before the first store (q/k alias the same buffer,
@@ -850,7 +852,20 @@ extern "C" int vs_rope_rows(void* qkv, int64_t ld, int rows, int H, int q_col, i
   if (rows <= 0) return VS_OK;
   rope_rows_kernel<<<blocks_for(static_cast<long long>(rows) * 32, 256), 256, 0,
                      to_stream(stream)>>>(static_cast<bf16*>(qkv), ld, rows, H, q_col, k_col, pos,
-                                          base, cam_theta);
+                                          base, cam_theta, 1.0f);
+  VS_LAUNCH_CHECK();
+  return VS_OK;
+}
+
+extern "C" int vs_rope_rows_backward(void* dqkv, int64_t ld, int rows, int H, int q_col, int k_col,
+                                     const int32_t* pos, float base, float cam_theta,
+                                     vs_stream_t stream) {
+  VS_REQUIRE(dqkv && pos, "rope_rows_backward: null tensor");
+  VS_REQUIRE(ld % 2 == 0 && q_col % 2 == 0 && k_col % 2 == 0, "rope_rows_backward: columns must be even");
+  if (rows <= 0) return VS_OK;
+  rope_rows_kernel<<<blocks_for(static_cast<long long>(rows) * 32, 256), 256, 0,
+                     to_stream(stream)>>>(static_cast<bf16*>(dqkv), ld, rows, H, q_col, k_col, pos,
+                                          base, cam_theta, -1.0f);
   VS_LAUNCH_CHECK();
   return VS_OK;
 }

@@ -322,3 +322,76 @@ def mse_loss(pred, target, weight=1.0, want_grad=True):
                               C.c_float(weight), C.c_void_p(ptr(loss)), C.c_void_p(ptr(grad)),
                               C.c_void_p(ptr(_mse_ws[key])), C.c_void_p(stream_ptr())), "vs_mse_loss")
     return loss, grad
+
+
+# ------------------------------------------------------------------ encoder training path (backward)
+def grad_prep(src, *, z=None, want_copy=True, want_t=True, colsum=None):
+    """One pass over a gradient matrix (rows, cols) f32 / bf16 (vs_grad_prep): optional gelu'(z)
+    factor, bf16 row-major copy, bf16 transposed copy (returned as a (cols, rows) view of a buffer
+    whose row stride is rows rounded up to 8) and column sums accumulated into `colsum` (f32)."""
+    lib = _lib.load()
+    _need_cuda(src, z, colsum)
+    assert src.dim() == 2 and src.stride(1) == 1 and src.dtype in (torch.float32, torch.bfloat16)
+    rows, cols = src.shape
+    copy = torch.empty((rows, cols), dtype=torch.bfloat16, device=src.device) if want_copy else None
+    tr = None
+    ld_t = (rows + 7) // 8 * 8
+    if want_t:
+        tr = torch.empty((cols, ld_t), dtype=torch.bfloat16, device=src.device)
+    if z is not None:
+        assert z.shape == src.shape and z.dtype == torch.bfloat16 and z.stride(1) == 1
+    if colsum is not None:
+        assert colsum.dtype == torch.float32 and colsum.numel() == cols and colsum.is_contiguous()
+    with _timed("grad_prep"):
+        check(lib.vs_grad_prep(C.c_void_p(ptr(src)), _DT[src.dtype], C.c_int64(src.stride(0)),
+                               C.c_void_p(ptr(z)), C.c_int64(z.stride(0) if z is not None else 0),
+                               rows, cols, C.c_void_p(ptr(copy)), C.c_int64(cols),
+                               C.c_void_p(ptr(tr)), C.c_int64(ld_t), C.c_void_p(ptr(colsum)),
+                               C.c_void_p(stream_ptr())), "vs_grad_prep")
+    return copy, (tr[:, :rows] if tr is not None else None)
+
+
+def gelu_bf16(z, out=None):
+    """a = gelu(z) (exact erf), bf16 -> bf16 (vs_gelu_bf16): the training-mode activation."""
+    lib = _lib.load()
+    _need_cuda(z)
+    assert z.dim() == 2 and z.dtype == torch.bfloat16 and z.stride(1) == 1
+    if out is None:
+        out = torch.empty_like(z)
+    check(lib.vs_gelu_bf16(C.c_void_p(ptr(z)), C.c_int64(z.stride(0)), C.c_void_p(ptr(out)),
+                           C.c_int64(out.stride(0)), z.shape[0], z.shape[1],
+                           C.c_void_p(stream_ptr())), "vs_gelu_bf16")
+    return out
+
+
+def layernorm_backward(x, dy, gamma, *, dres=None, dx=None, dgamma=None, dbeta=None, eps=1e-6):
+    """dx = dres + d LayerNorm / dx; dgamma / dbeta accumulated (vs_layernorm_backward)."""
+    lib = _lib.load()
+    _need_cuda(x, dy, gamma)
+    rows, Cc = x.shape
+    assert dy.shape == x.shape and x.dtype == torch.float32
+    if dx is None:
+        dx = torch.empty((rows, Cc), dtype=torch.float32, device=x.device)
+    p = _lib.LayerNormBwdParams()
+    p.x, p.ldx = ptr(x), x.stride(0)
+    p.dy, p.dy_dtype, p.ldy = ptr(dy), _DT[dy.dtype], dy.stride(0)
+    p.gamma = ptr(gamma)
+    if dres is not None:
+        p.dres, p.ldres = ptr(dres), dres.stride(0)
+    p.dx, p.lddx = ptr(dx), dx.stride(0)
+    p.dgamma, p.dbeta = ptr(dgamma), ptr(dbeta)
+    p.rows, p.C, p.eps = rows, Cc, eps
+    with _timed("layernorm_bwd"):
+        check(lib.vs_layernorm_backward(C.byref(p), C.c_void_p(stream_ptr())), "vs_layernorm_backward")
+    return dx
+
+
+def rope_rows_backward(dqkv, pos_i32, *, heads, q_col, k_col, base=100.0, cam_theta=30.0):
+    """Inverse rotation on the q / k columns of the packed bf16 gradient (in place)."""
+    lib = _lib.load()
+    _need_cuda(dqkv, pos_i32)
+    check(lib.vs_rope_rows_backward(C.c_void_p(ptr(dqkv)), C.c_int64(dqkv.stride(0)), dqkv.shape[0],
+                                    heads, q_col, k_col, C.c_void_p(ptr(pos_i32)), C.c_float(base),
+                                    C.c_float(cam_theta), C.c_void_p(stream_ptr())),
+          "vs_rope_rows_backward")
+    return dqkv
