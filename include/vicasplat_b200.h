@@ -165,6 +165,8 @@ typedef struct vs_attention_params {
   int32_t max_kv_len;   /* upper bound of kv_len0 + kv_len1 over the items (0 = unknown) */
   int32_t causal_block;
   float scale;
+  float* lse; /* optional output (q_rows, heads) f32 for vs_attention_backward: log2-domain
+                 log-sum-exp of the scaled scores of every query row (+inf for a row without keys) */
 } vs_attention_params;
 int vs_attention(const vs_attention_params* p, vs_stream_t stream);
 
@@ -375,6 +377,22 @@ typedef struct vs_layernorm_bwd_params {
   float eps;
 } vs_layernorm_bwd_params;
 int vs_layernorm_backward(const vs_layernorm_bwd_params* p, vs_stream_t stream);
+
+/* Backward of vs_attention (same items / segments / mask; `fwd` holds the forward call's arguments,
+ * including O and the lse it wrote): dQ, dK, dV (bf16, row matrices like Q / K / V, head h at columns
+ * [h*64, h*64+64); they may alias a packed dqkv buffer) from dO.  delta: scratch (q_rows, heads) f32.
+ * fwd.max_kv_len must be given.  The key rows of different items must not overlap (dK / dV are
+ * written, not accumulated).  Flash-style: scores are recomputed on the tensor cores, no (q, kv)
+ * matrix is ever stored.  Replaces autograd through croco/blocks.py:105-109. */
+typedef struct vs_attention_bwd_params {
+  vs_attention_params fwd;
+  const void* dO;
+  int64_t lddo;
+  void *dQ, *dK, *dV;
+  int64_t lddq, lddk, lddv;
+  float* delta;
+} vs_attention_bwd_params;
+int vs_attention_backward(const vs_attention_bwd_params* p, vs_stream_t stream);
 
 /* Backward of vs_rope_rows / of the rope fused into the qkv epilogue: the inverse rotation applied in
  * place to the q and k columns of the packed bf16 gradient dqkv (cuRoPE2D_func.backward calls

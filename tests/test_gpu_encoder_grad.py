@@ -187,3 +187,153 @@ def test_mlp_half_forward_backward(cuda, lib):
     assert _rel(dx, xr.grad) < 1e-2
     _check_grads(g, sd, ["mlp.fc1.weight", "mlp.fc1.bias", "mlp.fc2.weight", "mlp.fc2.bias",
                          "norm2.weight", "norm2.bias"], 2e-2)
+
+
+# ------------------------------------------------------------------------------------ attention backward
+def _sdpa_grads(q, k, v, dO, mask=None):
+    """fp32 autograd through the oracle's softmax attention on the bf16-rounded operands.
+    q, k, v, dO: (..., rows, 64) float."""
+    q, k, v = (t.clone().requires_grad_(True) for t in (q, k, v))
+    o = er.sdpa(q, k, v, mask)
+    o.backward(dO)
+    s = (q.detach() @ k.detach().transpose(-1, -2)) * 0.125
+    if mask is not None:
+        s = s.masked_fill(~mask, float("-inf"))
+    return o.detach(), q.grad, k.grad, v.grad, torch.logsumexp(s, -1)
+
+
+def test_attention_backward_encoder_style(cuda, lib):
+    """per-frame self-attention on a packed qkv buffer, 257 tokens (partial query and key tiles)."""
+    from vicasplat_b200 import ops
+    g = torch.Generator().manual_seed(21)
+    Fr, N, H = 3, 257, 16
+    C = H * 64
+    qkv = _bf(torch.randn((Fr * N, 3 * C), generator=g)).to(cuda)
+    dO = _bf(torch.randn((Fr * N, C), generator=g)).to(cuda)
+    O = torch.zeros((Fr * N, C), dtype=torch.bfloat16, device=cuda)
+    lse = torch.zeros((Fr * N, H), device=cuda)
+    st = torch.arange(Fr, dtype=torch.int32, device=cuda) * N
+    ln = torch.full((Fr,), N, dtype=torch.int32, device=cuda)
+    kw = dict(heads=H, q_start=st, q_len=ln, kv_start0=st, kv_len0=ln, max_q_len=N, max_kv_len=N, scale=0.125)
+    ops.attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], O, lse=lse, **kw)
+    dqkv = torch.full_like(qkv, float("nan"))                 # every element must be written
+    ops.attention_backward(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], O, dO, lse,
+                           dqkv[:, :C], dqkv[:, C:2 * C], dqkv[:, 2 * C:], **kw)
+    t = qkv.float().view(Fr, N, 3, H, 64).permute(2, 0, 3, 1, 4)
+    o_ref, dq, dk, dv, lse_ref = _sdpa_grads(t[0], t[1], t[2], dO.float().view(Fr, N, H, 64).permute(0, 2, 1, 3))
+    back = lambda x: x.permute(0, 2, 1, 3).reshape(Fr * N, C)
+    assert _rel(O, back(o_ref)) < 1e-2
+    assert (lse * math.log(2.0) - lse_ref.permute(0, 2, 1).reshape(Fr * N, H)).abs().max().item() < 2e-3
+    assert torch.isfinite(dqkv.float()).all()
+    assert _rel(dqkv[:, :C], back(dq)) < 2e-2
+    assert _rel(dqkv[:, C:2 * C], back(dk)) < 2e-2
+    assert _rel(dqkv[:, 2 * C:], back(dv)) < 2e-2
+    tail = torch.arange(Fr, device=cuda) * N + N - 1          # the 257-th row of every frame
+    assert _rel(dqkv[tail], torch.cat([back(dq), back(dk), back(dv)], 1)[tail]) < 2e-2
+
+
+def test_attention_backward_video_with_camera_mask(cuda, lib):
+    """one scene: T frames x (1 camera + N image) rows; camera rows see frames <= t only."""
+    from vicasplat_b200 import ops
+    g = torch.Generator().manual_seed(22)
+    T, N, H = 4, 65, 12
+    rpf = N + 1
+    rows = T * rpf
+    C = H * 64
+    qkv = _bf(torch.randn((rows, 3 * C), generator=g)).to(cuda)
+    dO = _bf(torch.randn((rows, C), generator=g)).to(cuda)
+    O = torch.zeros((rows, C), dtype=torch.bfloat16, device=cuda)
+    lse = torch.zeros((rows, H), device=cuda)
+    i32 = dict(dtype=torch.int32, device=cuda)
+    kw = dict(heads=H, q_start=torch.zeros(1, **i32), q_len=torch.full((1,), rows, **i32),
+              kv_start0=torch.zeros(1, **i32), kv_len0=torch.full((1,), rows, **i32),
+              max_q_len=rows, max_kv_len=rows, causal_block=rpf, scale=0.125)
+    ops.attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], O, lse=lse, **kw)
+    dqkv = torch.full_like(qkv, float("nan"))
+    ops.attention_backward(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], O, dO, lse,
+                           dqkv[:, :C], dqkv[:, C:2 * C], dqkv[:, 2 * C:], **kw)
+    t = qkv.float().view(rows, 3, H, 64).permute(1, 2, 0, 3)                  # (3,H,rows,64)
+    mask = torch.ones((rows, rows), dtype=torch.bool, device=cuda)
+    for f in range(T):
+        mask[f * rpf, (f + 1) * rpf:] = False
+    o_ref, dq, dk, dv, _ = _sdpa_grads(t[0], t[1], t[2], dO.float().view(rows, H, 64).permute(1, 0, 2), mask)
+    back = lambda x: x.permute(1, 0, 2).reshape(rows, C)
+    assert _rel(O, back(o_ref)) < 1e-2
+    assert _rel(dqkv[:, :C], back(dq)) < 2e-2
+    assert _rel(dqkv[:, C:2 * C], back(dk)) < 2e-2
+    assert _rel(dqkv[:, 2 * C:], back(dv)) < 2e-2
+    cam = torch.arange(T, device=cuda) * rpf
+    assert _rel(dqkv[cam, :C], back(dq)[cam]) < 2e-2
+
+
+def test_attention_backward_two_segments(cuda, lib):
+    """keys of an item = two disjoint row segments (the layout of the neighbour attention, with
+    key rows private to the item as this version of the backward pass requires)."""
+    from vicasplat_b200 import ops
+    g = torch.Generator().manual_seed(23)
+    Fr, N, H = 3, 150, 4
+    C = H * 64
+    q = _bf(torch.randn((Fr * N, C), generator=g)).to(cuda)
+    k = _bf(torch.randn((2 * Fr * N, C), generator=g)).to(cuda)
+    v = _bf(torch.randn((2 * Fr * N, C), generator=g)).to(cuda)
+    dO = _bf(torch.randn((Fr * N, C), generator=g)).to(cuda)
+    O = torch.zeros((Fr * N, C), dtype=torch.bfloat16, device=cuda)
+    lse = torch.zeros((Fr * N, H), device=cuda)
+    fr = torch.arange(Fr)
+    i32 = dict(dtype=torch.int32, device=cuda)
+    len1 = torch.tensor([N, 0, 70])                            # full, absent and partial second segment
+    kw = dict(heads=H, q_start=(fr * N).to(**i32), q_len=torch.full((Fr,), N, **i32),
+              kv_start0=(fr * N).to(**i32), kv_len0=torch.full((Fr,), N, **i32),
+              kv_start1=((Fr + fr) * N).to(**i32), kv_len1=len1.to(**i32),
+              max_q_len=N, max_kv_len=2 * N, scale=0.125)
+    ops.attention(q, k, v, O, lse=lse, **kw)
+    dq = torch.full_like(q, float("nan"))
+    dk, dv = torch.zeros_like(k), torch.zeros_like(v)
+    ops.attention_backward(q, k, v, O, dO, lse, dq, dk, dv, **kw)
+    for i in range(Fr):
+        rows0 = slice(i * N, (i + 1) * N)
+        rows1 = slice((Fr + i) * N, (Fr + i) * N + int(len1[i]))
+        heads = lambda x: x.float().view(-1, H, 64).permute(1, 0, 2)
+        kk = torch.cat([heads(k[rows0]), heads(k[rows1])], 1)
+        vv = torch.cat([heads(v[rows0]), heads(v[rows1])], 1)
+        o_ref, rq, rk, rv, _ = _sdpa_grads(heads(q[rows0]), kk, vv, heads(dO[rows0]))
+        back = lambda x: x.permute(1, 0, 2).reshape(-1, C)
+        assert _rel(O[rows0], back(o_ref)) < 1e-2, i
+        assert _rel(dq[rows0], back(rq)) < 2e-2, i
+        assert _rel(torch.cat([dk[rows0], dk[rows1]]), back(rk)) < 2e-2, i
+        assert _rel(torch.cat([dv[rows0], dv[rows1]]), back(rv)) < 2e-2, i
+    # rows of K / V that belong to no item are left alone
+    unused = slice((Fr + 1) * N, (Fr + 2) * N)
+    assert (dk[unused] == 0).all() and (dv[unused] == 0).all()
+
+
+# ------------------------------------------------------------------------------------ the whole ViT block
+def test_vit_block_forward_backward(cuda, lib):
+    """croco/blocks.py:81-130 end to end: every parameter gradient and the input gradient of one
+    encoder block against torch.autograd over the fp32 oracle block."""
+    from vicasplat_b200 import encoder_grad as eg
+    cfg = _cfg()
+    sd = _block_sd(cfg, 1, cuda)
+    key = "backbone.enc_blocks.0"
+    w = eg.pack_block(sd, key, cuda)
+    g = eg.zero_grads(w)
+    Fr, gh = 3, 16
+    lay = eg.FrameLayout.make(Fr, gh, gh, cfg.enc_num_heads, cuda)
+    M, E = Fr * lay.n, cfg.enc_embed_dim
+    gen = torch.Generator().manual_seed(12)
+    x = torch.randn((M, E), generator=gen).to(cuda)
+    dout = torch.randn((M, E), generator=gen).to(cuda)
+    saved = eg.Saved()
+    out = eg.block_forward(x, w, lay, saved)
+    dx = eg.block_backward(dout, w, g, lay, saved)
+    for v in sd.values():
+        v.requires_grad_(True)
+    xr = x.view(Fr, lay.n, E).clone().requires_grad_(True)
+    pos = er.positions(Fr, gh, gh, True, device=cuda)
+    ref = er.enc_block(sd, key, xr, pos, cfg)
+    ref.backward(dout.view(Fr, lay.n, E))
+    assert _rel(out, ref.reshape(M, E)) < 5e-3
+    assert _rel(dx, xr.grad.reshape(M, E)) < 1.5e-2
+    _check_grads(g, sd, ["mlp.fc1.weight", "mlp.fc1.bias", "mlp.fc2.weight", "mlp.fc2.bias",
+                         "norm2.weight", "norm2.bias", "attn.proj.weight", "attn.proj.bias",
+                         "attn.qkv.weight", "attn.qkv.bias", "norm1.weight", "norm1.bias"], 3e-2)

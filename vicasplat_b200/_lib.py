@@ -74,6 +74,15 @@ class AttentionParams(C.Structure):
         ("q_start", _vp), ("q_len", _vp), ("kv_start0", _vp), ("kv_len0", _vp),
         ("kv_start1", _vp), ("kv_len1", _vp),
         ("max_q_len", _i32), ("max_kv_len", _i32), ("causal_block", _i32), ("scale", _f32),
+        ("lse", _vp),
+    ]
+
+
+class AttentionBwdParams(C.Structure):
+    _fields_ = [
+        ("fwd", AttentionParams), ("dO", _vp), ("lddo", _i64),
+        ("dQ", _vp), ("dK", _vp), ("dV", _vp), ("lddq", _i64), ("lddk", _i64), ("lddv", _i64),
+        ("delta", _vp),
     ]
 
 
@@ -109,6 +118,7 @@ STRUCTS = {
     "vs_raster_bwd_params": RasterBwdParams,
     "vs_adamw_params": AdamWParams,
     "vs_layernorm_bwd_params": LayerNormBwdParams,
+    "vs_attention_bwd_params": AttentionBwdParams,
 }
 
 _DECL = re.compile(r"^\s*(?:const\s+char\s*\*|int64_t|int)\s+(vs_\w+)\s*\(", re.M)

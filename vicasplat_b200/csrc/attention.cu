@@ -45,6 +45,8 @@ struct AttnDev {
   int causal_block;
   float scale_log2;
   int tail;  // the last `tail` query rows of every item are left to attention_tail_kernel
+  float* lse;  // optional (rows, heads): log2-domain log-sum-exp of the scaled scores, for the backward pass
+  int heads;
 };
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -314,6 +316,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 3)
       tc_fence_after();
     }
     const float inv = l > 0.f ? 1.0f / l : 0.f;
+    if (a.lse != nullptr && row_valid)   // p = exp2(s * scale_log2 - lse) reproduces the probabilities
+      a.lse[static_cast<long long>(grow) * a.heads + head] = l > 0.f ? m + log2f(l) : INFINITY;
     __nv_bfloat16* dst = a.O + static_cast<long long>(grow) * a.ldo + head * HD;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
@@ -451,6 +455,8 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
   for (int i = 0; i < 8; ++i) s_o[part][d8 + i] = acc[i];
   __syncthreads();
+  if (threadIdx.x == 0 && a.lse != nullptr)
+    a.lse[static_cast<long long>(grow) * a.heads + head] = sum > 0.f ? m_use + log2f(sum) : INFINITY;
   if (threadIdx.x < 64) {
     float o = 0.f;
 #pragma unroll
@@ -504,6 +510,8 @@ extern "C" int vs_attention(const vs_attention_params* p, vs_stream_t stream_) {
   a.kv_len1 = p->kv_len1;
   a.causal_block = p->causal_block;
   a.scale_log2 = p->scale * 1.4426950408889634f;
+  a.lse = p->lse;
+  a.heads = p->heads;
   const int rem = p->max_q_len % QT;
   a.tail = (rem > 0 && rem <= TAIL_MAX_ROWS && p->max_kv_len > 0 && p->max_kv_len <= TAIL_MAX_KEYS)
                ? rem : 0;

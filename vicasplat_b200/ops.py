@@ -155,8 +155,9 @@ def layernorm(x, w=None, b=None, *, eps=1e-6, w0=None, b0=None, scale=None, shif
 
 
 def attention(Q, K, V, O, *, heads, q_start, q_len, kv_start0, kv_len0, kv_start1=None,
-              kv_len1=None, max_q_len, max_kv_len=0, causal_block=0, scale=0.125):
-    """softmax(Q K^T * scale) V per (item, head); Q/K/V/O are 2-D bf16 views (rows, >= heads*64)."""
+              kv_len1=None, max_q_len, max_kv_len=0, causal_block=0, scale=0.125, lse=None):
+    """softmax(Q K^T * scale) V per (item, head); Q/K/V/O are 2-D bf16 views (rows, >= heads*64).
+    lse (rows, heads) f32, optional: log2-domain log-sum-exp per query row (kept for the backward pass)."""
     _need_cuda(Q, K, V, O)
     lib = _lib.load()
     p = AttentionParams()
@@ -168,6 +169,9 @@ def attention(Q, K, V, O, *, heads, q_start, q_len, kv_start0, kv_len0, kv_start
     p.kv_start0, p.kv_len0 = ptr(kv_start0), ptr(kv_len0)
     p.kv_start1, p.kv_len1 = ptr(kv_start1), ptr(kv_len1)
     p.max_q_len, p.max_kv_len, p.causal_block, p.scale = max_q_len, max_kv_len, causal_block, scale
+    if lse is not None:
+        assert lse.dtype == torch.float32 and lse.is_contiguous() and lse.shape == (Q.shape[0], heads)
+        p.lse = ptr(lse)
     with _timed("attention", ("attn", p.items, heads, max_q_len, max_kv_len, causal_block)):
         check(lib.vs_attention(C.byref(p), C.c_void_p(stream_ptr())), "vs_attention")
     return O
@@ -384,6 +388,34 @@ def layernorm_backward(x, dy, gamma, *, dres=None, dx=None, dgamma=None, dbeta=N
     with _timed("layernorm_bwd"):
         check(lib.vs_layernorm_backward(C.byref(p), C.c_void_p(stream_ptr())), "vs_layernorm_backward")
     return dx
+
+
+def attention_backward(Q, K, V, O, dO, lse, dQ, dK, dV, *, heads, q_start, q_len, kv_start0, kv_len0,
+                       kv_start1=None, kv_len1=None, max_q_len, max_kv_len, causal_block=0,
+                       scale=0.125):
+    """dQ, dK, dV of ops.attention from dO, the forward output O and its lse (vs_attention_backward)."""
+    _need_cuda(Q, K, V, O, dO, lse, dQ, dK, dV)
+    lib = _lib.load()
+    p = _lib.AttentionBwdParams()
+    f = p.fwd
+    f.Q, f.K, f.V, f.O = ptr(Q), ptr(K), ptr(V), ptr(O)
+    f.ldq, f.ldk, f.ldv, f.ldo = Q.stride(0), K.stride(0), V.stride(0), O.stride(0)
+    f.q_rows, f.kv_rows = Q.shape[0], K.shape[0]
+    f.heads, f.items = heads, q_start.numel()
+    f.q_start, f.q_len = ptr(q_start), ptr(q_len)
+    f.kv_start0, f.kv_len0 = ptr(kv_start0), ptr(kv_len0)
+    f.kv_start1, f.kv_len1 = ptr(kv_start1), ptr(kv_len1)
+    f.max_q_len, f.max_kv_len, f.causal_block, f.scale = max_q_len, max_kv_len, causal_block, scale
+    assert lse.dtype == torch.float32 and lse.is_contiguous() and lse.shape == (Q.shape[0], heads)
+    f.lse = ptr(lse)
+    p.dO, p.lddo = ptr(dO), dO.stride(0)
+    p.dQ, p.dK, p.dV = ptr(dQ), ptr(dK), ptr(dV)
+    p.lddq, p.lddk, p.lddv = dQ.stride(0), dK.stride(0), dV.stride(0)
+    delta = torch.empty((Q.shape[0], heads), dtype=torch.float32, device=Q.device)
+    p.delta = ptr(delta)
+    with _timed("attention_bwd", ("attn_bwd", f.items, heads, max_q_len, max_kv_len, causal_block)):
+        check(lib.vs_attention_backward(C.byref(p), C.c_void_p(stream_ptr())), "vs_attention_backward")
+    return dQ, dK, dV
 
 
 def rope_rows_backward(dqkv, pos_i32, *, heads, q_col, k_col, base=100.0, cam_theta=30.0):
