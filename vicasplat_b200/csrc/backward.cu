@@ -33,13 +33,32 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
   return *reinterpret_cast<const uint32_t*>(&v);
 }
 
-// exact-erf GELU (nn.GELU default, croco/blocks.py:60) and its derivative
-__device__ __forceinline__ float gelu_f(float z) {
-  return 0.5f * z * (1.0f + erff(z * 0.70710678118654752f));
+// exact-erf GELU (nn.GELU default, croco/blocks.py:60) and its derivative, erf from Abramowitz-Stegun
+// 7.1.26 (|err| <= 1.5e-7, as in the GEMM's fused GELU epilogue): with z = |x| / sqrt(2),
+//   E = exp(-z^2),  R = p(t) t E,  t = 1 / (1 + 0.3275911 z)   =>   erf(z) = 1 - R
+// gelu and gelu' share E (the Gaussian factor of the derivative): 2 MUFU + ~12 FMA-pipe slots per value.
+__device__ __forceinline__ void erf_terms(float x, float& R, float& E) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  float t, e;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * z * -1.4426950408889634f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  E = e;
+  R = p * t * e;
 }
-__device__ __forceinline__ float gelu_grad_f(float z) {
-  return 0.5f * (1.0f + erff(z * 0.70710678118654752f)) +
-         z * 0.3989422804014327f * __expf(-0.5f * z * z);
+__device__ __forceinline__ float gelu_f(float x) {
+  float R, E;
+  erf_terms(x, R, E);
+  return fmaf(-0.5f * fabsf(x), R, fmaxf(x, 0.f));
+}
+__device__ __forceinline__ float gelu_grad_f(float x) {
+  float R, E;
+  erf_terms(x, R, E);
+  const float cdf = x >= 0.f ? fmaf(-0.5f, R, 1.0f) : 0.5f * R;   // Phi(x)
+  return fmaf(x * 0.3989422804014327f, E, cdf);                    // + x phi(x)
 }
 
 // ------------------------------------------------------------------ grad_prep
@@ -145,101 +164,115 @@ __global__ void gelu_kernel(const bf16* __restrict__ z, long long ld_z, bf16* __
 // y = (x - mean) * rstd * gamma + beta  (nn.LayerNorm, eps 1e-6: croco/blocks.py:88-96).  One warp per
 // row, the row in registers (C = k * 128 <= 1024), statistics recomputed from x:
 //   g = dy * gamma;  dx = rstd * (g - mean(g) - xhat * mean(g * xhat))  (+ dres, the gradient that
-// reaches x through the residual connection).  d gamma / d beta are accumulated per warp in registers
-// over the warp's rows, folded per CTA in shared memory and added to global memory once per CTA.
+// reaches x through the residual connection).
+// d gamma / d beta: the 8 warps of a CTA stage their rows' (dy * xhat, dy) in shared memory, thread t
+// then folds the 8 rows of columns 4t..4t+3 into its own registers (no atomics inside the CTA, and
+// only 8 accumulator registers per thread so that two CTAs fit on an SM); one global atomicAdd per
+// column and CTA at the end.
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 layernorm_backward_kernel(const float* __restrict__ x, long long ldx, const T* __restrict__ dy,
                           long long ldy, const float* __restrict__ gamma,
                           const float* dres, long long ldres, float* dx,  // may alias
-                         
                           long long lddx, float* __restrict__ dgamma, float* __restrict__ dbeta,
                           int rows, int C, float eps) {
-  extern __shared__ float fold[];  // [2][C]
+  extern __shared__ float4 stage[];  // [2][8][C / 4]
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int nv = C / 128;
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) fold[i] = 0.f;
-  __syncthreads();
-  float4 ag[8], ab[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) ag[i] = ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int c4 = C / 4;
+  const bool params = dgamma != nullptr;
+  float4 accg = make_float4(0.f, 0.f, 0.f, 0.f), accb = accg;
   const float inv_c = 1.0f / C;
-  for (int row = blockIdx.x * 8 + warp; row < rows; row += gridDim.x * 8) {
-    const float* xr = x + static_cast<long long>(row) * ldx;
-    const T* dyr = dy + static_cast<long long>(row) * ldy;
-    float4 v[8], g[8];
-    float s = 0.f;
+  for (int base = blockIdx.x * 8; base < rows; base += gridDim.x * 8) {   // uniform for the CTA
+    const int row = base + warp;
+    const bool valid = row < rows;
+    if (valid) {
+      const float* xr = x + static_cast<long long>(row) * ldx;
+      const T* dyr = dy + static_cast<long long>(row) * ldy;
+      float4 v[8], g[8];
+      float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
-      if (i < nv) {
-        v[i] = load4(xr + (i * 32 + lane) * 4);
-        g[i] = load4(dyr + (i * 32 + lane) * 4);
-        s += v[i].x + v[i].y + v[i].z + v[i].w;
-      }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    const float mean = s * inv_c;
-    float q = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-      if (i < nv) {
-        v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
-        q += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
-      }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-    const float rstd = rsqrtf(q * inv_c + eps);
-    float sg = 0.f, sgx = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-      if (i < nv) {
-        const float4 w = load4(gamma + (i * 32 + lane) * 4);
-        v[i].x *= rstd; v[i].y *= rstd; v[i].z *= rstd; v[i].w *= rstd;  // xhat
-        ab[i].x += g[i].x; ab[i].y += g[i].y; ab[i].z += g[i].z; ab[i].w += g[i].w;
-        ag[i].x += g[i].x * v[i].x; ag[i].y += g[i].y * v[i].y;
-        ag[i].z += g[i].z * v[i].z; ag[i].w += g[i].w * v[i].w;
-        g[i].x *= w.x; g[i].y *= w.y; g[i].z *= w.z; g[i].w *= w.w;
-        sg += g[i].x + g[i].y + g[i].z + g[i].w;
-        sgx += g[i].x * v[i].x + g[i].y * v[i].y + g[i].z * v[i].z + g[i].w * v[i].w;
-      }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      sg += __shfl_xor_sync(0xffffffffu, sg, o);
-      sgx += __shfl_xor_sync(0xffffffffu, sgx, o);
-    }
-    const float mg = sg * inv_c, mgx = sgx * inv_c;
-    float* dxr = dx + static_cast<long long>(row) * lddx;
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-      if (i < nv) {
-        float4 o;
-        o.x = rstd * (g[i].x - mg - v[i].x * mgx);
-        o.y = rstd * (g[i].y - mg - v[i].y * mgx);
-        o.z = rstd * (g[i].z - mg - v[i].z * mgx);
-        o.w = rstd * (g[i].w - mg - v[i].w * mgx);
-        if (dres != nullptr) {
-          const float4 r = load4(dres + static_cast<long long>(row) * ldres + (i * 32 + lane) * 4);
-          o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+      for (int i = 0; i < 8; ++i)
+        if (i < nv) {
+          v[i] = load4(xr + (i * 32 + lane) * 4);
+          g[i] = load4(dyr + (i * 32 + lane) * 4);
+          s += v[i].x + v[i].y + v[i].z + v[i].w;
         }
-        *reinterpret_cast<float4*>(dxr + (i * 32 + lane) * 4) = o;
-      }
-  }
-  if (dgamma != nullptr) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
-      if (i < nv) {
-        const int cidx = (i * 32 + lane) * 4;
-        atomicAdd(&fold[cidx + 0], ag[i].x); atomicAdd(&fold[cidx + 1], ag[i].y);
-        atomicAdd(&fold[cidx + 2], ag[i].z); atomicAdd(&fold[cidx + 3], ag[i].w);
-        atomicAdd(&fold[C + cidx + 0], ab[i].x); atomicAdd(&fold[C + cidx + 1], ab[i].y);
-        atomicAdd(&fold[C + cidx + 2], ab[i].z); atomicAdd(&fold[C + cidx + 3], ab[i].w);
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      const float mean = s * inv_c;
+      float q = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (i < nv) {
+          v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+          q += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
+        }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+      const float rstd = rsqrtf(q * inv_c + eps);
+      float sg = 0.f, sgx = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (i < nv) {
+          const float4 w = load4(gamma + (i * 32 + lane) * 4);
+          v[i].x *= rstd; v[i].y *= rstd; v[i].z *= rstd; v[i].w *= rstd;  // xhat
+          if (params) {
+            stage[warp * c4 + i * 32 + lane] =
+                make_float4(g[i].x * v[i].x, g[i].y * v[i].y, g[i].z * v[i].z, g[i].w * v[i].w);
+            stage[(8 + warp) * c4 + i * 32 + lane] = g[i];
+          }
+          g[i].x *= w.x; g[i].y *= w.y; g[i].z *= w.z; g[i].w *= w.w;
+          sg += g[i].x + g[i].y + g[i].z + g[i].w;
+          sgx += g[i].x * v[i].x + g[i].y * v[i].y + g[i].z * v[i].z + g[i].w * v[i].w;
+        }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        sg += __shfl_xor_sync(0xffffffffu, sg, o);
+        sgx += __shfl_xor_sync(0xffffffffu, sgx, o);
       }
-    __syncthreads();
-    for (int i = threadIdx.x; i < C; i += blockDim.x) {
-      atomicAdd(dgamma + i, fold[i]);
-      atomicAdd(dbeta + i, fold[C + i]);
+      const float mg = sg * inv_c, mgx = sgx * inv_c;
+      float* dxr = dx + static_cast<long long>(row) * lddx;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (i < nv) {
+          float4 o;
+          o.x = rstd * (g[i].x - mg - v[i].x * mgx);
+          o.y = rstd * (g[i].y - mg - v[i].y * mgx);
+          o.z = rstd * (g[i].z - mg - v[i].z * mgx);
+          o.w = rstd * (g[i].w - mg - v[i].w * mgx);
+          if (dres != nullptr) {
+            const float4 r = load4(dres + static_cast<long long>(row) * ldres + (i * 32 + lane) * 4);
+            o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+          }
+          *reinterpret_cast<float4*>(dxr + (i * 32 + lane) * 4) = o;
+        }
+    } else if (params) {
+      const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int i = lane; i < c4; i += 32) {
+        stage[warp * c4 + i] = zero;
+        stage[(8 + warp) * c4 + i] = zero;
+      }
     }
+    if (params) {
+      __syncthreads();
+      if (threadIdx.x < c4) {
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+          const float4 a = stage[w * c4 + threadIdx.x], b = stage[(8 + w) * c4 + threadIdx.x];
+          accg.x += a.x; accg.y += a.y; accg.z += a.z; accg.w += a.w;
+          accb.x += b.x; accb.y += b.y; accb.z += b.z; accb.w += b.w;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  if (params && threadIdx.x < c4) {
+    float* dg = dgamma + threadIdx.x * 4;
+    float* db = dbeta + threadIdx.x * 4;
+    atomicAdd(dg + 0, accg.x); atomicAdd(dg + 1, accg.y); atomicAdd(dg + 2, accg.z); atomicAdd(dg + 3, accg.w);
+    atomicAdd(db + 0, accb.x); atomicAdd(db + 1, accb.y); atomicAdd(db + 2, accb.z); atomicAdd(db + 3, accb.w);
   }
 }
 
@@ -307,7 +340,15 @@ extern "C" int vs_layernorm_backward(const vs_layernorm_bwd_params* p, vs_stream
   VS_CUDA(cudaGetDevice(&dev));
   VS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int grid = std::min(ceil_div(p->rows, 8), 2 * sms);
-  const size_t smem = 2 * sizeof(float) * p->C;
+  const size_t smem = 2 * 8 * sizeof(float) * p->C;   // <= 64 KB
+  static bool configured = false;
+  if (!configured) {
+    VS_CUDA(cudaFuncSetAttribute(layernorm_backward_kernel<float>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    VS_CUDA(cudaFuncSetAttribute(layernorm_backward_kernel<__nv_bfloat16>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    configured = true;
+  }
   cudaStream_t s = to_stream(stream);
   if (p->dy_dtype == VS_F32)
     layernorm_backward_kernel<float><<<grid, 256, smem, s>>>(
