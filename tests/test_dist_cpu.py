@@ -63,3 +63,66 @@ def test_bench_models_match_survey_figures():
     cfg = bench.config_dict(4)
     assert "workload" in cfg and cfg["scenes_per_step_per_gpu"] == 4 and "model" not in cfg
     json.dumps(cfg)
+
+
+# ------------------------------------------------------------------ gradient buckets + reducer (C4's collective)
+def test_grad_bucket_layout():
+    sys.path.insert(0, str(ROOT))
+    from vicasplat_b200.encoder_train import GradBucket
+    shapes = {"b": torch.Size([6]), "g": torch.Size([10]), "w": torch.Size([6, 10])}
+    bk = GradBucket(shapes, ["b", "g"], ["w"], "cpu")
+    assert bk.flat.numel() == 8 + 12 + 60 and bk.n_small == 20          # 16-byte aligned views
+    assert bk.views["w"].shape == (6, 10) and bk.views["w"].data_ptr() == bk.flat[20:].data_ptr()
+    bk.flat.fill_(1.0)
+    bk.zero(weights_too=False)
+    assert bk.views["b"].abs().sum() == 0 and bk.views["g"].abs().sum() == 0 and bk.views["w"].sum() == 60
+    bk.zero()
+    assert bk.flat.abs().sum() == 0
+
+
+def _reduce_worker(rank, world, port, out):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank),
+                      MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    sys.path.insert(0, str(ROOT))
+    from vicasplat_b200.encoder_train import GradBucket, GradReducer
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    shapes = {"b": torch.Size([4]), "w": torch.Size([3, 4])}
+    buckets = [GradBucket(shapes, ["b"], ["w"], "cpu") for _ in range(3)]
+    red = GradReducer()
+    for i in reversed(range(3)):                              # reverse layer order, like the backward pass
+        buckets[i].views["b"].fill_(float(rank + 1) * (i + 1))
+        buckets[i].views["w"].copy_(torch.arange(12.0).view(3, 4) * (rank + 1))
+        red.bucket_ready(buckets[i])
+    red.finish()
+    if rank == 0:
+        out.put(([b.views["b"].tolist() for b in buckets], buckets[1].views["w"].tolist(),
+                 red.world, red.bytes_reduced))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_gradient_buckets_are_averaged():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_reduce_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    bs, w, world, nbytes = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert world == 2 and nbytes == 3 * 16 * 4
+    assert bs == [[1.5 * (i + 1)] * 4 for i in range(3)]                 # mean of rank 1x and 2x
+    assert w == (torch.arange(12.0).view(3, 4) * 1.5).tolist()
+
+
+def test_reducer_is_a_noop_without_a_process_group():
+    sys.path.insert(0, str(ROOT))
+    from vicasplat_b200.encoder_train import GradBucket, GradReducer
+    bk = GradBucket({"b": torch.Size([4])}, ["b"], [], "cpu")
+    bk.flat.fill_(2.0)
+    red = GradReducer()
+    red.bucket_ready(bk)
+    red.finish()
+    assert red.world == 1 and bk.flat.tolist() == [2.0] * 4

@@ -337,3 +337,65 @@ def test_vit_block_forward_backward(cuda, lib):
     _check_grads(g, sd, ["mlp.fc1.weight", "mlp.fc1.bias", "mlp.fc2.weight", "mlp.fc2.bias",
                          "norm2.weight", "norm2.bias", "attn.proj.weight", "attn.proj.bias",
                          "attn.qkv.weight", "attn.qkv.bias", "norm1.weight", "norm1.bias"], 3e-2)
+
+
+# ------------------------------------------------------------------------------------ the ViT encoder (E1-E3)
+@pytest.mark.parametrize("frames,hw,depth", [(2, 64, 2), (3, 256, 2)])
+def test_vit_encoder_trainer_gradients(cuda, lib, frames, hw, depth):
+    """patch embedding + intrinsic token + blocks + enc_norm (backbone_vica.py:450-480,535-541):
+    every parameter gradient against torch.autograd over the oracle's encode_image."""
+    from vicasplat_b200.encoder_train import VitEncoderTrainer
+    cfg = er.EncoderConfig(enc_depth=depth, dec_depth=4)
+    sd = {k: v.to(cuda) for k, v in er.synth_state_dict(cfg, seed=3).items()
+          if k.startswith(("backbone.enc_", "backbone.patch_embed", "backbone.intrinsic_encoder"))}
+    g = torch.Generator().manual_seed(4)
+    for k in sd:                                               # non-trivial biases / LayerNorm parameters
+        if k.endswith("bias"):
+            sd[k] = (0.1 * torch.randn(sd[k].shape, generator=g)).to(cuda)
+        elif "norm" in k:
+            sd[k] = (1 + 0.1 * torch.randn(sd[k].shape, generator=g)).to(cuda)
+    img = (torch.rand((frames, 3, hw, hw), generator=g) * 2 - 1).to(cuda)
+    K = torch.tensor([[0.86, 0, 0.5], [0, 0.86, 0.5], [0, 0, 1.0]]).repeat(frames, 1, 1)
+    K = (K + 0.05 * torch.randn(K.shape, generator=g)).to(cuda)
+    tr = VitEncoderTrainer(sd, cfg, frames, (hw, hw), cuda)
+    out = tr.forward(img, K)
+    d_out = torch.randn(out.shape, generator=g).to(cuda)
+    tr.backward(d_out)
+    for v in sd.values():
+        v.requires_grad_(True)
+    ref, _ = er.encode_image(sd, img, K, cfg)
+    ref.backward(d_out.view_as(ref))
+    assert _rel(out, ref.reshape(out.shape)) < 1e-2
+    worst = {}
+    for name, prm in tr.params.items():
+        worst[name] = _rel(prm.grad, sd[name].grad)
+    bad = {k: v for k, v in worst.items() if not v < 4e-2}
+    assert not bad, bad
+    assert set(tr.params) == set(sd)                           # nothing of E1-E3 is left without a gradient
+
+
+def test_trainer_step_with_fused_adamw(cuda, lib):
+    """forward / backward / FusedAdamW / repack: the loss of a fixed regression target goes down and
+    the re-packed bf16 operands follow the fp32 masters."""
+    from vicasplat_b200.encoder_train import VitEncoderTrainer
+    from vicasplat_b200.optim import FusedAdamW
+    cfg = er.EncoderConfig(enc_depth=2, dec_depth=4)
+    sd = {k: v.to(cuda) for k, v in er.synth_state_dict(cfg, seed=5).items()}
+    g = torch.Generator().manual_seed(6)
+    img = (torch.rand((2, 3, 64, 64), generator=g) * 2 - 1).to(cuda)
+    K = torch.tensor([[0.86, 0, 0.5], [0, 0.86, 0.5], [0, 0, 1.0]]).repeat(2, 1, 1).to(cuda)
+    tr = VitEncoderTrainer(sd, cfg, 2, (64, 64), cuda)
+    opt = FusedAdamW(tr.parameters(), lr=1e-3, betas=(0.9, 0.95), weight_decay=0.05, max_grad_norm=0.5)
+    target = torch.randn((2 * tr.lay.n, cfg.enc_embed_dim), generator=g).to(cuda)
+    losses = []
+    for _ in range(6):
+        out = tr.forward(img, K).float()
+        losses.append(((out - target) ** 2).mean().item())
+        tr.backward(2 * (out - target) / out.numel())
+        opt.step()
+        tr.repack()
+    assert losses[-1] < losses[0]
+    k = "backbone.enc_blocks.1.mlp.fc1.weight"
+    assert torch.equal(tr.w[1]["mlp.fc1"], tr.params[k].detach().to(torch.bfloat16))
+    assert torch.equal(tr.w[1]["mlp.fc1.t"], tr.params[k].detach().to(torch.bfloat16).t())
+    assert not torch.equal(tr.params[k].detach(), sd[k])       # the masters moved
