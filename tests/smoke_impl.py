@@ -42,3 +42,27 @@ def run_smoke():
     e_raw = ((a - b).norm() / b.norm()).item()
     assert e_pose < 2e-2 and e_raw < 3e-2, (e_pose, e_raw)
     print(f"smoke: encoder ok (pose abs err {e_pose:.2e}, Gaussian-parameter rel-L2 {e_raw:.2e})")
+
+    # encoder training path: one ViT block forward + hand-written backward against torch.autograd
+    # over the oracle block (fp32, CPU)
+    from vicasplat_b200 import encoder_grad as eg
+    key = "backbone.enc_blocks.0"
+    bsd = {k: v.clone() for k, v in sd.items() if k.startswith(key + ".")}
+    w = eg.pack_block(bsd, key, dev)
+    gacc = eg.zero_grads(w)
+    lay = eg.FrameLayout.make(2, 4, 4, cfg.enc_num_heads, dev)
+    x = torch.randn((2 * lay.n, cfg.enc_embed_dim), generator=g)
+    dy = torch.randn((2 * lay.n, cfg.enc_embed_dim), generator=g)
+    saved = eg.Saved()
+    eg.block_forward(x.to(dev), w, lay, saved)
+    dx = eg.block_backward(dy.to(dev), w, gacc, lay, saved)
+    for v in bsd.values():
+        v.requires_grad_(True)
+    xr = x.view(2, lay.n, -1).clone().requires_grad_(True)
+    er.enc_block(bsd, key, xr, er.positions(2, 4, 4, True), cfg).backward(dy.view(2, lay.n, -1))
+    torch.cuda.synchronize()
+    rel = lambda a, b: ((a.cpu().float() - b).norm() / b.norm()).item()
+    e_dx = rel(dx, xr.grad.reshape(dx.shape))
+    e_dw = rel(gacc["attn.qkv.weight"], bsd[key + ".attn.qkv.weight"].grad)
+    assert e_dx < 2e-2 and e_dw < 3e-2, (e_dx, e_dw)
+    print(f"smoke: encoder block backward ok (dx rel-L2 {e_dx:.2e}, d qkv.weight rel-L2 {e_dw:.2e})")

@@ -399,3 +399,46 @@ def test_trainer_step_with_fused_adamw(cuda, lib):
     assert torch.equal(tr.w[1]["mlp.fc1"], tr.params[k].detach().to(torch.bfloat16))
     assert torch.equal(tr.w[1]["mlp.fc1.t"], tr.params[k].detach().to(torch.bfloat16).t())
     assert not torch.equal(tr.params[k].detach(), sd[k])       # the masters moved
+
+
+# ------------------------------------------------------------------------------------ drop-in nn.Module
+def test_dropin_block_trains_through_torch_autograd(cuda, lib):
+    """vicasplat_b200.blocks.Block in the place of croco/blocks.py:115-130: ordinary nn.Parameters,
+    gradients through torch.autograd, parity with the oracle block; operand copies follow the
+    parameters after an in-place update."""
+    from functools import partial
+    from torch import nn
+    from vicasplat_b200.blocks import Block
+
+    class Rope:
+        base = 100.0
+
+    cfg = _cfg()
+    sd = _block_sd(cfg, 2, cuda)
+    key = "backbone.enc_blocks.0"
+    blk = Block(cfg.enc_embed_dim, cfg.enc_num_heads, cfg.mlp_ratio, qkv_bias=True,
+                norm_layer=partial(nn.LayerNorm, eps=cfg.ln_eps), rope=Rope()).to(cuda)
+    blk.load_state_dict({k[len(key) + 1:]: v for k, v in sd.items()}, strict=True)
+    Fr, gh = 2, 16
+    pos = er.positions(Fr, gh, gh, True, device=cuda)
+    gen = torch.Generator().manual_seed(31)
+    x = torch.randn((Fr, pos.shape[1], cfg.enc_embed_dim), generator=gen).to(cuda).requires_grad_(True)
+    dout = torch.randn(x.shape, generator=gen).to(cuda)
+    out = blk(x, pos)
+    out.backward(dout)
+    for v in sd.values():
+        v.requires_grad_(True)
+    xr = x.detach().clone().requires_grad_(True)
+    ref = er.enc_block(sd, key, xr, pos, cfg)
+    ref.backward(dout)
+    assert _rel(out, ref) < 5e-3
+    assert _rel(x.grad, xr.grad) < 1.5e-2
+    for name, p in blk.named_parameters():
+        assert _rel(p.grad, sd[f"{key}.{name}"].grad) < 3e-2, name
+    # an optimizer step moves the parameters in place -> the bf16 operand copies are rebuilt
+    before = blk._packed()["mlp.fc1"].clone()
+    with torch.no_grad():
+        blk.mlp.fc1.weight.add_(0.5)
+    out2 = blk(x.detach(), pos)
+    assert not torch.equal(blk._packed()["mlp.fc1"], before)
+    assert not torch.allclose(out2, out.detach())

@@ -94,7 +94,7 @@ def linear_backward(dy_copy, dy_t, x_t, w_t, dW, *, dx_dtype=torch.float32):
 # ------------------------------------------------------------------ MLP half: x + fc2(gelu(fc1(LN2(x))))
 def mlp_half_forward(x, w, saved: Optional[Saved] = None):
     """croco/blocks.py:58-79,128: returns x + mlp(norm2(x)); keeps what the backward pass needs."""
-    h, _ = ops.layernorm(x, w["norm2.weight"], w["norm2.bias"])
+    h, _ = ops.layernorm(x, w["norm2.weight"], w["norm2.bias"], eps=w.get("ln_eps", 1e-6))
     z = ops.gemm(h, w["mlp.fc1"], bias=w["mlp.fc1.bias"], act=VS_ACT_NONE)
     a = ops.gelu_bf16(z)
     out = ops.gemm(a, w["mlp.fc2"], bias=w["mlp.fc2.bias"], res1=x, out_dtype=torch.float32)
@@ -114,14 +114,14 @@ def mlp_half_backward(dout, w, g, saved: Saved):
     _, h_t = ops.grad_prep(s["mlp_h"], want_copy=False)
     dh = linear_backward(dz, dz_t, h_t, w["mlp.fc1.t"], g["mlp.fc1.weight"])
     return ops.layernorm_backward(s["mlp_x"], dh, w["norm2.weight"], dres=dout,
-                                  dgamma=g["norm2.weight"], dbeta=g["norm2.bias"])
+                                  dgamma=g["norm2.weight"], dbeta=g["norm2.bias"], eps=w.get("ln_eps", 1e-6))
 
 
 # ------------------------------------------------------------------ attention half: x + proj(attn(LN1(x)))
 def attn_half_forward(x, w, lay: FrameLayout, saved: Optional[Saved] = None):
     """croco/blocks.py:81-127 with RoPE2D fused into the qkv epilogue."""
     E = x.shape[1]
-    h, _ = ops.layernorm(x, w["norm1.weight"], w["norm1.bias"])
+    h, _ = ops.layernorm(x, w["norm1.weight"], w["norm1.bias"], eps=w.get("ln_eps", 1e-6))
     qkv = ops.gemm(h, w["attn.qkv"], bias=w["attn.qkv.bias"],
                    rope=(lay.pos, 0, E, lay.heads, lay.rope_base, 30.0))
     o = torch.empty((x.shape[0], E), dtype=torch.bfloat16, device=x.device)
@@ -152,7 +152,7 @@ def attn_half_backward(dout, w, g, lay: FrameLayout, saved: Saved):
     _, h_t = ops.grad_prep(s["att_h"], want_copy=False)
     dh = linear_backward(dqkv, dqkv_t, h_t, w["attn.qkv.t"], g["attn.qkv.weight"])
     return ops.layernorm_backward(s["att_x"], dh, w["norm1.weight"], dres=dout,
-                                  dgamma=g["norm1.weight"], dbeta=g["norm1.bias"])
+                                  dgamma=g["norm1.weight"], dbeta=g["norm1.bias"], eps=w.get("ln_eps", 1e-6))
 
 
 # ------------------------------------------------------------------ whole block
