@@ -76,6 +76,10 @@ int vs_rope_rows(void* qkv, int64_t ld, int rows, int H, int q_col, int k_col, c
  *   dense NHWC element strides of the input view -- overlapping views are allowed (stride_x <
  *   cin turns cin into a sliding window over pixels: the 7x7 stem of dpt_gs_head.py:113-118 is run
  *   as kh = 7, kw = 1 over windows of 8 pixels x 8 padded channels).
+ * a_mode 2 (tn): both operands are given K-row-wise ("MN-major"): A is (K, a_rows) with row stride
+ *   a_row_stride, W is (K, N) with row stride w_row_stride, C[m, n] = sum_k A[k, m] * W[k, n].  This is
+ *   the weight-gradient form dW = dY^T X with dY (tokens, N_out) and X (tokens, K_in) used as they
+ *   are stored -- no transposed copies (the tensor core reads MN-major shared-memory tiles).
  *   res_up2 != 0: res1 is an NHWC bf16 map at HALF resolution [cn, ch/2, cw/2, N] that is
  *   bilinearly upsampled x2 (align_corners=True, dpt_block.py:214-216) on the fly.
  * Output row mapping: out_row = (m / out_gin) * out_gout + out_off + (m % out_gin).

@@ -117,6 +117,36 @@ def test_rope_rows_backward_is_the_transpose(cuda, lib):
     assert _rel(Rtb[:, :E], ref) < 6e-3
 
 
+# ------------------------------------------------------------------------------------ wgrad-form GEMM
+@pytest.mark.parametrize("K,rows,N", [(64, 64, 64), (300, 200, 132), (2056, 1024, 1024), (514, 3072, 1024),
+                                      (2056, 1024, 4096), (1000, 4096, 1024), (257, 128, 83), (72, 520, 8)])
+@pytest.mark.parametrize("block_n", [0, 64])
+def test_gemm_tn_mn_major_operands(cuda, lib, K, rows, N, block_n):
+    """a_mode 2: C = A^T W with A (K, rows), W (K, N) used as stored (MN-major shared-memory tiles)."""
+    from vicasplat_b200 import ops
+    g = torch.Generator().manual_seed(K + rows + N)
+    # row strides must be multiples of 8 elements (TMA): odd widths are column slices of padded storage
+    A = _bf(torch.randn((K, (rows + 7) // 8 * 8), generator=g)).to(cuda)[:, :rows]
+    W = _bf(torch.randn((K, (N + 7) // 8 * 8), generator=g) / math.sqrt(K)).to(cuda)[:, :N]
+    ref = A.float().t() @ W.float()
+    out = ops.gemm(A, W, tn=True, out_dtype=torch.float32, block_n=block_n)
+    assert out.shape == (rows, N)
+    assert _rel(out, ref) < 2e-5
+    acc = torch.full((rows, N), 0.5, device=cuda)              # accumulate in place (the wgrad use)
+    ops.gemm(A, W, tn=True, out=acc, res1=acc, block_n=block_n)
+    assert _rel(acc - 0.5, ref) < 2e-5
+
+
+def test_gemm_tn_strided_views(cuda, lib):
+    from vicasplat_b200 import ops
+    g = torch.Generator().manual_seed(77)
+    bigA = _bf(torch.randn((700, 3 * 256), generator=g)).to(cuda)
+    bigW = _bf(torch.randn((700, 512), generator=g)).to(cuda)
+    A, W = bigA[:, 256:512], bigW[:, 128:328]                   # column slices: row strides 768 / 512
+    out = ops.gemm(A, W, tn=True, out_dtype=torch.float32)
+    assert _rel(out, A.float().t() @ W.float()) < 2e-5
+
+
 # ------------------------------------------------------------------------------------ linear layer
 @pytest.mark.parametrize("M,K,N", [(2056, 1024, 3072), (514, 768, 768), (2056, 4096, 1024), (300, 128, 64)])
 def test_linear_backward(cuda, lib, M, K, N):
@@ -127,9 +157,8 @@ def test_linear_backward(cuda, lib, M, K, N):
     dy32 = torch.randn((M, N), generator=g).to(cuda)
     db = torch.zeros((N,), device=cuda)
     dW = torch.full((N, K), 0.25, device=cuda)               # accumulated in place
-    dy, dy_t = ops.grad_prep(dy32, colsum=db)
-    _, x_t = ops.grad_prep(x, want_copy=False)
-    dx = eg.linear_backward(dy, dy_t, x_t, W.t().contiguous(), dW)
+    dy, _ = ops.grad_prep(dy32, want_t=False, colsum=db)
+    dx = eg.linear_backward(dy, x, W.t().contiguous(), dW)
     dyf = dy.float()                                          # the operands the GEMMs really see
     assert _rel(dx, dyf @ W.float()) < 2e-5
     assert _rel(dW - 0.25, dyf.t() @ x.float()) < 2e-5

@@ -51,6 +51,7 @@ enum : int {  // vector-access flags, decided on the host from pointer / stride 
 
 struct GemmDev {
   int mode;
+  int tn;   // rows mode with both operands stored [k][mn] (MN-major): the wgrad form
   int N;
   int num_kb;
   int m_tiles, n_tiles;
@@ -501,7 +502,27 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
           mbar_wait(&empty[s], ph ^ 1);
           uint8_t* sA = smem + s * STAGE_BYTES;
           uint8_t* sB = sA + A_BYTES;
-          if (CL == 1) {
+          if (g.tn) {
+            // MN-major operands: one [64 k-rows][64 mn] box (8 KB) per 64-wide block of the tile
+            if (CL == 1) {
+              mbar_expect_tx(&full[s], STAGE_BYTES);
+#pragma unroll
+              for (int i = 0; i < BM / 64; ++i)
+                tma_load_2d(sA + i * 8192, &tmA, &full[s], tc.r0 + i * 64, kb * BK);
+#pragma unroll
+              for (int i = 0; i < BN / 64; ++i)
+                tma_load_2d(sB + i * 8192, &tmW, &full[s], tc.n0 + i * 64, kb * BK);
+            } else {
+              if (rank == 0) mbar_expect_tx(&full[s], 2 * STAGE_BYTES);
+#pragma unroll
+              for (int i = 0; i < BM / 64; ++i)
+                tma_load_2d_pair(sA + i * 8192, &tmA, &full[s], tc.r0 + i * 64, kb * BK);
+#pragma unroll
+              for (int i = 0; i < (BN / CL) / 64; ++i)
+                tma_load_2d_pair(sB + i * 8192, &tmW, &full[s], tc.n0 + rank * (BN / CL) + i * 64,
+                                 kb * BK);
+            }
+          } else if (CL == 1) {
             mbar_expect_tx(&full[s], STAGE_BYTES);
             if (g.mode == 0) {
               tma_load_3d(sA, &tmA, &full[s], kb * BK, tc.r0, tc.grp);
@@ -533,6 +554,7 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
     // ------------------------------------------------------------ MMA issuer (pair: leader only)
     if (lane == 0 && rank == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(BM * CL, BN);
+      constexpr uint32_t idesc_tn = umma_idesc_bf16(BM * CL, BN, 1, 1);
       uint32_t it = 0, ti = 0;
       for (int u = unit0; u < total_units; u += unit_step, ++ti) {
         const uint32_t a = ti & 1;
@@ -546,6 +568,15 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
           const uint32_t b_addr = a_addr + A_BYTES;
+          if (g.tn) {
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) {   // 16 k-rows of 128 B per step
+              const uint64_t da = umma_desc_mn_sw128_lbo(a_addr + k * 2048, 8192);
+              const uint64_t db = umma_desc_mn_sw128_lbo(b_addr + k * 2048, 8192);
+              if (CL == 1) umma_bf16_ss(d_tmem, da, db, idesc_tn, (kb | k) != 0 ? 1u : 0u);
+              else umma_bf16_ss_pair(d_tmem, da, db, idesc_tn, (kb | k) != 0 ? 1u : 0u);
+            }
+          } else {
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             if (CL == 1)
@@ -554,6 +585,7 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
             else
               umma_bf16_ss_pair(d_tmem, umma_desc_k_sw128(a_addr + k * 32),
                                 umma_desc_k_sw128(b_addr + k * 32), idesc, (kb | k) != 0 ? 1u : 0u);
+          }
           }
           // slot reusable (in both CTAs of a pair) once these MMAs have read it
           if (CL == 1) umma_commit(&empty[s]);
@@ -877,7 +909,7 @@ extern "C" int vs_gemm(const vs_gemm_params* p, vs_stream_t stream_) {
   cudaStream_t stream = to_stream(stream_);
 
   GemmDev g{};
-  g.mode = p->a_mode;
+  g.mode = p->a_mode == 2 ? 0 : p->a_mode;   // a_mode 2 = rows mode with MN-major operands (g.tn)
   g.N = p->N;
   g.bias = p->bias;
   g.act = p->act;
@@ -997,6 +1029,25 @@ extern "C" int vs_gemm(const vs_gemm_params* p, vs_stream_t stream_) {
                          static_cast<cuuint32_t>(bn)};
     int rc = encode_map(&tmA, p->A, 4, dims, str, box);
     if (rc) return rc;
+  } else if (p->a_mode == 2) {
+    // both operands given as [K][mn] row matrices (MN-major): C[m, n] = sum_k A[k, m] * W[k, n]
+    VS_REQUIRE(p->a_rows > 0 && p->K > 0, "vs_gemm: empty problem");
+    VS_REQUIRE(p->a_groups <= 1, "vs_gemm: a_mode 2 has no row groups");
+    VS_REQUIRE(p->a_row_stride % 8 == 0 && p->a_row_stride >= p->a_rows,
+               "vs_gemm: a_mode 2: a_row_stride (the stride between k-rows of A) must be a multiple of 8");
+    VS_REQUIRE(p->w_row_stride >= p->N, "vs_gemm: a_mode 2: w_row_stride is the stride between k-rows of W");
+    VS_REQUIRE(p->rope_pos == nullptr && p->out_gin == 0, "vs_gemm: a_mode 2 goes with a plain output mapping");
+    g.tn = 1;
+    g.a_rows = p->a_rows;
+    g.a_groups = 1;
+    g.tiles_per_group = ceil_div(p->a_rows, BM);
+    m_tiles = g.tiles_per_group;
+    ktot = p->K;
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(p->a_rows), static_cast<cuuint64_t>(p->K)};
+    cuuint64_t str[1] = {static_cast<cuuint64_t>(p->a_row_stride) * 2};
+    cuuint32_t box[2] = {64, BK};
+    int rc = encode_map(&tmA, p->A, 2, dims, str, box);
+    if (rc) return rc;
   } else {
     set_error("vs_gemm: unknown a_mode %d", p->a_mode);
     return VS_ERR_INVALID;
@@ -1019,7 +1070,13 @@ extern "C" int vs_gemm(const vs_gemm_params* p, vs_stream_t stream_) {
   g.n_tiles = ceil_div(p->N, bn);
   // vertically adjacent tiles are computed by a CTA pair that splits the W tile (see header)
   const int cl = (bn >= 128 && m_tiles >= 2) ? 2 : 1;
-  {
+  if (g.tn) {
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(p->N), static_cast<cuuint64_t>(ktot)};
+    cuuint64_t str[1] = {static_cast<cuuint64_t>(p->w_row_stride) * 2};
+    cuuint32_t box[2] = {64, BK};
+    int rc = encode_map(&tmW, p->W, 2, dims, str, box);
+    if (rc) return rc;
+  } else {
     cuuint64_t dims[2] = {static_cast<cuuint64_t>(ktot), static_cast<cuuint64_t>(p->N)};
     cuuint64_t str[1] = {static_cast<cuuint64_t>(p->w_row_stride) * 2};
     cuuint32_t box[2] = {BK, static_cast<cuuint32_t>(bn / cl)};

@@ -275,9 +275,21 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(2) << 61;
   return d;
 }
+// MN-major operand wider than one 64-element swizzle atom: the 64-wide MN blocks ([k rows][128 B],
+// each as above) lie `lbo_bytes` apart (canonical ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units).
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128_lbo(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
 // kind::f16 instruction descriptor: bf16 x bf16 -> fp32; b_mn != 0 selects an MN-major B operand
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, int b_mn = 0) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(b_mn ? 1 : 0) << 16) |
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, int b_mn = 0, int a_mn = 0) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(a_mn ? 1 : 0) << 15) |
+         (static_cast<uint32_t>(b_mn ? 1 : 0) << 16) |
          (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
 }
 

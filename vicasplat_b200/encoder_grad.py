@@ -8,9 +8,10 @@ Numerics follow the forward path: bf16 GEMM operands (activations, weights AND g
 accumulation, fp32 residual-stream gradient, fp32 weight gradients accumulated in place.
 
 Per linear layer y = x W^T + b (W is (N, K)):
-    dgrad   dx  = dy W          vs_gemm(A = dy  (M, N),  W = W^T (K, N))
-    wgrad   dW += dy^T x        vs_gemm(A = dy^T (N, M), W = x^T (K, M), C = res1 = dW)
-    bias    db += colsum(dy)    a by-product of the pass that makes the bf16 copies of dy
+    dgrad   dx  = dy W          vs_gemm(A = dy (M, N), W = W^T (K, N))
+    wgrad   dW += dy^T x        vs_gemm a_mode 2: dy (M, N) and x (M, K) as they are stored -- the tensor
+                                core reads MN-major shared-memory tiles, there are no transposed copies
+    bias    db += colsum(dy)    a by-product of the pass that makes the bf16 copy of dy
 """
 from __future__ import annotations
 
@@ -84,11 +85,12 @@ class Saved:
 
 
 # ------------------------------------------------------------------ linear layer pieces
-def linear_backward(dy_copy, dy_t, x_t, w_t, dW, *, dx_dtype=torch.float32):
-    """dgrad + wgrad of one linear layer from prepared operands (see module docstring).
-    dy_copy (M, N) bf16, dy_t (N, M) bf16 view, x_t (K, M) bf16 view, w_t (K, N) bf16, dW (N, K) fp32."""
-    ops.gemm(dy_t, x_t, out=dW, res1=dW)                       # dW += dy^T x
-    return ops.gemm(dy_copy, w_t, out_dtype=dx_dtype)          # dx = dy W
+def linear_backward(dy, x, w_t, dW, *, dx_dtype=torch.float32):
+    """dgrad + wgrad of one linear layer (see module docstring).
+    dy (M, N) bf16, x (M, K) bf16 (the layer's input as saved by the forward pass), w_t (K, N) bf16,
+    dW (N, K) fp32 accumulated in place."""
+    ops.gemm(dy, x, tn=True, out=dW, res1=dW)                  # dW += dy^T x
+    return ops.gemm(dy, w_t, out_dtype=dx_dtype)               # dx = dy W
 
 
 # ------------------------------------------------------------------ MLP half: x + fc2(gelu(fc1(LN2(x))))
@@ -107,12 +109,10 @@ def mlp_half_backward(dout, w, g, saved: Saved):
     """dout: fp32 gradient of the block output (M, E).  Returns the fp32 gradient of the half's input
     and accumulates the parameter gradients into `g`."""
     s = saved.t
-    dy, dy_t = ops.grad_prep(dout, colsum=g["mlp.fc2.bias"])
-    _, a_t = ops.grad_prep(s["mlp_a"], want_copy=False)
-    da = linear_backward(dy, dy_t, a_t, w["mlp.fc2.t"], g["mlp.fc2.weight"], dx_dtype=torch.bfloat16)
-    dz, dz_t = ops.grad_prep(da, z=s["mlp_z"], colsum=g["mlp.fc1.bias"])     # da * gelu'(z)
-    _, h_t = ops.grad_prep(s["mlp_h"], want_copy=False)
-    dh = linear_backward(dz, dz_t, h_t, w["mlp.fc1.t"], g["mlp.fc1.weight"])
+    dy, _ = ops.grad_prep(dout, want_t=False, colsum=g["mlp.fc2.bias"])
+    da = linear_backward(dy, s["mlp_a"], w["mlp.fc2.t"], g["mlp.fc2.weight"], dx_dtype=torch.bfloat16)
+    dz, _ = ops.grad_prep(da, z=s["mlp_z"], want_t=False, colsum=g["mlp.fc1.bias"])   # da * gelu'(z)
+    dh = linear_backward(dz, s["mlp_h"], w["mlp.fc1.t"], g["mlp.fc1.weight"])
     return ops.layernorm_backward(s["mlp_x"], dh, w["norm2.weight"], dres=dout,
                                   dgamma=g["norm2.weight"], dbeta=g["norm2.bias"], eps=w.get("ln_eps", 1e-6))
 
@@ -138,9 +138,8 @@ def attn_half_forward(x, w, lay: FrameLayout, saved: Optional[Saved] = None):
 def attn_half_backward(dout, w, g, lay: FrameLayout, saved: Saved):
     s = saved.t
     E = dout.shape[1]
-    dy, dy_t = ops.grad_prep(dout, colsum=g["attn.proj.bias"])
-    _, o_t = ops.grad_prep(s["att_o"], want_copy=False)
-    do = linear_backward(dy, dy_t, o_t, w["attn.proj.t"], g["attn.proj.weight"], dx_dtype=torch.bfloat16)
+    dy, _ = ops.grad_prep(dout, want_t=False, colsum=g["attn.proj.bias"])
+    do = linear_backward(dy, s["att_o"], w["attn.proj.t"], g["attn.proj.weight"], dx_dtype=torch.bfloat16)
     qkv = s["att_qkv"]
     dqkv = torch.empty_like(qkv)
     ops.attention_backward(qkv[:, :E], qkv[:, E:2 * E], qkv[:, 2 * E:], s["att_o"], do, s["att_lse"],
@@ -148,9 +147,8 @@ def attn_half_backward(dout, w, g, lay: FrameLayout, saved: Saved):
                            q_start=lay.start, q_len=lay.length, kv_start0=lay.start,
                            kv_len0=lay.length, max_q_len=lay.n, max_kv_len=lay.n, scale=0.125)
     ops.rope_rows_backward(dqkv, lay.pos, heads=lay.heads, q_col=0, k_col=E, base=lay.rope_base)
-    _, dqkv_t = ops.grad_prep(dqkv, want_copy=False, colsum=g["attn.qkv.bias"])
-    _, h_t = ops.grad_prep(s["att_h"], want_copy=False)
-    dh = linear_backward(dqkv, dqkv_t, h_t, w["attn.qkv.t"], g["attn.qkv.weight"])
+    ops.grad_prep(dqkv, want_copy=False, want_t=False, colsum=g["attn.qkv.bias"])     # bias gradient only
+    dh = linear_backward(dqkv, s["att_h"], w["attn.qkv.t"], g["attn.qkv.weight"])
     return ops.layernorm_backward(s["att_x"], dh, w["norm1.weight"], dres=dout,
                                   dgamma=g["norm1.weight"], dbeta=g["norm1.bias"], eps=w.get("ln_eps", 1e-6))
 

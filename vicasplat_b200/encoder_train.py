@@ -103,7 +103,7 @@ class VitEncoderTrainer:
                                       list(_STEM_SMALL), list(_STEM_BIG), device)
         for n, v in self.stem_bucket.views.items():
             self.params[n].grad = v
-        self._dw_intr = torch.zeros((self.E, 12), dtype=torch.float32, device=device)
+        self._dw_intr = torch.zeros((self.E, 16), dtype=torch.float32, device=device)
         self._colsum_all = torch.zeros((self.E,), dtype=torch.float32, device=device)
         self.w: List[Dict[str, torch.Tensor]] = [dict() for _ in range(self.depth)]
         self.repack()
@@ -175,18 +175,16 @@ class VitEncoderTrainer:
         # intrinsic rows are zero rows of the padded im2col matrix.  Intrinsic token (Linear 9 -> E,
         # backbone_vica.py:535-536): the strided rows frame * n + Np.
         self._colsum_all.zero_()
-        _, dy_t = ops.grad_prep(dx, want_copy=False, colsum=self._colsum_all)
+        dy, _ = ops.grad_prep(dx, want_t=False, colsum=self._colsum_all)
         cols_full = torch.zeros((Fr, N, s["cols"].shape[1]), dtype=torch.bfloat16, device=self.dev)
         cols_full[:, :Np] = s["cols"].view(Fr, Np, -1)
-        _, cols_t = ops.grad_prep(cols_full.view(M, -1), want_copy=False)
         dWp = sg["backbone.patch_embed.proj.weight"].view(E, -1)
-        ops.gemm(dy_t, cols_t, out=dWp, res1=dWp)
+        ops.gemm(dy, cols_full.view(M, -1), tn=True, out=dWp, res1=dWp)
         d_intr = dx.view(Fr, N * E)[:, Np * E:]                     # (Fr, E) view, row stride N * E
-        _, di_t = ops.grad_prep(d_intr, want_copy=False, colsum=sg["backbone.intrinsic_encoder.bias"])
-        K12 = torch.zeros((Fr, 12), dtype=torch.float32, device=self.dev)
-        K12[:, :9] = s["K9"]
-        _, k_t = ops.grad_prep(K12, want_copy=False)
-        ops.gemm(di_t, k_t, out=self._dw_intr, out_dtype=torch.float32)
+        di, _ = ops.grad_prep(d_intr, want_t=False, colsum=sg["backbone.intrinsic_encoder.bias"])
+        K16 = torch.zeros((Fr, 16), dtype=torch.bfloat16, device=self.dev)
+        K16[:, :9] = s["K9"]
+        ops.gemm(di, K16, tn=True, out=self._dw_intr)
         sg["backbone.intrinsic_encoder.weight"].copy_(self._dw_intr[:, :9])
         torch.sub(self._colsum_all, sg["backbone.intrinsic_encoder.bias"],
                   out=sg["backbone.patch_embed.proj.bias"])

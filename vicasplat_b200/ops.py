@@ -52,20 +52,28 @@ def gemm(A, W, *, N=None, K=None, a_rows=None, a_groups=1, a_row_stride=None, a_
          bias=None, act=VS_ACT_NONE, gate=None, gate_rows=0, first_row_mode=0, res1=None,
          res2=None, out=None, out_dtype=torch.bfloat16, ldc=None, out2=None, ldc2=None,
          out_gin=0, out_gout=0, out_off=0, out_rows=None, block_n=0, w_row_stride=None,
-         rope=None):
+         rope=None, tn=False):
     """C = epilogue(A @ W^T): rows mode of vs_gemm.  A bf16 (rows, K) [or strided groups], W bf16 (N, K).
     rope = (pos_i32 (out_rows, 2), q_col, k_col, heads, base, cam_theta): rotary embedding of the
     q / k columns applied in the epilogue (see vs_gemm_params.rope_pos)."""
     _need_cuda(A, W)
     lib = _lib.load()
     p = GemmParams()
-    K = K if K is not None else A.shape[-1]
-    N = N if N is not None else W.shape[0]
-    rows = a_rows if a_rows is not None else A.numel() // A.shape[-1]
-    p.A, p.a_mode, p.a_rows, p.a_groups = ptr(A), 0, rows, a_groups
-    p.a_row_stride = a_row_stride if a_row_stride is not None else A.stride(-2)
-    p.a_group_stride = a_group_stride
-    p.W, p.w_row_stride, p.N, p.K = ptr(W), (w_row_stride or W.stride(0)), N, K
+    if tn:
+        # a_mode 2: A (K, rows), W (K, N) as stored -> C (rows, N) = A^T W  (the wgrad form)
+        assert A.dim() == 2 and W.dim() == 2 and A.shape[0] == W.shape[0] and a_groups == 1
+        K, rows, N = A.shape[0], A.shape[1], W.shape[1]
+        p.A, p.a_mode, p.a_rows, p.a_groups = ptr(A), 2, rows, 1
+        p.a_row_stride = A.stride(0)
+        p.W, p.w_row_stride, p.N, p.K = ptr(W), W.stride(0), N, K
+    else:
+        K = K if K is not None else A.shape[-1]
+        N = N if N is not None else W.shape[0]
+        rows = a_rows if a_rows is not None else A.numel() // A.shape[-1]
+        p.A, p.a_mode, p.a_rows, p.a_groups = ptr(A), 0, rows, a_groups
+        p.a_row_stride = a_row_stride if a_row_stride is not None else A.stride(-2)
+        p.a_group_stride = a_group_stride
+        p.W, p.w_row_stride, p.N, p.K = ptr(W), (w_row_stride or W.stride(0)), N, K
     _fill_epilogue(p, bias, act, gate, gate_rows, first_row_mode, res1, res2)
     total = rows * a_groups
     if out is None:
