@@ -190,8 +190,17 @@ __global__ void __launch_bounds__(BWD_THREADS, 2)
     const float Dr = row_valid ? a.delta[static_cast<long long>(grow) * a.heads + head] : 0.f;
     const int sw = r & 7;
     uint8_t* ds_row = sdS + r * 128;
+    // a warp whose 32 query rows all lie beyond the item (the 257-th token leaves 127 such rows in the
+    // third tile) only keeps the barriers going: its dS rows feed nothing but its own unused dQ rows
+    const bool warp_active = __any_sync(0xffffffffu, row_valid);
 
     for (int j = 0; j < nt; ++j) {
+      if (!warp_active) {
+        mbar_wait(s_full, j & 1);
+        mbar_arrive(s_free);
+        mbar_arrive(ds_full);
+        continue;
+      }
       const int row0 = j < n0 ? s0 + j * KT : s1 + (j - n0) * KT;
       const int seg_left = j < n0 ? l0 - j * KT : l1 - (j - n0) * KT;
       const int nvalid = row_valid ? min(min(seg_left, KT), lim - row0) : 0;
@@ -383,6 +392,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 2)
     const int sw = r & 7;
     uint8_t* p_row = sP + r * 128;
     uint8_t* ds_row = sdS + r * 128;
+    const bool warp_active = __any_sync(0xffffffffu, key_valid);   // see the dQ kernel
 
     for (int j = 0; j < nq; ++j) {
       // per-query statistics of this 64-query tile -> shared memory (double buffered by tile parity)
@@ -402,6 +412,12 @@ __global__ void __launch_bounds__(BWD_THREADS, 2)
         }
       }
       bar_sync_softmax();
+      if (!warp_active) {
+        mbar_wait(s_full, j & 1);
+        mbar_arrive(s_free);
+        mbar_arrive(p_full);
+        continue;
+      }
       const float* Lb = sL + (j & 1) * 64;
       const float* Db = sD + (j & 1) * 64;
       const int* limb = sLim + (j & 1) * 64;

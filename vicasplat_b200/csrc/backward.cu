@@ -165,10 +165,10 @@ __global__ void gelu_kernel(const bf16* __restrict__ z, long long ld_z, bf16* __
 // row, the row in registers (C = k * 128 <= 1024), statistics recomputed from x:
 //   g = dy * gamma;  dx = rstd * (g - mean(g) - xhat * mean(g * xhat))  (+ dres, the gradient that
 // reaches x through the residual connection).
-// d gamma / d beta: the 8 warps of a CTA stage their rows' (dy * xhat, dy) in shared memory, thread t
-// then folds the 8 rows of columns 4t..4t+3 into its own registers (no atomics inside the CTA, and
-// only 8 accumulator registers per thread so that two CTAs fit on an SM); one global atomicAdd per
-// column and CTA at the end.
+// d gamma / d beta: every warp keeps a PRIVATE fp32 accumulator row pair in shared memory (8 warps x
+// 2 x C floats = 64 KB at C = 1024) and adds its row's (dy * xhat, dy) with conflict-free float4
+// read-modify-writes -- no barrier and no atomics inside the row loop, 128 registers so that two CTAs
+// fit on an SM; the 8 accumulators are folded once at the end, one global atomicAdd per column and CTA.
 template <typename T>
 __global__ void __launch_bounds__(256, 2)
 layernorm_backward_kernel(const float* __restrict__ x, long long ldx, const T* __restrict__ dy,
@@ -176,103 +176,100 @@ layernorm_backward_kernel(const float* __restrict__ x, long long ldx, const T* _
                           const float* dres, long long ldres, float* dx,  // may alias
                           long long lddx, float* __restrict__ dgamma, float* __restrict__ dbeta,
                           int rows, int C, float eps) {
-  extern __shared__ float4 stage[];  // [2][8][C / 4]
+  extern __shared__ float4 stage[];  // [8 warps][2][C / 4]
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int nv = C / 128;
   const int c4 = C / 4;
   const bool params = dgamma != nullptr;
-  float4 accg = make_float4(0.f, 0.f, 0.f, 0.f), accb = accg;
-  const float inv_c = 1.0f / C;
-  for (int base = blockIdx.x * 8; base < rows; base += gridDim.x * 8) {   // uniform for the CTA
-    const int row = base + warp;
-    const bool valid = row < rows;
-    if (valid) {
-      const float* xr = x + static_cast<long long>(row) * ldx;
-      const T* dyr = dy + static_cast<long long>(row) * ldy;
-      float4 v[8], g[8];
-      float s = 0.f;
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-        if (i < nv) {
-          v[i] = load4(xr + (i * 32 + lane) * 4);
-          g[i] = load4(dyr + (i * 32 + lane) * 4);
-          s += v[i].x + v[i].y + v[i].z + v[i].w;
-        }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      const float mean = s * inv_c;
-      float q = 0.f;
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-        if (i < nv) {
-          v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
-          q += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
-        }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-      const float rstd = rsqrtf(q * inv_c + eps);
-      float sg = 0.f, sgx = 0.f;
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-        if (i < nv) {
-          const float4 w = load4(gamma + (i * 32 + lane) * 4);
-          v[i].x *= rstd; v[i].y *= rstd; v[i].z *= rstd; v[i].w *= rstd;  // xhat
-          if (params) {
-            stage[warp * c4 + i * 32 + lane] =
-                make_float4(g[i].x * v[i].x, g[i].y * v[i].y, g[i].z * v[i].z, g[i].w * v[i].w);
-            stage[(8 + warp) * c4 + i * 32 + lane] = g[i];
-          }
-          g[i].x *= w.x; g[i].y *= w.y; g[i].z *= w.z; g[i].w *= w.w;
-          sg += g[i].x + g[i].y + g[i].z + g[i].w;
-          sgx += g[i].x * v[i].x + g[i].y * v[i].y + g[i].z * v[i].z + g[i].w * v[i].w;
-        }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        sg += __shfl_xor_sync(0xffffffffu, sg, o);
-        sgx += __shfl_xor_sync(0xffffffffu, sgx, o);
-      }
-      const float mg = sg * inv_c, mgx = sgx * inv_c;
-      float* dxr = dx + static_cast<long long>(row) * lddx;
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-        if (i < nv) {
-          float4 o;
-          o.x = rstd * (g[i].x - mg - v[i].x * mgx);
-          o.y = rstd * (g[i].y - mg - v[i].y * mgx);
-          o.z = rstd * (g[i].z - mg - v[i].z * mgx);
-          o.w = rstd * (g[i].w - mg - v[i].w * mgx);
-          if (dres != nullptr) {
-            const float4 r = load4(dres + static_cast<long long>(row) * ldres + (i * 32 + lane) * 4);
-            o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
-          }
-          *reinterpret_cast<float4*>(dxr + (i * 32 + lane) * 4) = o;
-        }
-    } else if (params) {
-      const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int i = lane; i < c4; i += 32) {
-        stage[warp * c4 + i] = zero;
-        stage[(8 + warp) * c4 + i] = zero;
-      }
-    }
-    if (params) {
-      __syncthreads();
-      if (threadIdx.x < c4) {
-#pragma unroll
-        for (int w = 0; w < 8; ++w) {
-          const float4 a = stage[w * c4 + threadIdx.x], b = stage[(8 + w) * c4 + threadIdx.x];
-          accg.x += a.x; accg.y += a.y; accg.z += a.z; accg.w += a.w;
-          accb.x += b.x; accb.y += b.y; accb.z += b.z; accb.w += b.w;
-        }
-      }
-      __syncthreads();
-    }
+  float4* mine_g = stage + (2 * warp) * c4;
+  float4* mine_b = mine_g + c4;
+  if (params) {
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = lane; i < c4; i += 32) { mine_g[i] = zero; mine_b[i] = zero; }
+    __syncwarp();
   }
-  if (params && threadIdx.x < c4) {
-    float* dg = dgamma + threadIdx.x * 4;
-    float* db = dbeta + threadIdx.x * 4;
-    atomicAdd(dg + 0, accg.x); atomicAdd(dg + 1, accg.y); atomicAdd(dg + 2, accg.z); atomicAdd(dg + 3, accg.w);
-    atomicAdd(db + 0, accb.x); atomicAdd(db + 1, accb.y); atomicAdd(db + 2, accb.z); atomicAdd(db + 3, accb.w);
+  const float inv_c = 1.0f / C;
+  for (int row = blockIdx.x * 8 + warp; row < rows; row += gridDim.x * 8) {
+    const float* xr = x + static_cast<long long>(row) * ldx;
+    const T* dyr = dy + static_cast<long long>(row) * ldy;
+    float4 v[8], g[8];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (i < nv) {
+        v[i] = load4(xr + (i * 32 + lane) * 4);
+        g[i] = load4(dyr + (i * 32 + lane) * 4);
+        s += v[i].x + v[i].y + v[i].z + v[i].w;
+      }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s * inv_c;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (i < nv) {
+        v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+        q += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
+      }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q * inv_c + eps);
+    float sg = 0.f, sgx = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (i < nv) {
+        const int idx = i * 32 + lane;
+        const float4 w = load4(gamma + idx * 4);
+        v[i].x *= rstd; v[i].y *= rstd; v[i].z *= rstd; v[i].w *= rstd;  // xhat
+        if (params) {
+          float4 a = mine_g[idx], b = mine_b[idx];
+          a.x += g[i].x * v[i].x; a.y += g[i].y * v[i].y; a.z += g[i].z * v[i].z; a.w += g[i].w * v[i].w;
+          b.x += g[i].x; b.y += g[i].y; b.z += g[i].z; b.w += g[i].w;
+          mine_g[idx] = a;
+          mine_b[idx] = b;
+        }
+        g[i].x *= w.x; g[i].y *= w.y; g[i].z *= w.z; g[i].w *= w.w;
+        sg += g[i].x + g[i].y + g[i].z + g[i].w;
+        sgx += g[i].x * v[i].x + g[i].y * v[i].y + g[i].z * v[i].z + g[i].w * v[i].w;
+      }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      sg += __shfl_xor_sync(0xffffffffu, sg, o);
+      sgx += __shfl_xor_sync(0xffffffffu, sgx, o);
+    }
+    const float mg = sg * inv_c, mgx = sgx * inv_c;
+    float* dxr = dx + static_cast<long long>(row) * lddx;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (i < nv) {
+        float4 o;
+        o.x = rstd * (g[i].x - mg - v[i].x * mgx);
+        o.y = rstd * (g[i].y - mg - v[i].y * mgx);
+        o.z = rstd * (g[i].z - mg - v[i].z * mgx);
+        o.w = rstd * (g[i].w - mg - v[i].w * mgx);
+        if (dres != nullptr) {
+          const float4 r = load4(dres + static_cast<long long>(row) * ldres + (i * 32 + lane) * 4);
+          o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+        }
+        *reinterpret_cast<float4*>(dxr + (i * 32 + lane) * 4) = o;
+      }
+  }
+  if (params) {
+    __syncthreads();
+    if (threadIdx.x < c4) {
+      float4 accg = make_float4(0.f, 0.f, 0.f, 0.f), accb = accg;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) {
+        const float4 a = stage[(2 * w) * c4 + threadIdx.x], b = stage[(2 * w + 1) * c4 + threadIdx.x];
+        accg.x += a.x; accg.y += a.y; accg.z += a.z; accg.w += a.w;
+        accb.x += b.x; accb.y += b.y; accb.z += b.z; accb.w += b.w;
+      }
+      float* dg = dgamma + threadIdx.x * 4;
+      float* db = dbeta + threadIdx.x * 4;
+      atomicAdd(dg + 0, accg.x); atomicAdd(dg + 1, accg.y); atomicAdd(dg + 2, accg.z); atomicAdd(dg + 3, accg.w);
+      atomicAdd(db + 0, accb.x); atomicAdd(db + 1, accb.y); atomicAdd(db + 2, accb.z); atomicAdd(db + 3, accb.w);
+    }
   }
 }
 
