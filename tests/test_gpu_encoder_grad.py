@@ -471,3 +471,33 @@ def test_dropin_block_trains_through_torch_autograd(cuda, lib):
     out2 = blk(x.detach(), pos)
     assert not torch.equal(blk._packed()["mlp.fc1"], before)
     assert not torch.allclose(out2, out.detach())
+
+
+def test_vit_encoder_trainer_against_reference_gradient_golden(cuda, lib):
+    """The CUDA backward pass against gradients of the UNMODIFIED reference modules
+    (tests/golden/encoder_grad_small.npz, written by oracle/make_encoder_grad_golden.py): same seeded
+    weights, clip, intrinsics and output gradient; every one of the 30 parameters."""
+    from pathlib import Path
+    import numpy as np
+    from oracle import make_encoder_grad_golden as gg
+    from oracle.make_encoder_golden import synth_inputs
+    from vicasplat_b200.encoder_train import VitEncoderTrainer
+    gold = np.load(Path(__file__).parent / "golden" / "encoder_grad_small.npz")
+    cfg = er.EncoderConfig(**gg.CASE)
+    sd = er.synth_state_dict(cfg, seed=0)
+    image, K = synth_inputs(1, gg.FRAMES, cfg.img_size)
+    tr = VitEncoderTrainer(sd, cfg, gg.FRAMES, (cfg.img_size, cfg.img_size), cuda)
+    out = tr.forward(image[0].to(cuda), K[0].to(cuda))
+    n = tr.lay.n
+    got = out.float().view(gg.FRAMES, n, -1)[:, ::4, ::16].cpu().numpy()
+    assert np.abs(got - gold["out_sub"]).max() <= 2e-2 * np.abs(gold["out_sub"]).max()
+    tr.backward(gg.output_grad((gg.FRAMES, n, cfg.enc_embed_dim)).reshape(gg.FRAMES * n, -1).to(cuda))
+    keys = gg.path_keys(sd)
+    assert set(keys) == set(tr.params)
+    for k in keys:
+        g = tr.params[k].grad
+        ref_norm = float(gold["norm/" + k])
+        assert abs(g.double().norm().item() - ref_norm) <= 2e-2 * ref_norm, (k, g.norm().item(), ref_norm)
+        sample = torch.from_numpy(gold["sample/" + k])
+        mine = g.flatten()[::gg.SAMPLE].cpu()
+        assert ((mine - sample).norm() / sample.norm().clamp_min(1e-12)).item() < 4e-2, k

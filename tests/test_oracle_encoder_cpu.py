@@ -60,3 +60,29 @@ def test_golden_is_not_degenerate():
     assert np.abs(g["pred_extrins"] - np.array([0, 0, 0, 1, 0, 0, 0, 0])).max() > 1e-3
     assert (g["raw_std"] > 1e-3).all()
     assert (g["inter_std"] > 0.1).all()
+
+
+def test_oracle_autograd_matches_reference_gradients():
+    """The oracle of the BACKWARD path: torch.autograd over oracle/encoder_ref.encode_image against
+    the gradients of the unmodified reference modules (oracle/make_encoder_grad_golden.py) for all 30
+    parameters of the image encoder in the small case.  The GPU tests of the hand-written backward
+    pass (tests/test_gpu_encoder_grad.py) compare against this autograd-over-the-oracle."""
+    from oracle import make_encoder_grad_golden as gg
+    gold = np.load(GOLD / "encoder_grad_small.npz")
+    cfg = er.EncoderConfig(**gg.CASE)
+    sd = er.synth_state_dict(cfg, seed=0)
+    keys = gg.path_keys(sd)
+    assert len(keys) == 30 and all("norm/" + k in gold.files for k in keys)
+    for k in keys:
+        sd[k].requires_grad_(True)
+    image, K = synth_inputs(1, gg.FRAMES, cfg.img_size)
+    x, _ = er.encode_image(sd, image[0], K[0], cfg)
+    _close(x.detach()[:, ::4, ::16], gold["out_sub"], 1e-4, 1e-4, "encoder output")
+    (x * gg.output_grad(x.shape)).sum().backward()
+    for k in keys:
+        g = sd[k].grad
+        assert g is not None, k
+        ref_norm = float(gold["norm/" + k])
+        assert abs(g.double().norm().item() - ref_norm) <= 1e-4 * ref_norm + 1e-7, k
+        sample = gold["sample/" + k]
+        _close(g.flatten()[::gg.SAMPLE], sample, 1e-3, 1e-4 * max(np.abs(sample).max(), 1e-6), k)
