@@ -126,3 +126,31 @@ def test_reducer_is_a_noop_without_a_process_group():
     red.bucket_ready(bk)
     red.finish()
     assert red.world == 1 and bk.flat.tolist() == [2.0] * 4
+
+
+def test_bucket_plan_covers_every_parameter_and_skips_the_dead_ones():
+    """C4's static plan against the reference: the parameters left out of the buckets are exactly the
+    ones the unmodified reference never gives a gradient (tests/golden/unused_params.json, measured
+    by oracle/make_unused_params_golden.py), everything else sits in exactly one bucket, and buckets
+    come in reverse execution order."""
+    sys.path.insert(0, str(ROOT))
+    from oracle import encoder_ref as er
+    from vicasplat_b200.encoder import VicaSplat, VicaSplatCfg, default_backbone_cfg
+    from vicasplat_b200.encoder_train import _BLOCK_BIG, _BLOCK_SMALL, plan_buckets
+    gold = json.loads((ROOT / "tests" / "golden" / "unused_params.json").read_text())
+    bb = dict(default_backbone_cfg(), img_size=64, enc_depth=2, dec_depth=10)
+    model = VicaSplat(VicaSplatCfg(backbone=bb))
+    names = [k for k, _ in model.named_parameters()]
+    assert len(names) == gold["n_parameters"]
+    buckets, unused = plan_buckets(names, enc_depth=2, dec_depth=10)
+    assert sorted(unused) == gold["no_grad"] and gold["zero_grad"] == []
+    flat = [k for _, ks in buckets for k in ks]
+    assert len(flat) == len(set(flat)) and set(flat) | set(unused) == set(names)
+    order = [n for n, _ in buckets]
+    assert order[:4] == ["gs_head", "pts_head", "cam_head", "dec_norms"]
+    assert order[4:15] == [f"dec{i}" for i in range(9, -1, -1)] + ["dec_stem"]
+    assert order[15:] == ["enc1", "enc0", "enc_stem"]
+    enc1 = dict(buckets)["enc1"]
+    assert sorted(enc1) == sorted(f"backbone.enc_blocks.1.{n}" for n in _BLOCK_SMALL + _BLOCK_BIG)
+    with __import__("pytest").raises(KeyError):
+        plan_buckets(["backbone.enc_blocks.7.norm1.weight"], enc_depth=2, dec_depth=10)

@@ -191,3 +191,54 @@ class VitEncoderTrainer:
         self.reducer.bucket_ready(self.stem_bucket)
         self.reducer.finish()
         self._saved = None
+
+
+# ------------------------------------------------------------------ bucket plan of the WHOLE model (C4)
+# Parameters that are constructed but never executed (refinenet4 is called with one input, so its
+# resConfUnit1 is dead: dpt_block.py:184,196; dpt_head.py:58; dpt_gs_head.py:143).  Measured on the
+# unmodified reference by oracle/make_unused_params_golden.py -> tests/golden/unused_params.json.
+# They stay in state_dict (checkpoints) but are left out of every gradient bucket: the reference
+# needs DDP's find_unused_parameters=True for them (src/main.py:111), a static plan does not.
+UNUSED_PARAMETER_MARK = ".scratch.refinenet4.resConfUnit1."
+
+
+def plan_buckets(param_names, enc_depth: int, dec_depth: int):
+    """Static gradient-bucket plan for all parameters of VicaSplat, in the order their gradients
+    become final during the backward pass (reverse execution order: heads, decoder norms, decoder
+    blocks N-1..0, decoder stem, encoder blocks N-1..0, encoder stem) -- the order ``GradReducer``
+    is fed in.  Returns (buckets: list of (name, [parameter names]), unused: [parameter names])."""
+    order = ["gs_head", "pts_head", "cam_head", "dec_norms"]
+    order += [f"dec{i}" for i in reversed(range(dec_depth))] + ["dec_stem"]
+    order += [f"enc{i}" for i in reversed(range(enc_depth))] + ["enc_stem"]
+    members = {n: [] for n in order}
+    unused = []
+
+    def bucket_of(k: str) -> str:
+        if k.startswith("gaussian_param_head."):
+            return "gs_head"
+        if k.startswith("downstream_head1."):
+            return "pts_head"
+        if k.startswith(("camera_extrinsic_head.", "camera_intrinsic_head.")):
+            return "cam_head"
+        if k.startswith(("backbone.dec_norm.", "backbone.camera_dec_norm.")):
+            return "dec_norms"
+        if k.startswith("backbone.dec_blocks."):
+            return "dec" + k.split(".")[2]
+        if k.startswith(("backbone.decoder_embed.", "backbone.camera_extrinsic_token",
+                         "backbone.camera_intrinsic_token")):
+            return "dec_stem"
+        if k.startswith("backbone.enc_blocks."):
+            return "enc" + k.split(".")[2]
+        if k.startswith(("backbone.patch_embed.", "backbone.intrinsic_encoder.", "backbone.enc_norm.")):
+            return "enc_stem"
+        raise KeyError(f"plan_buckets: no bucket rule for parameter {k!r}")
+
+    for k in param_names:
+        if UNUSED_PARAMETER_MARK in k:
+            unused.append(k)
+            continue
+        b = bucket_of(k)
+        if b not in members:
+            raise KeyError(f"plan_buckets: {k!r} maps to {b!r}, beyond the configured depth")
+        members[b].append(k)
+    return [(n, members[n]) for n in order if members[n]], unused
