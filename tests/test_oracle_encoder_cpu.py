@@ -86,3 +86,47 @@ def test_oracle_autograd_matches_reference_gradients():
         assert abs(g.double().norm().item() - ref_norm) <= 1e-4 * ref_norm + 1e-7, k
         sample = gold["sample/" + k]
         _close(g.flatten()[::gg.SAMPLE], sample, 1e-3, 1e-4 * max(np.abs(sample).max(), 1e-6), k)
+
+
+def test_oracle_autograd_matches_reference_gradients_whole_model():
+    """Oracle of the decoder / DPT-head / adapter backward (the next rows to be built): autograd over
+    oracle/encoder_ref.forward against the gradients of the unmodified reference's VicaSplat.forward
+    for all 499 parameters that receive one (oracle/make_model_grad_golden.py)."""
+    from oracle import make_model_grad_golden as mg2
+    gold = np.load(GOLD / "model_grad_small.npz")
+    kw, B, T, _ = CASES["small"]
+    cfg = er.EncoderConfig(**kw)
+    sd = er.synth_state_dict(cfg, seed=0)
+    for v in sd.values():
+        if v.is_floating_point():
+            v.requires_grad_(True)
+    image, K = synth_inputs(B, T, cfg.img_size)
+    loss = mg2.loss_of(er.forward(sd, image, K, cfg))
+    assert abs(loss.item() - float(gold["loss"])) <= 1e-4 * abs(float(gold["loss"]))
+    loss.backward()
+    # the reference shares scratch.layerK_rn with scratch.layer_rn.(K-1): the oracle reads one of the
+    # two equal state_dict entries, so the gradient of a shared parameter may sit on its twin
+    def grad_of(k):
+        if sd[k].grad is not None:
+            return sd[k].grad
+        for a, b in ((f".scratch.layer{i + 1}_rn.", f".scratch.layer_rn.{i}.") for i in range(4)):
+            for src, dst in ((a, b), (b, a)):
+                if src in k and sd.get(k.replace(src, dst)) is not None and sd[k.replace(src, dst)].grad is not None:
+                    return sd[k.replace(src, dst)].grad
+        return None
+    keys = [f[len("norm/"):] for f in gold.files if f.startswith("norm/")]
+    assert len(keys) == 499
+    worst = 0.0
+    for k in keys:
+        g = grad_of(k)
+        assert g is not None, k
+        ref_norm = float(gold["norm/" + k])
+        assert abs(g.double().norm().item() - ref_norm) <= 2e-3 * ref_norm + 1e-6, (k, g.norm().item(), ref_norm)
+        sample = gold["sample/" + k]
+        mine = g.flatten()[::mg2.SAMPLE].numpy()
+        # error of the sample relative to the RMS size of this gradient (a sample of a small tensor
+        # is one or two elements, which may happen to be near zero)
+        scale = ref_norm * np.sqrt(len(sample) / g.numel())
+        err = np.linalg.norm(mine - sample) / max(scale, 1e-12)
+        worst = max(worst, err)
+        assert err <= 5e-3, (k, err)
