@@ -117,6 +117,20 @@ class VitEncoderTrainer:
         return dict(self.params)
 
     @torch.no_grad()
+    def load_state_dict(self, sd: Dict[str, torch.Tensor], strict: bool = True) -> None:
+        """Copies reference-named tensors INTO the fp32 masters (gradient views, optimizer state and
+        device pointer tables stay valid) and re-derives the bf16 operands."""
+        missing = [k for k in self.params if k not in sd]
+        if strict and missing:
+            raise KeyError(f"VitEncoderTrainer.load_state_dict: missing {missing[:4]}{' ...' if len(missing) > 4 else ''}")
+        for k, p in self.params.items():
+            if k in sd:
+                if tuple(sd[k].shape) != tuple(p.shape):
+                    raise ValueError(f"VitEncoderTrainer.load_state_dict: {k} has shape {tuple(sd[k].shape)}, expected {tuple(p.shape)}")
+                p.copy_(sd[k])
+        self.repack()
+
+    @torch.no_grad()
     def repack(self) -> None:
         """bf16 operand copies of every weight, both orientations, one pass per weight."""
         for i in range(self.depth):

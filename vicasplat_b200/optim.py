@@ -37,9 +37,9 @@ class FusedAdamW:
         self.step_count = 0
         self._params = [p for g in self.param_groups for p in g["params"]]
         for p in self._params:
-            if not (p.is_cuda and p.dtype == torch.float32 and p.is_contiguous()):
-                raise RuntimeError("FusedAdamW needs contiguous fp32 CUDA parameters (no CPU fallback)")
-        self.dev = self._params[0].device
+            if not (p.dtype == torch.float32 and p.is_contiguous()):
+                raise RuntimeError("FusedAdamW needs contiguous fp32 parameters")
+        self.dev = self._params[0].device       # CPU parameters can hold / exchange state; step() needs CUDA
         self.state = {p: dict(exp_avg=torch.zeros_like(p), exp_avg_sq=torch.zeros_like(p)) for p in self._params}
         i64 = dict(dtype=torch.int64, device=self.dev)
         self._t_params = torch.tensor([p.data_ptr() for p in self._params], **i64)
@@ -73,6 +73,8 @@ class FusedAdamW:
     def step(self) -> None:
         """One AdamW step on every parameter (all must have a gradient).  ``self.grad_norm`` (before
         clipping) and ``self.found_inf`` are device scalars: reading them is the caller's sync."""
+        if self.dev.type != "cuda":
+            raise RuntimeError("FusedAdamW.step needs CUDA parameters (there is no CPU fallback)")
         lib = _lib.load()
         gp = []
         for p in self._params:
@@ -99,3 +101,54 @@ class FusedAdamW:
         q.partials, q.counter = ptr(self._partials), ptr(self._counter)
         q.grad_norm_out, q.found_inf_out = ptr(self.grad_norm), ptr(self.found_inf)
         check(lib.vs_adamw_step(C.byref(q), C.c_void_p(stream_ptr())), "vs_adamw_step")
+
+    # ---- checkpoint / resume in torch.optim.AdamW's layout (Lightning saves ``optimizer.state_dict()``
+    # with every checkpoint of the reference: src/main.py:80-99, resumed through ``ckpt_path``)
+    def state_dict(self) -> dict:
+        state, groups, idx = {}, [], 0
+        for g in self.param_groups:
+            ids = []
+            for p in g["params"]:
+                st = self.state[p]
+                state[idx] = {"step": torch.tensor(float(self.step_count)),
+                              "exp_avg": st["exp_avg"], "exp_avg_sq": st["exp_avg_sq"]}
+                ids.append(idx)
+                idx += 1
+            meta = {k: v for k, v in g.items() if k != "params"}
+            meta.setdefault("betas", tuple(self.betas))
+            meta.setdefault("eps", self.eps)
+            meta.setdefault("weight_decay", self.weight_decay)
+            groups.append({**meta, "params": ids})
+        return {"state": state, "param_groups": groups}
+
+    @torch.no_grad()
+    def load_state_dict(self, sd: dict) -> None:
+        """Accepts ``torch.optim.AdamW.state_dict()`` (or this class's).  Moments are copied INTO the
+        existing buffers (the device tables keep pointing at them); learning rates follow the saved
+        groups; an empty state (an optimizer that never stepped) resets the step counter."""
+        groups = sd["param_groups"]
+        if len(groups) != len(self.param_groups) or any(
+                len(a["params"]) != len(b["params"]) for a, b in zip(groups, self.param_groups)):
+            raise ValueError("FusedAdamW.load_state_dict: parameter groups do not match")
+        steps = set()
+        for saved, mine in zip(groups, self.param_groups):
+            if "lr" in saved:
+                mine["lr"] = saved["lr"]
+            for i, p in zip(saved["params"], mine["params"]):
+                st = sd["state"].get(i)
+                if st is None:
+                    self.state[p]["exp_avg"].zero_()
+                    self.state[p]["exp_avg_sq"].zero_()
+                    steps.add(0)
+                    continue
+                if st["exp_avg"].shape != p.shape:
+                    raise ValueError(f"FusedAdamW.load_state_dict: state {i} has shape {tuple(st['exp_avg'].shape)}, "
+                                     f"parameter has {tuple(p.shape)}")
+                self.state[p]["exp_avg"].copy_(st["exp_avg"])
+                self.state[p]["exp_avg_sq"].copy_(st["exp_avg_sq"])
+                steps.add(int(round(float(st["step"]))))
+        if len(steps) > 1:
+            raise ValueError(f"FusedAdamW.load_state_dict: parameters disagree on the step count {sorted(steps)} "
+                             "(one bias correction is shared by all tensors)")
+        self.step_count = steps.pop() if steps else 0
+        self._lrs_host = None
