@@ -35,6 +35,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--depth", type=int, default=24)
     ap.add_argument("--no-reduce", action="store_true", help="skip the all-reduce (N > 1): its cost by difference")
+    ap.add_argument("--bf16-reduce", action="store_true", help="all-reduce bf16 copies of the gradient buckets")
     a = ap.parse_args()
     rank, world, local = dist_util.rank_world()
     torch.cuda.set_device(local)
@@ -44,7 +45,7 @@ def main():
     cfg = er.EncoderConfig(enc_depth=a.depth, dec_depth=4)
     sd = er.synth_state_dict(cfg, seed=0)
     frames = a.scenes * 8
-    reducer = GradReducer()
+    reducer = GradReducer(compress_bf16=a.bf16_reduce)
     if a.no_reduce:
         reducer.world = 1
     tr = VitEncoderTrainer(sd, cfg, frames, (256, 256), dev, reducer=reducer)
@@ -106,7 +107,7 @@ def main():
             "params": n_params, "allreduce_bytes_per_step": reducer.bytes_reduced // max(1, a.steps + a.warmup),
             "algorithmic_tflops": round(flop / red[0] / 1e9, 1), "dtype": "bf16 operands, fp32 accumulate / master",
             "data": "synthetic (random-init weights, seeded images, synthetic output gradient)",
-            "reduce": not a.no_reduce,
+            "reduce": not a.no_reduce, "reduce_dtype": "bf16" if a.bf16_reduce else "fp32",
         }))
     if world > 1:
         dist.destroy_process_group()

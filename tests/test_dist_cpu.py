@@ -80,7 +80,7 @@ def test_grad_bucket_layout():
     assert bk.flat.abs().sum() == 0
 
 
-def _reduce_worker(rank, world, port, out):
+def _reduce_worker(rank, world, port, out, compress=False):
     os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank),
                       MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     sys.path.insert(0, str(ROOT))
@@ -88,7 +88,7 @@ def _reduce_worker(rank, world, port, out):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     shapes = {"b": torch.Size([4]), "w": torch.Size([3, 4])}
     buckets = [GradBucket(shapes, ["b"], ["w"], "cpu") for _ in range(3)]
-    red = GradReducer()
+    red = GradReducer(compress_bf16=compress)
     for i in reversed(range(3)):                              # reverse layer order, like the backward pass
         buckets[i].views["b"].fill_(float(rank + 1) * (i + 1))
         buckets[i].views["w"].copy_(torch.arange(12.0).view(3, 4) * (rank + 1))
@@ -101,18 +101,19 @@ def _reduce_worker(rank, world, port, out):
     dist.destroy_process_group()
 
 
-def test_two_rank_gloo_gradient_buckets_are_averaged():
+@__import__("pytest").mark.parametrize("compress", [False, True])
+def test_two_rank_gloo_gradient_buckets_are_averaged(compress):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 31500 + os.getpid() % 2000
-    procs = [ctx.Process(target=_reduce_worker, args=(r, 2, port, q)) for r in range(2)]
+    port = 31500 + os.getpid() % 2000 + (7 if compress else 0)
+    procs = [ctx.Process(target=_reduce_worker, args=(r, 2, port, q, compress)) for r in range(2)]
     for p in procs:
         p.start()
     bs, w, world, nbytes = q.get(timeout=120)
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    assert world == 2 and nbytes == 3 * 16 * 4
+    assert world == 2 and nbytes == 3 * 16 * (2 if compress else 4)      # bf16 on the wire halves the bytes
     assert bs == [[1.5 * (i + 1)] * 4 for i in range(3)]                 # mean of rank 1x and 2x
     assert w == (torch.arange(12.0).view(3, 4) * 1.5).tolist()
 

@@ -52,11 +52,16 @@ class GradReducer:
     """Averages gradient buckets over the ranks of the default process group.  ``bucket_ready`` starts
     an asynchronous all-reduce on the bucket's flat buffer (NCCL orders it after the kernels already
     enqueued on the current stream and runs it beside the ones enqueued later); ``finish`` makes the
-    current stream wait for all of them.  World size 1 / no process group: no-ops."""
+    current stream wait for all of them.  World size 1 / no process group: no-ops.
 
-    def __init__(self) -> None:
+    ``compress_bf16=True`` sends bf16 copies of the buckets (half the bytes on the wire, SURVEY §8e:
+    1.16 GB instead of 2.31 GB for the whole model) and writes the averaged result back into the fp32
+    bucket; the default keeps the reference's fp32 all-reduce."""
+
+    def __init__(self, compress_bf16: bool = False) -> None:
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self._nccl = self.world > 1 and dist.get_backend() == "nccl"
+        self.compress_bf16 = compress_bf16
         self._pending: list = []
         self.bytes_reduced = 0
 
@@ -64,12 +69,15 @@ class GradReducer:
         if self.world == 1:
             return
         op = dist.ReduceOp.AVG if self._nccl else dist.ReduceOp.SUM
-        self._pending.append((dist.all_reduce(bucket.flat, op=op, async_op=True), bucket))
-        self.bytes_reduced += bucket.flat.numel() * 4
+        wire = bucket.flat.to(torch.bfloat16) if self.compress_bf16 else bucket.flat
+        self._pending.append((dist.all_reduce(wire, op=op, async_op=True), bucket, wire))
+        self.bytes_reduced += wire.numel() * wire.element_size()
 
     def finish(self) -> None:
-        for work, bucket in self._pending:
+        for work, bucket, wire in self._pending:
             work.wait()
+            if wire is not bucket.flat:
+                bucket.flat.copy_(wire)
             if not self._nccl:                                # gloo has no AVG
                 bucket.flat.div_(self.world)
         self._pending.clear()
