@@ -1,0 +1,73 @@
+"""The hand-derived backward pass of MixDecoderBlock (oracle/decoder_backward_ref.py: the formulas the
+decoder's CUDA training kernels will implement) against torch.autograd over encoder_ref.dec_block,
+which tests/golden/model_grad_small.npz pins to the unmodified reference's own gradients."""
+import pytest
+import torch
+
+from oracle import decoder_backward_ref as db
+from oracle import encoder_ref as er
+
+
+def _setup(T, dtype):
+    cfg = er.EncoderConfig(img_size=64, enc_depth=1, dec_depth=2)
+    key = "backbone.dec_blocks.1"
+    sd = {k: v.to(dtype) for k, v in er.synth_state_dict(cfg, seed=3).items() if k.startswith(key + ".")}
+    g = torch.Generator().manual_seed(T)
+    for k in sd:                                   # non-trivial biases / norm weights
+        if k.endswith(".bias"):
+            sd[k] = (0.1 * torch.randn(sd[k].shape, generator=g)).to(dtype)
+        elif "norm" in k:
+            sd[k] = (1 + 0.1 * torch.randn(sd[k].shape, generator=g)).to(dtype)
+    B, N, C = 2, 17, cfg.dec_embed_dim
+    img = torch.randn((B, T, N, C), generator=g).to(dtype)
+    cam = torch.randn((B, T, C), generator=g).to(dtype)
+    pos = er.positions(B * T, 4, 4, True).reshape(B, T, N, 2)
+    d_img = torch.randn((B, T, N, C), generator=g).to(dtype)
+    d_cam = torch.randn((B, T, C), generator=g).to(dtype)
+    return cfg, key, sd, img, cam, pos, d_img, d_cam
+
+
+@pytest.mark.parametrize("T", [2, 3, 4])            # T = 2: single neighbour; T >= 3: end frames see one frame twice
+def test_manual_decoder_block_backward_matches_autograd(T):
+    cfg, key, sd, img, cam, pos, d_img, d_cam = _setup(T, torch.float64)
+    out_img, out_cam, cache = db.dec_block_fwd(sd, key, img, cam, pos, cfg)
+    gi, gc, grads = db.dec_block_bwd(sd, key, d_img, d_cam, cache, cfg)
+    for v in sd.values():
+        v.requires_grad_(True)
+    ri, rc = img.clone().requires_grad_(True), cam.clone().requires_grad_(True)
+    ref_img, ref_cam = er.dec_block(sd, key, ri, rc, pos, cfg)
+    assert torch.allclose(out_img, ref_img.detach(), rtol=1e-9, atol=1e-9)
+    assert torch.allclose(out_cam, ref_cam.detach(), rtol=1e-9, atol=1e-9)
+    ((ref_img * d_img).sum() + (ref_cam * d_cam).sum()).backward()
+    rel = lambda a, b: ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+    assert rel(gi, ri.grad) < 1e-9 and rel(gc, rc.grad) < 1e-9
+    assert set(grads) == set(sd), sorted(set(sd) ^ set(grads))
+    for k in sd:
+        assert sd[k].grad is not None, k
+        assert rel(grads[k], sd[k].grad) < 1e-8, (k, rel(grads[k], sd[k].grad))
+
+
+def test_stage_formulas():
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn((5, 7, 32), generator=g, dtype=torch.float64, requires_grad=True)
+    w = torch.randn((32,), generator=g, dtype=torch.float64, requires_grad=True)
+    b = torch.randn((32,), generator=g, dtype=torch.float64, requires_grad=True)
+    dy = torch.randn((5, 7, 32), generator=g, dtype=torch.float64)
+    y, cache = db.ln_fwd(x.detach(), w.detach(), b.detach(), 1e-6)
+    torch.nn.functional.layer_norm(x, (32,), w, b, 1e-6).backward(dy)
+    dx, dw, dbias = db.ln_bwd(dy, cache, w.detach())
+    assert torch.allclose(dx, x.grad) and torch.allclose(dw, w.grad) and torch.allclose(dbias, b.grad)
+    z = torch.randn((64,), generator=g, dtype=torch.float64, requires_grad=True)
+    torch.nn.functional.gelu(z).sum().backward()
+    assert torch.allclose(db.gelu_grad(z.detach()), z.grad)
+    z.grad = None
+    torch.nn.functional.silu(z).sum().backward()
+    assert torch.allclose(db.silu_grad(z.detach()), z.grad)
+    # rope transposes: <R a, b> == <a, R^T b>
+    a = torch.randn((2, 3, 9, 64), generator=g, dtype=torch.float64)
+    bb = torch.randn((2, 3, 9, 64), generator=g, dtype=torch.float64)
+    pos = torch.randint(0, 5, (2, 9, 2), generator=g)
+    assert torch.allclose((er.rope2d(a, pos, 100.0) * bb).sum(), (a * db.rope2d_bwd(bb, pos, 100.0)).sum())
+    fr = torch.arange(9)
+    assert torch.allclose((er.rope1d_interleaved(a, fr, 30.0) * bb).sum(),
+                          (a * db.rope1d_bwd(bb, fr, 30.0)).sum())
