@@ -71,3 +71,40 @@ def test_stage_formulas():
     fr = torch.arange(9)
     assert torch.allclose((er.rope1d_interleaved(a, fr, 30.0) * bb).sum(),
                           (a * db.rope1d_bwd(bb, fr, 30.0)).sum())
+
+
+def test_adapter_postprocess_and_pose_tail_backward():
+    from oracle import adapter_backward_ref as ab
+    cfg = er.EncoderConfig()
+    g = torch.Generator().manual_seed(9)
+    raw = torch.randn((2, 3, 5, 86), generator=g, dtype=torch.float64)
+    raw[..., 4:7] += torch.tensor([0.0, 6.5, -3.0], dtype=torch.float64)   # one scale channel beyond the 0.3 clamp
+    raw[0, 0, 0, 4:7] = 400.0                                               # clamped: zero gradient
+    rr = raw.clone().requires_grad_(True)
+    out = er.gaussian_adapter(rr, cfg)
+    D = {k: torch.randn(out[k].shape, generator=g, dtype=torch.float64)
+         for k in ("means", "covariances", "harmonics", "opacities", "scales", "rotations")}
+    sum((out[k] * D[k]).sum() for k in D).backward()
+    got = ab.adapter_backward(raw, cfg, D["means"], D["covariances"], D["harmonics"], D["opacities"],
+                              d_scales=D["scales"], d_rot=D["rotations"])
+    assert torch.allclose(got, rr.grad, rtol=1e-9, atol=1e-12)
+    assert (got[0, 0, 0, 4:7] == 0).all()
+    # raster-only case: no direct gradient on scales / rotations
+    rr.grad = None
+    out = er.gaussian_adapter(rr, cfg)
+    sum((out[k] * D[k]).sum() for k in ("means", "covariances", "harmonics", "opacities")).backward()
+    got = ab.adapter_backward(raw, cfg, D["means"], D["covariances"], D["harmonics"], D["opacities"])
+    assert torch.allclose(got, rr.grad, rtol=1e-9, atol=1e-12)
+
+    x = torch.randn((4, 6, 3), generator=g, dtype=torch.float64, requires_grad=True)
+    dxyz = torch.randn((4, 6, 3), generator=g, dtype=torch.float64)
+    d = x.norm(dim=-1, keepdim=True)
+    (x / d.clip(min=1e-8) * torch.expm1(d) * dxyz).sum().backward()          # encoder_ref.pts_head's tail
+    assert torch.allclose(ab.exp_postprocess_backward(x.detach(), dxyz), x.grad, rtol=1e-10, atol=1e-12)
+
+    v = torch.randn((2, 7, 8), generator=g, dtype=torch.float64)
+    v[..., 3] += 1.0
+    vr = v.clone().requires_grad_(True)
+    dp = torch.randn((2, 7, 8), generator=g, dtype=torch.float64)
+    ((vr / vr[..., :4].norm(dim=-1, keepdim=True)) * dp).sum().backward()    # encoder_ref.camera_head's tail
+    assert torch.allclose(ab.dq_normalise_backward(v, dp), vr.grad, rtol=1e-10, atol=1e-12)
