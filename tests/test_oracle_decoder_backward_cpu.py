@@ -108,3 +108,56 @@ def test_adapter_postprocess_and_pose_tail_backward():
     dp = torch.randn((2, 7, 8), generator=g, dtype=torch.float64)
     ((vr / vr[..., :4].norm(dim=-1, keepdim=True)) * dp).sum().backward()    # encoder_ref.camera_head's tail
     assert torch.allclose(ab.dq_normalise_backward(v, dp), vr.grad, rtol=1e-10, atol=1e-12)
+
+
+def test_dpt_operator_backward_formulas():
+    import torch.nn.functional as F
+    from oracle import dpt_backward_ref as dp
+    g = torch.Generator().manual_seed(4)
+    rnd = lambda *s: torch.randn(s, generator=g, dtype=torch.float64)
+    # stride-1 convolutions: 3x3 pad 1, 1x1 pad 0, 7x7 pad 3
+    for k, pad in ((3, 1), (1, 0), (7, 3)):
+        x, W, b = rnd(2, 5, 9, 8).requires_grad_(True), rnd(6, 5, k, k).requires_grad_(True), rnd(6).requires_grad_(True)
+        dy = rnd(2, 6, 9, 8)
+        F.conv2d(x, W, b, padding=pad).backward(dy)
+        assert torch.allclose(dp.conv_dgrad_s1(dy, W.detach(), pad), x.grad, atol=1e-11)
+        assert torch.allclose(dp.conv_wgrad(dy, x.detach(), k, pad), W.grad, atol=1e-11)
+        assert torch.allclose(dy.sum((0, 2, 3)), b.grad, atol=1e-11)
+    # stride-2 3x3 pad 1 (act_postprocess.3.1), even and odd input sizes
+    for hw in ((8, 8), (7, 9)):
+        x, W = rnd(2, 4, *hw).requires_grad_(True), rnd(3, 4, 3, 3).requires_grad_(True)
+        y = F.conv2d(x, W, stride=2, padding=1)
+        dy = rnd(*y.shape)
+        y.backward(dy)
+        assert torch.allclose(dp.conv_dgrad_strided(dy, W.detach(), 1, 2, hw), x.grad, atol=1e-11)
+        assert torch.allclose(dp.conv_wgrad(dy, x.detach(), 3, 1, stride=2), W.grad, atol=1e-11)
+    # ConvTranspose2d kernel = stride
+    for s in (2, 4):
+        x, Wt, b = rnd(2, 5, 3, 4).requires_grad_(True), rnd(5, 6, s, s).requires_grad_(True), rnd(6).requires_grad_(True)
+        y = F.conv_transpose2d(x, Wt, b, stride=s)
+        dy = rnd(*y.shape)
+        y.backward(dy)
+        dx, dW, db_ = dp.conv_transpose_ks_backward(dy, x.detach(), Wt.detach())
+        assert torch.allclose(dx, x.grad, atol=1e-11) and torch.allclose(dW, Wt.grad, atol=1e-11)
+        assert torch.allclose(db_, b.grad, atol=1e-11)
+    # bilinear x2, align_corners=True
+    x = rnd(2, 3, 5, 4).requires_grad_(True)
+    y = F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=True)
+    assert torch.allclose(dp.up2_forward(x.detach()), y.detach(), atol=1e-12)
+    dy = rnd(*y.shape)
+    y.backward(dy)
+    assert torch.allclose(dp.up2_backward(dy), x.grad, atol=1e-12)
+    # residual conv unit (pre-activation), against the oracle's rcu
+    sd = {"u.conv1.weight": rnd(4, 4, 3, 3), "u.conv1.bias": rnd(4), "u.conv2.weight": rnd(4, 4, 3, 3),
+          "u.conv2.bias": rnd(4)}
+    for v in sd.values():
+        v.requires_grad_(True)
+    x = rnd(2, 4, 6, 5).requires_grad_(True)
+    dy = rnd(2, 4, 6, 5)
+    er.rcu(sd, "u", x).backward(dy)
+    y1 = er.conv(sd, "u.conv1", F.relu(x), padding=1).detach()
+    dx, (dW1, db1), (dW2, db2) = dp.rcu_backward(dy, x.detach(), sd["u.conv1.weight"].detach(),
+                                                 sd["u.conv2.weight"].detach(), y1)
+    assert torch.allclose(dx, x.grad, atol=1e-11)
+    assert torch.allclose(dW1, sd["u.conv1.weight"].grad, atol=1e-11) and torch.allclose(db1, sd["u.conv1.bias"].grad, atol=1e-11)
+    assert torch.allclose(dW2, sd["u.conv2.weight"].grad, atol=1e-11) and torch.allclose(db2, sd["u.conv2.bias"].grad, atol=1e-11)
