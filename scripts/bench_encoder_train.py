@@ -32,7 +32,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--scenes", type=int, default=8)
     ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--depth", type=int, default=24)
     ap.add_argument("--no-reduce", action="store_true", help="skip the all-reduce (N > 1): its cost by difference")
     ap.add_argument("--bf16-reduce", action="store_true", help="all-reduce bf16 copies of the gradient buckets")
