@@ -161,3 +161,53 @@ def test_dpt_operator_backward_formulas():
     assert torch.allclose(dx, x.grad, atol=1e-11)
     assert torch.allclose(dW1, sd["u.conv1.weight"].grad, atol=1e-11) and torch.allclose(db1, sd["u.conv1.bias"].grad, atol=1e-11)
     assert torch.allclose(dW2, sd["u.conv2.weight"].grad, atol=1e-11) and torch.allclose(db2, sd["u.conv2.bias"].grad, atol=1e-11)
+
+
+def test_shared_host_device_tail_math_against_the_fp64_oracle():
+    """vicasplat_b200/csrc/tail_math.h (the per-element chain rules the backward kernels of the
+    encoder tails run; host build oracle/_build/libtail_math_host.so) against
+    oracle/adapter_backward_ref.py."""
+    import ctypes as C
+    import subprocess
+    from pathlib import Path
+    from oracle import adapter_backward_ref as ab
+    root = Path(__file__).resolve().parent.parent
+    so = root / "oracle" / "_build" / "libtail_math_host.so"
+    if not so.exists():
+        subprocess.run(["make", "-C", str(root / "oracle"), "_build/libtail_math_host.so"], check=True)
+    lib = C.CDLL(str(so))
+    fp = lambda t: C.c_void_p(t.data_ptr())
+    cfg = er.EncoderConfig()
+    g = torch.Generator().manual_seed(21)
+    n = 4096
+    raw = torch.randn((n, 86), generator=g)
+    raw[:, 4:7] += torch.tensor([0.0, 6.5, -3.0])
+    raw[:7, 4:7] = 400.0                                         # clamped scales
+    d_means, d_opac = torch.randn((n, 3), generator=g), torch.randn((n, 1), generator=g)
+    d_cov6 = torch.randn((n, 6), generator=g)
+    iu = torch.triu_indices(3, 3)
+    d_cov = torch.zeros((n, 3, 3), dtype=torch.float64)
+    d_cov[:, iu[0], iu[1]] = d_cov6.double()                     # gradient of the packed upper triangle
+    want = ab.adapter_backward(raw.double(), cfg, d_means.double(), d_cov,
+                               torch.zeros((n, 3, 25), dtype=torch.float64), d_opac.double())[:, :11]
+    got = torch.empty((n, 11))
+    lib.tm_adapter_backward(fp(raw), C.c_longlong(86), fp(d_means), fp(d_cov6), fp(d_opac), fp(got),
+                            C.c_longlong(n))
+    err = (got.double() - want).norm(dim=0) / want.norm(dim=0).clamp_min(1e-30)
+    assert (err < 2e-5).all(), err
+    assert (got[:7, 4:7] == 0).all()
+
+    x, gx = torch.randn((n, 3), generator=g), torch.randn((n, 3), generator=g)
+    x[:5] *= 1e-3                                                # small norms: f(d) -> 1, f'(d) -> 1/2
+    got = torch.empty((n, 3))
+    lib.tm_exp_postprocess_backward(fp(x), fp(gx), fp(got), C.c_longlong(n))
+    want = ab.exp_postprocess_backward(x.double(), gx.double())
+    assert ((got.double() - want).norm() / want.norm()).item() < 1e-5
+    assert torch.allclose(got[:5].double(), want[:5], rtol=2e-3, atol=1e-6)   # cancellation in f32 at tiny |x|
+
+    v, dp = torch.randn((n, 8), generator=g), torch.randn((n, 8), generator=g)
+    v[:, 3] += 1.0
+    got = torch.empty((n, 8))
+    lib.tm_dq_normalise_backward(fp(v), fp(dp), fp(got), C.c_longlong(n))
+    want = ab.dq_normalise_backward(v.double(), dp.double())
+    assert ((got.double() - want).norm() / want.norm()).item() < 1e-5
