@@ -17,7 +17,6 @@ import os
 import sys
 from pathlib import Path
 
-import torch
 
 ROOT = Path(__file__).resolve().parent.parent
 REF = Path("/root/reference")

@@ -12,7 +12,6 @@ step and the overlap of its all-reduce, not a full VicaSplat training step.
 """
 import argparse
 import json
-import os
 import sys
 from pathlib import Path
 
