@@ -14,16 +14,16 @@ import torch
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 
-from oracle import encoder_ref as er          # weights only (synthetic state_dict)
-from vicasplat_b200 import encoder_grad as eg, ops
+from vicasplat_b200 import encoder_grad as eg, ops, synthetic
+from vicasplat_b200.encoder_train import ViTEncoderConfig
 
 
 def main():
     scenes = int(sys.argv[1]) if len(sys.argv) > 1 else 8
     iters = int(sys.argv[2]) if len(sys.argv) > 2 else 10
     dev = torch.device("cuda:0")
-    cfg = er.EncoderConfig(enc_depth=1, dec_depth=4)
-    sd = {k: v.to(dev) for k, v in er.synth_state_dict(cfg, seed=0).items()
+    cfg = ViTEncoderConfig(enc_depth=1)
+    sd = {k: v.to(dev) for k, v in synthetic.vit_encoder_state_dict(depth=1, seed=0).items()
           if k.startswith("backbone.enc_blocks.0.")}
     w = eg.pack_block(sd, "backbone.enc_blocks.0", dev)
     g = eg.zero_grads(w)

@@ -21,9 +21,8 @@ import torch.distributed as dist
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 
-from oracle import encoder_ref as er          # synthetic weights only
-from vicasplat_b200 import dist_util
-from vicasplat_b200.encoder_train import GradReducer, VitEncoderTrainer
+from vicasplat_b200 import dist_util, synthetic
+from vicasplat_b200.encoder_train import GradReducer, ViTEncoderConfig, VitEncoderTrainer
 from vicasplat_b200.optim import FusedAdamW
 
 
@@ -41,8 +40,8 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
-    cfg = er.EncoderConfig(enc_depth=a.depth, dec_depth=4)
-    sd = er.synth_state_dict(cfg, seed=0)
+    cfg = ViTEncoderConfig(enc_depth=a.depth)
+    sd = synthetic.vit_encoder_state_dict(depth=a.depth, seed=0)
     frames = a.scenes * 8
     reducer = GradReducer(compress_bf16=a.bf16_reduce)
     if a.no_reduce:

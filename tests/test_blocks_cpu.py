@@ -44,3 +44,21 @@ def test_cpu_tensors_fail_loudly():
     blk = _block()
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         blk(torch.zeros(1, 5, 1024), torch.zeros(1, 5, 2, dtype=torch.long))
+
+
+def test_synthetic_vit_weights_follow_the_reference_names_and_shapes():
+    """scripts/bench_*train*.py draw their weights from vicasplat_b200.synthetic (not from oracle/):
+    names and shapes are the reference's for the image encoder."""
+    from vicasplat_b200 import synthetic
+    from vicasplat_b200.encoder_train import ViTEncoderConfig
+    cfg = er.EncoderConfig(enc_depth=2, dec_depth=4)
+    want = {k: tuple(v) for k, v in er.param_shapes(cfg).items()
+            if k.startswith(("backbone.enc_blocks.", "backbone.enc_norm.", "backbone.patch_embed.",
+                             "backbone.intrinsic_encoder."))}
+    sd = synthetic.vit_encoder_state_dict(depth=2, seed=1)
+    assert {k: tuple(v.shape) for k, v in sd.items()} == want
+    again = synthetic.vit_encoder_state_dict(depth=2, seed=1)
+    assert all(torch.equal(sd[k], again[k]) for k in sd)               # seeded
+    v = ViTEncoderConfig(enc_depth=2)
+    assert (v.enc_embed_dim, v.enc_num_heads, v.patch_size, v.ln_eps) == (cfg.enc_embed_dim, cfg.enc_num_heads,
+                                                                         cfg.patch_size, cfg.ln_eps)

@@ -15,6 +15,7 @@ with hand-written backward, bucketed gradient all-reduce and the fused AdamW.
 """
 from __future__ import annotations
 
+from dataclasses import dataclass
 from typing import Dict, List, Optional
 
 import torch
@@ -28,6 +29,18 @@ _BLOCK_BIG = ("attn.qkv.weight", "attn.proj.weight", "mlp.fc1.weight", "mlp.fc2.
 _STEM_SMALL = ("backbone.patch_embed.proj.bias", "backbone.intrinsic_encoder.bias",
                "backbone.enc_norm.weight", "backbone.enc_norm.bias")
 _STEM_BIG = ("backbone.intrinsic_encoder.weight", "backbone.patch_embed.proj.weight")
+
+
+@dataclass(frozen=True)
+class ViTEncoderConfig:
+    """The values of backbone/vica.yaml that shape the image encoder (any object with these attributes
+    works as `cfg`, e.g. the oracle's EncoderConfig in the tests)."""
+    enc_embed_dim: int = 1024
+    enc_depth: int = 24
+    enc_num_heads: int = 16
+    patch_size: int = 16
+    mlp_ratio: float = 4.0
+    ln_eps: float = 1e-6
 
 
 class GradBucket:

@@ -67,3 +67,39 @@ def gaussian_scene(n_ctx: int, h: int, w: int, n_tgt: int, seed: int = 250307, d
     out.update(extrinsics=tgt.float(), intrinsics=K.float()[None].repeat(n_tgt, 1, 1),
                near=torch.full((n_tgt,), 0.01), far=torch.full((n_tgt,), 100.0))
     return out
+
+
+def vit_encoder_state_dict(depth: int = 24, embed: int = 1024, patch: int = 16, mlp_ratio: float = 4.0,
+                           seed: int = 0):
+    """Seeded random weights of the image encoder (patch embedding, intrinsic token, `depth` ViT blocks,
+    final norm) under the reference's state_dict names (backbone_vica.py:380-399,431-448: xavier-uniform
+    linears) -- with non-trivial biases / LayerNorm parameters so that every gradient path is exercised.
+    fp32 CPU tensors."""
+    g = torch.Generator().manual_seed(seed)
+
+    def xavier(out_f, in_f, shape=None):
+        a = (6.0 / (in_f + out_f)) ** 0.5
+        return (torch.rand(shape or (out_f, in_f), generator=g) * 2 - 1) * a
+
+    def small(n):
+        return 0.02 * torch.randn((n,), generator=g)
+
+    hidden = int(embed * mlp_ratio)
+    sd = {
+        "backbone.patch_embed.proj.weight": xavier(embed, 3 * patch * patch, (embed, 3, patch, patch)),
+        "backbone.patch_embed.proj.bias": small(embed),
+        "backbone.intrinsic_encoder.weight": xavier(embed, 9),
+        "backbone.intrinsic_encoder.bias": small(embed),
+        "backbone.enc_norm.weight": 1 + small(embed),
+        "backbone.enc_norm.bias": small(embed),
+    }
+    for i in range(depth):
+        k = f"backbone.enc_blocks.{i}."
+        for name, (o, n) in (("attn.qkv", (3 * embed, embed)), ("attn.proj", (embed, embed)),
+                             ("mlp.fc1", (hidden, embed)), ("mlp.fc2", (embed, hidden))):
+            sd[k + name + ".weight"] = xavier(o, n)
+            sd[k + name + ".bias"] = small(o)
+        for name in ("norm1", "norm2"):
+            sd[k + name + ".weight"] = 1 + small(embed)
+            sd[k + name + ".bias"] = small(embed)
+    return sd
