@@ -211,3 +211,61 @@ def test_shared_host_device_tail_math_against_the_fp64_oracle():
     lib.tm_dq_normalise_backward(fp(v), fp(dp), fp(got), C.c_longlong(n))
     want = ab.dq_normalise_backward(v.double(), dp.double())
     assert ((got.double() - want).norm() / want.norm()).item() < 1e-5
+
+
+@pytest.mark.parametrize("T", [2, 3, 5])
+def test_neighbour_backward_tables_write_every_key_row_once(T):
+    """Key-frame-centric item tables of the neighbour attention's dK / dV pass
+    (vicasplat_b200.encoder_grad.neighbour_backward_tables): emulating the pass item by item -- key frame
+    j with its (<= 2) reading query frames, probabilities from each query row's OWN softmax -- reproduces
+    the hand-derived oracle's dK / dV, which accumulates over the reference's duplicated key lists."""
+    from vicasplat_b200.encoder_grad import neighbour_backward_tables
+    cfg = er.EncoderConfig(img_size=64, enc_depth=1, dec_depth=2)
+    B, N, H, hd = 2, 9, cfg.dec_num_heads, 64
+    rpf = N + 1
+    g = torch.Generator().manual_seed(40 + T)
+    rnd = lambda: torch.randn((B * T * rpf, H, hd), generator=g, dtype=torch.float64)
+    q, k, v, do = rnd(), rnd(), rnd(), rnd()
+    img = lambda t: t.view(B, T, rpf, H, hd)[:, :, 1:].permute(0, 1, 3, 2, 4)      # (B,T,H,N,hd) image rows
+    # the oracle's way: per query frame over its (possibly duplicated) neighbour list, scatter-add
+    want_dk, want_dv = torch.zeros_like(img(k)), torch.zeros_like(img(v))
+    P_rows = {}
+    for t in range(T):
+        nb = db._neighbours(t, T)
+        kk = torch.cat([img(k)[:, j] for j in nb], 2)
+        vv = torch.cat([img(v)[:, j] for j in nb], 2)
+        o, P = db.sdpa_fwd(img(q)[:, t], kk, vv)
+        _, dkk, dvv = db.sdpa_bwd(img(do)[:, t], img(q)[:, t], kk, vv, P)
+        for i, j in enumerate(nb):
+            want_dk[:, j] += dkk[:, :, i * N:(i + 1) * N]
+            want_dv[:, j] += dvv[:, :, i * N:(i + 1) * N]
+        # statistics the kernels keep per query row: lse over the DEDUPLICATED key set, delta = rowsum(dO O)
+        uniq = sorted(set(nb))
+        s = img(q)[:, t] @ torch.cat([img(k)[:, j] for j in uniq], 2).transpose(-1, -2) * hd ** -0.5
+        P_rows[t] = (torch.logsumexp(s, -1), (img(do)[:, t] * o).sum(-1))
+    tab = neighbour_backward_tables(B, T, rpf, N)
+    got_dk, got_dv = torch.zeros_like(q), torch.zeros_like(v)
+    written = torch.zeros(B * T * rpf, dtype=torch.int32)
+    flat = lambda t: t.permute(1, 0, 2)                                              # (H, rows, hd)
+    for item in range(B * T):
+        ks = slice(int(tab["kv_start"][item]), int(tab["kv_start"][item]) + int(tab["kv_len"][item]))
+        kj, vj = flat(k[ks]), flat(v[ks])
+        dk_j, dv_j = torch.zeros_like(kj), torch.zeros_like(vj)
+        for s0, ln in ((tab["q_start0"][item], tab["q_len0"][item]), (tab["q_start1"][item], tab["q_len1"][item])):
+            if int(ln) == 0:
+                continue
+            qs = slice(int(s0), int(s0) + int(ln))
+            frame = int(s0) // rpf
+            b, t = divmod(frame, T)
+            lse, delta = P_rows[t][0][b], P_rows[t][1][b]                            # (H, N)
+            qq, dd = flat(q[qs]), flat(do[qs])
+            P = torch.exp(qq @ kj.transpose(-1, -2) * hd ** -0.5 - lse[..., None])
+            dS = P * (dd @ vj.transpose(-1, -2) - delta[..., None]) * hd ** -0.5
+            dk_j += dS.transpose(-1, -2) @ qq
+            dv_j += P.transpose(-1, -2) @ dd
+        got_dk[ks] = dk_j.permute(1, 0, 2)
+        got_dv[ks] = dv_j.permute(1, 0, 2)
+        written[ks] += 1
+    assert (written.view(B * T, rpf)[:, 1:] == 1).all() and (written.view(B * T, rpf)[:, 0] == 0).all()
+    assert torch.allclose(img(got_dk), want_dk, rtol=1e-9, atol=1e-10)
+    assert torch.allclose(img(got_dv), want_dv, rtol=1e-9, atol=1e-10)

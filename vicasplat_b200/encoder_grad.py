@@ -160,3 +160,40 @@ def block_forward(x, w, lay: FrameLayout, saved: Optional[Saved] = None):
 
 def block_backward(dout, w, g, lay: FrameLayout, saved: Saved):
     return attn_half_backward(mlp_half_backward(dout, w, g, saved), w, g, lay, saved)
+
+
+# ------------------------------------------------------------------ neighbour attention: backward item tables
+def neighbour_backward_tables(B: int, T: int, rows_per_frame: int, n_img: int, first_img_row: int = 1):
+    """Item tables for the dK / dV pass of CrossNeighborAttention (backbone_vica.py:129-191).
+
+    Forward: query frame t reads the image rows of frames prev(t) = t-1 (t+1 for t = 0) and nxt(t) = t+1
+    (t-1 for t = T-1); when both coincide (end frames, T = 2) the frame is read ONCE -- softmax over a
+    duplicated key set equals softmax over the set, and so does the gradient summed over the copies.
+    A key frame j is therefore read by at most two query frames; dK / dV are computed per KEY frame
+    with those query frames as (up to) two query segments, so every dK / dV row is written exactly once
+    -- no atomics, no accumulation pass.  The softmax statistics (lse, delta) are indexed by absolute
+    query row, each over the query frame's own key set.
+
+    Rows: frame f of scene b starts at (b * T + f) * rows_per_frame; its n_img image rows start
+    `first_img_row` rows later (row 0 is the camera token).  Returns int32 CPU tensors of B * T items:
+    kv_start, kv_len, q_start0, q_len0, q_start1, q_len1."""
+    def prev(t):
+        return t - 1 if t > 0 else t + 1
+
+    def nxt(t):
+        return t + 1 if t < T - 1 else t - 1
+
+    kv_start, q0, l0, q1, l1 = [], [], [], [], []
+    for b in range(B):
+        for j in range(T):
+            readers = [t for t in range(T) if j in {prev(t), nxt(t)}] if T > 1 else []
+            assert len(readers) <= 2
+            row = lambda f: (b * T + f) * rows_per_frame + first_img_row
+            kv_start.append(row(j))
+            q0.append(row(readers[0]) if readers else 0)
+            l0.append(n_img if readers else 0)
+            q1.append(row(readers[1]) if len(readers) > 1 else 0)
+            l1.append(n_img if len(readers) > 1 else 0)
+    i32 = lambda v: torch.tensor(v, dtype=torch.int32)
+    return dict(kv_start=i32(kv_start), kv_len=torch.full((B * T,), n_img, dtype=torch.int32),
+                q_start0=i32(q0), q_len0=i32(l0), q_start1=i32(q1), q_len1=i32(l1))
