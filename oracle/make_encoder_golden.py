@@ -170,6 +170,11 @@ CASES = {
     # name: (EncoderConfig kwargs, B, T, pixel stride of the stored raw_gaussians sample)
     "small": (dict(img_size=64, enc_depth=2, dec_depth=10), 1, 3, 4),
     "full2v": (dict(), 1, 2, 16),
+    # the headline shape of BASELINE.json configs[1] (8 views, full depth): the 2 064-key video attention,
+    # the 8-row blocked-causal camera mask and the two-segment neighbour attention at full size
+    "full8v": (dict(), 1, 8, 16),
+    # two DIFFERENT clips in one batch (cross-scene isolation of every attention / modulation table)
+    "full4v_b2": (dict(), 2, 4, 32),
 }
 
 
@@ -181,7 +186,10 @@ def main():
     from oracle import encoder_ref as er
     out_dir = ROOT / "tests" / "golden"
     out_dir.mkdir(parents=True, exist_ok=True)
+    only = set(sys.argv[1:])                # optional: names of the cases to (re)generate
     for name, (kw, B, T, stride) in CASES.items():
+        if only and name not in only:
+            continue
         cfg = er.EncoderConfig(**kw)
         sd = er.synth_state_dict(cfg, seed=0)
         model = build_reference(cfg)

@@ -81,9 +81,24 @@ def test_small_config_stage_by_stage(cuda, lib):
     assert _rel(g["cov"], rg["covariances"]) < 5e-2
 
 
-@pytest.mark.parametrize("name", ["small", "full2v"])
+def _record(name, errs):
+    """achieved errors -> stdout (pytest -s / -rP) and gpurun_out/encoder_parity_<case>.json"""
+    import json
+    import os
+    print(f"[encoder parity {name}] " + " ".join(f"{k}={v:.3e}" for k, v in errs.items()))
+    out = Path(os.environ.get("GRAFT_REPO_ROOT", Path(__file__).parent.parent)) / "gpurun_out"
+    try:
+        out.mkdir(exist_ok=True)
+        (out / f"encoder_parity_{name}.json").write_text(json.dumps(errs, indent=1))
+    except OSError:
+        pass
+
+
+@pytest.mark.parametrize("name", ["small", "full2v", "full8v", "full4v_b2"])
 def test_forward_matches_reference_golden(cuda, lib, name):
-    """the public plugin call, graph replay path, against vectors from the UNMODIFIED reference."""
+    """the public plugin call, graph replay path, against vectors from the UNMODIFIED reference:
+    toy depth, 2 views, the HEADLINE shape (8 views, 24 + 12 layers, 256 x 256: two-segment neighbour
+    attention, 2 064-key video attention, 8 camera rows) and a batch of two different clips."""
     cfg, model, sd, image, K, s = _build(name, cuda)
     g = np.load(GOLD / f"encoder_{name}.npz")
     for rep in range(2):                                                  # 2nd call = graph replay
@@ -92,19 +107,31 @@ def test_forward_matches_reference_golden(cuda, lib, name):
     assert set(out.keys()) >= {"gaussians", "pred_extrins", "pred_intrins", "raw_gaussians",
                                "gaussian_camera_extrins", "gaussian_camera_intrins",
                                "gaussian_centers", "confidence", "context_view_depths"}
-    assert (out["pred_extrins"] - t("pred_extrins")).abs().max() < 2e-2
-    assert (out["gaussian_camera_extrins"] - t("gaussian_camera_extrins")).abs().max() < 3e-2
     raw = out["raw_gaussians"]
+    gs = out["gaussians"]
+    errs = dict(
+        pred_extrins_abs=(out["pred_extrins"] - t("pred_extrins")).abs().max().item(),
+        c2w_abs=(out["gaussian_camera_extrins"] - t("gaussian_camera_extrins")).abs().max().item(),
+        raw_params_rel=_rel(raw[:, :, ::s, ::s, 3:], t("raw_sub")[..., 3:]),
+        centers_log_rel=_rel(torch.log1p(raw[:, :, ::s, ::s, :3].norm(dim=-1)),
+                             torch.log1p(t("raw_sub")[..., :3].norm(dim=-1))),
+        sh_rel=_rel(gs.harmonics[:, :, ::s, ::s], t("sh_sub")),
+        cov_rel=_rel(gs.covariances[:, :, ::s, ::s], t("cov_sub")),
+        opac_abs_max=(gs.opacities[:, :, ::s, ::s] - t("opac_sub")).abs().max().item(),
+        opac_abs_mean=(gs.opacities[:, :, ::s, ::s] - t("opac_sub")).abs().mean().item())
+    _record(name, errs)
+    assert errs["pred_extrins_abs"] < 2e-2
+    assert errs["c2w_abs"] < 3e-2
     assert raw.shape == (image.shape[0], image.shape[1], cfg.img_size, cfg.img_size, 86)
     _centers_close(raw[:, :, ::s, ::s, :3], t("raw_sub")[..., :3])
-    assert _rel(raw[:, :, ::s, ::s, 3:], t("raw_sub")[..., 3:]) < 3e-2
-    gs = out["gaussians"]
+    # SURVEY §7's bf16 budget: rel-L2 <= 2e-2 on the raw Gaussian parameters
+    assert errs["raw_params_rel"] < 2e-2
     assert gs.means.shape[-1] == 3 and gs.covariances.shape[-2:] == (3, 3)
     assert gs.harmonics.shape[-2:] == (3, 25) and gs.opacities.shape[-1] == 1
-    assert _rel(gs.harmonics[:, :, ::s, ::s], t("sh_sub")) < 3e-2
-    assert _rel(gs.covariances[:, :, ::s, ::s], t("cov_sub")) < 5e-2
-    assert (gs.opacities[:, :, ::s, ::s] - t("opac_sub")).abs().max() < 6e-2
-    assert (gs.opacities[:, :, ::s, ::s] - t("opac_sub")).abs().mean() < 5e-3
+    assert errs["sh_rel"] < 2e-2
+    assert errs["cov_rel"] < 3e-2
+    assert errs["opac_abs_max"] < 6e-2
+    assert errs["opac_abs_mean"] < 5e-3
 
 
 def test_viewspace_depth_and_distill_subset(cuda, lib):
