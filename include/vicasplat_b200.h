@@ -80,6 +80,20 @@ int vs_rope_rows(void* qkv, int64_t ld, int rows, int H, int q_col, int k_col, c
  *   a_row_stride, W is (K, N) with row stride w_row_stride, C[m, n] = sum_k A[k, m] * W[k, n].  This is
  *   the weight-gradient form dW = dY^T X with dY (tokens, N_out) and X (tokens, K_in) used as they
  *   are stored -- no transposed copies (the tensor core reads MN-major shared-memory tiles).
+ * a_mode 3 (conv wgrad): the weight gradient of the a_mode 1 convolution, with the pixels as the
+ *   contraction dimension and no im2col buffer: A = dY, an NHWC bf16 map [cn, ch, cw, a_rows] (pixel
+ *   stride a_row_stride elements; a_rows = Cout); W = X, the convolution's INPUT, described by
+ *   cn/ch/cw/cin/kh/kw/pad/conv_in_h/conv_stride_* exactly as a_mode 1 describes its A operand;
+ *   C[o, tap * cin_pad + c] = sum over pixels of dY[pixel, o] * X[pixel + tap, c]  (N = kh*kw*cin_pad,
+ *   i.e. the packed weight layout of a_mode 1).  Each 64-column block of a W tile is one 4-D TMA box
+ *   of X shifted by its filter tap (out-of-bounds = the zero padding).
+ * c_accumulate != 0: C (fp32) is ACCUMULATED with vectorised atomic adds (red.global.add.v4.f32)
+ *   instead of written: "dW +=" of the weight-gradient GEMMs.  It also enables split-K: the K range is
+ *   cut into split_k parts (0 = chosen so that every SM has work; the wgrad GEMMs have few output
+ *   tiles and a long K) that run as independent tiles.  Needs a plain epilogue (no bias / act / gate
+ *   / residual).
+ * mask_mode: 1 = res2 (bf16) is a ReLU mask: v = res2 > 0 ? v : 0, THEN v += res1; 2 = res1 (bf16) is
+ *   the mask and nothing is added (backward of a ReLU whose output was kept: dpt_block.py:129-135).
  *   res_up2 != 0: res1 is an NHWC bf16 map at HALF resolution [cn, ch/2, cw/2, N] that is
  *   bilinearly upsampled x2 (align_corners=True, dpt_block.py:214-216) on the fly.
  * Output row mapping: out_row = (m / out_gin) * out_gout + out_off + (m % out_gin).
@@ -121,6 +135,10 @@ typedef struct vs_gemm_params {
   const int32_t* rope_pos;            /* (out_rows, 2) int32 or NULL */
   int32_t rope_q_col, rope_k_col, rope_heads;
   float rope_base, rope_cam_theta;
+  int32_t mask_mode;    /* 0 none, 1 res2 masks then res1 is added, 2 res1 masks */
+  int32_t c_accumulate; /* C += result (atomic, fp32 only) */
+  int32_t split_k;      /* with c_accumulate: number of K ranges (0 = choose) */
+  float out_scale;      /* 0 = 1: the accumulator is multiplied by this first (e.g. 1 / keep of a dropout) */
 } vs_gemm_params;
 
 int vs_gemm(const vs_gemm_params* p, vs_stream_t stream);
@@ -185,6 +203,10 @@ int vs_im2col(const void* src, int src_nchw_f32, void* out, int n, int h, int w,
               int stride, int pad, int kpad, vs_stream_t stream);
 /* bilinear x2, align_corners=True, NHWC bf16 (heads/dpt_block.py:214-216) */
 int vs_upsample2x(const void* src, void* dst, int n, int h, int w, int c, vs_stream_t stream);
+/* dst = bilinear_x2(src) + add (add: full-resolution NHWC bf16 map; the image-feature merge of
+ * dpt_gs_head.py:148-150 in its un-fused, training form) */
+int vs_upsample2x_add(const void* src, const void* add, void* dst, int n, int h, int w, int c,
+                      vs_stream_t stream);
 /* ConvTranspose2d with kernel == stride == k, expressed as GEMM output [n*h*w, k*k*c]
  * (column = (dy*k+dx)*c + co) scattered to NHWC [n, h*k, w*k, c] (bf16 -> bf16). */
 int vs_pixel_shuffle(const void* src, void* dst, int n, int h, int w, int c, int k,
@@ -386,7 +408,7 @@ int vs_layernorm_backward(const vs_layernorm_bwd_params* p, vs_stream_t stream);
  * including O and the lse it wrote): dQ, dK, dV (bf16, row matrices like Q / K / V, head h at columns
  * [h*64, h*64+64); they may alias a packed dqkv buffer) from dO.  delta: scratch (q_rows, heads) f32.
  * fwd.max_kv_len must be given.  The key rows of different items must not overlap (dK / dV are
- * written, not accumulated).  Flash-style: scores are recomputed on the tensor cores, no (q, kv)
+ * written, not accumulated) unless the key-centric dkv_* tables below are given.  Flash-style: scores are recomputed on the tensor cores, no (q, kv)
  * matrix is ever stored.  Replaces autograd through croco/blocks.py:105-109. */
 typedef struct vs_attention_bwd_params {
   vs_attention_params fwd;
@@ -395,6 +417,15 @@ typedef struct vs_attention_bwd_params {
   void *dQ, *dK, *dV;
   int64_t lddq, lddk, lddv;
   float* delta;
+  /* Optional KEY-centric item tables for the dK / dV pass (dkv_items > 0).  Needed when key rows are
+   * shared between the forward items (CrossNeighborAttention, backbone_vica.py:173-183: frame j is a
+   * neighbour of up to two query frames): item i = keys [dkv_kv_start[i], + dkv_kv_len[i]) and the
+   * queries of up to two row segments that attended to them; every dK / dV row is written once.  The
+   * statistics (lse, delta) stay indexed by absolute query row.  A key frame that a query frame lists
+   * twice (end frames see their single neighbour twice) must appear ONCE in that query's forward item
+   * (kv_len1 = 0), as vs_attention's callers already do. */
+  int32_t dkv_items, dkv_max_kv_len;
+  const int32_t *dkv_kv_start, *dkv_kv_len, *dkv_q_start0, *dkv_q_len0, *dkv_q_start1, *dkv_q_len1;
 } vs_attention_bwd_params;
 int vs_attention_backward(const vs_attention_bwd_params* p, vs_stream_t stream);
 
@@ -403,6 +434,86 @@ int vs_attention_backward(const vs_attention_bwd_params* p, vs_stream_t stream);
  * rope_2d with fwd = -1 the same way, curope2d.py:24-29). */
 int vs_rope_rows_backward(void* dqkv, int64_t ld, int rows, int H, int q_col, int k_col,
                           const int32_t* pos, float base, float cam_theta, vs_stream_t stream);
+
+/* ------------------------------------------------------------------ decoder / head training path (backward)
+ * MixDecoderBlock (backbone_vica.py:194-335), DPT heads (heads/dpt_block.py:79-229,264-459,
+ * heads/dpt_gs_head.py:98-157) and the per-pixel tails, differentiated by hand; the reference gets these
+ * gradients from torch.autograd.  Contractions run on vs_gemm (dgrad: flipped-tap a_mode 1 / rows mode,
+ * wgrad: a_mode 2 / 3 with c_accumulate), attention on vs_attention_backward. */
+
+/* Backward of h = LN(x) * gamma + beta, modulated per frame: h = h * (1 + scale_f) + shift_f
+ * (vs_layernorm with rows_per_frame; scale == NULL: plain LayerNorm).  dx = dres + dLN/dx for the rows
+ * of every frame except (skip_first) its first row, whose gradient is passed through (dx = dres);
+ * frame_a[f] += sum_rows dh * xhat, frame_b[f] += sum_rows dh (atomics, caller zeroes): vs_adaln_reduce
+ * turns them into d scale / d shift / d gamma / d beta.  x, dx, dres fp32; dh f32 or bf16. */
+typedef struct vs_ln_mod_bwd_params {
+  const float* x;
+  int64_t ldx;
+  const void* dh;
+  int32_t dh_dtype;
+  int64_t lddh;
+  const float* gamma;
+  const float* scale;
+  int64_t mod_ld;
+  const float* dres;
+  int64_t ldres;
+  float* dx;
+  int64_t lddx;
+  float* frame_a;
+  float* frame_b;
+  int64_t frame_ld;
+  int32_t frames, rows_per_frame, skip_first, C;
+  float eps;
+} vs_ln_mod_bwd_params;
+int vs_layernorm_mod_backward(const vs_ln_mod_bwd_params* p, vs_stream_t stream);
+/* dscale[f] = gamma * A_f + beta * B_f, dshift[f] = B_f (written; nullable pair);
+ * dgamma += sum_f (1 + scale_f) A_f, dbeta += sum_f (1 + scale_f) B_f (nullable pair; scale NULL = 0). */
+int vs_adaln_reduce(const float* frame_a, const float* frame_b, int64_t frame_ld, const float* gamma,
+                    const float* beta, const float* scale, int64_t mod_ld, float* dscale, float* dshift,
+                    int64_t dmod_ld, float* dgamma, float* dbeta, int frames, int C, vs_stream_t stream);
+/* Training-forward form of the gated residual: out[row] = x[row] + (1 + gate[row / rows_per_frame]) *
+ * branch[row] (out may alias x; branch bf16 = the projection output the backward pass needs; the
+ * inference path fuses this into the GEMM epilogue).  first_row_mode for the first row of each frame:
+ * 0 as others, 1 no gate, 2 copied unchanged. */
+int vs_gate_residual(const float* x, int64_t ldx, float* out, int64_t ldo, const void* branch, int64_t ldb,
+                     const float* gate, int64_t gate_ld, int64_t rows, int C, int rows_per_frame,
+                     int first_row_mode, vs_stream_t stream);
+/* Backward of the gated residual: dbranch (bf16) = dout * (1 + gate_f) [first rows: mode 1 = dout, mode 2
+ * = 0]; dgate[f] += sum_rows dout * branch (nullable); colsum += column sums of dbranch (the bias gradient
+ * of the projection; nullable).  Atomic accumulation, caller zeroes.  gate == NULL: plain copy + colsum. */
+int vs_gate_backward(const float* dout, int64_t ldd, const void* branch, int64_t ldb, const float* gate,
+                     int64_t gate_ld, void* dbranch, int64_t lddb, float* dgate, int64_t dgate_ld,
+                     float* colsum, int frames, int rows_per_frame, int C, int first_row_mode,
+                     vs_stream_t stream);
+/* dx (=|+=) dy * silu'(x) on fp32 rows (AdaLNModulation.nonlinear, backbone_vica.py:210-212) */
+int vs_silu_backward(const float* x, int64_t ldx, const float* dy, int64_t lddy, float* dx, int64_t lddx,
+                     int rows, int C, int accumulate, vs_stream_t stream);
+/* transpose of vs_upsample2x: dy NHWC bf16 [n, 2h, 2w, c] -> dx [n, h, w, c] */
+int vs_upsample2x_backward(const void* dy, void* dx, int n, int h, int w, int c, vs_stream_t stream);
+/* inverse of vs_pixel_shuffle: NHWC bf16 [n, h*k, w*k, c] -> rows [n*h*w, k*k*c] */
+int vs_pixel_unshuffle(const void* src, void* dst, int n, int h, int w, int c, int k, vs_stream_t stream);
+/* transpose of vs_im2col (NHWC bf16): dcols [n*ho*wo, kpad] -> dx [n, h, w, c], overlapping taps summed */
+int vs_col2im(const void* dcols, void* dx, int n, int h, int w, int c, int k, int stride, int pad, int kpad,
+              vs_stream_t stream);
+/* dx = dy * (y > 0) on bf16 [rows, C] (dx nullable / may alias dy); colsum += column sums (nullable) */
+int vs_relu_backward(const void* dy, int64_t lddy, const void* y, int64_t ldy, void* dx, int64_t lddx,
+                     float* colsum, int64_t rows, int C, vs_stream_t stream);
+/* Backward of vs_pts_tail: d_xyz fp32 rows (leading dimension d_ld) -> d_feat bf16 [px, Cf] (already
+ * masked by feat > 0), dw (3, Cf) and db (3) accumulated. */
+int vs_pts_tail_backward(const void* feat, int Cf, const float* w, const float* b, const float* d_xyz,
+                         int64_t d_ld, void* d_feat, float* dw, float* db, int64_t px, vs_stream_t stream);
+/* Backward of vs_gaussian_adapter: gradients of its outputs (any may be NULL: d_raw (G, 11 + 3 d_sh),
+ * d_means (G,3), d_cov (G,3,3), d_cov6 (G,6), d_shs (G,3,d_sh), d_opac (G)) -> d_src rows in the layout of
+ * `src` (centre columns and the 8 + 3 d_sh parameter columns are WRITTEN, others untouched). */
+int vs_gaussian_adapter_backward(const float* src, int64_t src_ld, int center_col, int param_col, int64_t G,
+                                 int d_sh, const float* sh_mask, const float* d_raw, const float* d_means,
+                                 const float* d_cov, const float* d_cov6, const float* d_shs,
+                                 const float* d_opac, float* d_src, int64_t dsrc_ld, vs_stream_t stream);
+/* Backward of vs_camera_head w.r.t. pred_dq: d_feat (B*T, ldd) written (frame 0 rows = 0), dw (8, C) and
+ * db (8) accumulated. */
+int vs_camera_head_backward(const float* cam_feat, int64_t ld, const float* w, const float* b, int B, int T,
+                            int C, const float* d_pred, float* d_feat, int64_t ldd, float* dw, float* db,
+                            vs_stream_t stream);
 
 #ifdef __cplusplus
 }

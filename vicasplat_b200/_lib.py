@@ -34,6 +34,7 @@ class GemmParams(C.Structure):
         ("out_gin", _i32), ("out_gout", _i32), ("out_off", _i32), ("block_n", _i32),
         ("rope_pos", _vp), ("rope_q_col", _i32), ("rope_k_col", _i32), ("rope_heads", _i32),
         ("rope_base", _f32), ("rope_cam_theta", _f32),
+        ("mask_mode", _i32), ("c_accumulate", _i32), ("split_k", _i32), ("out_scale", _f32),
     ]
 
 
@@ -66,6 +67,15 @@ class LayerNormBwdParams(C.Structure):
     ]
 
 
+class LnModBwdParams(C.Structure):
+    _fields_ = [
+        ("x", _vp), ("ldx", _i64), ("dh", _vp), ("dh_dtype", _i32), ("lddh", _i64),
+        ("gamma", _vp), ("scale", _vp), ("mod_ld", _i64), ("dres", _vp), ("ldres", _i64),
+        ("dx", _vp), ("lddx", _i64), ("frame_a", _vp), ("frame_b", _vp), ("frame_ld", _i64),
+        ("frames", _i32), ("rows_per_frame", _i32), ("skip_first", _i32), ("C", _i32), ("eps", _f32),
+    ]
+
+
 class AttentionParams(C.Structure):
     _fields_ = [
         ("Q", _vp), ("K", _vp), ("V", _vp), ("O", _vp),
@@ -83,6 +93,9 @@ class AttentionBwdParams(C.Structure):
         ("fwd", AttentionParams), ("dO", _vp), ("lddo", _i64),
         ("dQ", _vp), ("dK", _vp), ("dV", _vp), ("lddq", _i64), ("lddk", _i64), ("lddv", _i64),
         ("delta", _vp),
+        ("dkv_items", _i32), ("dkv_max_kv_len", _i32),
+        ("dkv_kv_start", _vp), ("dkv_kv_len", _vp), ("dkv_q_start0", _vp), ("dkv_q_len0", _vp),
+        ("dkv_q_start1", _vp), ("dkv_q_len1", _vp),
     ]
 
 
@@ -119,6 +132,7 @@ STRUCTS = {
     "vs_adamw_params": AdamWParams,
     "vs_layernorm_bwd_params": LayerNormBwdParams,
     "vs_attention_bwd_params": AttentionBwdParams,
+    "vs_ln_mod_bwd_params": LnModBwdParams,
 }
 
 _DECL = re.compile(r"^\s*(?:const\s+char\s*\*|int64_t|int)\s+(vs_\w+)\s*\(", re.M)

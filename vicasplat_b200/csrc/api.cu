@@ -80,6 +80,7 @@ extern "C" int64_t vs_struct_size(const char* name) {
   VS_SZ(vs_adamw_params)
   VS_SZ(vs_layernorm_bwd_params)
   VS_SZ(vs_attention_bwd_params)
+  VS_SZ(vs_ln_mod_bwd_params)
 #undef VS_SZ
   return -1;
 }

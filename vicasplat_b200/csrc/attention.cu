@@ -515,12 +515,10 @@ extern "C" int vs_attention(const vs_attention_params* p, vs_stream_t stream_) {
   const int rem = p->max_q_len % QT;
   a.tail = (rem > 0 && rem <= TAIL_MAX_ROWS && p->max_kv_len > 0 && p->max_kv_len <= TAIL_MAX_KEYS)
                ? rem : 0;
-  static bool configured = false;
-  if (!configured) {
+    VS_CONFIGURE_PER_DEVICE(
     VS_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  SMEM_BYTES));
-    configured = true;
-  }
+  );
   const int main_rows = p->max_q_len - a.tail;
   if (main_rows > 0) {
     dim3 grid(ceil_div(main_rows, QT), p->heads, p->items);

@@ -15,10 +15,11 @@
 //       dV += P^T dO, dK += dS^T Q in TMEM (dO / Q tiles consumed MN-major).
 //   attention_bwd_delta_kernel D[row, head] = sum_d dO . O.
 //
-// Restriction of this version: dK / dV are written, not accumulated, so the key rows of different
-// items must not overlap (true for the ViT encoder's per-frame attention and the decoder's video
-// attention; the neighbour cross-attention shares key frames between items and needs an fp32
-// accumulation pass on top).
+// dK / dV are written, not accumulated, so the key rows of different items of the dK/dV kernel must not
+// overlap.  True for the ViT encoder's per-frame attention and the decoder's video attention with the
+// forward tables; the neighbour cross-attention shares key frames between query frames: there the dK/dV
+// kernel runs over KEY-centric items (one key frame + the up to two query frames that read it as two
+// query segments), so every dK / dV row is still written exactly once -- no atomics, no extra pass.
 #include <cuda.h>
 #include <cuda_bf16.h>
 
@@ -46,6 +47,10 @@ struct BwdDev {
   __nv_bfloat16 *dQ, *dK, *dV;
   long long lddq, lddk, lddv;
   const int *q_start, *q_len, *kv_start0, *kv_len0, *kv_start1, *kv_len1;
+  // item tables of the dK / dV kernel: up to two key segments AND up to two query segments per item
+  // (query-centric items: the forward tables; key-centric items: one key frame + the query frames
+  // that read it, so that every dK / dV row is written exactly once)
+  const int *dk_start0, *dk_len0, *dk_start1, *dk_len1, *dq_start0, *dq_len0, *dq_start1, *dq_len1;
   int causal_block;
   int heads;
   float scale, scale_log2;
@@ -279,14 +284,19 @@ __global__ void __launch_bounds__(BWD_THREADS, 2)
                              const BwdDev a) {
   constexpr int KT = 128, QT = 64;
   const int item = blockIdx.z, head = blockIdx.y, kt = blockIdx.x;
-  const int l0 = a.kv_len0[item], l1 = a.kv_len1 ? a.kv_len1[item] : 0;
+  const int l0 = a.dk_len0[item], l1 = a.dk_len1 ? a.dk_len1[item] : 0;
   const int n0 = (l0 + KT - 1) / KT, n1 = (l1 + KT - 1) / KT;
   if (kt >= n0 + n1) return;
   const bool seg1 = kt >= n0;
-  const int k_row0 = seg1 ? a.kv_start1[item] + (kt - n0) * KT : a.kv_start0[item] + kt * KT;
+  const int k_row0 = seg1 ? a.dk_start1[item] + (kt - n0) * KT : a.dk_start0[item] + kt * KT;
   const int k_valid = min(KT, seg1 ? l1 - (kt - n0) * KT : l0 - kt * KT);
-  const int q0 = a.q_start[item], q_len = a.q_len[item];
-  const int nq = (q_len + QT - 1) / QT;
+  const int qs0 = a.dq_start0[item], ql0 = a.dq_len0[item];
+  const int qs1 = a.dq_start1 ? a.dq_start1[item] : 0, ql1 = a.dq_len1 ? a.dq_len1[item] : 0;
+  const int nq0 = (ql0 + QT - 1) / QT;
+  const int nq = nq0 + (ql1 + QT - 1) / QT;
+  // 64-query tile j: first row, and how many of its rows belong to the segment
+  auto tile_row0 = [&](int j) { return j < nq0 ? qs0 + j * QT : qs1 + (j - nq0) * QT; };
+  auto tile_rows = [&](int j) { return j < nq0 ? ql0 - j * QT : ql1 - (j - nq0) * QT; };
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(
@@ -340,8 +350,8 @@ __global__ void __launch_bounds__(BWD_THREADS, 2)
       for (int j = 0, st = 0, ph = 0; j < nq; ++j) {
         mbar_wait(qd_empty + st, ph ^ 1);
         mbar_expect_tx(qd_full + st, 2 * T64);
-        tma_load_2d(sQ + st * T64, &tmQ, qd_full + st, head * HD, q0 + j * QT);
-        tma_load_2d(sdO + st * T64, &tmdO, qd_full + st, head * HD, q0 + j * QT);
+        tma_load_2d(sQ + st * T64, &tmQ, qd_full + st, head * HD, tile_row0(j));
+        tma_load_2d(sdO + st * T64, &tmdO, qd_full + st, head * HD, tile_row0(j));
         if (++st == STAGES) { st = 0; ph ^= 1; }
       }
     }
@@ -399,8 +409,8 @@ __global__ void __launch_bounds__(BWD_THREADS, 2)
       {
         const int b = (j & 1) * 64;
         const int qi = t & 63;
-        const int qrow = q0 + j * QT + qi;
-        const bool qv = (j * QT + qi) < q_len;
+        const int qrow = tile_row0(j) + qi;
+        const bool qv = qi < tile_rows(j);
         if (t < 64) {
           sL[b + qi] = qv ? a.lse[static_cast<long long>(qrow) * a.heads + head] : INFINITY;
           int lim = qv ? 0x7fffffff : 0;   // queries beyond the item see no key
@@ -573,19 +583,41 @@ extern "C" int vs_attention_backward(const vs_attention_bwd_params* p, vs_stream
   a.kv_len0 = f.kv_len0;
   a.kv_start1 = f.kv_start1;
   a.kv_len1 = f.kv_len1;
+  const bool key_centric = p->dkv_items > 0;
+  if (key_centric) {
+    VS_REQUIRE(p->dkv_kv_start && p->dkv_kv_len && p->dkv_q_start0 && p->dkv_q_len0 && p->dkv_max_kv_len > 0,
+               "vs_attention_backward: key-centric dK/dV tables incomplete");
+    VS_REQUIRE((p->dkv_q_start1 == nullptr) == (p->dkv_q_len1 == nullptr),
+               "vs_attention_backward: dkv_q_start1 / dkv_q_len1 go together");
+    a.dk_start0 = p->dkv_kv_start;
+    a.dk_len0 = p->dkv_kv_len;
+    a.dk_start1 = nullptr;
+    a.dk_len1 = nullptr;
+    a.dq_start0 = p->dkv_q_start0;
+    a.dq_len0 = p->dkv_q_len0;
+    a.dq_start1 = p->dkv_q_start1;
+    a.dq_len1 = p->dkv_q_len1;
+  } else {
+    a.dk_start0 = f.kv_start0;
+    a.dk_len0 = f.kv_len0;
+    a.dk_start1 = f.kv_start1;
+    a.dk_len1 = f.kv_len1;
+    a.dq_start0 = f.q_start;
+    a.dq_len0 = f.q_len;
+    a.dq_start1 = nullptr;
+    a.dq_len1 = nullptr;
+  }
   a.causal_block = f.causal_block;
   a.heads = f.heads;
   a.scale = f.scale;
   a.scale_log2 = f.scale * 1.4426950408889634f;
 
-  static bool configured = false;
-  if (!configured) {
+    VS_CONFIGURE_PER_DEVICE(
     VS_CUDA(cudaFuncSetAttribute(attention_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  DQ_SMEM));
     VS_CUDA(cudaFuncSetAttribute(attention_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  DKV_SMEM));
-    configured = true;
-  }
+  );
   CUtensorMap tmQ, tmdO, tmK, tmV;
   int rc;
   // dQ: 128-row Q / dO boxes, 64-row K / V boxes
@@ -605,8 +637,9 @@ extern "C" int vs_attention_backward(const vs_attention_bwd_params* p, vs_stream
   if ((rc = make_map(&tmV, f.V, f.heads, f.kv_rows, f.ldv, 128))) return rc;
   {
     // upper bound of the 128-key tiles of an item: each of the two segments may end in a partial tile
-    const int tiles = ceil_div(f.max_kv_len, 128) + (f.kv_start1 ? 1 : 0);
-    dim3 grid(tiles, f.heads, f.items);
+    const int tiles = key_centric ? ceil_div(p->dkv_max_kv_len, 128)
+                                  : ceil_div(f.max_kv_len, 128) + (f.kv_start1 ? 1 : 0);
+    dim3 grid(tiles, f.heads, key_centric ? p->dkv_items : f.items);
     attention_bwd_dkv_kernel<<<grid, BWD_THREADS, DKV_SMEM, s>>>(tmQ, tmdO, tmK, tmV, a);
     VS_LAUNCH_CHECK();
   }

@@ -338,14 +338,12 @@ extern "C" int vs_layernorm_backward(const vs_layernorm_bwd_params* p, vs_stream
   VS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int grid = std::min(ceil_div(p->rows, 8), 2 * sms);
   const size_t smem = 2 * 8 * sizeof(float) * p->C;   // <= 64 KB
-  static bool configured = false;
-  if (!configured) {
+    VS_CONFIGURE_PER_DEVICE(
     VS_CUDA(cudaFuncSetAttribute(layernorm_backward_kernel<float>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     VS_CUDA(cudaFuncSetAttribute(layernorm_backward_kernel<__nv_bfloat16>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    configured = true;
-  }
+  );
   cudaStream_t s = to_stream(stream);
   if (p->dy_dtype == VS_F32)
     layernorm_backward_kernel<float><<<grid, 256, smem, s>>>(

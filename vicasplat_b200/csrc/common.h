@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 
@@ -35,6 +36,21 @@ void count_launch();
   do {                             \
     ::vs::count_launch();          \
     VS_CUDA(cudaGetLastError());   \
+  } while (0)
+
+// cudaFuncSetAttribute is PER DEVICE: one-time kernel configuration is keyed by the current device (a
+// bit per device, set after the attributes are in place, so a racing second thread at worst repeats
+// the idempotent calls).
+#define VS_CONFIGURE_PER_DEVICE(...)                                                   \
+  do {                                                                                 \
+    static std::atomic<unsigned long long> vs_done_{0ull};                             \
+    int vs_dev_ = 0;                                                                   \
+    VS_CUDA(cudaGetDevice(&vs_dev_));                                                  \
+    const unsigned long long vs_bit_ = 1ull << (vs_dev_ & 63);                         \
+    if (!(vs_done_.load(std::memory_order_acquire) & vs_bit_)) {                       \
+      __VA_ARGS__                                                                      \
+      vs_done_.fetch_or(vs_bit_, std::memory_order_release);                           \
+    }                                                                                  \
   } while (0)
 
 inline cudaStream_t to_stream(vs_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }

@@ -275,8 +275,8 @@ __global__ void im2col_kernel(const void* __restrict__ src, int nchw_f32, bf16* 
 
 // bilinear x2 align_corners=True on NHWC bf16; one thread per 8 channels of an output pixel;
 // grid = (segments of an output row, output row, image): no 64-bit index arithmetic
-__global__ void upsample2x_kernel(const bf16* __restrict__ src, bf16* __restrict__ dst, int n,
-                                  int h, int w, int c) {
+__global__ void upsample2x_kernel(const bf16* __restrict__ src, const bf16* __restrict__ add,
+                                  bf16* __restrict__ dst, int n, int h, int w, int c) {
   const unsigned c8 = c / 8;
   const int ho = 2 * h, wo = 2 * w;
   const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -296,20 +296,28 @@ __global__ void upsample2x_kernel(const bf16* __restrict__ src, bf16* __restrict
   };
   const uint4 a = ld(y0, x0), b = ld(y0, x1), cq = ld(y1, x0), d = ld(y1, x1);
   uint4 o;
+  const size_t oidx = ((static_cast<size_t>(im) * ho + yo) * wo + xo) * c + cc * 8;
+  uint4 e = make_uint4(0u, 0u, 0u, 0u);
+  if (add != nullptr) e = __ldg(reinterpret_cast<const uint4*>(add + oidx));
   const uint32_t* pa = &a.x; const uint32_t* pb = &b.x; const uint32_t* pc = &cq.x;
-  const uint32_t* pd = &d.x; uint32_t* po = &o.x;
+  const uint32_t* pd = &d.x; const uint32_t* pe = &e.x; uint32_t* po = &o.x;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const float2 fa = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(pa + j));
     const float2 fb = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(pb + j));
     const float2 fc = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(pc + j));
     const float2 fd = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(pd + j));
-    const __nv_bfloat162 r2 =
+    __nv_bfloat162 r2 =
         __floats2bfloat162_rn(w00 * fa.x + w01 * fb.x + w10 * fc.x + w11 * fd.x,
                               w00 * fa.y + w01 * fb.y + w10 * fc.y + w11 * fd.y);
+    if (add != nullptr) {   // the upsampled map is rounded to bf16 first, like the fused GEMM epilogue does
+      const float2 fu = __bfloat1622float2(r2);
+      const float2 fe = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(pe + j));
+      r2 = __floats2bfloat162_rn(fu.x + fe.x, fu.y + fe.y);
+    }
     po[j] = *reinterpret_cast<const uint32_t*>(&r2);
   }
-  *reinterpret_cast<uint4*>(dst + ((static_cast<size_t>(im) * ho + yo) * wo + xo) * c + cc * 8) = o;
+  *reinterpret_cast<uint4*>(dst + oidx) = o;
 }
 
 __global__ void pixel_shuffle_kernel(const bf16* __restrict__ src, bf16* __restrict__ dst, int n,
@@ -919,7 +927,20 @@ extern "C" int vs_upsample2x(const void* src, void* dst, int n, int h, int w, in
   VS_REQUIRE(2 * h <= 65535 && n <= 65535, "upsample2x: map too large for the launch grid");
   dim3 grid(blocks_for(static_cast<long long>(2 * w) * (c / 8), 256), 2 * h, n);
   upsample2x_kernel<<<grid, 256, 0, to_stream(stream)>>>(
-      static_cast<const bf16*>(src), static_cast<bf16*>(dst), n, h, w, c);
+      static_cast<const bf16*>(src), nullptr, static_cast<bf16*>(dst), n, h, w, c);
+  VS_LAUNCH_CHECK();
+  return VS_OK;
+}
+
+extern "C" int vs_upsample2x_add(const void* src, const void* add, void* dst, int n, int h, int w, int c,
+                                 vs_stream_t stream) {
+  VS_REQUIRE(src && add && dst, "upsample2x_add: null tensor");
+  VS_REQUIRE(c % 8 == 0, "upsample2x_add: channels must be a multiple of 8");
+  if (static_cast<long long>(n) * h * w == 0) return VS_OK;
+  VS_REQUIRE(2 * h <= 65535 && n <= 65535, "upsample2x_add: map too large for the launch grid");
+  dim3 grid(blocks_for(static_cast<long long>(2 * w) * (c / 8), 256), 2 * h, n);
+  upsample2x_kernel<<<grid, 256, 0, to_stream(stream)>>>(
+      static_cast<const bf16*>(src), static_cast<const bf16*>(add), static_cast<bf16*>(dst), n, h, w, c);
   VS_LAUNCH_CHECK();
   return VS_OK;
 }
@@ -1013,11 +1034,9 @@ extern "C" int vs_gaussian_adapter(const float* src, int64_t src_ld, int center_
   VS_REQUIRE(d_sh >= 0 && d_sh <= 49, "gaussian_adapter: d_sh out of range");
   const int raw_w = 11 + 3 * d_sh;
   const size_t smem = (static_cast<size_t>((AD_G * raw_w + 3) & ~3) + AD_G * 26) * sizeof(float);
-  static bool configured = false;
-  if (!configured) {
+    VS_CONFIGURE_PER_DEVICE(
     VS_CUDA(cudaFuncSetAttribute(adapter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    configured = true;
-  }
+  );
   adapter_kernel<<<blocks_for(G, AD_G), AD_THREADS, smem, to_stream(stream)>>>(
       src, src_ld, center_col, param_col, G, d_sh, sh_mask, raw_out, means, cov, cov6, sh, opac,
       scales, rot);

@@ -24,6 +24,7 @@
 // and every stride-1 nn.Conv2d in heads/dpt_block.py:79-229,264-459, heads/dpt_gs_head.py:98-157.
 #include <cuda.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <cuda_bf16.h>
@@ -52,9 +53,15 @@ enum : int {  // vector-access flags, decided on the host from pointer / stride 
 struct GemmDev {
   int mode;
   int tn;   // rows mode with both operands stored [k][mn] (MN-major): the wgrad form
+  int wg;   // tn with both operands addressed as NHWC maps (conv wgrad): k-block = 64-pixel box
+  int cin_pad;
   int N;
   int num_kb;
   int m_tiles, n_tiles;
+  int splits, kb_per_split;   // split-K: unit = (split, n tile, m group); needs the atomic epilogue
+  int atomic;                 // C += (red.global.add) instead of C =
+  int mask_mode;              // 0 none, 1 res2 masks then + res1, 2 res1 masks (bf16 residual kinds)
+  float out_scale;
   // rows mode
   int a_rows, a_groups, tiles_per_group;
   // conv mode
@@ -147,6 +154,7 @@ struct TileCoord {
   int n0;
   int grp, r0;          // rows mode
   int x0, y0, img0;     // conv mode
+  int kb0, kb1;         // k-block range of this unit (split-K)
 };
 
 // work unit u of a cluster -> tile of CTA `rank`: units enumerate (n tile, group of CL m tiles),
@@ -155,6 +163,15 @@ struct TileCoord {
 __device__ __forceinline__ TileCoord tile_coord(const GemmDev& g, int u, int rank, int CL, int BN) {
   TileCoord c{};
   const int m_groups = (g.m_tiles + CL - 1) / CL;
+  c.kb0 = 0;
+  c.kb1 = g.num_kb;
+  if (g.splits > 1) {
+    const int per = m_groups * g.n_tiles;
+    const int sp = u / per;
+    u -= sp * per;
+    c.kb0 = sp * g.kb_per_split;
+    c.kb1 = min(g.num_kb, c.kb0 + g.kb_per_split);
+  }
   const int nt = u / m_groups;
   const int mt = (u - nt * m_groups) * CL + rank;
   c.n0 = nt * BN;
@@ -280,6 +297,19 @@ __device__ __forceinline__ void fma_bf16x4(float4& f, const float w, const uint2
   f.x = fmaf(w, a.x, f.x); f.y = fmaf(w, a.y, f.y); f.z = fmaf(w, b.x, f.z); f.w = fmaf(w, b.y, f.w);
 }
 
+// ReLU mask from the kept (post-ReLU, bf16) output: v = m > 0 ? v : 0
+__device__ __forceinline__ void mask_bf16x4(float4& f, const uint2 t) {
+  // positive <=> sign bit clear and magnitude non-zero
+  if (((t.x & 0x8000u) != 0u) || ((t.x & 0x7fffu) == 0u)) f.x = 0.f;
+  if (((t.x & 0x80000000u) != 0u) || ((t.x & 0x7fff0000u) == 0u)) f.y = 0.f;
+  if (((t.y & 0x8000u) != 0u) || ((t.y & 0x7fffu) == 0u)) f.z = 0.f;
+  if (((t.y & 0x80000000u) != 0u) || ((t.y & 0x7fff0000u) == 0u)) f.w = 0.f;
+}
+__device__ __forceinline__ void red_add_f4(float* p, const float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+
 struct Up2Taps { int x0, x1, y0, y1; float lx, ly; };
 // bilinear x2, align_corners=True: source taps / weights of output pixel (x, y) of a ch x cw map
 __device__ __forceinline__ Up2Taps up2_taps(int x, int y, int ch, int cw, float sx, float sy) {
@@ -382,8 +412,15 @@ __device__ __forceinline__ void epi_store(const GemmDev& g, const uint32_t (&lds
         t.x += __uint_as_float(rb[j].x); t.y += __uint_as_float(rb[j].y);
         t.z += __uint_as_float(rb[j].z); t.w += __uint_as_float(rb[j].w);
       } else if (RK == 2) {
-        add_bf16x4(t, make_uint2(rb[j].x, rb[j].y));
-        add_bf16x4(t, make_uint2(rb[j].z, rb[j].w));
+        if (g.mask_mode == 0) {
+          add_bf16x4(t, make_uint2(rb[j].x, rb[j].y));
+          add_bf16x4(t, make_uint2(rb[j].z, rb[j].w));
+        } else if (g.mask_mode == 1) {
+          mask_bf16x4(t, make_uint2(rb[j].z, rb[j].w));
+          add_bf16x4(t, make_uint2(rb[j].x, rb[j].y));
+        } else {
+          mask_bf16x4(t, make_uint2(rb[j].x, rb[j].y));
+        }
       } else if (RK == 3) {
         const float lx = lxs[j4], ly = lys[j4];
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -404,8 +441,12 @@ __device__ __forceinline__ void epi_store(const GemmDev& g, const uint32_t (&lds
 #pragma unroll
       for (int j4 = 0; j4 < 4; ++j4) {
         const long long o = oj[jh + j4];
-        if (CF32) *reinterpret_cast<float4*>(cf + o * g.ldc) = tv[j4];
-        else store4_bf16(cb + o * g.ldc, 4, true, tv[j4], false);
+        if (CF32) {
+          if (g.atomic) red_add_f4(cf + o * g.ldc, tv[j4]);
+          else *reinterpret_cast<float4*>(cf + o * g.ldc) = tv[j4];
+        } else {
+          store4_bf16(cb + o * g.ldc, 4, true, tv[j4], false);
+        }
       }
       if (c2 != nullptr) {
 #pragma unroll
@@ -417,8 +458,12 @@ __device__ __forceinline__ void epi_store(const GemmDev& g, const uint32_t (&lds
       for (int j4 = 0; j4 < 4; ++j4) {
         const int j = jh + j4;
         if (oj[j] >= 0) {
-          if (CF32) *reinterpret_cast<float4*>(cf + static_cast<long long>(oj[j]) * g.ldc) = tv[j4];
-          else store4_bf16(cb + static_cast<long long>(oj[j]) * g.ldc, 4, true, tv[j4], false);
+          if (CF32) {
+            if (g.atomic) red_add_f4(cf + static_cast<long long>(oj[j]) * g.ldc, tv[j4]);
+            else *reinterpret_cast<float4*>(cf + static_cast<long long>(oj[j]) * g.ldc) = tv[j4];
+          } else {
+            store4_bf16(cb + static_cast<long long>(oj[j]) * g.ldc, 4, true, tv[j4], false);
+          }
           if (c2 != nullptr) store4_bf16(c2 + static_cast<long long>(oj[j]) * g.ldc2, 4, true, tv[j4], true);
         }
       }
@@ -454,7 +499,7 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int rank = CL > 1 ? static_cast<int>(cluster_ctarank()) : 0;
-  const int total_units = ((g.m_tiles + CL - 1) / CL) * g.n_tiles;
+  const int total_units = ((g.m_tiles + CL - 1) / CL) * g.n_tiles * g.splits;
   const int unit0 = blockIdx.x / CL, unit_step = gridDim.x / CL;
   constexpr uint16_t PAIR_MASK = 3;
 
@@ -496,13 +541,37 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
       uint32_t it = 0;  // k-block counter across tiles (ring position)
       for (int u = unit0; u < total_units; u += unit_step) {
         const TileCoord tc = tile_coord(g, u, rank, CL, BN);
-        for (int kb = 0; kb < g.num_kb; ++kb, ++it) {
+        for (int kb = tc.kb0; kb < tc.kb1; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(&empty[s], ph ^ 1);
           uint8_t* sA = smem + s * STAGE_BYTES;
           uint8_t* sB = sA + A_BYTES;
-          if (g.tn) {
+          if (g.wg) {
+            // conv wgrad: the k-block is a 64-pixel box (bw x bh x bn) of both NHWC maps; every
+            // 64-column block of the W tile is the input map shifted by that block's filter tap
+            const int tx = kb % g.tiles_x;
+            const int ty = (kb / g.tiles_x) % g.tiles_y;
+            const int x0 = tx * g.bw, y0 = ty * g.bh, img0 = (kb / (g.tiles_x * g.tiles_y)) * g.bn;
+            if (CL == 1) mbar_expect_tx(&full[s], STAGE_BYTES);
+            else if (rank == 0) mbar_expect_tx(&full[s], 2 * STAGE_BYTES);
+#pragma unroll
+            for (int i = 0; i < BM / 64; ++i) {
+              if (CL == 1) tma_load_4d(sA + i * 8192, &tmA, &full[s], tc.r0 + i * 64, x0, y0, img0);
+              else tma_load_4d_pair(sA + i * 8192, &tmA, &full[s], tc.r0 + i * 64, x0, y0, img0);
+            }
+#pragma unroll
+            for (int i = 0; i < (BN / CL) / 64; ++i) {
+              const int col = tc.n0 + rank * (BN / CL) + i * 64;
+              const int tap = col / g.cin_pad;
+              const int c0 = col - tap * g.cin_pad;
+              const int dy = tap / g.kw, dx = tap - dy * g.kw;
+              if (CL == 1)
+                tma_load_4d(sB + i * 8192, &tmW, &full[s], c0, x0 + dx - g.pad, y0 + dy - g.pad, img0);
+              else
+                tma_load_4d_pair(sB + i * 8192, &tmW, &full[s], c0, x0 + dx - g.pad, y0 + dy - g.pad, img0);
+            }
+          } else if (g.tn) {
             // MN-major operands: one [64 k-rows][64 mn] box (8 KB) per 64-wide block of the tile
             if (CL == 1) {
               mbar_expect_tx(&full[s], STAGE_BYTES);
@@ -561,7 +630,8 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
         mbar_wait(&tmem_empty[a], ((ti >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + a * BN;
-        for (int kb = 0; kb < g.num_kb; ++kb, ++it) {
+        const TileCoord tcm = tile_coord(g, u, 0, CL, BN);
+        for (int kb = tcm.kb0; kb < tcm.kb1; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(&full[s], ph);
@@ -573,18 +643,18 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
             for (int k = 0; k < BK / 16; ++k) {   // 16 k-rows of 128 B per step
               const uint64_t da = umma_desc_mn_sw128_lbo(a_addr + k * 2048, 8192);
               const uint64_t db = umma_desc_mn_sw128_lbo(b_addr + k * 2048, 8192);
-              if (CL == 1) umma_bf16_ss(d_tmem, da, db, idesc_tn, (kb | k) != 0 ? 1u : 0u);
-              else umma_bf16_ss_pair(d_tmem, da, db, idesc_tn, (kb | k) != 0 ? 1u : 0u);
+              if (CL == 1) umma_bf16_ss(d_tmem, da, db, idesc_tn, (kb != tcm.kb0 || k != 0) ? 1u : 0u);
+              else umma_bf16_ss_pair(d_tmem, da, db, idesc_tn, (kb != tcm.kb0 || k != 0) ? 1u : 0u);
             }
           } else {
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             if (CL == 1)
               umma_bf16_ss(d_tmem, umma_desc_k_sw128(a_addr + k * 32),
-                           umma_desc_k_sw128(b_addr + k * 32), idesc, (kb | k) != 0 ? 1u : 0u);
+                           umma_desc_k_sw128(b_addr + k * 32), idesc, (kb != tcm.kb0 || k != 0) ? 1u : 0u);
             else
               umma_bf16_ss_pair(d_tmem, umma_desc_k_sw128(a_addr + k * 32),
-                                umma_desc_k_sw128(b_addr + k * 32), idesc, (kb | k) != 0 ? 1u : 0u);
+                                umma_desc_k_sw128(b_addr + k * 32), idesc, (kb != tcm.kb0 || k != 0) ? 1u : 0u);
           }
           }
           // slot reusable (in both CTAs of a pair) once these MMAs have read it
@@ -694,6 +764,10 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
         float f[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+        if (g.out_scale != 1.0f) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) f[i] *= g.out_scale;
+        }
         if (g.bias != nullptr) {
           float b[32];
           load32_f32(g.bias + nb, nv, g.vec & VEC_BIAS, b);
@@ -790,12 +864,27 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
             if (g.res1 != nullptr && g.res_up2) {
               add4_res_up2(static_cast<const __nv_bfloat16*>(g.res1), g.res_ld, pim, px, py, g.ch, g.cw,
                            col, nvl, g.vec & VEC_RES, t);
+            } else if (g.res1 != nullptr && g.mask_mode != 0) {
+              // ReLU mask (bf16 maps): mode 1 masks with res2 and adds res1, mode 2 masks with res1
+              const __nv_bfloat16* mk = static_cast<const __nv_bfloat16*>(g.mask_mode == 1 ? g.res2 : g.res1) +
+                                        o * g.res_ld + col;
+              if (nvl > 0 && !(__bfloat162float(mk[0]) > 0.f)) t.x = 0.f;
+              if (nvl > 1 && !(__bfloat162float(mk[1]) > 0.f)) t.y = 0.f;
+              if (nvl > 2 && !(__bfloat162float(mk[2]) > 0.f)) t.z = 0.f;
+              if (nvl > 3 && !(__bfloat162float(mk[3]) > 0.f)) t.w = 0.f;
+              if (g.mask_mode == 1) add4_res(g.res1, g.res_dtype, o * g.res_ld + col, nvl, false, t);
             } else if (g.res1 != nullptr) {
               add4_res(g.res1, g.res_dtype, o * g.res_ld + col, nvl, g.vec & VEC_RES, t);
               if (g.res2 != nullptr)
                 add4_res(g.res2, g.res_dtype, o * g.res_ld + col, nvl, g.vec & VEC_RES, t);
             }
-            if (g.C != nullptr) {
+            if (g.C != nullptr && g.atomic) {
+              float* cp = static_cast<float*>(g.C) + o * g.ldc + col;
+              if (nvl > 0) atomicAdd(cp + 0, t.x);
+              if (nvl > 1) atomicAdd(cp + 1, t.y);
+              if (nvl > 2) atomicAdd(cp + 2, t.z);
+              if (nvl > 3) atomicAdd(cp + 3, t.w);
+            } else if (g.C != nullptr) {
               if (g.c_dtype == VS_F32)
                 store4_f32(static_cast<float*>(g.C) + o * g.ldc + col, nvl, g.vec & VEC_C, t);
               else
@@ -854,12 +943,10 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmW, const GemmDev& g, cud
                        2 * EPI_WARPS * 4096 /*epilogue transposition tiles + residual staging*/;
   static_assert(SMEM <= 227 * 1024, "shared memory budget");
   auto kernel = gemm_tc05_kernel<BN, STAGES, EPI_WARPS, CL>;
-  static bool configured = false;  // attribute is per-function, set once per process
-  if (!configured) {
+    VS_CONFIGURE_PER_DEVICE(
     VS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-    configured = true;
-  }
-  const int units = ceil_div(g.m_tiles, CL) * g.n_tiles;
+  );
+  const int units = ceil_div(g.m_tiles, CL) * g.n_tiles * g.splits;
   const int slots = num_sms() / CL;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(static_cast<unsigned>((units < slots ? units : slots) * CL));
@@ -909,7 +996,21 @@ extern "C" int vs_gemm(const vs_gemm_params* p, vs_stream_t stream_) {
   cudaStream_t stream = to_stream(stream_);
 
   GemmDev g{};
-  g.mode = p->a_mode == 2 ? 0 : p->a_mode;   // a_mode 2 = rows mode with MN-major operands (g.tn)
+  // a_mode 2 / 3 = rows mode with MN-major operands (g.tn); 3 addresses both through NHWC maps (g.wg)
+  g.mode = (p->a_mode == 2 || p->a_mode == 3) ? 0 : p->a_mode;
+  g.splits = 1;
+  g.atomic = p->c_accumulate != 0;
+  g.mask_mode = p->mask_mode;
+  g.out_scale = p->out_scale == 0.f ? 1.0f : p->out_scale;
+  VS_REQUIRE(p->mask_mode >= 0 && p->mask_mode <= 2, "vs_gemm: mask_mode must be 0, 1 or 2");
+  VS_REQUIRE(p->mask_mode == 0 || (p->res1 && p->res_dtype == VS_BF16 && !p->res_up2 &&
+                                   (p->mask_mode == 2 ? p->res2 == nullptr : p->res2 != nullptr)),
+             "vs_gemm: mask_mode needs bf16 maps (mode 1: res1 + mask res2; mode 2: mask res1 only)");
+  VS_REQUIRE(!p->c_accumulate || (p->c_dtype == VS_F32 && p->C && !p->bias && p->act == VS_ACT_NONE &&
+                                  !p->gate && !p->res1 && !p->C2 && !p->rope_pos),
+             "vs_gemm: c_accumulate needs an fp32 C and a plain epilogue");
+  VS_REQUIRE(p->split_k >= 0 && (p->split_k <= 1 || p->c_accumulate),
+             "vs_gemm: split_k needs c_accumulate");
   g.N = p->N;
   g.bias = p->bias;
   g.act = p->act;
@@ -1048,6 +1149,63 @@ extern "C" int vs_gemm(const vs_gemm_params* p, vs_stream_t stream_) {
     cuuint32_t box[2] = {64, BK};
     int rc = encode_map(&tmA, p->A, 2, dims, str, box);
     if (rc) return rc;
+  } else if (p->a_mode == 3) {
+    // conv wgrad: A = dY NHWC [cn, ch, cw, a_rows], W = X (the conv's input view); K = pixels
+    VS_REQUIRE(p->a_rows > 0 && p->cn > 0 && p->ch > 0 && p->cw > 0 && p->cin > 0, "vs_gemm: empty conv wgrad");
+    VS_REQUIRE(p->cin % 8 == 0 && p->a_row_stride % 8 == 0 && p->a_row_stride >= p->a_rows,
+               "vs_gemm: conv wgrad: cin and the dY pixel stride must be multiples of 8");
+    VS_REQUIRE(p->kh > 0 && p->kw > 0 && p->pad >= 0, "vs_gemm: bad conv kernel");
+    VS_REQUIRE(p->rope_pos == nullptr && p->out_gin == 0, "vs_gemm: a_mode 3 goes with a plain output mapping");
+    g.tn = 1;
+    g.wg = 1;
+    g.a_rows = p->a_rows;
+    g.a_groups = 1;
+    g.tiles_per_group = ceil_div(p->a_rows, BM);
+    m_tiles = g.tiles_per_group;
+    g.cn = p->cn;
+    g.ch = p->ch;
+    g.cw = p->cw;
+    g.kw = p->kw;
+    g.pad = p->pad;
+    g.cin_pad = ceil_div(p->cin, BK) * BK;
+    VS_REQUIRE(p->N == p->kh * p->kw * g.cin_pad, "vs_gemm: conv wgrad: N must be kh * kw * round_up(cin, 64)");
+    int bw = 1;
+    while (bw < 8 && bw < p->cw) bw <<= 1;
+    int bh = 1;
+    while (bw * bh < BK && bh < p->ch) bh <<= 1;
+    const int bn = BK / (bw * bh);
+    g.bw = bw;
+    g.bh = bh;
+    g.bn = bn;
+    g.tiles_x = ceil_div(p->cw, bw);
+    g.tiles_y = ceil_div(p->ch, bh);
+    ktot = static_cast<long long>(g.tiles_x) * g.tiles_y * ceil_div(p->cn, bn) * BK;
+    {
+      cuuint64_t dims[4] = {static_cast<cuuint64_t>(p->a_rows), static_cast<cuuint64_t>(p->cw),
+                            static_cast<cuuint64_t>(p->ch), static_cast<cuuint64_t>(p->cn)};
+      const cuuint64_t sx = static_cast<cuuint64_t>(p->a_row_stride);
+      cuuint64_t str[3] = {sx * 2, sx * p->cw * 2, sx * p->cw * p->ch * 2};
+      cuuint32_t box[4] = {64, static_cast<cuuint32_t>(bw), static_cast<cuuint32_t>(bh),
+                           static_cast<cuuint32_t>(bn)};
+      int rc = encode_map(&tmA, p->A, 4, dims, str, box);
+      if (rc) return rc;
+    }
+    {
+      const long long in_h = p->conv_in_h > 0 ? p->conv_in_h : p->ch;
+      const long long sx = p->conv_stride_x > 0 ? p->conv_stride_x : p->cin;
+      const long long sy = p->conv_stride_y > 0 ? p->conv_stride_y : sx * p->cw;
+      const long long sn = p->conv_stride_n > 0 ? p->conv_stride_n : sy * in_h;
+      VS_REQUIRE(sx % 8 == 0 && sy % 8 == 0 && sn % 8 == 0,
+                 "vs_gemm: conv strides must be multiples of 8 elements");
+      cuuint64_t dims[4] = {static_cast<cuuint64_t>(p->cin), static_cast<cuuint64_t>(p->cw),
+                            static_cast<cuuint64_t>(in_h), static_cast<cuuint64_t>(p->cn)};
+      cuuint64_t str[3] = {static_cast<cuuint64_t>(sx) * 2, static_cast<cuuint64_t>(sy) * 2,
+                           static_cast<cuuint64_t>(sn) * 2};
+      cuuint32_t box[4] = {64, static_cast<cuuint32_t>(bw), static_cast<cuuint32_t>(bh),
+                           static_cast<cuuint32_t>(bn)};
+      int rc = encode_map(&tmW, p->W, 4, dims, str, box);
+      if (rc) return rc;
+    }
   } else {
     set_error("vs_gemm: unknown a_mode %d", p->a_mode);
     return VS_ERR_INVALID;
@@ -1070,7 +1228,19 @@ extern "C" int vs_gemm(const vs_gemm_params* p, vs_stream_t stream_) {
   g.n_tiles = ceil_div(p->N, bn);
   // vertically adjacent tiles are computed by a CTA pair that splits the W tile (see header)
   const int cl = (bn >= 128 && m_tiles >= 2) ? 2 : 1;
-  if (g.tn) {
+  if (g.atomic) {
+    // split-K: the wgrad GEMMs have few output tiles and a long K (tokens / pixels)
+    const int units = ceil_div(m_tiles, cl) * g.n_tiles;
+    const int slots = num_sms() / cl;
+    int splits = p->split_k;
+    if (splits <= 0) splits = units >= slots ? 1 : (2 * slots) / units;
+    splits = std::max(1, std::min(splits, g.num_kb / 4 > 0 ? g.num_kb / 4 : 1));
+    g.kb_per_split = ceil_div(g.num_kb, splits);
+    g.splits = ceil_div(g.num_kb, g.kb_per_split);
+  }
+  if (g.wg) {
+    // tmW was built with the A map above
+  } else if (g.tn) {
     cuuint64_t dims[2] = {static_cast<cuuint64_t>(p->N), static_cast<cuuint64_t>(ktot)};
     cuuint64_t str[1] = {static_cast<cuuint64_t>(p->w_row_stride) * 2};
     cuuint32_t box[2] = {64, BK};

@@ -624,14 +624,12 @@ int launch_tile_sorts(const Workspace& ws, int n_tiles, int key_bits, int id_bit
                       cudaStream_t stream) {
   const int smem_small = static_cast<int>(sort_smem_bytes<8>());
   const int smem_large = static_cast<int>(sort_smem_bytes<32>());
-  static bool configured = false;
-  if (!configured) {
+    VS_CONFIGURE_PER_DEVICE(
     VS_CUDA(cudaFuncSetAttribute(tile_sort_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  smem_small));
     VS_CUDA(cudaFuncSetAttribute(tile_sort_large_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  smem_large));
-    configured = true;
-  }
+  );
   tile_sort_small_kernel<<<n_tiles, SORT_THREADS, smem_small, stream>>>(
       ws.ranges, ws.keys_in, ws.vals_out, key_bits, id_bits, max_cap);
   VS_LAUNCH_CHECK();

@@ -18,9 +18,11 @@
 
 namespace vs {
 
-// raw = (x, y, z | o | s0, s1, s2 | qx, qy, qz, qw); d_cov6 = dL/d(xx, xy, xz, yy, yz, zz)
-VS_HD void adapter_backward_one(const float* raw, const float* d_means, const float* d_cov6,
-                                float d_opac, float* d_raw) {
+// raw = (x, y, z | o | s0, s1, s2 | qx, qy, qz, qw); G = dL/d covariance as ANY 3x3 matrix (a packed
+// upper-triangle gradient is the upper-triangular G, a full-matrix gradient is G itself): only
+// G + G^T enters.
+VS_HD void adapter_backward_general(const float* raw, const float* d_means, const float* G,
+                                    float d_opac, float* d_raw) {
   d_raw[0] = d_means[0]; d_raw[1] = d_means[1]; d_raw[2] = d_means[2];
   // opacity = sigmoid(o)
   const float op = 1.0f / (1.0f + expf(-raw[3]));
@@ -43,8 +45,7 @@ VS_HD void adapter_backward_one(const float* raw, const float* d_means, const fl
                       i * k - j * r, j * k + i * r, -(i * i + j * j)};
   float R[9];
   for (int a = 0; a < 9; ++a) R[a] = sq * A[a] + ((a == 0 || a == 4 || a == 8) ? 1.0f : 0.0f);
-  // covariance = R diag(sc^2) R^T;  G = upper-triangular matrix of d_cov6
-  const float G[9] = {d_cov6[0], d_cov6[1], d_cov6[2], 0.f, d_cov6[3], d_cov6[4], 0.f, 0.f, d_cov6[5]};
+  // covariance = R diag(sc^2) R^T
   float GR[9], GtR[9];   // G R and G^T R
   for (int a = 0; a < 3; ++a)
     for (int b = 0; b < 3; ++b) {
@@ -81,6 +82,13 @@ VS_HD void adapter_backward_one(const float* raw, const float* d_means, const fl
   }
   // through the normalisation r / |r|
   for (int a = 0; a < 4; ++a) d_raw[7 + a] = (dq[a] - q[a] * dot) / n;
+}
+
+// d_cov6 = dL/d(xx, xy, xz, yy, yz, zz): the packed upper triangle vs_raster_backward writes
+VS_HD void adapter_backward_one(const float* raw, const float* d_means, const float* d_cov6,
+                                float d_opac, float* d_raw) {
+  const float G[9] = {d_cov6[0], d_cov6[1], d_cov6[2], 0.f, d_cov6[3], d_cov6[4], 0.f, 0.f, d_cov6[5]};
+  adapter_backward_general(raw, d_means, G, d_opac, d_raw);
 }
 
 // xyz = x / max(|x|, 1e-8) * expm1(|x|)

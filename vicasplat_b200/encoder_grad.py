@@ -89,7 +89,7 @@ def linear_backward(dy, x, w_t, dW, *, dx_dtype=torch.float32):
     """dgrad + wgrad of one linear layer (see module docstring).
     dy (M, N) bf16, x (M, K) bf16 (the layer's input as saved by the forward pass), w_t (K, N) bf16,
     dW (N, K) fp32 accumulated in place."""
-    ops.gemm(dy, x, tn=True, out=dW, res1=dW)                  # dW += dy^T x
+    ops.gemm_tn_acc(dy, x, dW)                                 # dW += dy^T x (split-K over the tokens)
     return ops.gemm(dy, w_t, out_dtype=dx_dtype)               # dx = dy W
 
 

@@ -94,7 +94,8 @@ def gemm(A, W, *, N=None, K=None, a_rows=None, a_groups=1, a_row_stride=None, a_
 
 
 def conv_gemm(x_nhwc, Wp, *, kh, kw, pad, N, bias=None, act=VS_ACT_NONE, res1=None, res2=None,
-              out=None, out_dtype=torch.bfloat16, out2=None, block_n=0, res_up2=False, view=None):
+              out=None, out_dtype=torch.bfloat16, out2=None, block_n=0, res_up2=False, view=None,
+              out_gin=0, out_gout=0, out_off=0):
     """Stride-1 kh x kw convolution on an NHWC bf16 map as an implicit GEMM (conv mode of vs_gemm).
     Wp: packed weights (N, kh*kw*cin_pad) bf16, tap-major / channel-minor.
     view = (n, out_h, out_w, cin, in_h, stride_x, stride_y, stride_n): explicit (possibly
@@ -118,14 +119,20 @@ def conv_gemm(x_nhwc, Wp, *, kh, kw, pad, N, bias=None, act=VS_ACT_NONE, res1=No
     if out2 is not None:
         p.C2, p.ldc2 = ptr(out2), out2.stride(-2)
     p.block_n = block_n
+    p.out_gin, p.out_gout, p.out_off = out_gin, out_gout, out_off   # pixel rows -> grouped output rows
     with _timed("gemm", (f"conv{kh}x{kw}", n * h * w, N, kh * kw * ((cin + 63) // 64 * 64), act,
                          res1 is not None, out.dtype == torch.float32)):
         check(lib.vs_gemm(C.byref(p), C.c_void_p(stream_ptr())), "vs_gemm(conv)")
     return out
 
 
+_EXTRA = None   # mask_mode / out_scale of the call being assembled (set by _masked)
+
+
 def _fill_epilogue(p, bias, act, gate, gate_rows, first_row_mode, res1, res2):
     p.bias, p.act = ptr(bias), act
+    if _EXTRA is not None:
+        p.mask_mode, p.out_scale = _EXTRA["mask_mode"], _EXTRA["out_scale"]
     if gate is not None:
         p.gate, p.gate_ld = ptr(gate), gate.stride(-2)
     p.gate_rows, p.first_row_mode = gate_rows, first_row_mode
@@ -228,14 +235,20 @@ def image_nhwc8(img, pad=3):
     return out
 
 
-def upsample2x(x_nhwc):
+def upsample2x(x_nhwc, add=None):
+    """bilinear x2 (align_corners=True) of an NHWC bf16 map (+ `add`, a full-resolution map)."""
     lib = _lib.load()
-    _need_cuda(x_nhwc)
+    _need_cuda(x_nhwc, add)
     n, h, w, c = x_nhwc.shape
     out = torch.empty((n, 2 * h, 2 * w, c), dtype=torch.bfloat16, device=x_nhwc.device)
     with _timed("upsample2x"):
-        check(lib.vs_upsample2x(C.c_void_p(ptr(x_nhwc)), C.c_void_p(ptr(out)), n, h, w, c,
-                                C.c_void_p(stream_ptr())), "vs_upsample2x")
+        if add is None:
+            check(lib.vs_upsample2x(C.c_void_p(ptr(x_nhwc)), C.c_void_p(ptr(out)), n, h, w, c,
+                                    C.c_void_p(stream_ptr())), "vs_upsample2x")
+        else:
+            assert add.shape == out.shape and add.dtype == torch.bfloat16 and add.is_contiguous()
+            check(lib.vs_upsample2x_add(C.c_void_p(ptr(x_nhwc)), C.c_void_p(ptr(add)), C.c_void_p(ptr(out)),
+                                        n, h, w, c, C.c_void_p(stream_ptr())), "vs_upsample2x_add")
     return out
 
 
@@ -400,9 +413,15 @@ def layernorm_backward(x, dy, gamma, *, dres=None, dx=None, dgamma=None, dbeta=N
 
 def attention_backward(Q, K, V, O, dO, lse, dQ, dK, dV, *, heads, q_start, q_len, kv_start0, kv_len0,
                        kv_start1=None, kv_len1=None, max_q_len, max_kv_len, causal_block=0,
-                       scale=0.125):
-    """dQ, dK, dV of ops.attention from dO, the forward output O and its lse (vs_attention_backward)."""
+                       scale=0.125, dkv_tables=None):
+    """dQ, dK, dV of ops.attention from dO, the forward output O and its lse (vs_attention_backward).
+    dkv_tables: key-centric items of the dK / dV pass (dict of int32 device tensors kv_start, kv_len,
+    q_start0, q_len0, q_start1, q_len1 + int max_kv_len) -- REQUIRED when forward items share key rows
+    (neighbour attention); without them overlapping key rows would be overwritten, not accumulated."""
     _need_cuda(Q, K, V, O, dO, lse, dQ, dK, dV)
+    if kv_start1 is not None and dkv_tables is None and q_start.numel() > 1:
+        raise ValueError("attention_backward: two-segment items share key rows between items; pass the "
+                         "key-centric dkv_tables (encoder_grad.neighbour_backward_tables)")
     lib = _lib.load()
     p = _lib.AttentionBwdParams()
     f = p.fwd
@@ -421,6 +440,12 @@ def attention_backward(Q, K, V, O, dO, lse, dQ, dK, dV, *, heads, q_start, q_len
     p.lddq, p.lddk, p.lddv = dQ.stride(0), dK.stride(0), dV.stride(0)
     delta = torch.empty((Q.shape[0], heads), dtype=torch.float32, device=Q.device)
     p.delta = ptr(delta)
+    if dkv_tables is not None:
+        t = dkv_tables
+        p.dkv_items, p.dkv_max_kv_len = t["kv_start"].numel(), int(t["max_kv_len"])
+        p.dkv_kv_start, p.dkv_kv_len = ptr(t["kv_start"]), ptr(t["kv_len"])
+        p.dkv_q_start0, p.dkv_q_len0 = ptr(t["q_start0"]), ptr(t["q_len0"])
+        p.dkv_q_start1, p.dkv_q_len1 = ptr(t["q_start1"]), ptr(t["q_len1"])
     with _timed("attention_bwd", ("attn_bwd", f.items, heads, max_q_len, max_kv_len, causal_block)):
         check(lib.vs_attention_backward(C.byref(p), C.c_void_p(stream_ptr())), "vs_attention_backward")
     return dQ, dK, dV
@@ -435,3 +460,233 @@ def rope_rows_backward(dqkv, pos_i32, *, heads, q_col, k_col, base=100.0, cam_th
                                     C.c_float(cam_theta), C.c_void_p(stream_ptr())),
           "vs_rope_rows_backward")
     return dqkv
+
+
+# ------------------------------------------------------------------ decoder / head training path (backward)
+def conv_wgrad(dy_nhwc, x_nhwc, dW, *, kh, kw, pad, view=None, split_k=0):
+    """dW (Cout, kh*kw*cin_pad) fp32 += sum over pixels of dY[pixel, :] (x) X[pixel + tap, :]: the weight
+    gradient of ops.conv_gemm in its packed layout, without an im2col buffer (a_mode 3 of vs_gemm;
+    both operands are read as stored, pixels are the contraction dimension, split-K + atomic adds).
+    `view` describes the conv's INPUT exactly as in conv_gemm."""
+    _need_cuda(dy_nhwc, x_nhwc, dW)
+    lib = _lib.load()
+    p = GemmParams()
+    if view is None:
+        n, h, w, cin = x_nhwc.shape
+    else:
+        n, h, w, cin, p.conv_in_h, p.conv_stride_x, p.conv_stride_y, p.conv_stride_n = view
+    cout = dy_nhwc.shape[-1]
+    assert dy_nhwc.dtype == torch.bfloat16 and x_nhwc.dtype == torch.bfloat16 and dW.dtype == torch.float32
+    assert dy_nhwc.numel() == n * h * w * cout and dy_nhwc.is_contiguous()
+    cin_pad = (cin + 63) // 64 * 64
+    assert dW.shape == (cout, kh * kw * cin_pad) and dW.is_contiguous()
+    p.A, p.a_mode, p.a_rows, p.a_groups, p.a_row_stride = ptr(dy_nhwc), 3, cout, 1, cout
+    p.cn, p.ch, p.cw, p.cin, p.kh, p.kw, p.pad = n, h, w, cin, kh, kw, pad
+    p.W, p.w_row_stride, p.N = ptr(x_nhwc), 8, kh * kw * cin_pad
+    p.C, p.c_dtype, p.ldc = ptr(dW), VS_F32, dW.stride(0)
+    p.c_accumulate, p.split_k = 1, split_k
+    with _timed("gemm", (f"wgrad{kh}x{kw}", cout, kh * kw * cin_pad, n * h * w, 0, False, True)):
+        check(lib.vs_gemm(C.byref(p), C.c_void_p(stream_ptr())), "vs_gemm(conv wgrad)")
+    return dW
+
+
+def gemm_tn_acc(dy, x, dW, split_k=0):
+    """dW (N, K) fp32 += dy^T x with dy (M, N), x (M, K) bf16 as stored (a_mode 2, split-K, atomic adds)."""
+    _need_cuda(dy, x, dW)
+    lib = _lib.load()
+    assert dy.dim() == 2 and x.dim() == 2 and dy.shape[0] == x.shape[0]
+    assert dW.dtype == torch.float32 and dW.shape == (dy.shape[1], x.shape[1])
+    p = GemmParams()
+    p.A, p.a_mode, p.a_rows, p.a_groups, p.a_row_stride = ptr(dy), 2, dy.shape[1], 1, dy.stride(0)
+    p.W, p.w_row_stride, p.N, p.K = ptr(x), x.stride(0), x.shape[1], dy.shape[0]
+    p.C, p.c_dtype, p.ldc = ptr(dW), VS_F32, dW.stride(0)
+    p.c_accumulate, p.split_k = 1, split_k
+    with _timed("gemm", ("wgrad", dy.shape[1], x.shape[1], dy.shape[0], 0, False, True)):
+        check(lib.vs_gemm(C.byref(p), C.c_void_p(stream_ptr())), "vs_gemm(wgrad)")
+    return dW
+
+
+def gemm_masked(A, W, *, mask, res1=None, out_dtype=torch.bfloat16, out=None, out_scale=0.0, **kw):
+    """ops.gemm with the ReLU-mask epilogue: C = (mask > 0 ? A W^T * out_scale : 0) (+ res1)."""
+    return _masked(gemm, A, W, mask, res1, out_dtype, out, out_scale, kw)
+
+
+def conv_gemm_masked(x, Wp, *, mask, res1=None, out_dtype=torch.bfloat16, out=None, out_scale=0.0, **kw):
+    return _masked(conv_gemm, x, Wp, mask, res1, out_dtype, out, out_scale, kw)
+
+
+def _masked(fn, A, W, mask, res1, out_dtype, out, out_scale, kw):
+    assert mask.dtype == torch.bfloat16
+    global _EXTRA
+    if res1 is None:
+        _EXTRA = dict(mask_mode=2, out_scale=out_scale)
+        try:
+            return fn(A, W, res1=mask, out=out, out_dtype=out_dtype, **kw)
+        finally:
+            _EXTRA = None
+    _EXTRA = dict(mask_mode=1, out_scale=out_scale)
+    try:
+        return fn(A, W, res1=res1, res2=mask, out=out, out_dtype=out_dtype, **kw)
+    finally:
+        _EXTRA = None
+
+
+def layernorm_mod_backward(x, dh, gamma, *, frame_a, frame_b, frames, rows_per_frame, skip_first=False,
+                           scale=None, dres=None, dx=None, eps=1e-6):
+    """vs_layernorm_mod_backward (see the header): dx and the per-frame sums A_f, B_f (accumulated)."""
+    lib = _lib.load()
+    _need_cuda(x, dh, gamma, frame_a, frame_b)
+    rows, Cc = x.shape
+    assert rows == frames * rows_per_frame and dh.shape == x.shape and x.dtype == torch.float32
+    assert frame_a.shape == (frames, Cc) and frame_b.shape == (frames, Cc) and frame_a.stride(0) == frame_b.stride(0)
+    if dx is None:
+        dx = torch.empty((rows, Cc), dtype=torch.float32, device=x.device)
+    p = _lib.LnModBwdParams()
+    p.x, p.ldx = ptr(x), x.stride(0)
+    p.dh, p.dh_dtype, p.lddh = ptr(dh), _DT[dh.dtype], dh.stride(0)
+    p.gamma = ptr(gamma)
+    if scale is not None:
+        p.scale, p.mod_ld = ptr(scale), scale.stride(0)
+    if dres is not None:
+        p.dres, p.ldres = ptr(dres), dres.stride(0)
+    p.dx, p.lddx = ptr(dx), dx.stride(0)
+    p.frame_a, p.frame_b, p.frame_ld = ptr(frame_a), ptr(frame_b), frame_a.stride(0)
+    p.frames, p.rows_per_frame, p.skip_first, p.C, p.eps = frames, rows_per_frame, int(skip_first), Cc, eps
+    with _timed("layernorm_bwd"):
+        check(lib.vs_layernorm_mod_backward(C.byref(p), C.c_void_p(stream_ptr())), "vs_layernorm_mod_backward")
+    return dx
+
+
+def adaln_reduce(frame_a, frame_b, gamma, beta, *, scale=None, dscale=None, dshift=None, dgamma=None, dbeta=None):
+    lib = _lib.load()
+    frames, Cc = frame_a.shape
+    check(lib.vs_adaln_reduce(
+        C.c_void_p(ptr(frame_a)), C.c_void_p(ptr(frame_b)), C.c_int64(frame_a.stride(0)), C.c_void_p(ptr(gamma)),
+        C.c_void_p(ptr(beta)), C.c_void_p(ptr(scale)), C.c_int64(scale.stride(0) if scale is not None else 0),
+        C.c_void_p(ptr(dscale)), C.c_void_p(ptr(dshift)), C.c_int64(dscale.stride(0) if dscale is not None else 0),
+        C.c_void_p(ptr(dgamma)), C.c_void_p(ptr(dbeta)), frames, Cc, C.c_void_p(stream_ptr())), "vs_adaln_reduce")
+
+
+def gate_residual(x, branch, *, gate=None, rows_per_frame=0, first_row_mode=0, out=None):
+    """out = x + (1 + gate_f) * branch (out=None: in place): training forward of the gated residual."""
+    lib = _lib.load()
+    _need_cuda(x, branch)
+    assert x.dtype == torch.float32 and branch.dtype == torch.bfloat16 and x.shape == branch.shape
+    out = x if out is None else out
+    with _timed("gate"):
+        check(lib.vs_gate_residual(
+            C.c_void_p(ptr(x)), C.c_int64(x.stride(0)), C.c_void_p(ptr(out)), C.c_int64(out.stride(0)),
+            C.c_void_p(ptr(branch)), C.c_int64(branch.stride(0)),
+            C.c_void_p(ptr(gate)), C.c_int64(gate.stride(0) if gate is not None else 0), C.c_int64(x.shape[0]),
+            x.shape[1], rows_per_frame, first_row_mode, C.c_void_p(stream_ptr())), "vs_gate_residual")
+    return out
+
+
+def gate_backward(dout, *, frames, rows_per_frame, branch=None, gate=None, dgate=None, colsum=None,
+                  first_row_mode=0):
+    """-> dbranch bf16 (rows, C); dgate (frames, C) and colsum (C) accumulated."""
+    lib = _lib.load()
+    _need_cuda(dout)
+    rows, Cc = dout.shape
+    assert rows == frames * rows_per_frame and dout.dtype == torch.float32
+    dbr = torch.empty((rows, Cc), dtype=torch.bfloat16, device=dout.device)
+    with _timed("gate"):
+        check(lib.vs_gate_backward(
+            C.c_void_p(ptr(dout)), C.c_int64(dout.stride(0)), C.c_void_p(ptr(branch)),
+            C.c_int64(branch.stride(0) if branch is not None else 0), C.c_void_p(ptr(gate)),
+            C.c_int64(gate.stride(0) if gate is not None else 0), C.c_void_p(ptr(dbr)), C.c_int64(Cc),
+            C.c_void_p(ptr(dgate)), C.c_int64(dgate.stride(0) if dgate is not None else 0),
+            C.c_void_p(ptr(colsum)), frames, rows_per_frame, Cc, first_row_mode, C.c_void_p(stream_ptr())),
+            "vs_gate_backward")
+    return dbr
+
+
+def silu_backward(x, dy, dx, accumulate=True):
+    lib = _lib.load()
+    rows, Cc = x.shape
+    assert x.dtype == dy.dtype == dx.dtype == torch.float32
+    check(lib.vs_silu_backward(C.c_void_p(ptr(x)), C.c_int64(x.stride(0)), C.c_void_p(ptr(dy)),
+                               C.c_int64(dy.stride(0)), C.c_void_p(ptr(dx)), C.c_int64(dx.stride(0)), rows, Cc,
+                               int(accumulate), C.c_void_p(stream_ptr())), "vs_silu_backward")
+    return dx
+
+
+def upsample2x_backward(dy_nhwc):
+    lib = _lib.load()
+    _need_cuda(dy_nhwc)
+    n, h2, w2, c = dy_nhwc.shape
+    assert dy_nhwc.is_contiguous() and dy_nhwc.dtype == torch.bfloat16
+    out = torch.empty((n, h2 // 2, w2 // 2, c), dtype=torch.bfloat16, device=dy_nhwc.device)
+    with _timed("upsample2x"):
+        check(lib.vs_upsample2x_backward(C.c_void_p(ptr(dy_nhwc)), C.c_void_p(ptr(out)), n, h2 // 2, w2 // 2, c,
+                                         C.c_void_p(stream_ptr())), "vs_upsample2x_backward")
+    return out
+
+
+def pixel_unshuffle(src_nhwc, k):
+    lib = _lib.load()
+    n, hk, wk, c = src_nhwc.shape
+    h, w = hk // k, wk // k
+    out = torch.empty((n * h * w, k * k * c), dtype=torch.bfloat16, device=src_nhwc.device)
+    check(lib.vs_pixel_unshuffle(C.c_void_p(ptr(src_nhwc)), C.c_void_p(ptr(out)), n, h, w, c, k,
+                                 C.c_void_p(stream_ptr())), "vs_pixel_unshuffle")
+    return out
+
+
+def col2im(dcols, *, n, h, w, c, k, stride, pad):
+    lib = _lib.load()
+    out = torch.empty((n, h, w, c), dtype=torch.bfloat16, device=dcols.device)
+    check(lib.vs_col2im(C.c_void_p(ptr(dcols)), C.c_void_p(ptr(out)), n, h, w, c, k, stride, pad,
+                        dcols.shape[1], C.c_void_p(stream_ptr())), "vs_col2im")
+    return out
+
+
+def relu_backward(dy, y, *, out=None, colsum=None, want_dx=True):
+    """dx = dy * (y > 0) on bf16 (rows, C) matrices; colsum (C) f32 accumulated."""
+    lib = _lib.load()
+    _need_cuda(dy, y)
+    rows, Cc = dy.shape
+    if want_dx and out is None:
+        out = torch.empty_like(dy)
+    check(lib.vs_relu_backward(C.c_void_p(ptr(dy)), C.c_int64(dy.stride(0)), C.c_void_p(ptr(y)),
+                               C.c_int64(y.stride(0)), C.c_void_p(ptr(out)),
+                               C.c_int64(out.stride(0) if out is not None else 0), C.c_void_p(ptr(colsum)),
+                               C.c_int64(rows), Cc, C.c_void_p(stream_ptr())), "vs_relu_backward")
+    return out
+
+
+def pts_tail_backward(feat, Cf, w, b, d_xyz, dw, db):
+    """-> d_feat bf16 (px, Cf); dw (3, Cf) / db (3) accumulated.  d_xyz: fp32 rows, xyz at columns 0..2."""
+    lib = _lib.load()
+    px = d_xyz.shape[0]
+    d_feat = torch.empty((px, Cf), dtype=torch.bfloat16, device=d_xyz.device)
+    check(lib.vs_pts_tail_backward(C.c_void_p(ptr(feat)), Cf, C.c_void_p(ptr(w)), C.c_void_p(ptr(b)),
+                                   C.c_void_p(ptr(d_xyz)), C.c_int64(d_xyz.stride(0)), C.c_void_p(ptr(d_feat)),
+                                   C.c_void_p(ptr(dw)), C.c_void_p(ptr(db)), C.c_int64(px),
+                                   C.c_void_p(stream_ptr())), "vs_pts_tail_backward")
+    return d_feat
+
+
+def gaussian_adapter_backward(src, d_sh, sh_mask, d_src, *, center_col=0, param_col=3, d_raw=None, d_means=None,
+                              d_cov=None, d_cov6=None, d_shs=None, d_opac=None):
+    lib = _lib.load()
+    _need_cuda(src, d_src)
+    G = src.shape[0]
+    for t in (d_raw, d_means, d_cov, d_cov6, d_shs, d_opac):
+        assert t is None or (t.is_contiguous() and t.dtype == torch.float32)
+    check(lib.vs_gaussian_adapter_backward(
+        C.c_void_p(ptr(src)), C.c_int64(src.stride(0)), center_col, param_col, C.c_int64(G), d_sh,
+        C.c_void_p(ptr(sh_mask)), C.c_void_p(ptr(d_raw)), C.c_void_p(ptr(d_means)), C.c_void_p(ptr(d_cov)),
+        C.c_void_p(ptr(d_cov6)), C.c_void_p(ptr(d_shs)), C.c_void_p(ptr(d_opac)), C.c_void_p(ptr(d_src)),
+        C.c_int64(d_src.stride(0)), C.c_void_p(stream_ptr())), "vs_gaussian_adapter_backward")
+    return d_src
+
+
+def camera_head_backward(cam_feat, w, b, B, T, Cdim, d_pred, dw, db):
+    lib = _lib.load()
+    d_feat = torch.empty((B * T, Cdim), dtype=torch.float32, device=cam_feat.device)
+    check(lib.vs_camera_head_backward(
+        C.c_void_p(ptr(cam_feat)), C.c_int64(cam_feat.stride(0)), C.c_void_p(ptr(w)), C.c_void_p(ptr(b)), B, T,
+        Cdim, C.c_void_p(ptr(d_pred)), C.c_void_p(ptr(d_feat)), C.c_int64(Cdim), C.c_void_p(ptr(dw)),
+        C.c_void_p(ptr(db)), C.c_void_p(stream_ptr())), "vs_camera_head_backward")
+    return d_feat
