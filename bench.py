@@ -252,7 +252,7 @@ def run_ours(args) -> None:
     lib = _lib.load()
 
     torch.manual_seed(1234 + rank)
-    model = VicaSplat().to(dev)
+    model = VicaSplat().to(dev).eval()
     with torch.no_grad():                      # the reference zero-inits these; exercise them
         for n, p in model.named_parameters():
             if "modulation" in n or n.startswith("camera_extrinsic_head"):

@@ -256,6 +256,17 @@ def backbone(sd: SD, image: Tensor, intrinsics: Optional[Tensor], cfg: EncoderCo
 
 
 # --------------------------------------------------------------------------------- DPT heads
+# Every ReLU of the plugin goes through relu(x, tag) (tag = the state_dict key of the layer it feeds or
+# follows).  Tests may install RELU_HOOK(x, tag) -> Tensor, e.g. a ReLU with a PRESCRIBED mask: the
+# gradient of a ReLU network is discontinuous in its activations, so comparing the gradients of two
+# forward passes that differ by rounding is only sharp when both use the same masks.
+RELU_HOOK = None
+
+
+def relu(x: Tensor, tag: str) -> Tensor:
+    return F.relu(x) if RELU_HOOK is None else RELU_HOOK(x, tag)
+
+
 def conv(sd: SD, key: str, x: Tensor, stride=1, padding=0) -> Tensor:
     return F.conv2d(x, sd[key + ".weight"], sd.get(key + ".bias"), stride=stride, padding=padding)
 
@@ -266,8 +277,8 @@ def up2(x: Tensor) -> Tensor:
 
 def rcu(sd: SD, key: str, x: Tensor) -> Tensor:
     """ResidualConvUnit_custom (pre-activation), heads/dpt_block.py:79-137."""
-    y = conv(sd, key + ".conv1", F.relu(x), padding=1)
-    y = conv(sd, key + ".conv2", F.relu(y), padding=1)
+    y = conv(sd, key + ".conv1", relu(x, key + ".conv1"), padding=1)
+    y = conv(sd, key + ".conv2", relu(y, key + ".conv2"), padding=1)
     return y + x
 
 
@@ -307,7 +318,7 @@ def pts_head(sd: SD, inter, gh, gw, cfg: EncoderConfig) -> Tensor:
     k = "downstream_head1.dpt"
     x = dpt_trunk(sd, k, inter, gh, gw, cfg)
     x = conv(sd, k + ".head.0", x, padding=1)
-    x = F.relu(conv(sd, k + ".head.2", up2(x), padding=1))
+    x = relu(conv(sd, k + ".head.2", up2(x), padding=1), k + ".head.2")
     xyz = conv(sd, k + ".head.4", x).permute(0, 2, 3, 1)[..., :3]
     d = xyz.norm(dim=-1, keepdim=True)
     return xyz / d.clip(min=1e-8) * torch.expm1(d)
@@ -318,8 +329,8 @@ def gs_head(sd: SD, inter, imgs: Tensor, gh, gw, cfg: EncoderConfig) -> Tensor:
     imgs (F,3,H,W) normalised.  -> (F,H,W,83)."""
     k = "gaussian_param_head.dpt"
     x = up2(dpt_trunk(sd, k, inter, gh, gw, cfg))
-    x = x + F.relu(conv(sd, k + ".input_merger.0", imgs, padding=3))
-    x = F.relu(conv(sd, k + ".head.0", x, padding=1))
+    x = x + relu(conv(sd, k + ".input_merger.0", imgs, padding=3), k + ".input_merger.0")
+    x = relu(conv(sd, k + ".head.0", x, padding=1), k + ".head.0")
     return conv(sd, k + ".head.4", x).permute(0, 2, 3, 1)
 
 
@@ -345,7 +356,7 @@ def camera_head(sd: SD, cam: Tensor):
     """vicasplat.py:179-199 + misc/cam_utils.py:203-207 + misc/dq.py:224-262.
     cam (B,T,C) -> pred_extrins (B,T-1,8) unit dual quaternion, c2w (B,T,4,4), frame 0 identity."""
     B, T, _ = cam.shape
-    dq = linear(sd, "camera_extrinsic_head.1", F.relu(cam[:, 1:])).clone()
+    dq = linear(sd, "camera_extrinsic_head.1", relu(cam[:, 1:], "camera_extrinsic_head.1")).clone()
     dq[..., 3] = dq[..., 3] + 1.0
     dq = dq / dq[..., :4].norm(dim=-1, keepdim=True)
     qr, qd = dq[..., :4], dq[..., 4:]

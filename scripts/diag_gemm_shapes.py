@@ -11,7 +11,7 @@ from vicasplat_b200.encoder import VicaSplat, EncoderEngine
 NB = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
-model = VicaSplat().to(dev)
+model = VicaSplat().to(dev).eval()
 eng = EncoderEngine(model, use_graph=False)
 image, K = synthetic.clip(NB, 8, 256)
 image, K = image.to(dev), K.to(dev)

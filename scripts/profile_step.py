@@ -13,7 +13,7 @@ T, V, S = 8, 12, 256
 NB = int(sys.argv[1]) if len(sys.argv) > 1 else 1
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
-model = VicaSplat().to(dev)
+model = VicaSplat().to(dev).eval()
 with torch.no_grad():
     for n, p in model.named_parameters():
         if "modulation" in n or n.startswith("camera_extrinsic_head"):

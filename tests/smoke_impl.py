@@ -27,7 +27,7 @@ def run_smoke():
     from vicasplat_b200.encoder import VicaSplat, VicaSplatCfg, default_backbone_cfg
     cfg = er.EncoderConfig(img_size=64, enc_depth=2, dec_depth=10)
     bb = dict(default_backbone_cfg(), img_size=64, enc_depth=2, dec_depth=10)
-    model = VicaSplat(VicaSplatCfg(backbone=bb)).to(dev)
+    model = VicaSplat(VicaSplatCfg(backbone=bb)).to(dev).eval()
     sd = er.synth_state_dict(cfg, seed=0)
     model.load_state_dict(sd, strict=True)
     g = torch.Generator().manual_seed(7)

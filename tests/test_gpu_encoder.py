@@ -41,7 +41,7 @@ def _build(name, dev):
     cfg = er.EncoderConfig(**kw)
     bb = dict(default_backbone_cfg(), img_size=cfg.img_size, enc_depth=cfg.enc_depth,
               dec_depth=cfg.dec_depth)
-    model = VicaSplat(VicaSplatCfg(backbone=bb)).to(dev)
+    model = VicaSplat(VicaSplatCfg(backbone=bb)).to(dev).eval()
     sd = er.synth_state_dict(cfg, seed=0)
     assert set(model.state_dict().keys()) == set(sd.keys())
     model.load_state_dict(sd, strict=True)

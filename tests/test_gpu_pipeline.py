@@ -13,7 +13,7 @@ def test_pipeline_matches_sequential_calls(cuda, lib):
     from vicasplat_b200.pipeline import ScenePipeline
     torch.manual_seed(3)
     bb = dict(default_backbone_cfg(), enc_depth=2, dec_depth=10, img_size=64)
-    model = VicaSplat(VicaSplatCfg(backbone=bb)).to(cuda)
+    model = VicaSplat(VicaSplatCfg(backbone=bb)).to(cuda).eval()
     with torch.no_grad():
         for n, p in model.named_parameters():
             if "modulation" in n or n.startswith("camera_extrinsic_head"):

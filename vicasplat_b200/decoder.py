@@ -139,7 +139,9 @@ class DecoderSplattingCUDA(nn.Module):
         n = sh.shape[-1]
         degree = active_sh_degree or isqrt(n) - 1
         assert use_sh or n == 1
-        cov6 = _cov6(cov)
+        # the packed upper triangle the adapter already wrote (encoder.Gaussians.cov6), if it is there
+        cov6 = getattr(gaussians, "cov6", None)
+        cov6 = _cov6(cov) if cov6 is None else (cov6.flatten(1, 3) if cov6.ndim > 3 else cov6)
         bg = self.background_color[None].expand(v, 3)
         colors, depths = [], []
         for i in range(b):

@@ -85,6 +85,7 @@ class Gaussians:
     opacities: Tensor
     scales: Optional[Tensor] = None
     rotations: Optional[Tensor] = None
+    cov6: Optional[Tensor] = None      # packed upper triangle (xx,xy,xz,yy,yz,zz): what the rasterizer reads
 
 
 class _AttrDict(dict):
@@ -234,7 +235,8 @@ class VicaSplat(nn.Module):
                 nn.init.kaiming_uniform_(p, a=math.sqrt(5))
 
     def enable_gradient_checkpointing(self) -> None:
-        """Accepted for interface compatibility; this path is forward-only."""
+        """Accepted for interface compatibility (vicasplat.py:140): the training path keeps bf16
+        activations (~6 GB per scene at 8 views) and runs micro-batches instead of recomputing."""
 
     def get_data_shim(self):
         mean, std = self.cfg.input_mean, self.cfg.input_std
@@ -252,6 +254,21 @@ class VicaSplat(nn.Module):
     def invalidate(self) -> None:
         """Call after changing parameters (load_state_dict does it) so bf16 copies are re-packed."""
         self._engine = None
+        self._train_engine = None
+
+    def train_engine(self):
+        """The training-path engine behind the differentiable forward (vicasplat_b200.train.TrainEngine,
+        gradients returned through torch.autograd); its bf16 operand copies follow in-place parameter
+        updates (optimizer steps) through the parameters' version counters."""
+        from .train import TrainEngine
+        versions = tuple(p._version for p in self.parameters())
+        eng = getattr(self, "_train_engine", None)
+        if eng is None:
+            eng = self._train_engine = TrainEngine(self, attach_grads=False)
+        elif versions != self._train_versions:
+            eng.repack()
+        self._train_versions = versions
+        return eng
 
     def load_state_dict(self, *a, **k):
         r = super().load_state_dict(*a, **k)
@@ -260,6 +277,7 @@ class VicaSplat(nn.Module):
 
     def _apply(self, fn, *a, **k):
         self._engine = None
+        self._train_engine = None
         return super()._apply(fn, *a, **k)
 
     def engine(self) -> "EncoderEngine":
@@ -267,18 +285,49 @@ class VicaSplat(nn.Module):
             self._engine = EncoderEngine(self)
         return self._engine
 
-    @torch.no_grad()
     def forward(self, context: dict, global_step: int = 0, visualization_dump: Optional[dict] = None,
                 distill: bool = False, compute_viewspace_depth: bool = True,
                 clone_outputs: bool = True, **kwargs) -> dict:
-        """``clone_outputs=False`` returns views of the engine's static output buffers (valid until
-        the next forward on this module): what a consumer on the same stream needs, without the
-        ~3 GB of copies per 8-scene batch."""
+        """In training mode with gradients enabled the call is DIFFERENTIABLE (one autograd.Function over
+        the hand-written backward pass, ``_forward_train``): every output the reference's training step
+        consumes carries gradients to all parameters.  Otherwise (``eval()`` or ``torch.no_grad()``) the
+        forward-only engine replays its CUDA graph.
+
+        ``clone_outputs=False`` (forward-only path) returns views of the engine's static output buffers
+        (valid until the next forward on this module): what a consumer on the same stream needs,
+        without the ~3 GB of copies per 8-scene batch."""
         image = context["image"]
         if not image.is_cuda:
             raise RuntimeError("vicasplat_b200.VicaSplat runs on CUDA only (no CPU fallback)")
         intr = context.get("intrinsics", None)
         assert intr is not None, "use_intrinsic_embedding=True needs context['intrinsics']"
+        if self.training and torch.is_grad_enabled() and not distill:
+            return self._forward_train(context, image, intr, compute_viewspace_depth, visualization_dump)
+        with torch.no_grad():
+            return self._forward_infer(context, image, intr, distill, compute_viewspace_depth,
+                                       clone_outputs, visualization_dump)
+
+    def _forward_train(self, context, image, intr, compute_viewspace_depth, visualization_dump):
+        names = [n for n, _ in self.named_parameters()]
+        params = [p for _, p in self.named_parameters()]
+        raw, cov, cov6, sh, opac, pred, c2w, scales, rot = _TrainFn.apply(self, names, image, intr, *params)
+        centers = raw[..., :3]                      # a view, as in the reference (vicasplat.py:256-259)
+        depth = None
+        if compute_viewspace_depth:
+            ext = context["extrinsics"]
+            Rinv = torch.linalg.inv(ext[:, :, :3, :3])
+            rel = centers - ext[:, :, None, None, :3, 3]
+            depth = (rel * Rinv[:, :, None, None, 2, :]).sum(-1)
+        gaussians = Gaussians(means=centers, covariances=cov, harmonics=sh, opacities=opac[..., None],
+                              scales=scales, rotations=rot, cov6=cov6)
+        if visualization_dump is not None:
+            visualization_dump["depth"] = gaussians.means[..., -1:]
+        return dict(pred_extrins=pred, pred_intrins=None, gaussian_camera_extrins=c2w,
+                    gaussian_camera_intrins=None, gaussian_centers=centers, confidence=None,
+                    context_view_depths=depth, gaussians=gaussians, raw_gaussians=raw, cov6=cov6)
+
+    def _forward_infer(self, context, image, intr, distill, compute_viewspace_depth, clone_outputs,
+                       visualization_dump):
         B, T, _, H, W = image.shape
         out = self.engine().run(image, intr, heads=not distill, gs=not distill,
                                 clone_outputs=clone_outputs)
@@ -296,11 +345,41 @@ class VicaSplat(nn.Module):
             return res
         g = out["gaussians"]
         gaussians = Gaussians(means=centers, covariances=g["cov"], harmonics=g["sh"],
-                              opacities=g["opac"][..., None], scales=g["scales"], rotations=g["rot"])
+                              opacities=g["opac"][..., None], scales=g["scales"], rotations=g["rot"],
+                              cov6=g["cov6"])
         if visualization_dump is not None:
             visualization_dump["depth"] = gaussians.means[..., -1:]
         res.update(gaussians=gaussians, raw_gaussians=out["raw"], cov6=g["cov6"])
         return res
+
+
+class _TrainFn(torch.autograd.Function):
+    """VicaSplat.forward as ONE autograd node: forward = TrainEngine.forward (keeps activations), backward
+    = the hand-written backward pass; parameter gradients are handed back to autograd (so DDP hooks and
+    any optimizer see ordinary ``.grad`` accumulation)."""
+
+    @staticmethod
+    def forward(ctx, model, names, image, intr, *params):
+        eng = model.train_engine()
+        out = eng.forward(image, intr)
+        B, T, _, H, W = image.shape
+        shp = (B, T, H, W)
+        ctx.eng, ctx.names, ctx.G = eng, names, B * T * H * W
+        ctx.set_materialize_grads(False)
+        c2w, scales, rot = out["c2w"], out["scales"].view(*shp, 3), out["rot"].view(*shp, 4)
+        ctx.mark_non_differentiable(c2w, scales, rot)
+        return (out["raw"].view(*shp, -1), out["cov"].view(*shp, 3, 3), out["cov6"].view(*shp, 6),
+                out["sh"].view(*shp, 3, -1), out["opac"].view(*shp), out["pred_extrins"], c2w, scales, rot)
+
+    @staticmethod
+    def backward(ctx, d_raw, d_cov, d_cov6, d_sh, d_opac, d_pred, *_):
+        G = ctx.G
+        flat = lambda t, *s: None if t is None else t.reshape(G, *s).to(torch.float32).contiguous()
+        eng = ctx.eng
+        eng.backward(d_raw=flat(d_raw, -1), d_cov=flat(d_cov, 3, 3), d_cov6=flat(d_cov6, 6),
+                     d_sh=None if d_sh is None else flat(d_sh, 3, d_sh.shape[-1]), d_opac=flat(d_opac),
+                     d_pred=d_pred)
+        return (None, None, None, None, *[eng.g.get(n) for n in ctx.names])
 
 
 # ------------------------------------------------------------------------------------ engine

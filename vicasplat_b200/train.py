@@ -59,7 +59,10 @@ def _flipped(w: torch.Tensor) -> torch.Tensor:
 
 
 class TrainEngine:
-    def __init__(self, model: VicaSplat, reducer: Optional[GradReducer] = None):
+    def __init__(self, model: VicaSplat, reducer: Optional[GradReducer] = None, attach_grads: bool = True):
+        """attach_grads: make every ``param.grad`` a view of its bucket (the fast path: backward() writes
+        the gradients in place and the reducer / FusedAdamW work on the buckets).  False: the buckets are
+        private scratch and the caller (the autograd.Function of VicaSplat.forward) hands them on."""
         self.m = model
         self.bb = model._bb
         self.dev = next(model.parameters()).device
@@ -73,7 +76,8 @@ class TrainEngine:
             b = Bucket(bname, {n: self.p[n].shape for n in members}, self.dev)
             self.buckets[bname] = b
             for n, v in b.views.items():
-                self.p[n].grad = v
+                if attach_grads:
+                    self.p[n].grad = v
                 self.g[n] = v
         self.bucket_order = [bname for bname, _ in plan]
         D = self.bb["dec_embed_dim"]
@@ -413,6 +417,29 @@ class TrainEngine:
                                   raw_out=raw)
         s.update(tp=tp, tg=tg, gsp=gsp)
         return dict(raw=raw, pred_extrins=s["pred"], c2w=s["c2w"], **gq)
+
+    def relu_masks(self) -> Dict[str, torch.Tensor]:
+        """The ReLU masks of the kept forward pass, keyed by the reference's layer names (bool, NCHW for the
+        DPT maps; (B, T-1, C) for the pose head).  A checker that pins these masks in its own forward pass
+        compares gradients at the SAME linearisation point (tests/test_gpu_model_grad.py)."""
+        s = self._saved
+        assert s is not None, "relu_masks() needs a forward() first"
+        pl = s["pl"]
+        nchw = lambda t: (t > 0).permute(0, 3, 1, 2)
+        out = {}
+        for head, t in (("downstream_head1", s["tp"]), ("gaussian_param_head", s["tg"])):
+            k = f"{head}.dpt.scratch.refinenet"
+            for r in (1, 2, 3, 4):
+                if r < 4:
+                    out[f"{k}{r}.resConfUnit1.conv1"] = nchw(t["layers"][r - 1][1])
+                    out[f"{k}{r}.resConfUnit1.conv2"] = nchw(t[f"u1_{r}"])
+                out[f"{k}{r}.resConfUnit2.conv1"] = nchw(t[f"fx_{r}"])
+                out[f"{k}{r}.resConfUnit2.conv2"] = nchw(t[f"y1_{r}"])
+        out["downstream_head1.dpt.head.2"] = nchw(s["tp"]["y2"])
+        out["gaussian_param_head.dpt.input_merger.0"] = nchw(s["tg"]["c7"])
+        out["gaussian_param_head.dpt.head.0"] = nchw(s["tg"]["y"])
+        out["camera_extrinsic_head.1"] = (s["cam_out"] > 0).view(pl["B"], pl["T"], -1)[:, 1:]
+        return out
 
     # ------------------------------------------------------------------ backward
     @torch.no_grad()
