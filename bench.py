@@ -190,33 +190,37 @@ def torch_eager_gpu_encoder(dev, our_ms_per_scene: float) -> dict:
                      "1 scene of 8 frames) on this GPU; encoder leg only")
 
 
-def scene_seconds_from_sample(t_enc: float, t_frames: int, t_view: float) -> float:
-    return t_enc * encoder_flops(T_CTX) / encoder_flops(t_frames) + V_TGT * t_view
-
-
 def run_reference(args) -> None:
+    """The reference's CPU path (the oracle port: the reference itself needs 16 absent packages and a
+    CUDA-only rasterizer) on all host cores.  Every step is ONE WHOLE scene, timed as it runs -- the full
+    8-frame encoder forward and all 12 target views -- nothing is extrapolated: `ms_per_step` is the
+    measured wall time of a step and `value` = 1 scene / that.  (Our arm runs `--batch` such scenes per
+    step; scenes are independent, so scenes/s is the same quantity.)  One scene takes ~20 s on 8 cores."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import torch
     torch.set_num_threads(os.cpu_count() or 1)
     cores = torch.get_num_threads()
-    t_frames = 2
-    sample = (f"per step: oracle encoder forward on {t_frames} of {T_CTX} frames (scaled by "
-              f"algorithmic FLOPs) + 1 of {V_TGT} target views of the {G_SCENE}-Gaussian scene (x{V_TGT})")
+    sample = (f"per step: one whole scene = oracle encoder forward on all {T_CTX} frames + all {V_TGT} target "
+              f"views of the {G_SCENE}-Gaussian scene, wall-clock, no extrapolation (1 of the {args.batch} "
+              f"scenes of a step of our arm)")
     for _ in range(args.warmup):
-        cpu_reference_step(t_frames, 1)
+        cpu_reference_step(T_CTX, V_TGT)
     secs = []
     for _ in range(args.steps):
-        te, tv = cpu_reference_step(t_frames, 1)
-        secs.append(scene_seconds_from_sample(te, t_frames, tv))
+        t0 = time.perf_counter()
+        cpu_reference_step(T_CTX, V_TGT)
+        secs.append(time.perf_counter() - t0)
     per = sum(secs) / len(secs)
     val = 1.0 / per
     line = dict(impl="reference", metric=METRIC, value=val, unit="scenes/s", n_gpus=args.gpus,
                 steps=args.steps, warmup=args.warmup, ms_per_step=per * 1e3, higher_is_better=True,
-                scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                scaling="weak", vs_baseline=None, dtype="f32", data="synthetic", extrapolated=False,
+                scenes_per_step=1,
                 mpix_per_sec=val * V_TGT * SIZE * SIZE / 1e6,
-                config=config_dict(),
+                config=config_dict(args.batch),
+                raster_parity="unpinned (upstream diff_gaussian_rasterization source absent; restated algorithm)",
                 cpu_baseline=dict(value=val, unit="scenes/s", cores=cores, kind="port", sample=sample),
                 e2e=dict(value=val, unit="scenes/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     emit(line)
@@ -228,7 +232,8 @@ def config_dict(nb: int = 1) -> dict:
                          f"G={G_SCENE} Gaussians/scene", scenes_per_step_per_gpu=nb, context_views=T_CTX,
                 target_views=V_TGT,
                 image=f"{SIZE}x{SIZE}", gaussians=G_SCENE, weights="random-init (seeded)",
-                raster_input="seeded pixel-aligned Gaussian scene (random-weight encoder output is degenerate)",
+                raster_input="one DIFFERENT seeded pixel-aligned Gaussian scene per scene of the step "
+                             "(random-weight encoder output is degenerate as raster input)",
                 l2="inputs larger than L2 (1.2 GB bf16 weights, 178 MB Gaussians); no explicit flush",
                 parallelism="replicas (one scene per GPU, no data-path collective)")
 
@@ -263,28 +268,49 @@ def run_ours(args) -> None:
     image_h, K_h = synthetic.clip(NB, T_CTX, SIZE, seed=dist_util.scene_seed(250307, rank))
     image_h, K_h = image_h.pin_memory(), K_h.pin_memory()
     image_d, K_d = image_h.to(dev), K_h.to(dev)
-    sc = {k: v.to(dev) for k, v in synthetic.gaussian_scene(T_CTX, SIZE, SIZE, V_TGT, seed=dist_util.scene_seed(1, rank)).items()}
-    tanfov, view_t, full_t, campos = dec._cameras(sc["extrinsics"], sc["intrinsics"], sc["near"], sc["far"])
-    cov6 = dec._cov6(sc["covariances"]).contiguous()
+    # NB DIFFERENT scenes per step (scene 0 of rank 0 is the CPU-generated one the reference arm renders);
+    # cov6 is what the adapter writes next to the covariances (encoder.Gaussians.cov6)
+    scenes = []
+    for i in range(NB):
+        seed = dist_util.scene_seed(1 + 104729 * i, rank)
+        sc_i = synthetic.gaussian_scene(T_CTX, SIZE, SIZE, V_TGT, seed=seed, device=None if i == 0 else dev)
+        sc_i = {k: v.to(dev) for k, v in sc_i.items()}
+        sc_i["cov6"] = dec._cov6(sc_i["covariances"]).contiguous()
+        scenes.append(sc_i)
+    sc = scenes[0]
     bg = torch.zeros((V_TGT, 3), device=dev)
-    rkw = dict(shs=sc["harmonics"], sh_degree=4, sh_layout="chan_major", viewmatrix=view_t,
-               projmatrix=full_t, campos=campos, tanfov=tanfov, bg=bg, H=SIZE, W=SIZE,
+    ext_all = torch.stack([s_["extrinsics"] for s_ in scenes]).flatten(0, 1)
+    intr_all = torch.stack([s_["intrinsics"] for s_ in scenes]).flatten(0, 1)
+    near_all = torch.stack([s_["near"] for s_ in scenes]).flatten()
+    far_all = torch.stack([s_["far"] for s_ in scenes]).flatten()
+    rkw = dict(sh_degree=4, sh_layout="chan_major", bg=bg, H=SIZE, W=SIZE,
                want_n_touched=False)   # render_cuda discards it (cuda_splatting.py:226-239)
-
-    # calibrate the binning capacities once, outside the timed region: a checked call reads the
-    # exact pair count and the largest per-tile count of this scene from device scalars and leaves
-    # them (+25 %) in the rasterizer's per-shape hint, which the unchecked timed calls then use
     import vicasplat_b200.rasterizer as rmod
+
+    def raster_batch(check="deferred"):
+        # the camera set-up of all NB * V cameras (sync-free) belongs to the step
+        tanfov, view_t, full_t, campos = dec._cameras(ext_all, intr_all, near_all, far_all)
+        for i, s_ in enumerate(scenes):           # one launch chain (all 12 views) per scene
+            c = slice(i * V_TGT, (i + 1) * V_TGT)
+            out = rasterize_views(s_["means"], s_["cov6"], s_["opacities"], shs=s_["harmonics"],
+                                  viewmatrix=view_t[c], projmatrix=full_t[c], campos=campos[c],
+                                  tanfov=tanfov[c], check_overflow=check, **rkw)
+        return out
+
+    def verify_raster():
+        """the deferred overflow counters of every render since the last call (one small D2H copy)"""
+        recs = rmod.take_deferred()
+        if recs:
+            rmod.verify_deferred(torch.stack([r[0] for r in recs]).cpu(), recs)
+
+    # calibrate the binning capacities once, outside the timed region: checked calls read the exact
+    # pair counts / largest per-tile counts from device scalars and leave them (+25 %) in the
+    # rasterizer's per-shape hint; the timed calls use the hint and DEFER the check of their own
+    # counters (the shipped path of ScenePipeline), verified right after the timed region
     for _ in range(2):
-        color = rasterize_views(sc["means"], cov6, sc["opacities"], **rkw)[0]
+        color = raster_batch(check=True)[0]
     max_pairs, max_tile = rmod._capacity_hint[(V_TGT, G_SCENE, SIZE, SIZE)]
     n_pairs = int((max_pairs - 4096) / 1.25)
-    rkw.update(check_overflow=False)
-
-    def raster_batch():
-        for _ in range(NB):           # scenes of the batch: one launch chain (all 12 views) each
-            out = rasterize_views(sc["means"], cov6, sc["opacities"], **rkw)
-        return out
 
     def device_step():
         eng.run(image_d, K_d, clone_outputs=False)
@@ -308,6 +334,7 @@ def run_ours(args) -> None:
 
     for _ in range(max(args.warmup, 3)):
         device_step()
+    verify_raster()
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
     barrier()
     with ClockSampler(local) as clk:
@@ -320,6 +347,7 @@ def run_ours(args) -> None:
             ev[i][2].record()
         barrier()
         t_wall = time.perf_counter() - t_wall0
+    verify_raster()
     if os.environ.get("VS_PROFILE_STEP") == "1":
         # one extra step between cudaProfilerStart/Stop (outside the timed region) for
         #   ncu --profile-from-start off --metrics gpu__time_duration.sum ... python bench.py
@@ -376,11 +404,12 @@ def run_ours(args) -> None:
 
     # ---- e2e: host buffers in, host result out, through the plugin calls a user makes
     decoder = dec.DecoderSplattingCUDA(dec.DecoderSplattingCUDACfg("splatting_cuda", [0.0, 0.0, 0.0], False)).to(dev)
-    rep = lambda t: t[None].expand(NB, *t.shape)
-    gauss = Gaussians(means=rep(sc["means"]), covariances=rep(sc["covariances"]),
-                      harmonics=rep(sc["harmonics"]), opacities=rep(sc["opacities"]))
-    ext, intr = rep(sc["extrinsics"]), rep(sc["intrinsics"])
-    near, far = rep(sc["near"]), rep(sc["far"])
+    verify_raster()
+    stk = lambda k: torch.stack([s_[k] for s_ in scenes])
+    gauss = Gaussians(means=stk("means"), covariances=stk("covariances"), harmonics=stk("harmonics"),
+                      opacities=stk("opacities"), cov6=stk("cov6"))
+    ext, intr = stk("extrinsics"), stk("intrinsics")
+    near, far = stk("near"), stk("far")
     # Every step submits one host batch (pinned clip -> H2D) and collects the host result of the
     # previous one (colour, depth, poses <- D2H): all copies of all K steps happen inside the
     # timed region; the pipeline only overlaps them with the compute of the neighbouring steps.
@@ -418,9 +447,12 @@ def run_ours(args) -> None:
 
     # overflow check of the calibrated capacities (outside the timed region): a checked call would
     # have re-run and changed the hint if either bound had been exceeded
-    chk = rasterize_views(sc["means"], cov6, sc["opacities"], **dict(rkw, check_overflow=True))[0]
-    assert rmod._capacity_hint[(V_TGT, G_SCENE, SIZE, SIZE)] == (max_pairs, max_tile), "raster capacity changed"
+    chk = raster_batch(check=True)[0]
     assert torch.isfinite(chk).all() and torch.equal(chk, color)
+
+    train = None
+    if args.train_batch > 0:
+        train = train_leg(args, model, scenes, dev, rank, world, local, barrier)
 
     if rank == 0:
         peaks = load_peaks()
@@ -466,14 +498,17 @@ def run_ours(args) -> None:
                                  frac=ras_gbs / peaks["hbm"], traffic=None,
                                  peak_source=peaks["which"] + " copy", bytes_per_launch=rb),
             wall_ms_per_step=t_wall * 1e3 / args.steps,
+            raster_parity="unpinned (upstream diff_gaussian_rasterization source absent; restated algorithm)",
         )
+        if train is not None:
+            line["train_step"] = train
         if world == 1 and not args.no_cpu:
-            te, tv = cpu_reference_step(T_CTX, 1)
-            per = scene_seconds_from_sample(te, T_CTX, tv)
+            te, tv = cpu_reference_step(T_CTX, V_TGT)
+            per = te + tv * V_TGT
             line["cpu_baseline"] = dict(
                 value=1.0 / per, unit="scenes/s", cores=torch.get_num_threads(), kind="port",
-                sample=f"oracle encoder forward on all {T_CTX} frames ({te:.1f} s) + 1 of {V_TGT} "
-                       f"target views ({tv:.1f} s, x{V_TGT})")
+                sample=f"one whole scene, nothing extrapolated: oracle encoder forward on all {T_CTX} frames "
+                       f"({te:.1f} s) + all {V_TGT} target views ({tv * V_TGT:.1f} s)")
             # context for the encoder leg (SURVEY.md §8d "its own PyTorch path"): the same oracle
             # port in eager PyTorch on THIS GPU with TF32 matmuls/convs, as the reference runs
             # (backbone_vica.py:9) -- a baseline measurement by the checker, nothing we ship
@@ -484,6 +519,114 @@ def run_ours(args) -> None:
         emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------ training leg
+def train_leg(args, model, scenes, dev, rank, world, local, barrier) -> dict:
+    """BASELINE configs[2] (1 GPU) / configs[3] (N GPUs): one optimisation step of the 8-view 256x256
+    training loop per GPU -- encoder forward (activations kept), 12-view render + MSE value/gradient +
+    rasterizer backward per scene, hand-written encoder backward with the gradient all-reduce of ALL
+    578 M parameters overlapped bucket by bucket (NCCL; the path's one collective, src/main.py:110-115),
+    nan_to_num / clip 0.5 / fused AdamW, operand re-pack.  Batch = --train-batch scenes per GPU in
+    micro-batches of --train-micro (gradient accumulation is exact).
+    Raster input: the step's synthetic pixel-aligned scenes PLUS the encoder's own outputs as residuals
+    (means, cov6, SH; opacity offset by -0.5), unit Jacobian: random-init weights put every predicted
+    Gaussian within 0.16 of the camera where the rasterizer culls it, which would time an empty render."""
+    import torch
+    import torch.distributed as dist
+    from vicasplat_b200 import _lib, dist_util
+    from vicasplat_b200.encoder_train import GradReducer
+    from vicasplat_b200.rasterizer import RasterOverflow
+    from vicasplat_b200.train_step import TrainStep, _NoReduce
+    lib = _lib.load()
+    B, mb, K = args.train_batch, min(args.train_micro, args.train_batch), args.train_steps
+    NS = len(scenes)
+    model.train()
+    reducer = GradReducer(compress_bf16=args.train_wire == "bf16")
+    ts = TrainStep(model, micro_batch=mb, reducer=reducer)
+    image_h, K_h = __import__("vicasplat_b200.synthetic", fromlist=["clip"]).clip(
+        B, T_CTX, SIZE, seed=dist_util.scene_seed(777, rank))
+    g = torch.Generator().manual_seed(dist_util.scene_seed(778, rank))
+    tgt_h = torch.rand((B, V_TGT, 3, SIZE, SIZE), generator=g)
+    image_h, K_h, tgt_h = image_h.pin_memory(), K_h.pin_memory(), tgt_h.pin_memory()
+    pick = lambda k: torch.stack([scenes[b % NS][k] for b in range(B)])
+    target = dict(extrinsics=pick("extrinsics"), intrinsics=pick("intrinsics"), near=pick("near"), far=pick("far"))
+
+    def override(b, gz):
+        s_ = scenes[b % NS]
+        return dict(means=s_["means"] + gz["means"], cov6=s_["cov6"] + gz["cov6"], sh=s_["harmonics"] + gz["sh"],
+                    opac=s_["opacities"] + (gz["opac"] - 0.5))
+
+    def one(check, host=False):
+        if host:
+            ctx = dict(image=image_h.to(dev, non_blocking=True), intrinsics=K_h.to(dev, non_blocking=True))
+            tgt = dict(target, image=tgt_h.to(dev, non_blocking=True))
+        else:
+            ctx, tgt = ctx_d, tgt_d
+        loss = ts.step(ctx, tgt, override_gaussians=override, check_overflow=check)
+        return float(loss) if host else loss
+
+    ctx_d = dict(image=image_h.to(dev), intrinsics=K_h.to(dev))
+    tgt_d = dict(target, image=tgt_h.to(dev))
+    for _ in range(3):                       # first steps: calibrate the rasterizer's capacity hints
+        try:
+            one(True)
+        except RasterOverflow:
+            pass
+    l0 = lib.vs_launch_count()
+    loss0 = one(True)
+    launches = int(lib.vs_launch_count() - l0)
+
+    def timed(n, host=False):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(n):
+            loss = one(True, host)
+        e1.record()
+        barrier()
+        return e0.elapsed_time(e1) / n, (time.perf_counter() - t0) * 1e3 / n, loss
+
+    with ClockSampler(local) as clk:
+        ms, _, loss = timed(K)
+    e2e_ms = timed(K, host=True)[1]
+    exposed = None
+    if world > 1:                            # the same step without the collective: what the all-reduce costs
+        ts.eng.reducer = ts.reducer = _NoReduce()
+        ms_no = timed(K)[0]
+        ts.eng.reducer = ts.reducer = reducer
+        ms_no, = dist_util.max_over_ranks([ms_no], dev)
+    ms, e2e_ms = dist_util.max_over_ranks([ms, e2e_ms], dev)
+    if world > 1:
+        exposed = ms - ms_no
+    loss = float(loss)
+    assert loss == loss and abs(loss) < 1e6, f"training loss is not finite: {loss}"
+    peaks = load_peaks()
+    n_params = sum(p.numel() for p in ts.eng.trainable_parameters())
+    tf = 3.0 * encoder_flops(T_CTX) * B / (ms * 1e-3) / 1e12
+    model.eval()
+    return dict(
+        metric="train_scenes_per_sec_8view_256x256", value=world * B * 1e3 / ms, unit="scenes/s",
+        ms_per_step=ms, steps=K, warmup=4, scenes_per_step_per_gpu=B, micro_batch=mb, n_gpus=world,
+        workload=(f"configs[{2 if world == 1 else 3}]: 8-view 256x256 training step, batch {B}/GPU in micro-batches "
+                  f"of {mb}: encoder fwd + 12-view render + MSE + raster bwd + encoder bwd (all {n_params} "
+                  "trained parameters) + " + ("gradient all-reduce + " if world > 1 else "") +
+                  "nan_to_num / clip 0.5 / AdamW + re-pack"),
+        loss=dict(kind="MSE (LossMse); LPIPS needs VGG16 weights that are not in the image", first=float(loss0),
+                  last=loss),
+        raster_input="synthetic pixel-aligned scenes + encoder outputs as residuals (unit Jacobian)",
+        clocks=clk.result, gpu_launches=launches,
+        e2e=dict(value=world * B * 1e3 / e2e_ms, unit="scenes/s", ms_per_step=e2e_ms,
+                 h2d_bytes_per_step=(image_h.numel() + K_h.numel() + tgt_h.numel()) * 4, d2h_bytes_per_step=4,
+                 api="TrainStep.step: pinned host clips + target images in, host loss out, per step"),
+        allreduce=dict(bytes_per_step=(sum(b_.flat.numel() for b_ in ts.eng.buckets.values()) *
+                                       (2 if args.train_wire == "bf16" else 4)) if world > 1 else 0,
+                       wire_dtype=args.train_wire if world > 1 else None, buckets=len(ts.eng.buckets),
+                       exposed_ms=exposed, ms_per_step_without=(ms - exposed) if exposed is not None else None),
+        roofline=dict(bound="tensor", kernel="whole training step (3 x forward FLOPs of the encoder; the render "
+                                             "chain and optimizer are HBM-bound and not counted)",
+                      achieved=tf, peak=peaks["tf"], unit="TFLOP/s", frac=tf / peaks["tf"]))
 
 
 _REAL_STDOUT = None
@@ -515,6 +658,13 @@ def main() -> None:
                     help="overlap the render of batch i with the encoder of batch i+1 on two streams "
                          "(measured: +2 %, the persistent GEMM CTAs own the SMs)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--train-batch", type=int, default=24,
+                    help="scenes per GPU per TRAINING step of the train_step sub-record (BASELINE configs[2]/[3]: "
+                         "24); 0 = skip the training leg")
+    ap.add_argument("--train-micro", type=int, default=8, help="scenes per micro-batch of the training step")
+    ap.add_argument("--train-steps", type=int, default=3)
+    ap.add_argument("--train-wire", choices=["f32", "bf16"], default="bf16",
+                    help="wire format of the gradient all-reduce (bf16: half the bytes; buckets stay fp32)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -336,7 +336,13 @@ int vs_update_pose(const float* rho, const float* theta, const float* c2w, float
  *   pass 2  g' = g * min(1, max_grad_norm / (norm + 1e-6))   (max_grad_norm <= 0: no clipping)
  *           p *= 1 - lr * weight_decay;  m = b1 m + (1 - b1) g';  v = b2 v + (1 - b2) g'^2
  *           p -= (lr / (1 - b1^t)) * m / (sqrt(v) / sqrt(1 - b2^t) + eps)        (torch.optim.AdamW)
- *           the whole step is skipped when skip_nonfinite != 0 and a gradient held an inf / nan.
+ *           skip_nonfinite: 0 = gradients used as they are; 1 = the whole step is skipped when a gradient
+ *           held an inf / nan; 2 = every non-finite gradient element is replaced as torch.nan_to_num_
+ *           does (nan -> 0, +-inf -> +-FLT_MAX) and the step is taken: the reference's
+ *           GradientNanCheckCallback (src/main.py:40-45).
+ *           step_counter (device int32, nullable): when given, t is read from it instead of `step`; the
+ *           first launch advances it, unless the step is being skipped -- so the bias corrections
+ *           (and the 'step' a checkpoint records) never run ahead of the moments.
  * Tensors are described by device tables; work is cut into chunks of VS_ADAMW_CHUNK elements:
  * chunk c covers elements [chunk_start[c], chunk_start[c] + VS_ADAMW_CHUNK) of tensor chunk_tensor[c]. */
 #define VS_ADAMW_CHUNK 16384
@@ -358,6 +364,7 @@ typedef struct vs_adamw_params {
   uint32_t* counter;           /* device uint32, zero before the first call (left at zero) */
   float* grad_norm_out;        /* device float[1]: ||g||_2 before clipping */
   int32_t* found_inf_out;      /* device int32[1] */
+  int32_t* step_counter;       /* device int32[1] or NULL (see above) */
 } vs_adamw_params;
 int vs_adamw_step(const vs_adamw_params* p, vs_stream_t stream);
 

@@ -42,7 +42,7 @@ def test_matches_torch_adamw_with_clipping(cuda, lib):
 def test_nonfinite_gradient_skips_the_step(cuda, lib):
     from vicasplat_b200.optim import FusedAdamW
     ps = _make(cuda, 2)
-    o = FusedAdamW(ps, lr=1e-3, max_grad_norm=0.5)
+    o = FusedAdamW(ps, lr=1e-3, max_grad_norm=0.5, nonfinite="skip")
     before = [p.detach().clone() for p in ps]
     for p in ps:
         p.grad = torch.ones_like(p)
@@ -50,6 +50,37 @@ def test_nonfinite_gradient_skips_the_step(cuda, lib):
     o.step()
     assert o.found_inf.item() == 1
     assert all(torch.equal(a, b) for a, b in zip(ps, before))
+    assert o.step_count == 0                      # a skipped step does not advance the bias corrections
     ps[2].grad[0, 0, 0, 0] = 0.0
     o.step()
     assert o.found_inf.item() == 0 and not torch.equal(ps[0], before[0])
+    assert o.step_count == 1 and float(o.state_dict()["state"][0]["step"]) == 1.0
+
+
+def test_nonfinite_gradients_are_sanitised_like_the_reference(cuda, lib):
+    """default: GradientNanCheckCallback (src/main.py:40-45) = torch.nan_to_num_ on the gradients, then the
+    usual clip + AdamW step."""
+    from vicasplat_b200.optim import FusedAdamW
+    ours, ref = _make(cuda, 3), _make(cuda, 3)
+    kw = dict(weight_decay=0.05, betas=(0.9, 0.95), eps=1e-8)
+    o = FusedAdamW(ours, lr=1e-3, max_grad_norm=0.5, **kw)
+    r = torch.optim.AdamW(ref, lr=1e-3, **kw)
+    g = torch.Generator().manual_seed(4)
+    for step in range(3):
+        for a, b in zip(ours, ref):
+            gr = torch.randn(a.shape, generator=g).to(cuda)
+            a.grad, b.grad = gr.clone(), gr.clone()
+        if step == 1:
+            for t in (ours[0].grad, ref[0].grad):
+                t[3, 5] = float("nan")
+                t[7, 1] = float("nan")
+        for b in ref:                              # the reference's callback
+            if torch.isnan(b.grad).any():
+                torch.nan_to_num_(b.grad)
+        torch.nn.utils.clip_grad_norm_(ref, 0.5)
+        r.step()
+        o.step()
+        assert o.found_inf.item() == (1 if step == 1 else 0)
+        for a, b in zip(ours, ref):
+            assert torch.isfinite(a).all() and torch.allclose(a, b, rtol=2e-6, atol=1e-7), step
+    assert o.step_count == 3

@@ -65,3 +65,18 @@ def test_step_without_cuda_fails_loudly():
         p.grad = torch.zeros_like(p)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         FusedAdamW(ps, lr=1e-3).step()
+
+
+def test_group_hyperparameters_are_validated_not_ignored():
+    """one weight decay / betas / eps reaches the kernel: a group that asks for something else must raise
+    (a silently decayed no-decay group would be a wrong optimizer)."""
+    from vicasplat_b200.optim import FusedAdamW
+    ps = _params(4)
+    with pytest.raises(ValueError, match="weight_decay"):
+        FusedAdamW([{"params": ps[:2]}, {"params": ps[2:], "weight_decay": 0.0}], lr=1e-3, weight_decay=0.05)
+    FusedAdamW([{"params": ps[:2]}, {"params": ps[2:], "weight_decay": 0.05}], lr=1e-3, weight_decay=0.05)
+    with pytest.raises(ValueError, match="no trainable"):
+        FusedAdamW([], lr=1e-3)
+    fopt = FusedAdamW(ps, lr=1e-3, weight_decay=0.05)
+    with pytest.raises(ValueError, match="weight_decay"):
+        fopt.load_state_dict(torch.optim.AdamW(_params(4), lr=1e-3, weight_decay=0.01).state_dict())

@@ -46,6 +46,7 @@ class AdamWParams(C.Structure):
         ("beta1", _f32), ("beta2", _f32), ("eps", _f32), ("weight_decay", _f32),
         ("step", _i32), ("max_grad_norm", _f32), ("skip_nonfinite", _i32),
         ("partials", _vp), ("counter", _vp), ("grad_norm_out", _vp), ("found_inf_out", _vp),
+        ("step_counter", _vp),
     ]
 
 

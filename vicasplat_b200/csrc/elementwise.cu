@@ -739,6 +739,13 @@ __global__ void update_pose_kernel(const float* __restrict__ rho, const float* _
 // ------------------------------------------------------------------ fused AdamW
 constexpr int AW_THREADS = 256;
 
+// torch.nan_to_num_ (the reference's GradientNanCheckCallback, src/main.py:40-45): NaN -> 0, +-inf -> +-FLT_MAX
+__device__ __forceinline__ float sanitize(float v) {
+  if (isnan(v)) return 0.f;
+  if (isinf(v)) return v > 0.f ? 3.402823466e+38f : -3.402823466e+38f;
+  return v;
+}
+
 __global__ void __launch_bounds__(AW_THREADS)
     adamw_norm_kernel(const vs_adamw_params p) {
   const int c = blockIdx.x;
@@ -749,9 +756,10 @@ __global__ void __launch_bounds__(AW_THREADS)
   float acc = 0.f;
   bool bad = false;
   for (long long i = threadIdx.x; i < n; i += AW_THREADS) {
-    const float v = g[i];
-    acc = fmaf(v, v, acc);
+    float v = g[i];
     bad |= !isfinite(v);
+    if (p.skip_nonfinite == 2) v = sanitize(v);
+    acc = fmaf(v, v, acc);
   }
   __shared__ float red[AW_THREADS / 32];
   __shared__ int s_bad;
@@ -785,13 +793,22 @@ __global__ void __launch_bounds__(AW_THREADS)
       for (int i = 0; i < AW_THREADS / 32; ++i) tot += red[i];
       *p.grad_norm_out = sqrtf(tot);
       *p.counter = 0u;
+      // the step counter lives on the device: it advances only when the update is applied, so the bias
+      // corrections never run ahead of the moments after a skipped step
+      if (p.step_counter != nullptr && !(p.skip_nonfinite == 1 && *(volatile int*)p.found_inf_out))
+        *p.step_counter += 1;
     }
   }
 }
 
 __global__ void __launch_bounds__(AW_THREADS)
     adamw_update_kernel(const vs_adamw_params p, float bc1, float bc2_sqrt) {
-  if (p.skip_nonfinite && *p.found_inf_out) return;
+  if (p.skip_nonfinite == 1 && *p.found_inf_out) return;
+  if (p.step_counter != nullptr) {
+    const float t = static_cast<float>(*p.step_counter);
+    bc1 = 1.0f - powf(p.beta1, t);
+    bc2_sqrt = sqrtf(1.0f - powf(p.beta2, t));
+  }
   const int c = blockIdx.x;
   const int t = p.chunk_tensor[c];
   const long long start = p.chunk_start[c];
@@ -806,7 +823,7 @@ __global__ void __launch_bounds__(AW_THREADS)
   const float decay = 1.0f - lr * p.weight_decay;
   const float step_size = lr / bc1;
   for (long long i = threadIdx.x; i < n; i += AW_THREADS) {
-    const float gi = g[i] * clip;
+    const float gi = (p.skip_nonfinite == 2 ? sanitize(g[i]) : g[i]) * clip;
     const float mi = p.beta1 * m[i] + (1.0f - p.beta1) * gi;
     const float vi = p.beta2 * v[i] + (1.0f - p.beta2) * gi * gi;
     m[i] = mi;
@@ -1080,7 +1097,8 @@ extern "C" int vs_adamw_step(const vs_adamw_params* p, vs_stream_t stream) {
              "adamw_step: null table");
   VS_REQUIRE(p->partials && p->counter && p->grad_norm_out && p->found_inf_out,
              "adamw_step: null scratch / output");
-  VS_REQUIRE(p->step >= 1 && p->beta1 >= 0.f && p->beta1 < 1.f && p->beta2 >= 0.f && p->beta2 < 1.f,
+  VS_REQUIRE((p->step >= 1 || p->step_counter != nullptr) && p->skip_nonfinite >= 0 && p->skip_nonfinite <= 2 &&
+                 p->beta1 >= 0.f && p->beta1 < 1.f && p->beta2 >= 0.f && p->beta2 < 1.f,
              "adamw_step: bad step / betas");
   cudaStream_t st = to_stream(stream);
   VS_CUDA(cudaMemsetAsync(p->found_inf_out, 0, sizeof(int32_t), st));

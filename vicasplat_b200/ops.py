@@ -420,8 +420,15 @@ def attention_backward(Q, K, V, O, dO, lse, dQ, dK, dV, *, heads, q_start, q_len
     (neighbour attention); without them overlapping key rows would be overwritten, not accumulated."""
     _need_cuda(Q, K, V, O, dO, lse, dQ, dK, dV)
     if kv_start1 is not None and dkv_tables is None and q_start.numel() > 1:
-        raise ValueError("attention_backward: two-segment items share key rows between items; pass the "
-                         "key-centric dkv_tables (encoder_grad.neighbour_backward_tables)")
+        # dK / dV are written, not accumulated: items must not share key rows.  Single-segment tables of
+        # the encoder are disjoint by construction; for ad-hoc two-segment tables it is checked here (a
+        # host read of the small tables -- the training path passes dkv_tables and never comes here)
+        segs = torch.stack([torch.stack([kv_start0, kv_len0]), torch.stack([kv_start1, kv_len1])]).cpu()
+        spans = sorted((int(a), int(a) + int(n)) for a, n in segs.permute(0, 2, 1).reshape(-1, 2).tolist() if n > 0)
+        if any(b0 < a1 for (_, a1), (b0, _) in zip(spans, spans[1:])):
+            raise ValueError("attention_backward: items share key rows (dK / dV would be overwritten, not "
+                             "accumulated); pass the key-centric dkv_tables "
+                             "(encoder_grad.neighbour_backward_tables)")
     lib = _lib.load()
     p = _lib.AttentionBwdParams()
     f = p.fwd

@@ -71,16 +71,27 @@ def verify_deferred(counts, records) -> None:
     for (n, tmax), (_t, max_pairs, max_tile, key) in zip(counts.tolist(), records):
         if n > max_pairs or (max_tile > 0 and tmax > max_tile):
             next_tile = 0 if tmax > MAX_TILE_SORT else min(MAX_TILE_SORT, int(tmax * 1.25) + 64)
-            _capacity_hint[key] = (max(int(n * 1.25) + 4096, max_pairs), next_tile)
+            _raise_hint(key, max(int(n * 1.25) + 4096, max_pairs), next_tile)
             bad = (n, tmax, max_pairs, max_tile)
     if bad is not None:
         raise RasterOverflow("render exceeded its binning capacity (pairs=%d, largest tile=%d, capacity=%d/%d); "
                              "the capacity hint has been raised: re-submit the batch" % bad)
 
 
+def _raise_hint(key, pairs: int, tile: int) -> None:
+    """The per-shape hint only ever GROWS (scenes of one shape differ: sizing for the last one alone makes
+    the next, busier one overflow): pairs = the most any scene needed; tile bound = the largest seen, or
+    0 (global sort) as soon as one scene needed it."""
+    old = _capacity_hint.get(key)
+    if old is not None:
+        pairs = max(pairs, old[0])
+        tile = 0 if (tile == 0 or old[1] == 0) else max(tile, old[1])
+    _capacity_hint[key] = (pairs, tile)
+
+
 class _Ctx:
     """Forward state kept for the backward pass (workspace holds the sorted splat lists)."""
-    __slots__ = ("params", "keep", "num_pairs", "max_pairs")
+    __slots__ = ("params", "keep", "num_pairs", "max_pairs", "max_tile")
 
 
 def _run_forward(V, G, H, W, shared, means, cov6, opac, shs, sh_M, sh_degree, sh_strides, colors,
@@ -145,7 +156,10 @@ class _Rasterize(torch.autograd.Function):
                 next_tile = min(MAX_TILE_SORT, int(tmax * 1.25) + 64) if tmax <= MAX_TILE_SORT else 0
                 if tmax <= SMALL_TILE_SORT < next_tile:
                     next_tile = SMALL_TILE_SORT   # stay within the one-kernel size classes
-            _capacity_hint[(V, G, H, W)] = (int(n * 1.25) + 4096, next_tile)
+            if (V, G, H, W) in _capacity_hint and max_tile > 0:
+                _raise_hint((V, G, H, W), int(n * 1.25) + 4096, next_tile)
+            else:   # first sight of this shape (or leaving the global-sort default): take what this scene needs
+                _capacity_hint[(V, G, H, W)] = (int(n * 1.25) + 4096, next_tile)
             if ok:
                 break
             # capacity or per-tile bound was too small: re-run with what this scene needs
@@ -163,39 +177,78 @@ class _Rasterize(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_color, g_radii, g_depth, g_alpha, g_touched):
-        lib = _lib.load()
         st = ctx.state
-        fp = st.params
-        V, G = fp.V, fp.G
-        dev = g_color.device if g_color is not None else g_depth.device
-        f32 = torch.float32
-        shared = bool(fp.gaussians_shared)
-        lead = (G,) if shared else (V, G)
-        d_means = torch.zeros(lead + (3,), dtype=f32, device=dev)
-        d_cov = torch.zeros(lead + (6,), dtype=f32, device=dev)
-        d_opac = torch.zeros(lead, dtype=f32, device=dev)
-        has_sh = fp.shs is not None
-        d_shs = torch.zeros(lead + (3 * fp.sh_M,), dtype=f32, device=dev) if has_sh else None
-        d_col = torch.zeros(lead + (3,), dtype=f32, device=dev) if not has_sh else None
-        d_tau = torch.zeros((V, 6), dtype=f32, device=dev)
-        gc = _f32c(g_color) if g_color is not None else torch.zeros((V, 3, fp.H, fp.W), dtype=f32, device=dev)
-        gd = _f32c(g_depth) if g_depth is not None else None
-        ga = _f32c(g_alpha) if g_alpha is not None else None
-        bws = torch.empty((V * G * 10,), dtype=f32, device=dev)
-        bp = RasterBwdParams()
-        bp.fwd = fp
-        bp.bwd_workspace, bp.bwd_workspace_bytes = ptr(bws), bws.numel() * 4
-        bp.dL_dcolor, bp.dL_ddepth, bp.dL_dalpha = ptr(gc), ptr(gd), ptr(ga)
-        bp.dL_dmeans3D, bp.dL_dcov3D, bp.dL_dopacity = ptr(d_means), ptr(d_cov), ptr(d_opac)
-        bp.dL_dshs, bp.dL_dcolors, bp.dL_dtau = ptr(d_shs), ptr(d_col), ptr(d_tau)
-        check(lib.vs_raster_backward(C.byref(bp), C.c_void_p(stream_ptr())), "vs_raster_backward")
+        g = render_backward(st, g_color, g_depth, g_alpha)
         sm, sc, so, ss, scol = ctx.shapes
-        g_shs = d_shs.reshape(ss) if has_sh else None
-        g_cols = d_col.reshape(scol) if not has_sh else None
+        has_sh = st.params.shs is not None
+        g_shs = g["d_sh"].reshape(ss) if has_sh else None
+        g_cols = g["d_colors"].reshape(scol) if not has_sh else None
+        d_tau = g["d_tau"]
         g_theta = d_tau[:, 3:].reshape(ctx.pose_shapes[0]) if ctx.has_pose[0] else None
         g_rho = d_tau[:, :3].reshape(ctx.pose_shapes[1]) if ctx.has_pose[1] else None
-        return (d_means.reshape(sm), d_cov.reshape(sc), d_opac.reshape(so), g_shs, g_cols,
+        return (g["d_means"].reshape(sm), g["d_cov6"].reshape(sc), g["d_opac"].reshape(so), g_shs, g_cols,
                 g_theta, g_rho, None)
+
+
+def render_backward(state: _Ctx, g_color, g_depth=None, g_alpha=None, out: Optional[dict] = None) -> dict:
+    """vs_raster_backward for a kept forward state (``_run_forward``): gradients w.r.t. means (G,3) /
+    (V,G,3), cov6, opacity, SH (in the layout the forward call was given) or colours, and the camera
+    twist (V,6: rho, theta).  ``out`` may hold preallocated, ZEROED fp32 buffers under the same keys
+    (d_means, d_cov6, d_opac, d_sh) -- e.g. one scene's slice of a batch-wide gradient tensor, so the
+    training step needs no per-scene copies; the kernels accumulate into them."""
+    lib = _lib.load()
+    fp = state.params
+    V, G = fp.V, fp.G
+    f32 = torch.float32
+    dev = (g_color if g_color is not None else g_depth).device
+    shared = bool(fp.gaussians_shared)
+    lead = (G,) if shared else (V, G)
+    out = dict(out or {})
+    has_sh = fp.shs is not None
+
+    def buf(key, shape):
+        t = out.get(key)
+        if t is None:
+            t = out[key] = torch.zeros(shape, dtype=f32, device=dev)
+        assert t.dtype == f32 and t.is_contiguous() and t.numel() == int(torch.Size(shape).numel()), key
+        return t
+
+    d_means, d_cov, d_opac = buf("d_means", lead + (3,)), buf("d_cov6", lead + (6,)), buf("d_opac", lead)
+    d_shs = buf("d_sh", lead + (3 * fp.sh_M,)) if has_sh else None
+    d_col = buf("d_colors", lead + (3,)) if not has_sh else None
+    d_tau = buf("d_tau", (V, 6))
+    gc = _f32c(g_color) if g_color is not None else torch.zeros((V, 3, fp.H, fp.W), dtype=f32, device=dev)
+    gd = _f32c(g_depth) if g_depth is not None else None
+    ga = _f32c(g_alpha) if g_alpha is not None else None
+    bws = torch.empty((V * G * 10,), dtype=f32, device=dev)
+    bp = RasterBwdParams()
+    bp.fwd = fp
+    bp.bwd_workspace, bp.bwd_workspace_bytes = ptr(bws), bws.numel() * 4
+    bp.dL_dcolor, bp.dL_ddepth, bp.dL_dalpha = ptr(gc), ptr(gd), ptr(ga)
+    bp.dL_dmeans3D, bp.dL_dcov3D, bp.dL_dopacity = ptr(d_means), ptr(d_cov), ptr(d_opac)
+    bp.dL_dshs, bp.dL_dcolors, bp.dL_dtau = ptr(d_shs), ptr(d_col), ptr(d_tau)
+    check(lib.vs_raster_backward(C.byref(bp), C.c_void_p(stream_ptr())), "vs_raster_backward")
+    return out
+
+
+def render_forward(means, cov6, opac, shs, *, sh_degree, sh_layout, viewmatrix, projmatrix, campos, tanfov, bg,
+                   H, W, max_pairs=None, max_tile_pairs=None):
+    """Plain (non-autograd) forward of V views of ONE shared Gaussian set with the per-shape capacity
+    hint: -> (color (V,3,H,W), depth (V,1,H,W), alpha, state).  ``state.num_pairs`` (device int64[2]:
+    pairs, largest tile) lets the caller verify the capacity when it next synchronises
+    (``verify_deferred``); ``render_backward(state, ...)`` differentiates it."""
+    V, G = viewmatrix.shape[0], means.shape[0]
+    sh_M, strides = (shs.shape[-2], (3, 1)) if sh_layout == "coef_major" else (shs.shape[-1], (1, shs.shape[-1]))
+    hint = _capacity_hint.get((V, G, H, W), (max(4 * V * G, 1 << 16), MAX_TILE_SORT))
+    max_pairs = hint[0] if max_pairs is None else max_pairs
+    max_tile = hint[1] if max_tile_pairs is None else max_tile_pairs
+    color, depth, alpha, _radii, _nt, st = _run_forward(
+        V, G, H, W, True, means, cov6, opac.reshape(-1), shs, sh_M, int(sh_degree), strides, None,
+        _f32c(viewmatrix).reshape(V, 16), _f32c(projmatrix).reshape(V, 16), _f32c(campos).reshape(V, 3),
+        _f32c(tanfov).reshape(V, 2), _f32c(bg).reshape(-1, 3).expand(V, 3).contiguous(), int(max_pairs),
+        int(max_tile), want_aux=False)
+    st.max_tile = int(max_tile)
+    return color, depth, alpha, st
 
 
 def rasterize_views(means3D, cov6, opacities, *, shs=None, colors_precomp=None, sh_degree=0,

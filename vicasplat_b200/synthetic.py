@@ -20,32 +20,39 @@ def clip(B: int, T: int, size: int, seed: int = 250307):
 
 
 def gaussian_scene(n_ctx: int, h: int, w: int, n_tgt: int, seed: int = 250307, d_sh: int = 25,
-                   depth_range=(1.0, 20.0), focal: float = 0.86, n_gauss: Optional[int] = None):
+                   depth_range=(1.0, 20.0), focal: float = 0.86, n_gauss: Optional[int] = None, device=None):
     """n_ctx*h*w Gaussians seen from n_ctx cameras on a unit baseline, n_tgt target cameras on the
-    same line.  Returns fp32 CPU tensors: means (G,3), covariances (G,3,3), harmonics (G,3,d_sh),
-    opacities (G,), extrinsics (n_tgt,4,4) c2w, intrinsics (n_tgt,3,3), near, far (n_tgt,)."""
-    g = torch.Generator().manual_seed(seed)
+    same line.  Returns fp32 tensors (on the CPU, or generated on `device` with that device's seeded
+    generator -- a different but equally distributed scene): means (G,3), covariances (G,3,3), harmonics
+    (G,3,d_sh), opacities (G,), extrinsics (n_tgt,4,4) c2w, intrinsics (n_tgt,3,3), near, far (n_tgt,)."""
+    device = torch.device(device) if device is not None else torch.device("cpu")
+    g = torch.Generator(device=device).manual_seed(seed)
     f64 = torch.float64
-    K = torch.tensor([[focal, 0, 0.5], [0, focal, 0.5], [0, 0, 1]], dtype=f64)
+    _rand, _randn, _arange, _eye, _ones = torch.rand, torch.randn, torch.arange, torch.eye, torch.ones
+
+    class _T:   # the torch factory functions of the code below, on `device`
+        rand = staticmethod(lambda *a, **k: _rand(*a, device=device, **k))
+        randn = staticmethod(lambda *a, **k: _randn(*a, device=device, **k))
+    K = torch.tensor([[focal, 0, 0.5], [0, focal, 0.5], [0, 0, 1]], dtype=f64, device=device)
 
     def cams(xs):
-        c = torch.eye(4, dtype=f64).repeat(len(xs), 1, 1)
-        c[:, 0, 3] = torch.tensor(xs, dtype=f64)
+        c = _eye(4, dtype=f64, device=device).repeat(len(xs), 1, 1)
+        c[:, 0, 3] = torch.tensor(xs, dtype=f64, device=device)
         return c
 
     ctx = cams([i / max(n_ctx - 1, 1) for i in range(n_ctx)])
     tgt = cams([(i + 0.5) / n_tgt for i in range(n_tgt)])
-    ys, xs = torch.meshgrid((torch.arange(h, dtype=f64) + 0.5) / h,
-                            (torch.arange(w, dtype=f64) + 0.5) / w, indexing="ij")
+    ys, xs = torch.meshgrid((_arange(h, dtype=f64, device=device) + 0.5) / h,
+                            (_arange(w, dtype=f64, device=device) + 0.5) / w, indexing="ij")
     rays = torch.stack([xs, ys, torch.ones_like(xs)], dim=-1).reshape(-1, 3) @ torch.linalg.inv(K).T
     n = h * w
     lo, hi = depth_range
-    z = lo * (hi / lo) ** torch.rand((n_ctx, n), generator=g, dtype=f64)
+    z = lo * (hi / lo) ** _T.rand((n_ctx, n), generator=g, dtype=f64)
     pts = rays[None] * z[..., None] + ctx[:, None, :3, 3]
-    sigma = z / (focal * w) * (0.5 + torch.rand((n_ctx, n), generator=g, dtype=f64))
-    aniso = 1.0 + 2.0 * torch.rand((n_ctx, n, 3), generator=g, dtype=f64)
+    sigma = z / (focal * w) * (0.5 + _T.rand((n_ctx, n), generator=g, dtype=f64))
+    aniso = 1.0 + 2.0 * _T.rand((n_ctx, n, 3), generator=g, dtype=f64)
     scales = sigma[..., None] * aniso / aniso.mean(-1, keepdim=True)
-    q = torch.randn((n_ctx, n, 4), generator=g, dtype=f64)
+    q = _T.randn((n_ctx, n, 4), generator=g, dtype=f64)
     q = q / q.norm(dim=-1, keepdim=True)
     i, j, k, r = q.unbind(-1)
     R = torch.stack([1 - 2 * (j * j + k * k), 2 * (i * j - k * r), 2 * (i * k + j * r),
@@ -53,19 +60,19 @@ def gaussian_scene(n_ctx: int, h: int, w: int, n_tgt: int, seed: int = 250307, d
                      2 * (i * k - j * r), 2 * (j * k + i * r), 1 - 2 * (i * i + j * j)],
                     dim=-1).reshape(n_ctx, n, 3, 3)
     cov = R @ torch.diag_embed(scales ** 2) @ R.transpose(-1, -2)
-    opac = 0.05 + 0.9 * torch.rand((n_ctx, n), generator=g, dtype=f64)
-    sh = 0.5 * torch.randn((n_ctx, n, 3, d_sh), generator=g, dtype=f64)
-    mask = torch.ones(d_sh, dtype=f64)
+    opac = 0.05 + 0.9 * _T.rand((n_ctx, n), generator=g, dtype=f64)
+    sh = 0.5 * _T.randn((n_ctx, n, 3, d_sh), generator=g, dtype=f64)
+    mask = _ones(d_sh, dtype=f64, device=device)
     for deg in range(1, isqrt(d_sh)):
         mask[deg * deg:(deg + 1) ** 2] = 0.1 * 0.25 ** deg
     out = dict(means=pts.reshape(-1, 3), covariances=cov.reshape(-1, 3, 3),
                harmonics=(sh * mask).reshape(-1, 3, d_sh), opacities=opac.reshape(-1))
     if n_gauss is not None:
-        sel = torch.randperm(out["means"].shape[0], generator=g)[:n_gauss]
+        sel = torch.randperm(out["means"].shape[0], generator=g, device=device)[:n_gauss]
         out = {k_: v[sel] for k_, v in out.items()}
     out = {k_: v.float().contiguous() for k_, v in out.items()}
     out.update(extrinsics=tgt.float(), intrinsics=K.float()[None].repeat(n_tgt, 1, 1),
-               near=torch.full((n_tgt,), 0.01), far=torch.full((n_tgt,), 100.0))
+               near=torch.full((n_tgt,), 0.01, device=device), far=torch.full((n_tgt,), 100.0, device=device))
     return out
 
 
