@@ -76,7 +76,7 @@ grad_prep_kernel(const T* __restrict__ src, long long ld_src, const bf16* __rest
   __shared__ float csum[16][64];
   const int t = threadIdx.x;
   const int cg = t & 15, rp = t >> 4;
-  const int row0 = blockIdx.y * 64, col0 = blockIdx.x * 64;
+  const int row0 = blockIdx.x * 64, col0 = blockIdx.y * 64;   // rows on grid.x: up to 2^31 blocks
   const int c = col0 + 4 * cg;
   const bool col_ok = c < cols;  // cols % 4 == 0
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
@@ -295,8 +295,8 @@ extern "C" int vs_grad_prep(const void* src, int src_dtype, int64_t ld_src, cons
   VS_REQUIRE(transposed == nullptr || (ld_t % 8 == 0 && ld_t >= rows && al16(transposed)),
              "grad_prep: transposed leading dimension must be a multiple of 8 and >= rows");
   VS_REQUIRE(src_dtype == VS_F32 || ld_src % 4 == 0, "grad_prep: bf16 source rows must be 8-byte aligned");
-  const dim3 grid(ceil_div(cols, 64), ceil_div(rows, 64));
-  VS_REQUIRE(grid.y < 65536, "grad_prep: more than 2^22 rows");
+  const dim3 grid(ceil_div(rows, 64), ceil_div(cols, 64));
+  VS_REQUIRE(grid.y < 65536, "grad_prep: more than 2^22 columns");
   cudaStream_t s = to_stream(stream);
   if (src_dtype == VS_F32)
     grad_prep_kernel<float><<<grid, 256, 0, s>>>(
