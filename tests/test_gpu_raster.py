@@ -188,3 +188,57 @@ def test_stress_size_properties(cuda, lib):
     dc = (c_perm - color).abs()
     assert dc.max() < 2e-3 and dc.mean() < 1e-6 and (dc > 1e-5).float().mean() < 1e-3
     assert (d_perm - depth).abs().max() < 2e-2 and (d_perm - depth).abs().mean() < 1e-5
+
+
+def test_headline_scene_against_oracle(cuda, lib):
+    """The scene of bench.py / BASELINE configs[1] at FULL size -- 524 288 pixel-aligned Gaussians, 256 x 256
+    target views -- against the fp32 oracle: two of the twelve views (~1 s of CPU each; first and a middle
+    camera).  Measured on B200: 99.71 % of the pixels within 1e-4 absolute (colour), mean error 2.5e-6, worst
+    pixel 9.7e-3.  The small scenes above reach >= 99.9 %; here ~100 splats pile up on every pixel, so many
+    more alpha evaluations sit within an ulp of the hard thresholds (alpha < 1/255 skipped, stop at
+    T < 1e-4), and one flipped decision moves a pixel by up to ~1/255 of a colour.  Asserted: >= 99.5 %
+    within 1e-4, mean <= 1e-5, worst <= 2e-2."""
+    from vicasplat_b200 import synthetic
+    from vicasplat_b200.decoder import render_cuda
+    T, V, S = 8, 12, 256
+    sc = synthetic.gaussian_scene(T, S, S, V, seed=1)
+    pick = [0, 7]
+    sub = {k: (v[pick] if k in ("extrinsics", "intrinsics", "near", "far") else v) for k, v in sc.items()}
+    rc, rd = rr.render_cuda_ref(sub["extrinsics"], sub["intrinsics"], sub["near"], sub["far"], (S, S),
+                                torch.zeros((len(pick), 3)), sub["means"], sub["covariances"], sub["harmonics"],
+                                sub["opacities"])
+    d = {k: v.to(cuda) for k, v in sc.items()}
+    c, dep = render_cuda(d["extrinsics"], d["intrinsics"], d["near"], d["far"], (S, S), torch.zeros((V, 3), device=cuda),
+                         d["means"], d["covariances"], d["harmonics"], d["opacities"])
+    c, dep = c[pick].cpu().double(), dep[pick].cpu().double()
+    ec = (c - rc.double()).abs()
+    ed = (dep - rd.double()).abs() / rd.double().abs().clamp_min(1)
+    ok_c, ok_d = (ec <= 1e-4).double().mean().item(), (ed <= 1e-4).double().mean().item()
+    print(f"[raster headline scene] colour: {ok_c * 100:.4f} % of pixels within 1e-4, max {ec.max():.3e}, mean "
+          f"{ec.mean():.3e}; depth (relative): {ok_d * 100:.4f} % within 1e-4, max {ed.max():.3e}")
+    assert rc.abs().max() > 0.2 and rd.max() > 1.0
+    assert ok_c >= 0.995 and ok_d >= 0.995
+    assert ec.mean() <= 1e-5 and ed.mean() <= 1e-5
+    assert ec.max() < 2e-2 and ed.max() < 2e-2
+
+
+@pytest.mark.parametrize("probe", ["plain", "sh_degree4", "near_cull", "depth", "thresholds", "lowpass", "radius",
+                                   "tie_order", "n_touched"])
+def test_upstream_golden(cuda, lib, probe):
+    """Pins the rasterizer (kernels AND oracle) to the real diff_gaussian_rasterization the day its goldens
+    exist: oracle/make_raster_golden.py writes tests/golden/raster_upstream.npz on a box with the package.
+    Until then the parity of rows R1-R3 is UNPINNED and this test is skipped."""
+    from pathlib import Path
+    import numpy as np
+    from oracle import make_raster_golden as mg
+    path = Path(__file__).parent / "golden" / "raster_upstream.npz"
+    if not path.exists():
+        pytest.skip("no upstream goldens (diff_gaussian_rasterization is not installable here): parity UNPINNED")
+    gold = np.load(path)
+    sc, h, w = mg.build_scene(probe)
+    want_c = torch.from_numpy(gold[f"{probe}/image"]).double()
+    want_d = torch.from_numpy(gold[f"{probe}/depth"]).double()[:, 0]
+    rc, rd = _oracle(sc, h)
+    _check(rc, rd, want_c, want_d)                      # the oracle restates upstream
+    c, d = _ours(sc, h, cuda)
+    _check(c, d, want_c, want_d)                        # and so do the kernels
