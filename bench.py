@@ -450,6 +450,21 @@ def run_ours(args) -> None:
     chk = raster_batch(check=True)[0]
     assert torch.isfinite(chk).all() and torch.equal(chk, color)
 
+    # ---- parity mode (precision="fp16": TF32's mantissa, see VicaSplat): the same encoder step, timed alike
+    from vicasplat_b200.encoder import EncoderEngine as _Eng
+    eng16 = _Eng(model, precision="fp16")
+    for _ in range(3):
+        eng16.run(image_d, K_d, clone_outputs=False)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        eng16.run(image_d, K_d, clone_outputs=False)
+    e1.record()
+    barrier()
+    enc16_ms, = dist_util.max_over_ranks([e0.elapsed_time(e1) / args.steps], dev)
+    del eng16
+
     train = None
     if args.train_batch > 0:
         train = train_leg(args, model, scenes, dev, rank, world, local, barrier)
@@ -500,6 +515,12 @@ def run_ours(args) -> None:
             wall_ms_per_step=t_wall * 1e3 / args.steps,
             raster_parity="unpinned (upstream diff_gaussian_rasterization source absent; restated algorithm)",
         )
+        line["parity_mode"] = dict(
+            precision="fp16 operands (10-bit mantissa = TF32's, the reference's matmul precision), fp32 accumulation "
+                      "and residual streams", encoder_ms=enc16_ms,
+            value=world * NB * 1e3 / (enc16_ms + ras_ms), unit="scenes/s",
+            parity="raw Gaussians 1.1e-3 rel-L2 vs the reference's fp32 golden at full depth "
+                   "(tests/test_gpu_encoder.py; speed mode: 1.1e-2)")
         if train is not None:
             line["train_step"] = train
         if world == 1 and not args.no_cpu:

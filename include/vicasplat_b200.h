@@ -139,6 +139,9 @@ typedef struct vs_gemm_params {
   int32_t c_accumulate; /* C += result (atomic, fp32 only) */
   int32_t split_k;      /* with c_accumulate: number of K ranges (0 = choose) */
   float out_scale;      /* 0 = 1: the accumulator is multiplied by this first (e.g. 1 / keep of a dropout) */
+  int32_t operand_dtype; /* 16-bit format of A, W and of 16-bit C / C2 / residual maps: 0 or VS_BF16 = bf16 (speed
+                            mode), VS_F16 = fp16 (parity mode: TF32's 10-bit mantissa, same tensor rate; forward
+                            a_modes only) */
 } vs_gemm_params;
 
 int vs_gemm(const vs_gemm_params* p, vs_stream_t stream);
@@ -162,6 +165,7 @@ typedef struct vs_layernorm_params {
   int64_t ldy_bf16;
   float* y_f32;
   int64_t ldy_f32;
+  int32_t y16_dtype; /* format of y_bf16: 0 / VS_BF16 = bf16, VS_F16 = fp16 */
 } vs_layernorm_params;
 int vs_layernorm(const vs_layernorm_params* p, vs_stream_t stream);
 
@@ -189,24 +193,27 @@ typedef struct vs_attention_params {
   float scale;
   float* lse; /* optional output (q_rows, heads) f32 for vs_attention_backward: log2-domain
                  log-sum-exp of the scaled scores of every query row (+inf for a row without keys) */
+  int32_t dtype; /* 0 / VS_BF16: Q, K, V, O (and the probabilities) are bf16; VS_F16: fp16 (parity mode) */
 } vs_attention_params;
 int vs_attention(const vs_attention_params* p, vs_stream_t stream);
 
-/* ------------------------------------------------------------------ small fused ops */
+/* ------------------------------------------------------------------ small fused ops
+ * half_dtype (where present): the 16-bit format of the bf16-named operands -- 0 / VS_BF16 = bf16,
+ * VS_F16 = fp16 (the parity mode of the encoder path, see vs_gemm_params.operand_dtype). */
 /* Non-overlapping patch gather: img fp32 NCHW [n,3,h,w] -> bf16 [n*(h/P)*(w/P), 3*P*P]
  * (channel-major, then row, then column: the flattening order of Conv2d weight [E,3,P,P];
  * croco/blocks.py:195-225). */
-int vs_patchify(const float* img, void* out, int n, int h, int w, int P, vs_stream_t stream);
+int vs_patchify(const float* img, void* out, int n, int h, int w, int P, int half_dtype, vs_stream_t stream);
 /* kxk stride-s im2col of an NHWC bf16 map (or NCHW fp32 image when src_nchw_f32 != 0) into
  * bf16 [n*ho*wo, kpad], column order (tap-major, channel-minor), zero padded to kpad. */
 int vs_im2col(const void* src, int src_nchw_f32, void* out, int n, int h, int w, int c, int k,
-              int stride, int pad, int kpad, vs_stream_t stream);
+              int stride, int pad, int kpad, int half_dtype, vs_stream_t stream);
 /* bilinear x2, align_corners=True, NHWC bf16 (heads/dpt_block.py:214-216) */
-int vs_upsample2x(const void* src, void* dst, int n, int h, int w, int c, vs_stream_t stream);
+int vs_upsample2x(const void* src, void* dst, int n, int h, int w, int c, int half_dtype, vs_stream_t stream);
 /* dst = bilinear_x2(src) + add (add: full-resolution NHWC bf16 map; the image-feature merge of
  * dpt_gs_head.py:148-150 in its un-fused, training form) */
 int vs_upsample2x_add(const void* src, const void* add, void* dst, int n, int h, int w, int c,
-                      vs_stream_t stream);
+                      int half_dtype, vs_stream_t stream);
 /* ConvTranspose2d with kernel == stride == k, expressed as GEMM output [n*h*w, k*k*c]
  * (column = (dy*k+dx)*c + co) scattered to NHWC [n, h*k, w*k, c] (bf16 -> bf16). */
 int vs_pixel_shuffle(const void* src, void* dst, int n, int h, int w, int c, int k,
@@ -221,9 +228,9 @@ int vs_camera_tokens(const float* intr_tok, const float* extr_tok, float* x, int
                      int C, int rows_per_frame, vs_stream_t stream);
 /* fp32 NCHW image [n,3,h,w] -> bf16 NHWC with 8 channels (3 used) and a zero border of `pad`
  * rows above/below and `pad` / (8 - pad) columns left/right: [n, h + 2*pad, w + 8, 8]. */
-int vs_image_nhwc8(const float* img, void* out, int n, int h, int w, int pad, vs_stream_t stream);
+int vs_image_nhwc8(const float* img, void* out, int n, int h, int w, int pad, int half_dtype, vs_stream_t stream);
 /* SiLU on fp32 rows -> bf16 (AdaLNModulation.nonlinear, backbone_vica.py:210-212) */
-int vs_silu_bf16(const float* x, int64_t ldx, void* y, int64_t ldy, int rows, int C,
+int vs_silu_bf16(const float* x, int64_t ldx, void* y, int64_t ldy, int rows, int C, int half_dtype,
                  vs_stream_t stream);
 /* Camera head tail: cam_feat fp32 [B*T, ld] (rows of camera_dec_norm output, frame 0 unused) ->
  * pred (B, T-1, 8) normalised dual quaternion and c2w (B, T, 4, 4) with identity prepended.
@@ -234,7 +241,7 @@ int vs_camera_head(const float* cam_feat, int64_t ld, const float* w, const floa
 /* pts head tail: feat bf16 [px, Cf] (post-ReLU) -> 1x1 conv (w fp32 [3, Cf], b[3]) -> exp-depth
  * postprocess xyz = x/|x| * expm1(|x|) (heads/postprocess.py:42-61) -> raw[px, raw_ld] cols 0..2 */
 int vs_pts_tail(const void* feat, int Cf, const float* w, const float* b, float* raw, int64_t raw_ld,
-                int64_t px, vs_stream_t stream);
+                int64_t px, int half_dtype, vs_stream_t stream);
 /* MyGaussianAdapter.forward (gaussian_adapter.py:167-212).  Input rows (fp32, leading dimension
  * src_ld) hold the head outputs: xyz at columns [center_col, +3), the 8 + 3*d_sh Gaussian parameters
  * (opacity | scale 3 | quaternion xyzw 4 | SH (xyz d_sh)) at [param_col, ...).  The reference's

@@ -35,6 +35,7 @@ class GemmParams(C.Structure):
         ("rope_pos", _vp), ("rope_q_col", _i32), ("rope_k_col", _i32), ("rope_heads", _i32),
         ("rope_base", _f32), ("rope_cam_theta", _f32),
         ("mask_mode", _i32), ("c_accumulate", _i32), ("split_k", _i32), ("out_scale", _f32),
+        ("operand_dtype", _i32),
     ]
 
 
@@ -56,7 +57,7 @@ class LayerNormParams(C.Structure):
         ("w", _vp), ("b", _vp), ("w0", _vp), ("b0", _vp),
         ("scale", _vp), ("shift", _vp), ("mod_ld", _i64), ("rows_per_frame", _i32),
         ("eps", _f32), ("normalize", _i32),
-        ("y_bf16", _vp), ("ldy_bf16", _i64), ("y_f32", _vp), ("ldy_f32", _i64),
+        ("y_bf16", _vp), ("ldy_bf16", _i64), ("y_f32", _vp), ("ldy_f32", _i64), ("y16_dtype", _i32),
     ]
 
 
@@ -85,7 +86,7 @@ class AttentionParams(C.Structure):
         ("q_start", _vp), ("q_len", _vp), ("kv_start0", _vp), ("kv_len0", _vp),
         ("kv_start1", _vp), ("kv_len1", _vp),
         ("max_q_len", _i32), ("max_kv_len", _i32), ("causal_block", _i32), ("scale", _f32),
-        ("lse", _vp),
+        ("lse", _vp), ("dtype", _i32),
     ]
 
 

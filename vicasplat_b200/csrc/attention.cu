@@ -20,6 +20,7 @@
 #include <cuda_bf16.h>
 
 #include "common.h"
+#include "half16.cuh"
 #include "ptx.cuh"
 #include "tmap.h"
 
@@ -40,6 +41,7 @@ constexpr int TMEM_COLS = 128;  // S: [0,64)  O: [64,128)  -- 3 CTAs x 128 of th
 
 struct AttnDev {
   __nv_bfloat16* O;
+  int f16;   // Q / K / V / P / O are fp16 instead of bf16 (half16.cuh)
   long long ldo;
   const int *q_start, *q_len, *kv_start0, *kv_len0, *kv_start1, *kv_len1;
   int causal_block;
@@ -133,8 +135,9 @@ __global__ void __launch_bounds__(ATT_THREADS, 3)
     // buffered (128 TMEM columns and 65 KB of shared memory per CTA -> three CTAs per SM, whose
     // phases interleave); every barrier completes once per key tile, phase parity = j & 1.
     if (lane == 0) {
-      constexpr uint32_t idesc_s = umma_idesc_bf16(QT, KT, 0);
-      constexpr uint32_t idesc_o = umma_idesc_bf16(QT, HD, 1);
+      const uint32_t fmt_clear = a.f16 ? ~((1u << 7) | (1u << 10)) : ~0u;   // format bits: 1 = bf16, 0 = fp16
+      const uint32_t idesc_s = umma_idesc_bf16(QT, KT, 0) & fmt_clear;
+      const uint32_t idesc_o = umma_idesc_bf16(QT, HD, 1) & fmt_clear;
       const uint32_t q_addr = smem_u32(sQ), k_addr = smem_u32(sK), v_addr = smem_u32(sV),
                      p_addr = smem_u32(sP);
       auto issue_s = [&](int j, int st) {
@@ -278,8 +281,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 3)
             const float p1 = ex2_approx(__uint_as_float(v[i + 1]) * a.scale_log2 - m_use);
             rs0 += p0;
             rs1 += p1;
-            const __nv_bfloat162 b2 = __floats2bfloat162_rn(p0, p1);
-            pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&b2);
+            pk[i >> 1] = f2_to_h2(p0, p1, a.f16);
           }
         } else {
 #pragma unroll
@@ -290,8 +292,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 3)
             if (i + 1 >= my_valid) p1 = 0.f;
             rs0 += p0;
             rs1 += p1;
-            const __nv_bfloat162 b2 = __floats2bfloat162_rn(p0, p1);
-            pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&b2);
+            pk[i >> 1] = f2_to_h2(p0, p1, a.f16);
           }
         }
         if (!p_free) {
@@ -335,9 +336,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 3)
           uint32_t w[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const __nv_bfloat162 b2 = __floats2bfloat162_rn(__uint_as_float(v[ch * 8 + 2 * i]) * inv,
-                                                            __uint_as_float(v[ch * 8 + 2 * i + 1]) * inv);
-            w[i] = *reinterpret_cast<const uint32_t*>(&b2);
+            w[i] = f2_to_h2(__uint_as_float(v[ch * 8 + 2 * i]) * inv, __uint_as_float(v[ch * 8 + 2 * i + 1]) * inv,
+                            a.f16);
           }
           *reinterpret_cast<uint4*>(dst + h * 32 + ch * 8) = make_uint4(w[0], w[1], w[2], w[3]);
         }
@@ -398,8 +398,8 @@ __global__ void __launch_bounds__(256)
   const int s1 = a.kv_start1 ? a.kv_start1[item] : 0, l1 = a.kv_len1 ? a.kv_len1[item] : 0;
   const int nk = min(l0 + l1, TAIL_MAX_KEYS);
   if (threadIdx.x < 64)
-    s_q[threadIdx.x] = __bfloat162float(Q[static_cast<long long>(grow) * ldq + head * HD + threadIdx.x]) *
-                       a.scale_log2;
+    s_q[threadIdx.x] = h_to_f(reinterpret_cast<const uint16_t*>(Q)[static_cast<long long>(grow) * ldq + head * HD +
+                                                                      threadIdx.x], a.f16) * a.scale_log2;
   __syncthreads();
   float mx = -INFINITY;
   for (int j = threadIdx.x; j < nk; j += 256) {
@@ -416,7 +416,7 @@ __global__ void __launch_bounds__(256)
         const uint32_t w[4] = {kv[i].x, kv[i].y, kv[i].z, kv[i].w};
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[u]));
+          const float2 f = h2_to_f2(w[u], a.f16);
           s = fmaf(s_q[8 * i + 2 * u], f.x, s);
           s = fmaf(s_q[8 * i + 2 * u + 1], f.y, s);
         }
@@ -447,7 +447,7 @@ __global__ void __launch_bounds__(256)
     const float p = s_p[j];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[u]));
+      const float2 f = h2_to_f2(w[u], a.f16);
       acc[2 * u] = fmaf(p, f.x, acc[2 * u]);
       acc[2 * u + 1] = fmaf(p, f.y, acc[2 * u + 1]);
     }
@@ -461,8 +461,8 @@ __global__ void __launch_bounds__(256)
     float o = 0.f;
 #pragma unroll
     for (int i = 0; i < 32; ++i) o += s_o[i][threadIdx.x];
-    a.O[static_cast<long long>(grow) * a.ldo + head * HD + threadIdx.x] =
-        __float2bfloat16(sum > 0.f ? o / sum : 0.f);
+    reinterpret_cast<uint16_t*>(a.O)[static_cast<long long>(grow) * a.ldo + head * HD + threadIdx.x] =
+        f_to_h(sum > 0.f ? o / sum : 0.f, a.f16);
   }
 }
 
@@ -501,6 +501,8 @@ extern "C" int vs_attention(const vs_attention_params* p, vs_stream_t stream_) {
   if (rc) return rc;
   AttnDev a{};
   a.O = static_cast<__nv_bfloat16*>(p->O);
+  VS_REQUIRE(p->dtype == 0 || p->dtype == VS_BF16 || p->dtype == VS_F16, "vs_attention: dtype must be bf16 or fp16");
+  a.f16 = p->dtype == VS_F16;
   a.ldo = p->ldo;
   a.q_start = p->q_start;
   a.q_len = p->q_len;

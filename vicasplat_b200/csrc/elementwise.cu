@@ -6,6 +6,7 @@
 #include <cuda_bf16.h>
 
 #include "common.h"
+#include "half16.cuh"
 #include "ptx.cuh"
 
 namespace vs {
@@ -185,10 +186,10 @@ __global__ void layernorm_kernel(vs_layernorm_params p) {
       if (p.y_f32 != nullptr)
         reinterpret_cast<float4*>(p.y_f32 + static_cast<long long>(row) * p.ldy_f32)[idx] = y;
       if (p.y_bf16 != nullptr) {
-        __nv_bfloat162 lo = __floats2bfloat162_rn(y.x, y.y), hi = __floats2bfloat162_rn(y.z, y.w);
+        const bool f16 = p.y16_dtype == VS_F16;
         uint2 pk;
-        pk.x = *reinterpret_cast<uint32_t*>(&lo);
-        pk.y = *reinterpret_cast<uint32_t*>(&hi);
+        pk.x = f2_to_h2(y.x, y.y, f16);
+        pk.y = f2_to_h2(y.z, y.w, f16);
         reinterpret_cast<uint2*>(static_cast<bf16*>(p.y_bf16) +
                                  static_cast<long long>(row) * p.ldy_bf16)[idx] = pk;
       }
@@ -198,7 +199,7 @@ __global__ void layernorm_kernel(vs_layernorm_params p) {
 
 // ------------------------------------------------------------------ gathers
 __global__ void patchify_kernel(const float* __restrict__ img, bf16* __restrict__ out, int n, int h,
-                                int w, int P) {
+                                int w, int P, int f16) {
   const long long total = static_cast<long long>(n) * 3 * h * w;
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= total) return;
@@ -214,7 +215,7 @@ __global__ void patchify_kernel(const float* __restrict__ img, bf16* __restrict_
   const int t = static_cast<int>(tok - static_cast<long long>(im) * gw * gh);
   const int ty = t / gw, tx = t - ty * gw;
   const float v = img[((static_cast<long long>(im) * 3 + c) * h + ty * P + py) * w + tx * P + px];
-  out[i] = __float2bfloat16(v);
+  reinterpret_cast<uint16_t*>(out)[i] = f_to_h(v, f16);
 }
 
 // one thread = 8 consecutive output columns (one 16-byte store); for an NHWC source whose channel
@@ -222,7 +223,7 @@ __global__ void patchify_kernel(const float* __restrict__ img, bf16* __restrict_
 // grid = (segments of an output row of pixels, output y, image).
 __global__ void im2col_kernel(const void* __restrict__ src, int nchw_f32, bf16* __restrict__ out,
                               int n, int h, int w, int c, int k, int stride, int pad, int kpad,
-                              int ho, int wo) {
+                              int ho, int wo, int f16) {
   const unsigned k8 = kpad / 8;
   const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= static_cast<unsigned>(wo) * k8) return;
@@ -259,14 +260,12 @@ __global__ void im2col_kernel(const void* __restrict__ src, int nchw_f32, bf16* 
               v = __ldg(static_cast<const float*>(src) +
                         ((static_cast<size_t>(im) * c + ch) * h + y) * w + x);
             else
-              v = __bfloat162float(static_cast<const bf16*>(
-                  src)[((static_cast<size_t>(im) * h + y) * w + x) * c + ch]);
+              v = h_to_f(static_cast<const uint16_t*>(src)[((static_cast<size_t>(im) * h + y) * w + x) * c + ch], f16);
           }
         }
         v2[u] = v;
       }
-      const __nv_bfloat162 b2 = __floats2bfloat162_rn(v2[0], v2[1]);
-      pk[e >> 1] = *reinterpret_cast<const uint32_t*>(&b2);
+      pk[e >> 1] = f2_to_h2(v2[0], v2[1], f16);
     }
     o = make_uint4(pk[0], pk[1], pk[2], pk[3]);
   }
@@ -276,7 +275,7 @@ __global__ void im2col_kernel(const void* __restrict__ src, int nchw_f32, bf16* 
 // bilinear x2 align_corners=True on NHWC bf16; one thread per 8 channels of an output pixel;
 // grid = (segments of an output row, output row, image): no 64-bit index arithmetic
 __global__ void upsample2x_kernel(const bf16* __restrict__ src, const bf16* __restrict__ add,
-                                  bf16* __restrict__ dst, int n, int h, int w, int c) {
+                                  bf16* __restrict__ dst, int n, int h, int w, int c, int f16) {
   const unsigned c8 = c / 8;
   const int ho = 2 * h, wo = 2 * w;
   const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -303,19 +302,16 @@ __global__ void upsample2x_kernel(const bf16* __restrict__ src, const bf16* __re
   const uint32_t* pd = &d.x; const uint32_t* pe = &e.x; uint32_t* po = &o.x;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    const float2 fa = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(pa + j));
-    const float2 fb = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(pb + j));
-    const float2 fc = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(pc + j));
-    const float2 fd = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(pd + j));
-    __nv_bfloat162 r2 =
-        __floats2bfloat162_rn(w00 * fa.x + w01 * fb.x + w10 * fc.x + w11 * fd.x,
-                              w00 * fa.y + w01 * fb.y + w10 * fc.y + w11 * fd.y);
-    if (add != nullptr) {   // the upsampled map is rounded to bf16 first, like the fused GEMM epilogue does
-      const float2 fu = __bfloat1622float2(r2);
-      const float2 fe = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(pe + j));
-      r2 = __floats2bfloat162_rn(fu.x + fe.x, fu.y + fe.y);
+    const float2 fa = h2_to_f2(pa[j], f16), fb = h2_to_f2(pb[j], f16);
+    const float2 fc = h2_to_f2(pc[j], f16), fd = h2_to_f2(pd[j], f16);
+    uint32_t r2 = f2_to_h2(w00 * fa.x + w01 * fb.x + w10 * fc.x + w11 * fd.x,
+                           w00 * fa.y + w01 * fb.y + w10 * fc.y + w11 * fd.y, f16);
+    if (add != nullptr) {   // the upsampled map is rounded to 16 bits first, like the fused GEMM epilogue does
+      const float2 fu = h2_to_f2(r2, f16);
+      const float2 fe = h2_to_f2(pe[j], f16);
+      r2 = f2_to_h2(fu.x + fe.x, fu.y + fe.y, f16);
     }
-    po[j] = *reinterpret_cast<const uint32_t*>(&r2);
+    po[j] = r2;
   }
   *reinterpret_cast<uint4*>(dst + oidx) = o;
 }
@@ -342,7 +338,7 @@ __global__ void pixel_shuffle_kernel(const bf16* __restrict__ src, bf16* __restr
 
 // thread per padded pixel: 16-byte store of (r, g, b, 0, 0, 0, 0, 0) or zeros on the border
 __global__ void image_nhwc8_kernel(const float* __restrict__ img, bf16* __restrict__ out, int h,
-                                   int w, int pad) {
+                                   int w, int pad, int f16) {
   const int wp = w + 8;
   const int xp = blockIdx.x * blockDim.x + threadIdx.x;
   if (xp >= wp) return;
@@ -352,10 +348,8 @@ __global__ void image_nhwc8_kernel(const float* __restrict__ img, bf16* __restri
   if (x >= 0 && x < w && y >= 0 && y < h) {
     const size_t hw = static_cast<size_t>(h) * w;
     const float* p = img + static_cast<size_t>(im) * 3 * hw + static_cast<size_t>(y) * w + x;
-    const __nv_bfloat162 rg = __floats2bfloat162_rn(__ldg(p), __ldg(p + hw));
-    const __nv_bfloat162 b0 = __floats2bfloat162_rn(__ldg(p + 2 * hw), 0.f);
-    o.x = *reinterpret_cast<const uint32_t*>(&rg);
-    o.y = *reinterpret_cast<const uint32_t*>(&b0);
+    o.x = f2_to_h2(__ldg(p), __ldg(p + hw), f16);
+    o.y = f2_to_h2(__ldg(p + 2 * hw), 0.f, f16);
   }
   *reinterpret_cast<uint4*>(out + ((static_cast<size_t>(im) * (h + 2 * pad) + yp) * wp + xp) * 8) = o;
 }
@@ -384,12 +378,12 @@ __global__ void camera_tokens_kernel(const float* __restrict__ intr, const float
 }
 
 __global__ void silu_bf16_kernel(const float* __restrict__ x, long long ldx, bf16* __restrict__ y,
-                                 long long ldy, int rows, int C) {
+                                 long long ldy, int rows, int C, int f16) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * C) return;
   const int r = i / C, c = i - r * C;
   const float v = x[r * ldx + c];
-  y[r * ldy + c] = __float2bfloat16(v / (1.0f + expf(-v)));
+  reinterpret_cast<uint16_t*>(y)[r * ldy + c] = f_to_h(v / (1.0f + expf(-v)), f16);
 }
 
 // one block (8 warps) per (b, t): warp j computes output channel j of Linear(C->8) on relu(feat)
@@ -444,7 +438,7 @@ __global__ void camera_head_kernel(const float* __restrict__ feat, long long ld,
 __global__ void __launch_bounds__(128)
     pts_tail_kernel(const bf16* __restrict__ feat, int Cf, const float* __restrict__ w,
                     const float* __restrict__ b, float* __restrict__ raw, long long raw_ld,
-                    long long px) {
+                    long long px, int f16) {
   extern __shared__ float s_w[];   // [3][Cf]
   for (int i = threadIdx.x; i < 3 * Cf; i += blockDim.x) s_w[i] = w[i];
   __syncthreads();
@@ -458,7 +452,7 @@ __global__ void __launch_bounds__(128)
     const uint32_t u[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u[j]));
+      const float2 v = h2_to_f2(u[j], f16);
       const int c = c8 * 8 + 2 * j;
       a0 = fmaf(v.x, s_w[c], fmaf(v.y, s_w[c + 1], a0));
       a1 = fmaf(v.x, s_w[Cf + c], fmaf(v.y, s_w[Cf + c + 1], a1));
@@ -909,20 +903,24 @@ extern "C" int vs_layernorm(const vs_layernorm_params* p, vs_stream_t stream) {
   return VS_OK;
 }
 
-extern "C" int vs_patchify(const float* img, void* out, int n, int h, int w, int P,
+extern "C" int vs_patchify(const float* img, void* out, int n, int h, int w, int P, int half_dtype,
                            vs_stream_t stream) {
+  VS_REQUIRE(half_dtype == 0 || half_dtype == VS_BF16 || half_dtype == VS_F16, "half_dtype must be bf16 or fp16");
+  const int f16 = half_dtype == VS_F16;
   VS_REQUIRE(img && out, "patchify: null tensor");
   VS_REQUIRE(P > 0 && h % P == 0 && w % P == 0, "Input image size is not a multiple of patch size");
   const long long total = static_cast<long long>(n) * 3 * h * w;
   if (total == 0) return VS_OK;
   patchify_kernel<<<blocks_for(total, 256), 256, 0, to_stream(stream)>>>(
-      img, static_cast<bf16*>(out), n, h, w, P);
+      img, static_cast<bf16*>(out), n, h, w, P, f16);
   VS_LAUNCH_CHECK();
   return VS_OK;
 }
 
 extern "C" int vs_im2col(const void* src, int src_nchw_f32, void* out, int n, int h, int w, int c,
-                         int k, int stride, int pad, int kpad, vs_stream_t stream) {
+                         int k, int stride, int pad, int kpad, int half_dtype, vs_stream_t stream) {
+  VS_REQUIRE(half_dtype == 0 || half_dtype == VS_BF16 || half_dtype == VS_F16, "half_dtype must be bf16 or fp16");
+  const int f16 = half_dtype == VS_F16;
   VS_REQUIRE(src && out, "im2col: null tensor");
   VS_REQUIRE(k > 0 && stride > 0 && kpad >= k * k * c, "im2col: bad geometry");
   VS_REQUIRE(kpad % 8 == 0, "im2col: kpad must be a multiple of 8");
@@ -931,33 +929,37 @@ extern "C" int vs_im2col(const void* src, int src_nchw_f32, void* out, int n, in
   VS_REQUIRE(ho <= 65535 && n <= 65535, "im2col: map too large for the launch grid");
   dim3 grid(blocks_for(static_cast<long long>(wo) * (kpad / 8), 256), ho, n);
   im2col_kernel<<<grid, 256, 0, to_stream(stream)>>>(
-      src, src_nchw_f32, static_cast<bf16*>(out), n, h, w, c, k, stride, pad, kpad, ho, wo);
+      src, src_nchw_f32, static_cast<bf16*>(out), n, h, w, c, k, stride, pad, kpad, ho, wo, f16);
   VS_LAUNCH_CHECK();
   return VS_OK;
 }
 
-extern "C" int vs_upsample2x(const void* src, void* dst, int n, int h, int w, int c,
+extern "C" int vs_upsample2x(const void* src, void* dst, int n, int h, int w, int c, int half_dtype,
                              vs_stream_t stream) {
+  VS_REQUIRE(half_dtype == 0 || half_dtype == VS_BF16 || half_dtype == VS_F16, "half_dtype must be bf16 or fp16");
+  const int f16 = half_dtype == VS_F16;
   VS_REQUIRE(src && dst, "upsample2x: null tensor");
   VS_REQUIRE(c % 8 == 0, "upsample2x: channels must be a multiple of 8");
   if (static_cast<long long>(n) * h * w == 0) return VS_OK;
   VS_REQUIRE(2 * h <= 65535 && n <= 65535, "upsample2x: map too large for the launch grid");
   dim3 grid(blocks_for(static_cast<long long>(2 * w) * (c / 8), 256), 2 * h, n);
   upsample2x_kernel<<<grid, 256, 0, to_stream(stream)>>>(
-      static_cast<const bf16*>(src), nullptr, static_cast<bf16*>(dst), n, h, w, c);
+      static_cast<const bf16*>(src), nullptr, static_cast<bf16*>(dst), n, h, w, c, f16);
   VS_LAUNCH_CHECK();
   return VS_OK;
 }
 
 extern "C" int vs_upsample2x_add(const void* src, const void* add, void* dst, int n, int h, int w, int c,
-                                 vs_stream_t stream) {
+                                 int half_dtype, vs_stream_t stream) {
+  VS_REQUIRE(half_dtype == 0 || half_dtype == VS_BF16 || half_dtype == VS_F16, "half_dtype must be bf16 or fp16");
+  const int f16 = half_dtype == VS_F16;
   VS_REQUIRE(src && add && dst, "upsample2x_add: null tensor");
   VS_REQUIRE(c % 8 == 0, "upsample2x_add: channels must be a multiple of 8");
   if (static_cast<long long>(n) * h * w == 0) return VS_OK;
   VS_REQUIRE(2 * h <= 65535 && n <= 65535, "upsample2x_add: map too large for the launch grid");
   dim3 grid(blocks_for(static_cast<long long>(2 * w) * (c / 8), 256), 2 * h, n);
   upsample2x_kernel<<<grid, 256, 0, to_stream(stream)>>>(
-      static_cast<const bf16*>(src), static_cast<const bf16*>(add), static_cast<bf16*>(dst), n, h, w, c);
+      static_cast<const bf16*>(src), static_cast<const bf16*>(add), static_cast<bf16*>(dst), n, h, w, c, f16);
   VS_LAUNCH_CHECK();
   return VS_OK;
 }
@@ -974,13 +976,15 @@ extern "C" int vs_pixel_shuffle(const void* src, void* dst, int n, int h, int w,
   return VS_OK;
 }
 
-extern "C" int vs_image_nhwc8(const float* img, void* out, int n, int h, int w, int pad,
+extern "C" int vs_image_nhwc8(const float* img, void* out, int n, int h, int w, int pad, int half_dtype,
                               vs_stream_t stream) {
+  VS_REQUIRE(half_dtype == 0 || half_dtype == VS_BF16 || half_dtype == VS_F16, "half_dtype must be bf16 or fp16");
+  const int f16 = half_dtype == VS_F16;
   VS_REQUIRE(img && out, "image_nhwc8: null tensor");
   VS_REQUIRE(pad >= 0 && pad <= 8 && h + 2 * pad <= 65535 && n <= 65535, "image_nhwc8: bad geometry");
   if (n * h * w == 0) return VS_OK;
   dim3 grid(blocks_for(w + 8, 128), h + 2 * pad, n);
-  image_nhwc8_kernel<<<grid, 128, 0, to_stream(stream)>>>(img, static_cast<bf16*>(out), h, w, pad);
+  image_nhwc8_kernel<<<grid, 128, 0, to_stream(stream)>>>(img, static_cast<bf16*>(out), h, w, pad, f16);
   VS_LAUNCH_CHECK();
   return VS_OK;
 }
@@ -1007,11 +1011,13 @@ extern "C" int vs_camera_tokens(const float* intr_tok, const float* extr_tok, fl
 }
 
 extern "C" int vs_silu_bf16(const float* x, int64_t ldx, void* y, int64_t ldy, int rows, int C,
-                            vs_stream_t stream) {
+                            int half_dtype, vs_stream_t stream) {
+  VS_REQUIRE(half_dtype == 0 || half_dtype == VS_BF16 || half_dtype == VS_F16, "half_dtype must be bf16 or fp16");
+  const int f16 = half_dtype == VS_F16;
   VS_REQUIRE(x && y, "silu: null tensor");
   if (rows * C == 0) return VS_OK;
   silu_bf16_kernel<<<blocks_for(static_cast<long long>(rows) * C, 256), 256, 0,
-                     to_stream(stream)>>>(x, ldx, static_cast<bf16*>(y), ldy, rows, C);
+                     to_stream(stream)>>>(x, ldx, static_cast<bf16*>(y), ldy, rows, C, f16);
   VS_LAUNCH_CHECK();
   return VS_OK;
 }
@@ -1027,13 +1033,15 @@ extern "C" int vs_camera_head(const float* cam_feat, int64_t ld, const float* w,
 }
 
 extern "C" int vs_pts_tail(const void* feat, int Cf, const float* w, const float* b, float* raw,
-                           int64_t raw_ld, int64_t px, vs_stream_t stream) {
+                           int64_t raw_ld, int64_t px, int half_dtype, vs_stream_t stream) {
+  VS_REQUIRE(half_dtype == 0 || half_dtype == VS_BF16 || half_dtype == VS_F16, "half_dtype must be bf16 or fp16");
+  const int f16 = half_dtype == VS_F16;
   VS_REQUIRE(feat && w && b && raw, "pts_tail: null tensor");
   VS_REQUIRE(Cf % 64 == 0, "pts_tail: Cf must be a multiple of 64");
   if (px == 0) return VS_OK;
   VS_REQUIRE(Cf <= 1024, "pts_tail: Cf too large");
   pts_tail_kernel<<<blocks_for(px, 128), 128, 3 * Cf * sizeof(float), to_stream(stream)>>>(
-      static_cast<const bf16*>(feat), Cf, w, b, raw, raw_ld, px);
+      static_cast<const bf16*>(feat), Cf, w, b, raw, raw_ld, px, f16);
   VS_LAUNCH_CHECK();
   return VS_OK;
 }

@@ -30,6 +30,7 @@
 #include <cuda_bf16.h>
 
 #include "common.h"
+#include "half16.cuh"
 #include "ptx.cuh"
 #include "tmap.h"
 
@@ -62,6 +63,7 @@ struct GemmDev {
   int atomic;                 // C += (red.global.add) instead of C =
   int mask_mode;              // 0 none, 1 res2 masks then + res1, 2 res1 masks (bf16 residual kinds)
   float out_scale;
+  int f16;                    // 16-bit operands / outputs / residual maps are fp16 instead of bf16
   // rows mode
   int a_rows, a_groups, tiles_per_group;
   // conv mode
@@ -205,7 +207,7 @@ __device__ __forceinline__ void load32_f32(const float* p, int nv, bool vec, flo
 // ---- 4-column segment helpers of the transposed epilogue (one lane = 4 consecutive columns of a row)
 // plain (coherent) loads: the residual stream may be updated in place by this very kernel
 __device__ __forceinline__ void add4_res(const void* base, int dtype, long long off, int nv, bool vec,
-                                         float4& f) {
+                                         float4& f, bool f16 = false) {
   if (dtype == VS_F32) {
     const float* p = static_cast<const float*>(base) + off;
     if (vec && nv == 4) {
@@ -221,14 +223,15 @@ __device__ __forceinline__ void add4_res(const void* base, int dtype, long long 
     const __nv_bfloat16* p = static_cast<const __nv_bfloat16*>(base) + off;
     if (vec && nv == 4) {
       const uint2 t = *reinterpret_cast<const uint2*>(p);
-      const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.x));
-      const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.y));
+      const float2 a = h2_to_f2(t.x, f16);
+      const float2 b = h2_to_f2(t.y, f16);
       f.x += a.x; f.y += a.y; f.z += b.x; f.w += b.y;
     } else {
-      if (nv > 0) f.x += __bfloat162float(p[0]);
-      if (nv > 1) f.y += __bfloat162float(p[1]);
-      if (nv > 2) f.z += __bfloat162float(p[2]);
-      if (nv > 3) f.w += __bfloat162float(p[3]);
+      const uint16_t* q = reinterpret_cast<const uint16_t*>(p);
+      if (nv > 0) f.x += h_to_f(q[0], f16);
+      if (nv > 1) f.y += h_to_f(q[1], f16);
+      if (nv > 2) f.z += h_to_f(q[2], f16);
+      if (nv > 3) f.w += h_to_f(q[3], f16);
     }
   }
 }
@@ -237,7 +240,7 @@ __device__ __forceinline__ void add4_res(const void* base, int dtype, long long 
 // (x, y) of image im, channels [col, col+4)
 __device__ __forceinline__ void add4_res_up2(const __nv_bfloat16* base, long long ld, int im, int x,
                                              int y, int ch, int cw, int col, int nv, bool vec,
-                                             float4& f) {
+                                             float4& f, bool f16 = false) {
   const int h = ch >> 1, w = cw >> 1;
   const float sy = ch > 1 ? static_cast<float>(h - 1) / (ch - 1) : 0.f;
   const float sx = cw > 1 ? static_cast<float>(w - 1) / (cw - 1) : 0.f;
@@ -252,26 +255,26 @@ __device__ __forceinline__ void add4_res_up2(const __nv_bfloat16* base, long lon
   for (int t = 0; t < 4; ++t) {
     float4 tmp = make_float4(0.f, 0.f, 0.f, 0.f);
     add4_res(base, VS_BF16, ((static_cast<long long>(im) * h + ys[t]) * w + xs[t]) * ld + col, nv, vec,
-             tmp);
+             tmp, f16);
     acc.x = fmaf(wt[t], tmp.x, acc.x); acc.y = fmaf(wt[t], tmp.y, acc.y);
     acc.z = fmaf(wt[t], tmp.z, acc.z); acc.w = fmaf(wt[t], tmp.w, acc.w);
   }
   // the stand-alone kernel rounds the upsampled map to bf16 before it is consumed: do the same
-  f.x += __bfloat162float(__float2bfloat16(acc.x)); f.y += __bfloat162float(__float2bfloat16(acc.y));
-  f.z += __bfloat162float(__float2bfloat16(acc.z)); f.w += __bfloat162float(__float2bfloat16(acc.w));
+  f.x += round_h(acc.x, f16); f.y += round_h(acc.y, f16);
+  f.z += round_h(acc.z, f16); f.w += round_h(acc.w, f16);
 }
 
-__device__ __forceinline__ void store4_bf16(__nv_bfloat16* p, int nv, bool vec, float4 f, bool relu) {
+__device__ __forceinline__ void store4_bf16(__nv_bfloat16* p, int nv, bool vec, float4 f, bool relu,
+                                            bool f16 = false) {
   if (relu) { f.x = fmaxf(f.x, 0.f); f.y = fmaxf(f.y, 0.f); f.z = fmaxf(f.z, 0.f); f.w = fmaxf(f.w, 0.f); }
   if (vec && nv == 4) {
-    const __nv_bfloat162 a = __floats2bfloat162_rn(f.x, f.y), b = __floats2bfloat162_rn(f.z, f.w);
-    *reinterpret_cast<uint2*>(p) = make_uint2(*reinterpret_cast<const uint32_t*>(&a),
-                                              *reinterpret_cast<const uint32_t*>(&b));
+    *reinterpret_cast<uint2*>(p) = make_uint2(f2_to_h2(f.x, f.y, f16), f2_to_h2(f.z, f.w, f16));
   } else {
-    if (nv > 0) p[0] = __float2bfloat16(f.x);
-    if (nv > 1) p[1] = __float2bfloat16(f.y);
-    if (nv > 2) p[2] = __float2bfloat16(f.z);
-    if (nv > 3) p[3] = __float2bfloat16(f.w);
+    uint16_t* q = reinterpret_cast<uint16_t*>(p);
+    if (nv > 0) q[0] = f_to_h(f.x, f16);
+    if (nv > 1) q[1] = f_to_h(f.y, f16);
+    if (nv > 2) q[2] = f_to_h(f.z, f16);
+    if (nv > 3) q[3] = f_to_h(f.w, f16);
   }
 }
 
@@ -286,14 +289,14 @@ __device__ __forceinline__ void store4_f32(float* p, int nv, bool vec, const flo
   }
 }
 
-__device__ __forceinline__ void add_bf16x4(float4& f, const uint2 t) {
-  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.x));
-  const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.y));
+__device__ __forceinline__ void add_bf16x4(float4& f, const uint2 t, bool f16 = false) {
+  const float2 a = h2_to_f2(t.x, f16);
+  const float2 b = h2_to_f2(t.y, f16);
   f.x += a.x; f.y += a.y; f.z += b.x; f.w += b.y;
 }
-__device__ __forceinline__ void fma_bf16x4(float4& f, const float w, const uint2 t) {
-  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.x));
-  const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.y));
+__device__ __forceinline__ void fma_bf16x4(float4& f, const float w, const uint2 t, bool f16 = false) {
+  const float2 a = h2_to_f2(t.x, f16);
+  const float2 b = h2_to_f2(t.y, f16);
   f.x = fmaf(w, a.x, f.x); f.y = fmaf(w, a.y, f.y); f.z = fmaf(w, b.x, f.z); f.w = fmaf(w, b.y, f.w);
 }
 
@@ -413,24 +416,24 @@ __device__ __forceinline__ void epi_store(const GemmDev& g, const uint32_t (&lds
         t.z += __uint_as_float(rb[j].z); t.w += __uint_as_float(rb[j].w);
       } else if (RK == 2) {
         if (g.mask_mode == 0) {
-          add_bf16x4(t, make_uint2(rb[j].x, rb[j].y));
-          add_bf16x4(t, make_uint2(rb[j].z, rb[j].w));
+          add_bf16x4(t, make_uint2(rb[j].x, rb[j].y), g.f16);
+          add_bf16x4(t, make_uint2(rb[j].z, rb[j].w), g.f16);
         } else if (g.mask_mode == 1) {
           mask_bf16x4(t, make_uint2(rb[j].z, rb[j].w));
-          add_bf16x4(t, make_uint2(rb[j].x, rb[j].y));
+          add_bf16x4(t, make_uint2(rb[j].x, rb[j].y), g.f16);
         } else {
           mask_bf16x4(t, make_uint2(rb[j].x, rb[j].y));
         }
       } else if (RK == 3) {
         const float lx = lxs[j4], ly = lys[j4];
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        fma_bf16x4(acc, (1 - ly) * (1 - lx), up[RK == 3 ? j4 : 0][0]);
-        fma_bf16x4(acc, (1 - ly) * lx, up[RK == 3 ? j4 : 0][1]);
-        fma_bf16x4(acc, ly * (1 - lx), up[RK == 3 ? j4 : 0][2]);
-        fma_bf16x4(acc, ly * lx, up[RK == 3 ? j4 : 0][3]);
-        // the stand-alone kernel rounds the upsampled map to bf16 before it is consumed
-        t.x += __bfloat162float(__float2bfloat16(acc.x)); t.y += __bfloat162float(__float2bfloat16(acc.y));
-        t.z += __bfloat162float(__float2bfloat16(acc.z)); t.w += __bfloat162float(__float2bfloat16(acc.w));
+        fma_bf16x4(acc, (1 - ly) * (1 - lx), up[RK == 3 ? j4 : 0][0], g.f16);
+        fma_bf16x4(acc, (1 - ly) * lx, up[RK == 3 ? j4 : 0][1], g.f16);
+        fma_bf16x4(acc, ly * (1 - lx), up[RK == 3 ? j4 : 0][2], g.f16);
+        fma_bf16x4(acc, ly * lx, up[RK == 3 ? j4 : 0][3], g.f16);
+        // the stand-alone kernel rounds the upsampled map to the 16-bit format before it is consumed
+        t.x += round_h(acc.x, g.f16); t.y += round_h(acc.y, g.f16);
+        t.z += round_h(acc.z, g.f16); t.w += round_h(acc.w, g.f16);
       }
       tv[j4] = t;
     }
@@ -445,13 +448,13 @@ __device__ __forceinline__ void epi_store(const GemmDev& g, const uint32_t (&lds
           if (g.atomic) red_add_f4(cf + o * g.ldc, tv[j4]);
           else *reinterpret_cast<float4*>(cf + o * g.ldc) = tv[j4];
         } else {
-          store4_bf16(cb + o * g.ldc, 4, true, tv[j4], false);
+          store4_bf16(cb + o * g.ldc, 4, true, tv[j4], false, g.f16);
         }
       }
       if (c2 != nullptr) {
 #pragma unroll
         for (int j4 = 0; j4 < 4; ++j4)
-          store4_bf16(c2 + static_cast<long long>(oj[jh + j4]) * g.ldc2, 4, true, tv[j4], true);
+          store4_bf16(c2 + static_cast<long long>(oj[jh + j4]) * g.ldc2, 4, true, tv[j4], true, g.f16);
       }
     } else {
 #pragma unroll
@@ -462,9 +465,9 @@ __device__ __forceinline__ void epi_store(const GemmDev& g, const uint32_t (&lds
             if (g.atomic) red_add_f4(cf + static_cast<long long>(oj[j]) * g.ldc, tv[j4]);
             else *reinterpret_cast<float4*>(cf + static_cast<long long>(oj[j]) * g.ldc) = tv[j4];
           } else {
-            store4_bf16(cb + static_cast<long long>(oj[j]) * g.ldc, 4, true, tv[j4], false);
+            store4_bf16(cb + static_cast<long long>(oj[j]) * g.ldc, 4, true, tv[j4], false, g.f16);
           }
-          if (c2 != nullptr) store4_bf16(c2 + static_cast<long long>(oj[j]) * g.ldc2, 4, true, tv[j4], true);
+          if (c2 != nullptr) store4_bf16(c2 + static_cast<long long>(oj[j]) * g.ldc2, 4, true, tv[j4], true, g.f16);
         }
       }
     }
@@ -622,8 +625,10 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (pair: leader only)
     if (lane == 0 && rank == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BM * CL, BN);
-      constexpr uint32_t idesc_tn = umma_idesc_bf16(BM * CL, BN, 1, 1);
+      // a / b format bits [7,10) / [10,13): 1 = bf16, 0 = fp16
+      const uint32_t fmt_clear = g.f16 ? ~((1u << 7) | (1u << 10)) : ~0u;
+      const uint32_t idesc = umma_idesc_bf16(BM * CL, BN) & fmt_clear;
+      const uint32_t idesc_tn = umma_idesc_bf16(BM * CL, BN, 1, 1) & fmt_clear;
       uint32_t it = 0, ti = 0;
       for (int u = unit0; u < total_units; u += unit_step, ++ti) {
         const uint32_t a = ti & 1;
@@ -863,20 +868,21 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
             if (o < 0 || nvl <= 0) continue;
             if (g.res1 != nullptr && g.res_up2) {
               add4_res_up2(static_cast<const __nv_bfloat16*>(g.res1), g.res_ld, pim, px, py, g.ch, g.cw,
-                           col, nvl, g.vec & VEC_RES, t);
+                           col, nvl, g.vec & VEC_RES, t, g.f16);
             } else if (g.res1 != nullptr && g.mask_mode != 0) {
               // ReLU mask (bf16 maps): mode 1 masks with res2 and adds res1, mode 2 masks with res1
               const __nv_bfloat16* mk = static_cast<const __nv_bfloat16*>(g.mask_mode == 1 ? g.res2 : g.res1) +
                                         o * g.res_ld + col;
-              if (nvl > 0 && !(__bfloat162float(mk[0]) > 0.f)) t.x = 0.f;
-              if (nvl > 1 && !(__bfloat162float(mk[1]) > 0.f)) t.y = 0.f;
-              if (nvl > 2 && !(__bfloat162float(mk[2]) > 0.f)) t.z = 0.f;
-              if (nvl > 3 && !(__bfloat162float(mk[3]) > 0.f)) t.w = 0.f;
-              if (g.mask_mode == 1) add4_res(g.res1, g.res_dtype, o * g.res_ld + col, nvl, false, t);
+              const uint16_t* mq = reinterpret_cast<const uint16_t*>(mk);
+              if (nvl > 0 && !(h_to_f(mq[0], g.f16) > 0.f)) t.x = 0.f;
+              if (nvl > 1 && !(h_to_f(mq[1], g.f16) > 0.f)) t.y = 0.f;
+              if (nvl > 2 && !(h_to_f(mq[2], g.f16) > 0.f)) t.z = 0.f;
+              if (nvl > 3 && !(h_to_f(mq[3], g.f16) > 0.f)) t.w = 0.f;
+              if (g.mask_mode == 1) add4_res(g.res1, g.res_dtype, o * g.res_ld + col, nvl, false, t, g.f16);
             } else if (g.res1 != nullptr) {
-              add4_res(g.res1, g.res_dtype, o * g.res_ld + col, nvl, g.vec & VEC_RES, t);
+              add4_res(g.res1, g.res_dtype, o * g.res_ld + col, nvl, g.vec & VEC_RES, t, g.f16);
               if (g.res2 != nullptr)
-                add4_res(g.res2, g.res_dtype, o * g.res_ld + col, nvl, g.vec & VEC_RES, t);
+                add4_res(g.res2, g.res_dtype, o * g.res_ld + col, nvl, g.vec & VEC_RES, t, g.f16);
             }
             if (g.C != nullptr && g.atomic) {
               float* cp = static_cast<float*>(g.C) + o * g.ldc + col;
@@ -888,9 +894,9 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
               if (g.c_dtype == VS_F32)
                 store4_f32(static_cast<float*>(g.C) + o * g.ldc + col, nvl, g.vec & VEC_C, t);
               else
-                store4_bf16(static_cast<__nv_bfloat16*>(g.C) + o * g.ldc + col, nvl, g.vec & VEC_C, t, false);
+                store4_bf16(static_cast<__nv_bfloat16*>(g.C) + o * g.ldc + col, nvl, g.vec & VEC_C, t, false, g.f16);
             }
-            if (g.C2 != nullptr) store4_bf16(g.C2 + o * g.ldc2 + col, nvl, g.vec & VEC_C2, t, true);
+            if (g.C2 != nullptr) store4_bf16(g.C2 + o * g.ldc2 + col, nvl, g.vec & VEC_C2, t, true, g.f16);
           }
         }
         EPI_STAMP(6);
@@ -1003,7 +1009,7 @@ extern "C" int vs_gemm(const vs_gemm_params* p, vs_stream_t stream_) {
   g.mask_mode = p->mask_mode;
   g.out_scale = p->out_scale == 0.f ? 1.0f : p->out_scale;
   VS_REQUIRE(p->mask_mode >= 0 && p->mask_mode <= 2, "vs_gemm: mask_mode must be 0, 1 or 2");
-  VS_REQUIRE(p->mask_mode == 0 || (p->res1 && p->res_dtype == VS_BF16 && !p->res_up2 &&
+  VS_REQUIRE(p->mask_mode == 0 || (p->res1 && p->res_dtype != VS_F32 && !p->res_up2 &&
                                    (p->mask_mode == 2 ? p->res2 == nullptr : p->res2 != nullptr)),
              "vs_gemm: mask_mode needs bf16 maps (mode 1: res1 + mask res2; mode 2: mask res1 only)");
   VS_REQUIRE(!p->c_accumulate || (p->c_dtype == VS_F32 && p->C && !p->bias && p->act == VS_ACT_NONE &&
@@ -1023,7 +1029,7 @@ extern "C" int vs_gemm(const vs_gemm_params* p, vs_stream_t stream_) {
   g.res_dtype = p->res_dtype;
   g.res_up2 = p->res_up2;
   g.res_ld = static_cast<int>(p->res_ld);
-  VS_REQUIRE(!p->res_up2 || (p->a_mode == 1 && p->res1 && p->res_dtype == VS_BF16 && !p->res2 &&
+  VS_REQUIRE(!p->res_up2 || (p->a_mode == 1 && p->res1 && p->res_dtype != VS_F32 && !p->res2 &&
                              p->ch % 2 == 0 && p->cw % 2 == 0),
              "vs_gemm: res_up2 needs conv mode, one bf16 residual map and even output sizes");
   g.C = p->C;
@@ -1038,9 +1044,15 @@ extern "C" int vs_gemm(const vs_gemm_params* p, vs_stream_t stream_) {
   g.out_gout = p->out_gout;
   g.out_off = p->out_off;
   VS_REQUIRE(p->res2 == nullptr || p->res1 != nullptr, "vs_gemm: res2 requires res1");
-  VS_REQUIRE(p->c_dtype == VS_F32 || p->c_dtype == VS_BF16, "vs_gemm: c_dtype must be f32/bf16");
-  VS_REQUIRE(p->res_dtype == VS_F32 || p->res_dtype == VS_BF16,
-             "vs_gemm: res_dtype must be f32/bf16");
+  // 16-bit operand format: bf16 (0 / VS_BF16) or fp16 (VS_F16); 16-bit outputs / residual maps share it
+  VS_REQUIRE(p->operand_dtype == 0 || p->operand_dtype == VS_BF16 || p->operand_dtype == VS_F16,
+             "vs_gemm: operand_dtype must be bf16 or fp16");
+  g.f16 = p->operand_dtype == VS_F16;
+  const int half_t = g.f16 ? VS_F16 : VS_BF16;
+  VS_REQUIRE(p->c_dtype == VS_F32 || p->c_dtype == half_t, "vs_gemm: c_dtype must be f32 or the operand format");
+  VS_REQUIRE(p->res_dtype == VS_F32 || p->res_dtype == half_t || p->res1 == nullptr,
+             "vs_gemm: res_dtype must be f32 or the operand format");
+  VS_REQUIRE(!g.f16 || p->a_mode < 2, "vs_gemm: the fp16 operand format is a forward-path (a_mode 0 / 1) option");
   g.vec = 0;
   if (p->bias && al16(p->bias)) g.vec |= VEC_BIAS;
   if (p->gate && al16(p->gate) && p->gate_ld % 4 == 0) g.vec |= VEC_GATE;

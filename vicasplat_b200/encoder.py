@@ -181,8 +181,18 @@ class VicaSplat(nn.Module):
     """Drop-in for the reference encoder plugin (``ENCODERS['vicasplat']``)."""
     patch_size: int = 16
 
-    def __init__(self, cfg: Optional[VicaSplatCfg] = None, weight_dtype=None, device=None) -> None:
+    def __init__(self, cfg: Optional[VicaSplatCfg] = None, weight_dtype=None, device=None,
+                 precision: str = "bf16") -> None:
+        """precision: the 16-bit operand format of the forward-only engine --
+          "bf16"  speed mode (default): bf16 GEMM / attention operands, fp32 accumulation and residual streams;
+          "fp16"  parity mode: fp16 operands, i.e. the 10-bit mantissa the reference's TF32 matmuls round
+                  their fp32 operands to (backbone_vica.py:9) at the same tensor-core rate as bf16 (twice
+                  kind::tf32's) -- for callers who want reference-grade numerics.  Activations must stay
+                  below fp16's 65 504 (they do after LayerNorm; the residual streams are fp32 either way)."""
         super().__init__()
+        if precision not in ("bf16", "fp16"):
+            raise ValueError("precision must be 'bf16' or 'fp16'")
+        self.precision = precision
         self.cfg = cfg if cfg is not None else VicaSplatCfg()
         bb = dict(default_backbone_cfg(), **dict(self.cfg.backbone))
         if not bb["use_intrinsic_embedding"]:
@@ -280,9 +290,15 @@ class VicaSplat(nn.Module):
         self._train_engine = None
         return super()._apply(fn, *a, **k)
 
+    def set_precision(self, precision: str) -> None:
+        if precision not in ("bf16", "fp16"):
+            raise ValueError("precision must be 'bf16' or 'fp16'")
+        self.precision = precision
+        self._engine = None
+
     def engine(self) -> "EncoderEngine":
         if self._engine is None:
-            self._engine = EncoderEngine(self)
+            self._engine = EncoderEngine(self, precision=self.precision)
         return self._engine
 
     def forward(self, context: dict, global_step: int = 0, visualization_dump: Optional[dict] = None,
@@ -383,26 +399,27 @@ class _TrainFn(torch.autograd.Function):
 
 
 # ------------------------------------------------------------------------------------ engine
-def _bf(t: Tensor) -> Tensor:
-    return t.detach().to(BF16).contiguous()
+def _bf(t: Tensor, dtype=BF16) -> Tensor:
+    return t.detach().to(dtype).contiguous()
 
 
-def _pack_conv(w: Tensor) -> Tensor:
-    """[N, Cin, kh, kw] -> bf16 [N, kh*kw*cin_pad] (tap-major, channel-minor, zero padded)."""
+def _pack_conv(w: Tensor, dtype=BF16) -> Tensor:
+    """[N, Cin, kh, kw] -> 16-bit [N, kh*kw*cin_pad] (tap-major, channel-minor, zero padded)."""
     n, cin, kh, kw = w.shape
     cp = (cin + 63) // 64 * 64
     p = torch.zeros((n, kh * kw, cp), dtype=F32, device=w.device)
     p[:, :, :cin] = w.detach().permute(0, 2, 3, 1).reshape(n, kh * kw, cin)
-    return _bf(p.reshape(n, -1))
+    return _bf(p.reshape(n, -1), dtype)
 
 
 class EncoderEngine:
     """Packed weights + activation workspace + CUDA-graph replay for one VicaSplat module."""
 
-    def __init__(self, model: VicaSplat, use_graph: bool = True):
+    def __init__(self, model: VicaSplat, use_graph: bool = True, precision: str = "bf16"):
         self.m = model
         self.bb = model._bb
         self.use_graph = use_graph
+        self.half = torch.float16 if precision == "fp16" else BF16     # 16-bit operand format (see VicaSplat)
         # K = 448 stem: the bilinear-x2 residual gathered in the GEMM epilogue costs ~4x the main
         # loop in issue slots; a stand-alone upsample + plain bf16 residual is HBM-bound instead
         self.fuse_stem_upsample = os.environ.get("VS_FUSE_STEM_UP", "1") == "1"
@@ -417,6 +434,9 @@ class EncoderEngine:
     def _pack(self) -> None:
         sd, w, bb = self.sd, self.w, self.bb
         f = lambda k: sd[k].to(F32).contiguous()
+        half = self.half
+        _bf = lambda t: t.detach().to(half).contiguous()                # noqa: F811 (shadows the module helper)
+        _pack_conv = lambda t: globals()["_pack_conv"](t, half)         # noqa: F811
         for k, v in sd.items():
             if v.dim() == 1:
                 w[k] = f(k)
@@ -480,7 +500,7 @@ class EncoderEngine:
         N, rpf = Np + 1, Np + 2
         he, hd = int(E * bb["mlp_ratio"]), int(D * bb["mlp_ratio"])
         i32 = dict(dtype=torch.int32, device=dev)
-        z = lambda *s, dt=BF16: torch.zeros(s, dtype=dt, device=dev)
+        z = lambda *s, dt=self.half: torch.zeros(s, dtype=dt, device=dev)
         pl = dict(B=B, T=T, H=H, W=W, gh=gh, gw=gw, Fr=Fr, Np=Np, N=N, rpf=rpf)
         pl["image"] = z(Fr, 3, H, W, dt=F32)
         pl["K9"] = z(Fr, 9, dt=F32)
@@ -540,7 +560,7 @@ class EncoderEngine:
         E, H = bb["enc_embed_dim"], bb["enc_num_heads"]
         Fr, Np, N = pl["Fr"], pl["Np"], pl["N"]
         x = pl["x_enc"]
-        cols = ops.patchify(pl["image"], bb["patch_size"])
+        cols = ops.patchify(pl["image"], bb["patch_size"], half=self.half)
         ops.gemm(cols, w["patch"], bias=w["backbone.patch_embed.proj.bias"], out=x,
                  out_gin=Np, out_gout=N, out_off=0)
         ops.intrinsic_token(pl["K9"], w["intr.w"], w["backbone.intrinsic_encoder.bias"], x, Fr, E, N, Np)
@@ -580,7 +600,7 @@ class EncoderEngine:
             # --- video + camera self attention
             ops.layernorm(cam_rows, w[k + ".cam_norm1.weight"], w[k + ".cam_norm1.bias"],
                           out_f32=pl["cam_n"], want_bf16=False)
-            sil = ops.silu_bf16(pl["cam_n"], Fr, D)
+            sil = ops.silu_bf16(pl["cam_n"], Fr, D, half=self.half)
             ops.gemm(sil, w[k + ".modulation1.proj"], bias=w[k + ".modulation1.proj.bias"], out=pl["mod1"])
             m1 = pl["mod1"]
             ops.layernorm(x, w[k + ".norm1.weight"], w[k + ".norm1.bias"],
@@ -597,7 +617,7 @@ class EncoderEngine:
             # --- neighbour cross attention (image rows only)
             ops.layernorm(cam_rows, w[k + ".cam_norm2.weight"], w[k + ".cam_norm2.bias"],
                           out_f32=pl["cam_n"], out_bf16=pl["cam_nb"])
-            sil = ops.silu_bf16(pl["cam_n"], Fr, D)
+            sil = ops.silu_bf16(pl["cam_n"], Fr, D, half=self.half)
             ops.gemm(sil, w[k + ".modulation2.proj"], bias=w[k + ".modulation2.proj.bias"], out=pl["mod2"])
             m2 = pl["mod2"]
             ops.layernorm(x, w[k + ".norm2.weight"], w[k + ".norm2.bias"], scale=m2[:, :D],
@@ -640,7 +660,7 @@ class EncoderEngine:
 
     def _conv(self, x, key, *, k=3, N=FEAT, bias=None, act=VS_ACT_NONE, res1=None, res2=None,
               relu_copy=False, out_dtype=BF16):
-        out2 = torch.empty(x.shape[:3] + (N,), dtype=BF16, device=x.device) if relu_copy else None
+        out2 = torch.empty(x.shape[:3] + (N,), dtype=self.half, device=x.device) if relu_copy else None
         out = ops.conv_gemm(x, self.w[key], kh=k, kw=k, pad=k // 2, N=N, bias=bias, act=act,
                             res1=res1, res2=res2, out2=out2, out_dtype=out_dtype)
         return (out, out2) if relu_copy else out
@@ -712,7 +732,7 @@ class EncoderEngine:
         # --- Gaussian parameters: trunk x2 + relu(conv7x7(image)) -> conv3x3 + ReLU -> 1x1
         k = "gaussian_param_head.dpt"
         p1 = self._trunk(pl, "gaussian_param_head", taps)                  # (Fr, H/2, W/2, 256)
-        img8 = ops.image_nhwc8(pl["image"], pad=3)                        # (Fr, H+6, W+8, 8)
+        img8 = ops.image_nhwc8(pl["image"], pad=3, half=self.half)        # (Fr, H+6, W+8, 8)
         # relu(conv7x7(image)) + bilinear_x2(p1): the image is addressed through an overlapping TMA
         # view (no im2col buffer), the upsampling happens in the epilogue (no full-res copy of p1)
         if self.fuse_stem_upsample:

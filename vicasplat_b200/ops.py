@@ -14,6 +14,7 @@ from ._lib import (AttentionParams, GemmParams, LayerNormParams, VS_ACT_GELU, VS
                    VS_ACT_RELU, VS_BF16, VS_F16, VS_F32, check, ptr, stream_ptr)
 
 _DT = {torch.float32: VS_F32, torch.bfloat16: VS_BF16, torch.float16: VS_F16}
+_HALF = (torch.bfloat16, torch.float16)   # the two 16-bit operand formats (speed / parity mode)
 
 # Optional per-kernel-family timing (bench.py's roofline leg): when TIMERS is a dict, every wrapper
 # brackets its launch with CUDA events on the launching stream; `family_ms()` sums them afterwards.
@@ -75,6 +76,10 @@ def gemm(A, W, *, N=None, K=None, a_rows=None, a_groups=1, a_row_stride=None, a_
         p.a_group_stride = a_group_stride
         p.W, p.w_row_stride, p.N, p.K = ptr(W), (w_row_stride or W.stride(0)), N, K
     _fill_epilogue(p, bias, act, gate, gate_rows, first_row_mode, res1, res2)
+    assert A.dtype in _HALF and W.dtype == A.dtype, "GEMM operands are bf16 (speed) or fp16 (parity mode)"
+    p.operand_dtype = _DT[A.dtype]
+    if out_dtype in _HALF:
+        out_dtype = A.dtype
     total = rows * a_groups
     if out is None:
         n_out = out_rows if out_rows is not None else total
@@ -112,6 +117,10 @@ def conv_gemm(x_nhwc, Wp, *, kh, kw, pad, N, bias=None, act=VS_ACT_NONE, res1=No
     p.cn, p.ch, p.cw, p.cin, p.kh, p.kw, p.pad = n, h, w, cin, kh, kw, pad
     p.W, p.w_row_stride, p.N = ptr(Wp), Wp.stride(0), N
     _fill_epilogue(p, bias, act, None, 0, 0, res1, res2)
+    assert x_nhwc.dtype in _HALF and Wp.dtype == x_nhwc.dtype, "conv operands are bf16 (speed) or fp16 (parity mode)"
+    p.operand_dtype = _DT[x_nhwc.dtype]
+    if out_dtype in _HALF:
+        out_dtype = x_nhwc.dtype
     p.res_up2 = int(res_up2)
     if out is None:
         out = torch.empty((n, h, w, N), dtype=out_dtype, device=x_nhwc.device)
@@ -145,7 +154,7 @@ def _fill_epilogue(p, bias, act, gate, gate_rows, first_row_mode, res1, res2):
 
 def layernorm(x, w=None, b=None, *, eps=1e-6, w0=None, b0=None, scale=None, shift=None,
               rows_per_frame=0, normalize=True, out_bf16=None, out_f32=None, want_bf16=True,
-              want_f32=False):
+              want_f32=False, half=torch.bfloat16):
     """Row LayerNorm (+ per-frame AdaLN modulate) on fp32 rows; see vs_layernorm in the header."""
     _need_cuda(x)
     lib = _lib.load()
@@ -157,11 +166,11 @@ def layernorm(x, w=None, b=None, *, eps=1e-6, w0=None, b0=None, scale=None, shif
         p.scale, p.shift, p.mod_ld = ptr(scale), ptr(shift), scale.stride(-2)
     p.rows_per_frame, p.eps, p.normalize = rows_per_frame, eps, int(normalize)
     if out_bf16 is None and want_bf16:
-        out_bf16 = torch.empty((rows, Cc), dtype=torch.bfloat16, device=x.device)
+        out_bf16 = torch.empty((rows, Cc), dtype=half, device=x.device)
     if out_f32 is None and want_f32:
         out_f32 = torch.empty((rows, Cc), dtype=torch.float32, device=x.device)
     if out_bf16 is not None:
-        p.y_bf16, p.ldy_bf16 = ptr(out_bf16), out_bf16.stride(0)
+        p.y_bf16, p.ldy_bf16, p.y16_dtype = ptr(out_bf16), out_bf16.stride(0), _DT[out_bf16.dtype]
     if out_f32 is not None:
         p.y_f32, p.ldy_f32 = ptr(out_f32), out_f32.stride(0)
     with _timed("layernorm"):
@@ -184,6 +193,8 @@ def attention(Q, K, V, O, *, heads, q_start, q_len, kv_start0, kv_len0, kv_start
     p.kv_start0, p.kv_len0 = ptr(kv_start0), ptr(kv_len0)
     p.kv_start1, p.kv_len1 = ptr(kv_start1), ptr(kv_len1)
     p.max_q_len, p.max_kv_len, p.causal_block, p.scale = max_q_len, max_kv_len, causal_block, scale
+    assert Q.dtype in _HALF and K.dtype == V.dtype == O.dtype == Q.dtype
+    p.dtype = _DT[Q.dtype]
     if lse is not None:
         assert lse.dtype == torch.float32 and lse.is_contiguous() and lse.shape == (Q.shape[0], heads)
         p.lse = ptr(lse)
@@ -202,35 +213,36 @@ def rope_rows(qkv, pos_i32, *, heads, q_col, k_col, base=100.0, cam_theta=30.0):
     return qkv
 
 
-def patchify(img, P=16):
+def patchify(img, P=16, half=torch.bfloat16):
     lib = _lib.load()
     _need_cuda(img)
     n, c, h, w = img.shape
     assert c == 3 and img.dtype == torch.float32 and img.is_contiguous()
-    out = torch.empty((n * (h // P) * (w // P), 3 * P * P), dtype=torch.bfloat16, device=img.device)
-    check(lib.vs_patchify(C.c_void_p(ptr(img)), C.c_void_p(ptr(out)), n, h, w, P,
+    out = torch.empty((n * (h // P) * (w // P), 3 * P * P), dtype=half, device=img.device)
+    check(lib.vs_patchify(C.c_void_p(ptr(img)), C.c_void_p(ptr(out)), n, h, w, P, _DT[half],
                           C.c_void_p(stream_ptr())), "vs_patchify")
     return out
 
 
-def im2col(src, *, nchw_f32, n, h, w, c, k, stride, pad, kpad):
+def im2col(src, *, nchw_f32, n, h, w, c, k, stride, pad, kpad, half=None):
     lib = _lib.load()
     _need_cuda(src)
+    half = half or (src.dtype if src.dtype in _HALF else torch.bfloat16)
     ho, wo = (h + 2 * pad - k) // stride + 1, (w + 2 * pad - k) // stride + 1
-    out = torch.empty((n * ho * wo, kpad), dtype=torch.bfloat16, device=src.device)
+    out = torch.empty((n * ho * wo, kpad), dtype=half, device=src.device)
     check(lib.vs_im2col(C.c_void_p(ptr(src)), int(nchw_f32), C.c_void_p(ptr(out)), n, h, w, c, k,
-                        stride, pad, kpad, C.c_void_p(stream_ptr())), "vs_im2col")
+                        stride, pad, kpad, _DT[half], C.c_void_p(stream_ptr())), "vs_im2col")
     return out
 
 
-def image_nhwc8(img, pad=3):
-    """fp32 NCHW (n,3,h,w) -> zero-bordered bf16 (n, h+2*pad, w+8, 8) for the 7x7 stem."""
+def image_nhwc8(img, pad=3, half=torch.bfloat16):
+    """fp32 NCHW (n,3,h,w) -> zero-bordered 16-bit (n, h+2*pad, w+8, 8) for the 7x7 stem."""
     lib = _lib.load()
     _need_cuda(img)
     n, c, h, w = img.shape
     assert c == 3 and img.dtype == torch.float32 and img.is_contiguous()
-    out = torch.empty((n, h + 2 * pad, w + 8, 8), dtype=torch.bfloat16, device=img.device)
-    check(lib.vs_image_nhwc8(C.c_void_p(ptr(img)), C.c_void_p(ptr(out)), n, h, w, pad,
+    out = torch.empty((n, h + 2 * pad, w + 8, 8), dtype=half, device=img.device)
+    check(lib.vs_image_nhwc8(C.c_void_p(ptr(img)), C.c_void_p(ptr(out)), n, h, w, pad, _DT[half],
                              C.c_void_p(stream_ptr())), "vs_image_nhwc8")
     return out
 
@@ -240,22 +252,24 @@ def upsample2x(x_nhwc, add=None):
     lib = _lib.load()
     _need_cuda(x_nhwc, add)
     n, h, w, c = x_nhwc.shape
-    out = torch.empty((n, 2 * h, 2 * w, c), dtype=torch.bfloat16, device=x_nhwc.device)
+    assert x_nhwc.dtype in _HALF
+    out = torch.empty((n, 2 * h, 2 * w, c), dtype=x_nhwc.dtype, device=x_nhwc.device)
     with _timed("upsample2x"):
         if add is None:
-            check(lib.vs_upsample2x(C.c_void_p(ptr(x_nhwc)), C.c_void_p(ptr(out)), n, h, w, c,
+            check(lib.vs_upsample2x(C.c_void_p(ptr(x_nhwc)), C.c_void_p(ptr(out)), n, h, w, c, _DT[x_nhwc.dtype],
                                     C.c_void_p(stream_ptr())), "vs_upsample2x")
         else:
-            assert add.shape == out.shape and add.dtype == torch.bfloat16 and add.is_contiguous()
+            assert add.shape == out.shape and add.dtype == x_nhwc.dtype and add.is_contiguous()
             check(lib.vs_upsample2x_add(C.c_void_p(ptr(x_nhwc)), C.c_void_p(ptr(add)), C.c_void_p(ptr(out)),
-                                        n, h, w, c, C.c_void_p(stream_ptr())), "vs_upsample2x_add")
+                                        n, h, w, c, _DT[x_nhwc.dtype], C.c_void_p(stream_ptr())),
+                  "vs_upsample2x_add")
     return out
 
 
 def pixel_shuffle(src, n, h, w, c, k):
     lib = _lib.load()
     _need_cuda(src)
-    out = torch.empty((n, h * k, w * k, c), dtype=torch.bfloat16, device=src.device)
+    out = torch.empty((n, h * k, w * k, c), dtype=src.dtype, device=src.device)
     check(lib.vs_pixel_shuffle(C.c_void_p(ptr(src)), C.c_void_p(ptr(out)), n, h, w, c, k,
                                C.c_void_p(stream_ptr())), "vs_pixel_shuffle")
     return out
@@ -275,11 +289,11 @@ def camera_tokens(intr_tok, extr_tok, x, frames, T, Cdim, rows_per_frame):
                                C.c_void_p(stream_ptr())), "vs_camera_tokens")
 
 
-def silu_bf16(x, rows, Cdim, ldx=None):
+def silu_bf16(x, rows, Cdim, ldx=None, half=torch.bfloat16):
     lib = _lib.load()
-    y = torch.empty((rows, Cdim), dtype=torch.bfloat16, device=x.device)
+    y = torch.empty((rows, Cdim), dtype=half, device=x.device)
     check(lib.vs_silu_bf16(C.c_void_p(ptr(x)), C.c_int64(ldx if ldx is not None else x.stride(0)),
-                           C.c_void_p(ptr(y)), C.c_int64(Cdim), rows, Cdim,
+                           C.c_void_p(ptr(y)), C.c_int64(Cdim), rows, Cdim, _DT[half],
                            C.c_void_p(stream_ptr())), "vs_silu_bf16")
     return y
 
@@ -297,7 +311,7 @@ def camera_head(cam_feat, ld, w, b, B, T, Cdim):
 def pts_tail(feat, Cf, w, b, raw, px):
     lib = _lib.load()
     check(lib.vs_pts_tail(C.c_void_p(ptr(feat)), Cf, C.c_void_p(ptr(w)), C.c_void_p(ptr(b)),
-                          C.c_void_p(ptr(raw)), C.c_int64(raw.stride(-2)), C.c_int64(px),
+                          C.c_void_p(ptr(raw)), C.c_int64(raw.stride(-2)), C.c_int64(px), _DT[feat.dtype],
                           C.c_void_p(stream_ptr())), "vs_pts_tail")
 
 
