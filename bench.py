@@ -578,16 +578,20 @@ def train_leg(args, model, scenes, dev, rank, world, local, barrier) -> dict:
         return dict(means=s_["means"] + gz["means"], cov6=s_["cov6"] + gz["cov6"], sh=s_["harmonics"] + gz["sh"],
                     opac=s_["opacities"] + (gz["opac"] - 0.5))
 
+    ctx_ext = torch.eye(4, device=dev).repeat(B, T_CTX, 1, 1)       # context cameras on the unit baseline
+    ctx_ext[:, :, 0, 3] = torch.arange(T_CTX, device=dev) / (T_CTX - 1)
+
     def one(check, host=False):
         if host:
-            ctx = dict(image=image_h.to(dev, non_blocking=True), intrinsics=K_h.to(dev, non_blocking=True))
+            ctx = dict(image=image_h.to(dev, non_blocking=True), intrinsics=K_h.to(dev, non_blocking=True),
+                       extrinsics=ctx_ext)
             tgt = dict(target, image=tgt_h.to(dev, non_blocking=True))
         else:
             ctx, tgt = ctx_d, tgt_d
         loss = ts.step(ctx, tgt, override_gaussians=override, check_overflow=check)
         return float(loss) if host else loss
 
-    ctx_d = dict(image=image_h.to(dev), intrinsics=K_h.to(dev))
+    ctx_d = dict(image=image_h.to(dev), intrinsics=K_h.to(dev), extrinsics=ctx_ext)
     tgt_d = dict(target, image=tgt_h.to(dev))
     for _ in range(3):                       # first steps: calibrate the rasterizer's capacity hints
         try:
@@ -634,7 +638,8 @@ def train_leg(args, model, scenes, dev, rank, world, local, barrier) -> dict:
                   f"of {mb}: encoder fwd + 12-view render + MSE + raster bwd + encoder bwd (all {n_params} "
                   "trained parameters) + " + ("gradient all-reduce + " if world > 1 else "") +
                   "nan_to_num / clip 0.5 / AdamW + re-pack"),
-        loss=dict(kind="MSE (LossMse); LPIPS needs VGG16 weights that are not in the image", first=float(loss0),
+        loss=dict(kind="MSE (weight 1) + dual-quaternion camera loss (weight 0.1); LPIPS (weight 0.05) needs the "
+                       "lpips package's VGG16 weights, which are not in the image", first=float(loss0),
                   last=loss),
         raster_input="synthetic pixel-aligned scenes + encoder outputs as residuals (unit Jacobian)",
         clocks=clk.result, gpu_launches=launches,

@@ -41,18 +41,22 @@ class _NoReduce:
 
 
 class TrainStep:
-    def __init__(self, model: VicaSplat, *, lr: float = 4e-5, backbone_lr_multiplier: float = 0.1,
+    def __init__(self, model: VicaSplat, *, lr: float = 4e-5, backbone_lr_multiplier: float = 0.25,
                  new_param_keywords=("gaussian_param_head", "intrinsic_encoder"), weight_decay: float = 0.05,
                  betas=(0.9, 0.95), max_grad_norm: float = 0.5, micro_batch: int = 8, mse_weight: float = 1.0,
-                 reducer: Optional[GradReducer] = None, background=(0.0, 0.0, 0.0)):
+                 camera_weight: float = 0.1, reducer: Optional[GradReducer] = None, background=(0.0, 0.0, 0.0)):
         """lr / backbone_lr_multiplier / new_param_keywords: the reference's two parameter groups
-        (model_wrapper.py:884-927 with config/experiment/re10k_8view.yaml:48-51: parameters whose name
-        contains a keyword train at lr, the pretrained rest at lr * multiplier)."""
+        (model_wrapper.py:884-927 with config/experiment/re10k_8view.yaml:48-55: parameters whose name
+        contains a keyword train at lr, the pretrained rest at lr * multiplier).  Losses: MSE on the renders
+        (config/loss/mse.yaml, weight 1) and -- when the context carries ground-truth extrinsics -- the
+        dual-quaternion camera loss (config/loss/camera.yaml, weight 0.1); LPIPS (weight 0.05) needs the
+        VGG16 + linear-layer weights of the `lpips` package, which are not in this image."""
         self.model = model
         self.reducer = reducer or GradReducer()
         self.eng = TrainEngine(model, reducer=self.reducer)
         self.micro_batch = micro_batch
         self.mse_weight = mse_weight
+        self.camera_weight = camera_weight
         named = [(n, p) for n, p in model.named_parameters() if n not in set(self.eng.unused)]
         is_new = lambda n: any(k in n for k in new_param_keywords)
         new = [p for n, p in named if is_new(n)]
@@ -115,9 +119,18 @@ class TrainStep:
                 losses.append(loss)
                 render_backward(st, g_color, out=dict(d_means=d_means[g], d_cov6=d_cov6[g], d_opac=d_opac[g],
                                                       d_sh=d_sh[g].view(Gs, -1)))
+            d_pred = None
+            if self.camera_weight > 0 and "extrinsics" in context:
+                from .loss import camera_loss
+                with torch.enable_grad():      # (mb, T-1, 8) numbers: host-side torch arithmetic (loss.py)
+                    pred = out["pred_extrins"].detach().requires_grad_(True)
+                    lc = camera_loss(pred, context["extrinsics"][sl], self.camera_weight * mb / B)
+                    lc.backward()
+                d_pred = pred.grad
+                losses.append(lc.detach())
             last = mi == n_micro - 1
             eng.reducer = real if last else _NoReduce()
-            eng.backward(d_means=d_means, d_cov6=d_cov6, d_sh=d_sh, d_opac=d_opac, zero=(mi == 0))
+            eng.backward(d_means=d_means, d_cov6=d_cov6, d_sh=d_sh, d_opac=d_opac, d_pred=d_pred, zero=(mi == 0))
         eng.reducer = real
         if check_overflow:      # the counters travel with the loss: one synchronisation per step
             recs = take_deferred()
