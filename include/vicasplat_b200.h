@@ -512,6 +512,9 @@ int vs_col2im(const void* dcols, void* dx, int n, int h, int w, int c, int k, in
 /* dx = dy * (y > 0) on bf16 [rows, C] (dx nullable / may alias dy); colsum += column sums (nullable) */
 int vs_relu_backward(const void* dy, int64_t lddy, const void* y, int64_t ldy, void* dx, int64_t lddx,
                      float* colsum, int64_t rows, int C, vs_stream_t stream);
+/* nn.Dropout(p), training mode, in place on a bf16 buffer of n elements (dpt_block.py:341): keep with
+ * probability 1 - p, scale by 1 / (1 - p); the keep decision is a hash of (seed, element index). */
+int vs_dropout_bf16(void* x, int64_t n, float p, uint64_t seed, vs_stream_t stream);
 /* Backward of vs_pts_tail: d_xyz fp32 rows (leading dimension d_ld) -> d_feat bf16 [px, Cf] (already
  * masked by feat > 0), dw (3, Cf) and db (3) accumulated. */
 int vs_pts_tail_backward(const void* feat, int Cf, const float* w, const float* b, const float* d_xyz,

@@ -66,3 +66,43 @@ def run_smoke():
     e_dw = rel(gacc["attn.qkv.weight"], bsd[key + ".attn.qkv.weight"].grad)
     assert e_dx < 2e-2 and e_dw < 3e-2, (e_dx, e_dw)
     print(f"smoke: encoder block backward ok (dx rel-L2 {e_dx:.2e}, d qkv.weight rel-L2 {e_dw:.2e})")
+
+    # the whole training path: one TrainStep (encoder fwd, render, MSE, raster bwd, hand-written encoder bwd,
+    # fused AdamW) on a 2-scene toy batch (its gradients are held to the oracle by tests/test_gpu_model_grad.py)
+    from vicasplat_b200 import decoder as dec, synthetic
+    from vicasplat_b200.rasterizer import RasterOverflow
+    from vicasplat_b200.train_step import TrainStep
+    model.train()
+    model.gs_head_dropout = 0.0
+    ts = TrainStep(model, micro_batch=1)
+    B, V, S, T = 2, 2, 64, 3
+    image2 = torch.rand((B, T, 3, S, S), generator=g) * 2 - 1
+    K2 = K.expand(B, T, 3, 3).contiguous()
+    scenes = []
+    for b_ in range(B):
+        sc_ = {k: v.to(dev) for k, v in synthetic.gaussian_scene(T, S, S, V, seed=20 + b_).items()}
+        sc_["cov6"] = dec._cov6(sc_["covariances"]).contiguous()
+        scenes.append(sc_)
+    stk = lambda k: torch.stack([s_[k] for s_ in scenes])
+    target = dict(extrinsics=stk("extrinsics"), intrinsics=stk("intrinsics"), near=stk("near"), far=stk("far"),
+                  image=torch.rand((B, V, 3, S, S), generator=g).to(dev))
+    ctx = dict(image=image2.to(dev), intrinsics=K2.to(dev))
+
+    def override(b_, gz):
+        s_ = scenes[b_]
+        return dict(means=s_["means"] + gz["means"], cov6=s_["cov6"] + gz["cov6"], sh=s_["harmonics"] + gz["sh"],
+                    opac=s_["opacities"] + (gz["opac"] - 0.5))
+    before = [p.detach().clone() for p in model.parameters()]
+    for attempt in range(3):
+        try:
+            loss = ts.step(ctx, target, override_gaussians=override)
+            break
+        except RasterOverflow:
+            continue
+    torch.cuda.synchronize()
+    assert torch.isfinite(loss) and loss.item() > 0
+    moved = sum(int(not torch.equal(p, q)) for p, q in zip(model.parameters(), before))
+    assert moved >= 499, moved
+    assert all(torch.isfinite(p).all() for p in model.parameters())
+    print(f"smoke: training step ok (loss {loss.item():.4f}, {ts.opt.step_count} optimizer step, "
+          f"{len(ts.eng.buckets)} gradient buckets)")

@@ -29,6 +29,7 @@ def _build(dev, case="small"):
     bb = dict(default_backbone_cfg(), img_size=cfg.img_size, enc_depth=cfg.enc_depth, dec_depth=cfg.dec_depth)
     model = VicaSplat(VicaSplatCfg(backbone=bb)).to(dev)
     model.load_state_dict(er.synth_state_dict(cfg, seed=0), strict=True)
+    model.gs_head_dropout = 0.0        # the goldens / the oracle are dropout-free (eval mode)
     image, K = synth_inputs(B, T, cfg.img_size)
     return cfg, model, image.to(dev), K.to(dev)
 

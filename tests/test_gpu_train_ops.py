@@ -367,3 +367,16 @@ def test_camera_head_backward(cuda, lib):
     dw, dbias = torch.zeros((8, C), device=cuda), torch.zeros((8,), device=cuda)
     dfeat = ops.camera_head_backward(feat, w, b, B, T, C, dp, dw, dbias)
     assert _rel(dfeat, fr.grad) < 1e-4 and _rel(dw, wr.grad) < 1e-4 and _rel(dbias, br.grad) < 1e-4
+
+
+def test_dropout_in_place(cuda, lib):
+    """nn.Dropout(0.1) of the gs head (dpt_block.py:341): kept fraction, scale, determinism per seed."""
+    from vicasplat_b200 import ops
+    x = torch.ones((1 << 20,), dtype=torch.bfloat16, device=cuda)
+    y = ops.dropout_(x.clone(), 0.1, 7)
+    kept = (y != 0).float().mean().item()
+    assert abs(kept - 0.9) < 2e-3
+    assert torch.allclose(y[y != 0].float(), torch.tensor(1 / 0.9), rtol=4e-3)
+    assert torch.equal(y, ops.dropout_(x.clone(), 0.1, 7)) and not torch.equal(y, ops.dropout_(x.clone(), 0.1, 8))
+    assert torch.equal(ops.dropout_(x.clone(), 0.0, 1), x)
+    assert abs((y.float().mean().item()) - 1.0) < 3e-3          # unbiased

@@ -433,6 +433,35 @@ relu_backward_kernel(const bf16* __restrict__ dy, long long lddy, const bf16* __
   }
 }
 
+// nn.Dropout(p) of the gs head in training mode (dpt_block.py:341), in place on the bf16 post-ReLU map: an
+// element is kept with probability 1 - p and scaled by 1 / (1 - p).  Counter-based: the decision is a hash
+// of (seed, element index), so no generator state lives on the device and the mask never has to be stored
+// -- the backward pass reads it off the kept map (dropped or inactive = 0), vs_gemm's ReLU-mask epilogue
+// with out_scale = 1 / (1 - p).
+__device__ __forceinline__ uint32_t mix32(uint64_t v) {
+  v ^= v >> 33; v *= 0xff51afd7ed558ccdull;
+  v ^= v >> 33; v *= 0xc4ceb9fe1a85ec53ull;
+  v ^= v >> 33;
+  return static_cast<uint32_t>(v);
+}
+__global__ void dropout_kernel(bf16* __restrict__ x, long long n8, uint32_t threshold, float scale,
+                               uint64_t seed) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  uint4 v = *reinterpret_cast<const uint4*>(x + i * 8);
+  uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[j]));
+    const uint32_t r0 = mix32(seed ^ (static_cast<uint64_t>(i * 8 + 2 * j) * 0x9e3779b97f4a7c15ull));
+    const uint32_t r1 = mix32(seed ^ (static_cast<uint64_t>(i * 8 + 2 * j + 1) * 0x9e3779b97f4a7c15ull));
+    f.x = r0 < threshold ? 0.f : f.x * scale;
+    f.y = r1 < threshold ? 0.f : f.y * scale;
+    w[j] = pk2(f.x, f.y);
+  }
+  *reinterpret_cast<uint4*>(x + i * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
 // ------------------------------------------------------------------ tails
 // pts head tail backward: a = W feat + b (3-vector, recomputed), xyz = a / |a| * expm1(|a|);
 // d a from d xyz (tail_math.h); d feat = (W^T d a) . (feat > 0)  [feat is the post-ReLU head.2 output];
@@ -764,6 +793,17 @@ extern "C" int vs_relu_backward(const void* dy, int64_t lddy, const void* y, int
   relu_backward_kernel<<<grid, 256, 0, to_stream(stream)>>>(
       static_cast<const bf16*>(dy), lddy, static_cast<const bf16*>(y), ldy, static_cast<bf16*>(dx), lddx,
       colsum, rows, C);
+  VS_LAUNCH_CHECK();
+  return VS_OK;
+}
+
+extern "C" int vs_dropout_bf16(void* x, int64_t n, float p, uint64_t seed, vs_stream_t stream) {
+  VS_REQUIRE(x != nullptr && al16(x) && n % 8 == 0, "dropout: bf16 buffer, 16-byte aligned, n % 8 == 0");
+  VS_REQUIRE(p >= 0.f && p < 1.f, "dropout: p must be in [0, 1)");
+  if (n <= 0 || p == 0.f) return VS_OK;
+  const uint32_t threshold = static_cast<uint32_t>(static_cast<double>(p) * 4294967296.0);
+  dropout_kernel<<<blocks_for(n / 8, 256), 256, 0, to_stream(stream)>>>(static_cast<bf16*>(x), n / 8, threshold,
+                                                                          1.0f / (1.0f - p), seed);
   VS_LAUNCH_CHECK();
   return VS_OK;
 }

@@ -711,3 +711,13 @@ def camera_head_backward(cam_feat, w, b, B, T, Cdim, d_pred, dw, db):
         Cdim, C.c_void_p(ptr(d_pred)), C.c_void_p(ptr(d_feat)), C.c_int64(Cdim), C.c_void_p(ptr(dw)),
         C.c_void_p(ptr(db)), C.c_void_p(stream_ptr())), "vs_camera_head_backward")
     return d_feat
+
+
+def dropout_(x, p: float, seed: int):
+    """In-place training-mode dropout on a contiguous bf16 tensor (vs_dropout_bf16)."""
+    lib = _lib.load()
+    _need_cuda(x)
+    assert x.dtype == torch.bfloat16 and x.is_contiguous()
+    check(lib.vs_dropout_bf16(C.c_void_p(ptr(x)), C.c_int64(x.numel()), C.c_float(p), C.c_uint64(seed & (2 ** 64 - 1)),
+                              C.c_void_p(stream_ptr())), "vs_dropout_bf16")
+    return x

@@ -93,6 +93,11 @@ class TrainEngine:
                 fb[D:].data_ptr() == self.g[k + "projk.bias"].data_ptr() and \
                 fb[2 * D:].data_ptr() == self.g[k + "projv.bias"].data_ptr()
             self.g[k + "qkv.weight"], self.g[k + "qkv.bias"] = fw, fb
+        # nn.Dropout(0.1) between the gs head's ReLU and its 1x1 projection is active in training mode
+        # (dpt_block.py:341); `model.gs_head_dropout` overrides it (0 for the parity tests: the reference's
+        # goldens are taken in eval mode)
+        self.dropout_p = float(getattr(model, "gs_head_dropout", 0.1))
+        self._drop_seed = 0x5eed
         self.w: Dict[str, torch.Tensor] = {}
         self.dwp: Dict[str, torch.Tensor] = {}      # packed-layout conv weight gradients (scratch)
         self._plans: Dict[tuple, dict] = {}
@@ -410,6 +415,9 @@ class TrainEngine:
                            act=VS_ACT_RELU, view=view)
         merged = ops.upsample2x(g1, add=c7)
         y = self._conv(merged, k + "head.0", act=VS_ACT_RELU)
+        if self.dropout_p > 0:
+            self._drop_seed += 1
+            ops.dropout_(y, self.dropout_p, self._drop_seed)      # y now holds the kept, re-scaled activations
         ops.gemm(y.view(-1, FEAT), w[k + "head.4"], bias=w[k + "head.4.bias"], out=gsp, N=self.m.raw_gs_dim)
         tg.update(img8=img8, view=view, c7=c7, merged=merged, y=y)
         raw = torch.empty((G, 3 + self.m.raw_gs_dim), dtype=F32, device=self.dev)
@@ -589,7 +597,9 @@ class TrainEngine:
         y2d = t["y"].view(-1, FEAT)
         ops.gemm_tn_acc(dgs, y2d, dW4)
         self.g[k + "head.4.weight"].view(nraw, FEAT).add_(dW4[:nraw])
-        d_y = ops.gemm_masked(dgs, w[k + "head.4.t"], mask=y2d).view(Fr, H, W, FEAT)
+        # through the 1x1, the dropout (kept elements carry 1 / (1 - p)) and the ReLU: one masked epilogue
+        scale = 1.0 / (1.0 - self.dropout_p) if self.dropout_p > 0 else 0.0
+        d_y = ops.gemm_masked(dgs, w[k + "head.4.t"], mask=y2d, out_scale=scale).view(Fr, H, W, FEAT)
         d_merged = self._conv_bwd(d_y, t["merged"], k + "head.0")
         del d_y
         d_g1 = ops.upsample2x_backward(d_merged)
