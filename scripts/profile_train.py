@@ -3,6 +3,7 @@
 every launch family (vicasplat_b200.ops.TIMERS), plus the GEMM launches ranked by time.
 usage: profile_train.py [scenes_per_micro_batch]"""
 import json
+import os
 import sys
 from collections import defaultdict
 from pathlib import Path
@@ -51,6 +52,16 @@ for _ in range(3):
     except RasterOverflow:
         pass
 torch.cuda.synchronize()
+
+if os.environ.get("VS_PROFILE_STEP") == "1":
+    # one training step between cudaProfilerStart/Stop for
+    #   ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none ...
+    torch.cuda.cudart().cudaProfilerStart()
+    ts.step(ctx, target, override_gaussians=override)
+    torch.cuda.synchronize()
+    torch.cuda.cudart().cudaProfilerStop()
+    print("profiled one training step")
+    sys.exit(0)
 
 # ---- sections (monkey-patched event marks around the engine's stages)
 marks = []

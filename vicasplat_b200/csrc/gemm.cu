@@ -1228,6 +1228,12 @@ extern "C" int vs_gemm(const vs_gemm_params* p, vs_stream_t stream_) {
              "vs_gemm: more than 2^30 output rows");
 
   int bn = p->block_n;
+  if (bn == 0 && p->c_accumulate) {
+    // weight-gradient form: split-K keeps every SM busy whatever the number of output tiles, so the widest
+    // tile wins (bytes of operand per MMA cycle: 256-wide tiles need 64 B/clk/SM, 128-wide 96 B/clk/SM --
+    // ncu on the 3x3 wgrad at 256^2: tensor pipe 25 % active with BN = 128, L2 -> SM feed-bound)
+    bn = p->N > 128 ? 256 : (p->N > 64 ? 128 : 64);
+  }
   if (bn == 0) {
     double best = 0;
     for (int cand : {256, 128, 64}) {

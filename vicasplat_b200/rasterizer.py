@@ -178,19 +178,20 @@ class _Rasterize(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_color, g_radii, g_depth, g_alpha, g_touched):
         st = ctx.state
-        g = render_backward(st, g_color, g_depth, g_alpha)
+        g = render_backward(st, g_color, g_depth, g_alpha, want_tau=any(ctx.has_pose))
         sm, sc, so, ss, scol = ctx.shapes
         has_sh = st.params.shs is not None
         g_shs = g["d_sh"].reshape(ss) if has_sh else None
         g_cols = g["d_colors"].reshape(scol) if not has_sh else None
-        d_tau = g["d_tau"]
+        d_tau = g.get("d_tau")
         g_theta = d_tau[:, 3:].reshape(ctx.pose_shapes[0]) if ctx.has_pose[0] else None
         g_rho = d_tau[:, :3].reshape(ctx.pose_shapes[1]) if ctx.has_pose[1] else None
         return (g["d_means"].reshape(sm), g["d_cov6"].reshape(sc), g["d_opac"].reshape(so), g_shs, g_cols,
                 g_theta, g_rho, None)
 
 
-def render_backward(state: _Ctx, g_color, g_depth=None, g_alpha=None, out: Optional[dict] = None) -> dict:
+def render_backward(state: _Ctx, g_color, g_depth=None, g_alpha=None, out: Optional[dict] = None,
+                    want_tau: bool = True) -> dict:
     """vs_raster_backward for a kept forward state (``_run_forward``): gradients w.r.t. means (G,3) /
     (V,G,3), cov6, opacity, SH (in the layout the forward call was given) or colours, and the camera
     twist (V,6: rho, theta).  ``out`` may hold preallocated, ZEROED fp32 buffers under the same keys
@@ -216,7 +217,8 @@ def render_backward(state: _Ctx, g_color, g_depth=None, g_alpha=None, out: Optio
     d_means, d_cov, d_opac = buf("d_means", lead + (3,)), buf("d_cov6", lead + (6,)), buf("d_opac", lead)
     d_shs = buf("d_sh", lead + (3 * fp.sh_M,)) if has_sh else None
     d_col = buf("d_colors", lead + (3,)) if not has_sh else None
-    d_tau = buf("d_tau", (V, 6))
+    # the camera-twist gradient costs a block reduction per view and component: only when asked for
+    d_tau = buf("d_tau", (V, 6)) if want_tau else None
     gc = _f32c(g_color) if g_color is not None else torch.zeros((V, 3, fp.H, fp.W), dtype=f32, device=dev)
     gd = _f32c(g_depth) if g_depth is not None else None
     ga = _f32c(g_alpha) if g_alpha is not None else None

@@ -118,7 +118,7 @@ class TrainStep:
                 loss, g_color = ops.mse_loss(color, target["image"][b], self.mse_weight / B)
                 losses.append(loss)
                 render_backward(st, g_color, out=dict(d_means=d_means[g], d_cov6=d_cov6[g], d_opac=d_opac[g],
-                                                      d_sh=d_sh[g].view(Gs, -1)))
+                                                      d_sh=d_sh[g].view(Gs, -1)), want_tau=False)
             d_pred = None
             if self.camera_weight > 0 and "extrinsics" in context:
                 from .loss import camera_loss
