@@ -465,6 +465,9 @@ def run_ours(args) -> None:
     enc16_ms, = dist_util.max_over_ranks([e0.elapsed_time(e1) / args.steps], dev)
     del eng16
 
+    stress = None
+    if args.stress_steps > 0:
+        stress = stress_leg(args, dev, rank, world, local, barrier)
     train = None
     if args.train_batch > 0:
         train = train_leg(args, model, scenes, dev, rank, world, local, barrier)
@@ -521,6 +524,8 @@ def run_ours(args) -> None:
             value=world * NB * 1e3 / (enc16_ms + ras_ms), unit="scenes/s",
             parity="raw Gaussians 1.1e-3 rel-L2 vs the reference's fp32 golden at full depth "
                    "(tests/test_gpu_encoder.py; speed mode: 1.1e-2)")
+        if stress is not None:
+            line["raster_stress"] = stress
         if train is not None:
             line["train_step"] = train
         if world == 1 and not args.no_cpu:
@@ -540,6 +545,48 @@ def run_ours(args) -> None:
         emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------ C5 stress leg
+def stress_leg(args, dev, rank, world, local, barrier) -> dict:
+    """BASELINE configs[4]: 16-view 512x512 raster-only forward of a 2^21-Gaussian scene per GPU (replicas)."""
+    import torch
+    from vicasplat_b200 import decoder as dec, dist_util, synthetic
+    from vicasplat_b200.rasterizer import rasterize_views
+    import vicasplat_b200.rasterizer as rmod
+    T, V, S, G = 16, 16, 512, 1 << 21
+    sc = synthetic.gaussian_scene(T, S, S, V, seed=dist_util.scene_seed(4, rank), n_gauss=G, device=dev)
+    tanfov, view_t, full_t, campos = dec._cameras(sc["extrinsics"], sc["intrinsics"], sc["near"], sc["far"])
+    cov6 = dec._cov6(sc["covariances"]).contiguous()
+    kw = dict(shs=sc["harmonics"], sh_degree=4, sh_layout="chan_major", viewmatrix=view_t, projmatrix=full_t,
+              campos=campos, tanfov=tanfov, bg=torch.zeros((V, 3), device=dev), H=S, W=S, want_n_touched=False)
+    for _ in range(2):
+        ref = rasterize_views(sc["means"], cov6, sc["opacities"], check_overflow=True, **kw)[0]
+    n_pairs = int((rmod._capacity_hint[(V, G, S, S)][0] - 4096) / 1.25)
+    K = args.stress_steps
+    for _ in range(3):
+        rasterize_views(sc["means"], cov6, sc["opacities"], check_overflow="deferred", **kw)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        e0.record()
+        for _ in range(K):
+            out = rasterize_views(sc["means"], cov6, sc["opacities"], check_overflow="deferred", **kw)[0]
+        e1.record()
+        barrier()
+    recs = rmod.take_deferred()
+    rmod.verify_deferred(torch.stack([r[0] for r in recs]).cpu(), recs)
+    assert torch.equal(out, ref)
+    ms, = dist_util.max_over_ranks([e0.elapsed_time(e1) / K], dev)
+    peaks = load_peaks()
+    gbs = raster_bytes(V, G, S, S) / (ms * 1e-3) / 1e9
+    return dict(metric="raster_only_scenes_per_sec_16view_512x512", value=world * 1e3 / ms, unit="scenes/s",
+                ms_per_step=ms, steps=K, warmup=5, n_gpus=world, mpix_per_sec=world * 1e3 / ms * V * S * S / 1e6,
+                workload="configs[4]: 16-view 512x512 raster-only forward, G = 2^21 Gaussians per scene, one scene "
+                         "per GPU per step", raster_pairs=n_pairs, clocks=clk.result,
+                roofline=dict(bound="hbm", kernel="preprocess+sort+blend chain, 16 views", achieved=gbs,
+                              peak=peaks["hbm"], unit="GB/s", frac=gbs / peaks["hbm"],
+                              note="SURVEY 8d per-view bytes; the chain is issue-bound, not HBM-bound (profiles/)"))
 
 
 # ------------------------------------------------------------------------------------ training leg
@@ -689,6 +736,8 @@ def main() -> None:
                          "24); 0 = skip the training leg")
     ap.add_argument("--train-micro", type=int, default=8, help="scenes per micro-batch of the training step")
     ap.add_argument("--train-steps", type=int, default=3)
+    ap.add_argument("--stress-steps", type=int, default=5,
+                    help="timed steps of the raster_stress sub-record (BASELINE configs[4]); 0 = skip")
     ap.add_argument("--train-wire", choices=["f32", "bf16"], default="bf16",
                     help="wire format of the gradient all-reduce (bf16: half the bytes; buckets stay fp32)")
     args = ap.parse_args()

@@ -242,3 +242,25 @@ def test_upstream_golden(cuda, lib, probe):
     _check(rc, rd, want_c, want_d)                      # the oracle restates upstream
     c, d = _ours(sc, h, cuda)
     _check(c, d, want_c, want_d)                        # and so do the kernels
+
+
+def test_stress_size_view_against_oracle(cuda, lib):
+    """BASELINE configs[4] at full size -- 16 views of 512 x 512, G = 2^21 Gaussians -- with ONE view held to
+    the fp32 oracle (the CPU needs ~10 s per view at this size): same bar as the headline scene."""
+    from vicasplat_b200 import synthetic
+    from vicasplat_b200.decoder import render_cuda
+    V, S, G = 16, 512, 1 << 21
+    sc = synthetic.gaussian_scene(16, S, S, V, seed=4, n_gauss=G)
+    pick = [5]
+    rc, rd = rr.render_cuda_ref(sc["extrinsics"][pick], sc["intrinsics"][pick], sc["near"][pick], sc["far"][pick],
+                                (S, S), torch.zeros((1, 3)), sc["means"], sc["covariances"], sc["harmonics"],
+                                sc["opacities"])
+    d = {k: v.to(cuda) for k, v in sc.items()}
+    c, dep = render_cuda(d["extrinsics"], d["intrinsics"], d["near"], d["far"], (S, S), torch.zeros((V, 3), device=cuda),
+                         d["means"], d["covariances"], d["harmonics"], d["opacities"])
+    ec = (c[pick].cpu().double() - rc.double()).abs()
+    ed = (dep[pick].cpu().double() - rd.double()).abs() / rd.double().abs().clamp_min(1)
+    ok_c, ok_d = (ec <= 1e-4).double().mean().item(), (ed <= 1e-4).double().mean().item()
+    print(f"[raster stress scene] colour: {ok_c * 100:.4f} % of pixels within 1e-4, max {ec.max():.3e}, mean "
+          f"{ec.mean():.3e}; depth (relative): {ok_d * 100:.4f} % within 1e-4, max {ed.max():.3e}")
+    assert ok_c >= 0.995 and ok_d >= 0.995 and ec.mean() <= 1e-5 and ec.max() < 2e-2
