@@ -611,7 +611,11 @@ def train_leg(args, model, scenes, dev, rank, world, local, barrier) -> dict:
     NS = len(scenes)
     model.train()
     reducer = GradReducer(compress_bf16=args.train_wire == "bf16")
-    ts = TrainStep(model, micro_batch=mb, reducer=reducer)
+    lp = None
+    if args.train_lpips == "stand-in":
+        from vicasplat_b200.lpips import LpipsVgg
+        lp = LpipsVgg.stand_in(dev, seed=0)
+    ts = TrainStep(model, micro_batch=mb, reducer=reducer, lpips=lp)
     image_h, K_h = __import__("vicasplat_b200.synthetic", fromlist=["clip"]).clip(
         B, T_CTX, SIZE, seed=dist_util.scene_seed(777, rank))
     g = torch.Generator().manual_seed(dist_util.scene_seed(778, rank))
@@ -685,8 +689,10 @@ def train_leg(args, model, scenes, dev, rank, world, local, barrier) -> dict:
                   f"of {mb}: encoder fwd + 12-view render + MSE + raster bwd + encoder bwd (all {n_params} "
                   "trained parameters) + " + ("gradient all-reduce + " if world > 1 else "") +
                   "nan_to_num / clip 0.5 / AdamW + re-pack"),
-        loss=dict(kind="MSE (weight 1) + dual-quaternion camera loss (weight 0.1); LPIPS (weight 0.05) needs the "
-                       "lpips package's VGG16 weights, which are not in the image", first=float(loss0),
+        loss=dict(kind="MSE (weight 1) + dual-quaternion camera loss (weight 0.1) + LPIPS (weight 0.05) " +
+                       ("with a seeded RANDOM VGG16 of the real architecture (the lpips package's weights are not in "
+                        "the image): real cost, not a perceptual metric" if lp is not None else "switched off"),
+                  first=float(loss0),
                   last=loss),
         raster_input="synthetic pixel-aligned scenes + encoder outputs as residuals (unit Jacobian)",
         clocks=clk.result, gpu_launches=launches,
@@ -736,6 +742,8 @@ def main() -> None:
                          "24); 0 = skip the training leg")
     ap.add_argument("--train-micro", type=int, default=8, help="scenes per micro-batch of the training step")
     ap.add_argument("--train-steps", type=int, default=3)
+    ap.add_argument("--train-lpips", choices=["stand-in", "off"], default="stand-in",
+                    help="LPIPS term of the training step: a seeded random VGG16 (the real weights are not in the image)")
     ap.add_argument("--stress-steps", type=int, default=5,
                     help="timed steps of the raster_stress sub-record (BASELINE configs[4]); 0 = skip")
     ap.add_argument("--train-wire", choices=["f32", "bf16"], default="bf16",

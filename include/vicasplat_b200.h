@@ -532,6 +532,21 @@ int vs_camera_head_backward(const float* cam_feat, int64_t ld, const float* w, c
                             int C, const float* d_pred, float* d_feat, int64_t ldd, float* dw, float* db,
                             vs_stream_t stream);
 
+/* ------------------------------------------------------------------ LPIPS consumer (src/loss/loss_lpips.py:27-54)
+ * The VGG16 features run on vs_gemm (conv3x3 + bias + ReLU); these are the pieces around it. */
+/* 2x2 / stride 2 max pooling on NHWC bf16 maps, and its backward: dx = add (nullable) + dy routed to the first
+ * element of each window that equals the pooled value; relu_mask != 0: x is a post-ReLU map and dx is the
+ * gradient of its pre-activation (a zero maximum passes nothing). */
+int vs_maxpool2(const void* x, void* y, int n, int h, int w, int c, vs_stream_t stream);
+int vs_maxpool2_backward(const void* x, const void* y, const void* dy, const void* add, void* dx, int n, int h,
+                         int w, int c, int relu_mask, vs_stream_t stream);
+/* One LPIPS layer: per_image[i] += mean over the image's pixels of sum_c w[c] (f0/(|f0|+1e-10) - f1/(|f1|+1e-10))^2
+ * (atomics, caller zeroes), and -- if df0 != NULL -- the gradient of grad_scale * (that sum over pixels) w.r.t.
+ * f0, already masked by f0 > 0 (the features are post-ReLU), bf16.  f0 / f1: bf16 (pixels, C), hw pixels per
+ * image. */
+int vs_lpips_layer(const void* f0, const void* f1, const float* wlin, int64_t pixels, int C, int hw,
+                   float grad_scale, float* per_image, void* df0, vs_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

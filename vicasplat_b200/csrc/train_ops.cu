@@ -850,3 +850,177 @@ extern "C" int vs_camera_head_backward(const float* cam_feat, int64_t ld, const 
   VS_LAUNCH_CHECK();
   return VS_OK;
 }
+
+// ------------------------------------------------------------------ LPIPS consumer (src/loss/loss_lpips.py:27-54)
+// The VGG16 feature extractor of LPIPS runs on the implicit-GEMM convolution kernel (conv3x3 + bias + ReLU
+// epilogue); what is left is below: 2x2 max-pooling (forward / backward) and the per-layer distance
+//   d = mean_pixels sum_c w_c (f0_c / (|f0| + eps) - f1_c / (|f1| + eps))^2        (lpips: normalize_tensor,
+// eps = 1e-10, 1x1 `lin` layer with non-negative weights w, spatial average), whose VALUE and GRADIENT
+// w.r.t. the prediction's features f0 come out of ONE pass, like vs_mse_loss.
+namespace vs {
+namespace {
+
+__global__ void maxpool2_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int n, int h, int w, int c) {
+  const unsigned c8 = c / 8;
+  const int ho = h / 2, wo = w / 2;
+  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<unsigned>(wo) * c8) return;
+  const int xo = idx / c8, cc = idx - xo * c8;
+  const int yo = blockIdx.y, im = blockIdx.z;
+  const bf16* base = x + ((static_cast<size_t>(im) * h + 2 * yo) * w + 2 * xo) * c + cc * 8;
+  uint4 q[4] = {__ldg(reinterpret_cast<const uint4*>(base)), __ldg(reinterpret_cast<const uint4*>(base + c)),
+                __ldg(reinterpret_cast<const uint4*>(base + static_cast<size_t>(w) * c)),
+                __ldg(reinterpret_cast<const uint4*>(base + static_cast<size_t>(w) * c + c))};
+  uint32_t o[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float2 m = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&(&q[0].x)[j]));
+#pragma unroll
+    for (int t = 1; t < 4; ++t) {
+      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&(&q[t].x)[j]));
+      m.x = fmaxf(m.x, f.x);
+      m.y = fmaxf(m.y, f.y);
+    }
+    o[j] = pk2(m.x, m.y);
+  }
+  *reinterpret_cast<uint4*>(y + ((static_cast<size_t>(im) * ho + yo) * wo + xo) * c + cc * 8) =
+      make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+// dx[window] = dy routed to the FIRST element of the 2x2 window that equals the pooled maximum (torch's
+// tie rule), + add (the gradient arriving at x from its other consumer; nullable)
+__global__ void maxpool2_backward_kernel(const bf16* __restrict__ x, const bf16* __restrict__ y,
+                                         const bf16* __restrict__ dy, const bf16* __restrict__ add,
+                                         bf16* __restrict__ dx, int n, int h, int w, int c, int relu_mask) {
+  const unsigned c8 = c / 8;
+  const int ho = h / 2, wo = w / 2;
+  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<unsigned>(wo) * c8) return;
+  const int xo = idx / c8, cc = idx - xo * c8;
+  const int yo = blockIdx.y, im = blockIdx.z;
+  const size_t o_off = ((static_cast<size_t>(im) * ho + yo) * wo + xo) * c + cc * 8;
+  const size_t i_off[4] = {((static_cast<size_t>(im) * h + 2 * yo) * w + 2 * xo) * c + cc * 8, 0, 0, 0};
+  const size_t offs[4] = {i_off[0], i_off[0] + c, i_off[0] + static_cast<size_t>(w) * c,
+                          i_off[0] + static_cast<size_t>(w) * c + c};
+  const uint4 ym = __ldg(reinterpret_cast<const uint4*>(y + o_off));
+  const uint4 g = __ldg(reinterpret_cast<const uint4*>(dy + o_off));
+  const uint16_t* ymh = reinterpret_cast<const uint16_t*>(&ym);
+  const uint16_t* gh = reinterpret_cast<const uint16_t*>(&g);
+  bool taken[8] = {false, false, false, false, false, false, false, false};
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const uint4 xv = __ldg(reinterpret_cast<const uint4*>(x + offs[t]));
+    uint4 av = make_uint4(0u, 0u, 0u, 0u);
+    if (add != nullptr) av = __ldg(reinterpret_cast<const uint4*>(add + offs[t]));
+    const uint16_t* xh = reinterpret_cast<const uint16_t*>(&xv);
+    const uint16_t* ah = reinterpret_cast<const uint16_t*>(&av);
+    uint16_t oh[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float v = add != nullptr ? __bfloat162float(*reinterpret_cast<const bf16*>(&ah[e])) : 0.f;
+      if (!taken[e] && xh[e] == ymh[e]) {
+        taken[e] = true;
+        // relu_mask: x is a post-ReLU map and dx is wanted w.r.t. its PRE-activation: a zero maximum passes nothing
+        if (!relu_mask || (xh[e] & 0x7fffu) != 0u) v += __bfloat162float(*reinterpret_cast<const bf16*>(&gh[e]));
+      }
+      const bf16 b = __float2bfloat16(v);
+      oh[e] = *reinterpret_cast<const uint16_t*>(&b);
+    }
+    *reinterpret_cast<uint4*>(dx + offs[t]) = *reinterpret_cast<const uint4*>(oh);
+  }
+}
+
+// one warp per pixel; lanes stride over the channels (C % 64 == 0, C <= 512): value and d f0
+__global__ void __launch_bounds__(256)
+lpips_layer_kernel(const bf16* __restrict__ f0, const bf16* __restrict__ f1, const float* __restrict__ wlin,
+                   long long pixels, int C, int hw, float grad_scale, float* __restrict__ per_image,
+                   bf16* __restrict__ df0) {
+  const int lane = threadIdx.x & 31;
+  const long long pix = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (pix >= pixels) return;
+  const int nv = C / 64;   // bf16x2 per lane
+  float2 a[8], b[8];
+  float sa = 0.f, sb = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    if (i < nv) {
+      a[i] = __bfloat1622float2(reinterpret_cast<const __nv_bfloat162*>(f0 + pix * C)[i * 32 + lane]);
+      b[i] = __bfloat1622float2(reinterpret_cast<const __nv_bfloat162*>(f1 + pix * C)[i * 32 + lane]);
+      sa += a[i].x * a[i].x + a[i].y * a[i].y;
+      sb += b[i].x * b[i].x + b[i].y * b[i].y;
+    }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    sa += __shfl_xor_sync(0xffffffffu, sa, o);
+    sb += __shfl_xor_sync(0xffffffffu, sb, o);
+  }
+  const float ra = sqrtf(sa), rb = sqrtf(sb);
+  const float ia = 1.0f / (ra + 1e-10f), ib = 1.0f / (rb + 1e-10f);
+  float val = 0.f, dot = 0.f;   // dot = f0 . dn
+  float2 dn[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    if (i < nv) {
+      const float2 w = reinterpret_cast<const float2*>(wlin)[i * 32 + lane];
+      const float dx = a[i].x * ia - b[i].x * ib, dy = a[i].y * ia - b[i].y * ib;
+      val += w.x * dx * dx + w.y * dy * dy;
+      dn[i] = make_float2(2.f * w.x * dx * grad_scale, 2.f * w.y * dy * grad_scale);
+      dot += a[i].x * dn[i].x + a[i].y * dn[i].y;
+    }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    val += __shfl_xor_sync(0xffffffffu, val, o);
+    dot += __shfl_xor_sync(0xffffffffu, dot, o);
+  }
+  if (lane == 0) atomicAdd(per_image + pix / hw, val / hw);
+  if (df0 != nullptr) {
+    // n = f / (r + eps):  d f = (dn - f (f . dn) / (r (r + eps))) / (r + eps)
+    const float k = ra > 0.f ? dot * ia / ra : 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (i < nv) {
+        // through the ReLU that produced f0 (features are taken after the activation)
+        const float gx = a[i].x > 0.f ? (dn[i].x - a[i].x * k) * ia : 0.f;
+        const float gy = a[i].y > 0.f ? (dn[i].y - a[i].y * k) * ia : 0.f;
+        reinterpret_cast<__nv_bfloat162*>(df0 + pix * C)[i * 32 + lane] = __floats2bfloat162_rn(gx, gy);
+      }
+  }
+}
+
+}  // namespace
+}  // namespace vs
+
+extern "C" int vs_maxpool2(const void* x, void* y, int n, int h, int w, int c, vs_stream_t stream) {
+  VS_REQUIRE(x && y && c % 8 == 0 && h % 2 == 0 && w % 2 == 0 && al16(x) && al16(y), "maxpool2: NHWC bf16, even map, c % 8 == 0");
+  if (n <= 0) return VS_OK;
+  VS_REQUIRE(h / 2 < 65536 && n < 65536, "maxpool2: map too large");
+  const dim3 grid(blocks_for(static_cast<long long>(w / 2) * (c / 8), 256), h / 2, n);
+  maxpool2_kernel<<<grid, 256, 0, to_stream(stream)>>>(static_cast<const bf16*>(x), static_cast<bf16*>(y), n, h, w, c);
+  VS_LAUNCH_CHECK();
+  return VS_OK;
+}
+
+extern "C" int vs_maxpool2_backward(const void* x, const void* y, const void* dy, const void* add, void* dx, int n,
+                                    int h, int w, int c, int relu_mask, vs_stream_t stream) {
+  VS_REQUIRE(x && y && dy && dx && c % 8 == 0 && h % 2 == 0 && w % 2 == 0, "maxpool2_backward: NHWC bf16, even map");
+  if (n <= 0) return VS_OK;
+  VS_REQUIRE(h / 2 < 65536 && n < 65536, "maxpool2_backward: map too large");
+  const dim3 grid(blocks_for(static_cast<long long>(w / 2) * (c / 8), 256), h / 2, n);
+  maxpool2_backward_kernel<<<grid, 256, 0, to_stream(stream)>>>(
+      static_cast<const bf16*>(x), static_cast<const bf16*>(y), static_cast<const bf16*>(dy),
+      static_cast<const bf16*>(add), static_cast<bf16*>(dx), n, h, w, c, relu_mask);
+  VS_LAUNCH_CHECK();
+  return VS_OK;
+}
+
+extern "C" int vs_lpips_layer(const void* f0, const void* f1, const float* wlin, int64_t pixels, int C, int hw,
+                              float grad_scale, float* per_image, void* df0, vs_stream_t stream) {
+  VS_REQUIRE(f0 && f1 && wlin && per_image, "lpips_layer: null tensor");
+  VS_REQUIRE(C % 64 == 0 && C <= 512 && hw > 0 && pixels % hw == 0, "lpips_layer: C % 64 == 0 <= 512, whole images");
+  if (pixels <= 0) return VS_OK;
+  lpips_layer_kernel<<<blocks_for(pixels * 32, 256), 256, 0, to_stream(stream)>>>(
+      static_cast<const bf16*>(f0), static_cast<const bf16*>(f1), wlin, pixels, C, hw, grad_scale, per_image,
+      static_cast<bf16*>(df0));
+  VS_LAUNCH_CHECK();
+  return VS_OK;
+}

@@ -721,3 +721,35 @@ def dropout_(x, p: float, seed: int):
     check(lib.vs_dropout_bf16(C.c_void_p(ptr(x)), C.c_int64(x.numel()), C.c_float(p), C.c_uint64(seed & (2 ** 64 - 1)),
                               C.c_void_p(stream_ptr())), "vs_dropout_bf16")
     return x
+
+
+# ------------------------------------------------------------------ LPIPS consumer
+def maxpool2(x_nhwc):
+    lib = _lib.load()
+    n, h, w, c = x_nhwc.shape
+    assert x_nhwc.dtype == torch.bfloat16 and x_nhwc.is_contiguous()
+    y = torch.empty((n, h // 2, w // 2, c), dtype=torch.bfloat16, device=x_nhwc.device)
+    check(lib.vs_maxpool2(C.c_void_p(ptr(x_nhwc)), C.c_void_p(ptr(y)), n, h, w, c, C.c_void_p(stream_ptr())),
+          "vs_maxpool2")
+    return y
+
+
+def maxpool2_backward(x, y, dy, add=None, relu_mask=False):
+    lib = _lib.load()
+    n, h, w, c = x.shape
+    dx = torch.empty_like(x)
+    check(lib.vs_maxpool2_backward(C.c_void_p(ptr(x)), C.c_void_p(ptr(y)), C.c_void_p(ptr(dy)), C.c_void_p(ptr(add)),
+                                   C.c_void_p(ptr(dx)), n, h, w, c, int(relu_mask), C.c_void_p(stream_ptr())),
+          "vs_maxpool2_backward")
+    return dx
+
+
+def lpips_layer(f0, f1, wlin, per_image, grad_scale, want_grad=True):
+    """per_image (N,) += layer distance; returns d f0 (bf16, masked by f0 > 0) of grad_scale * sum over pixels."""
+    lib = _lib.load()
+    n, h, w, c = f0.shape
+    df0 = torch.empty_like(f0) if want_grad else None
+    check(lib.vs_lpips_layer(C.c_void_p(ptr(f0)), C.c_void_p(ptr(f1)), C.c_void_p(ptr(wlin)), C.c_int64(n * h * w), c,
+                             h * w, C.c_float(grad_scale), C.c_void_p(ptr(per_image)), C.c_void_p(ptr(df0)),
+                             C.c_void_p(stream_ptr())), "vs_lpips_layer")
+    return df0

@@ -44,19 +44,22 @@ class TrainStep:
     def __init__(self, model: VicaSplat, *, lr: float = 4e-5, backbone_lr_multiplier: float = 0.25,
                  new_param_keywords=("gaussian_param_head", "intrinsic_encoder"), weight_decay: float = 0.05,
                  betas=(0.9, 0.95), max_grad_norm: float = 0.5, micro_batch: int = 8, mse_weight: float = 1.0,
-                 camera_weight: float = 0.1, reducer: Optional[GradReducer] = None, background=(0.0, 0.0, 0.0)):
+                 camera_weight: float = 0.1, lpips=None, lpips_weight: float = 0.05,
+                 reducer: Optional[GradReducer] = None, background=(0.0, 0.0, 0.0)):
         """lr / backbone_lr_multiplier / new_param_keywords: the reference's two parameter groups
         (model_wrapper.py:884-927 with config/experiment/re10k_8view.yaml:48-55: parameters whose name
         contains a keyword train at lr, the pretrained rest at lr * multiplier).  Losses: MSE on the renders
         (config/loss/mse.yaml, weight 1) and -- when the context carries ground-truth extrinsics -- the
-        dual-quaternion camera loss (config/loss/camera.yaml, weight 0.1); LPIPS (weight 0.05) needs the
-        VGG16 + linear-layer weights of the `lpips` package, which are not in this image."""
+        dual-quaternion camera loss (config/loss/camera.yaml, weight 0.1); LPIPS (config/loss/lpips.yaml,
+        weight 0.05) when an ``lpips.LpipsVgg`` is given -- the `lpips` package's VGG16 + linear-layer weights
+        are not in this image, ``LpipsVgg.stand_in`` is a random network of the same cost."""
         self.model = model
         self.reducer = reducer or GradReducer()
         self.eng = TrainEngine(model, reducer=self.reducer)
         self.micro_batch = micro_batch
         self.mse_weight = mse_weight
         self.camera_weight = camera_weight
+        self.lpips, self.lpips_weight = lpips, lpips_weight
         named = [(n, p) for n, p in model.named_parameters() if n not in set(self.eng.unused)]
         is_new = lambda n: any(k in n for k in new_param_keywords)
         new = [p for n, p in named if is_new(n)]
@@ -117,6 +120,10 @@ class TrainStep:
                     _deferred.append((st.num_pairs, st.max_pairs, st.max_tile, (V, Gs, H, W)))
                 loss, g_color = ops.mse_loss(color, target["image"][b], self.mse_weight / B)
                 losses.append(loss)
+                if self.lpips is not None and self.lpips_weight > 0:
+                    ll, gl = self.lpips.loss_and_grad(color, target["image"][b], self.lpips_weight / B)
+                    losses.append(ll)
+                    g_color.add_(gl)
                 render_backward(st, g_color, out=dict(d_means=d_means[g], d_cov6=d_cov6[g], d_opac=d_opac[g],
                                                       d_sh=d_sh[g].view(Gs, -1)), want_tau=False)
             d_pred = None
