@@ -138,7 +138,7 @@ typedef struct vs_gemm_params {
   int32_t mask_mode;    /* 0 none, 1 res2 masks then res1 is added, 2 res1 masks */
   int32_t c_accumulate; /* C += result (atomic, fp32 only) */
   int32_t split_k;      /* with c_accumulate: number of K ranges (0 = choose) */
-  float out_scale;      /* 0 = 1: the accumulator is multiplied by this first (e.g. 1 / keep of a dropout) */
+  float out_scale;      /* with mask_mode != 0 only; 0 = 1: the accumulator is multiplied by this first (e.g. 1 / keep of a dropout) */
   int32_t operand_dtype; /* 16-bit format of A, W and of 16-bit C / C2 / residual maps: 0 or VS_BF16 = bf16 (speed
                             mode), VS_F16 = fp16 (parity mode: TF32's 10-bit mantissa, same tensor rate; forward
                             a_modes only) */

@@ -9,7 +9,9 @@ import re
 from pathlib import Path
 
 _ROOT = Path(__file__).resolve().parent
-LIB_PATH = _ROOT / "lib" / "libvicasplat_b200.so"
+import os as _os
+# VICASPLAT_B200_LIB: load another build of the same C-ABI (A/B of kernel variants); same loud failure if absent
+LIB_PATH = Path(_os.environ.get("VICASPLAT_B200_LIB") or _ROOT / "lib" / "libvicasplat_b200.so")
 HEADER_PATH = _ROOT.parent / "include" / "vicasplat_b200.h"
 
 VS_F32, VS_BF16, VS_F16, VS_F64 = 0, 1, 2, 3

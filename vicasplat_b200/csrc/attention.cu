@@ -57,6 +57,8 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+// F16 (the 16-bit format of Q / K / V / P / O) is a compile-time choice: the P conversions sit in the softmax loop
+template <bool F16>
 __global__ void __launch_bounds__(ATT_THREADS, 3)
     attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, const AttnDev a) {
@@ -135,7 +137,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 3)
     // buffered (128 TMEM columns and 65 KB of shared memory per CTA -> three CTAs per SM, whose
     // phases interleave); every barrier completes once per key tile, phase parity = j & 1.
     if (lane == 0) {
-      const uint32_t fmt_clear = a.f16 ? ~((1u << 7) | (1u << 10)) : ~0u;   // format bits: 1 = bf16, 0 = fp16
+      constexpr uint32_t fmt_clear = F16 ? ~((1u << 7) | (1u << 10)) : ~0u;   // format bits: 1 = bf16, 0 = fp16
       const uint32_t idesc_s = umma_idesc_bf16(QT, KT, 0) & fmt_clear;
       const uint32_t idesc_o = umma_idesc_bf16(QT, HD, 1) & fmt_clear;
       const uint32_t q_addr = smem_u32(sQ), k_addr = smem_u32(sK), v_addr = smem_u32(sV),
@@ -281,7 +283,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 3)
             const float p1 = ex2_approx(__uint_as_float(v[i + 1]) * a.scale_log2 - m_use);
             rs0 += p0;
             rs1 += p1;
-            pk[i >> 1] = f2_to_h2(p0, p1, a.f16);
+            pk[i >> 1] = f2_to_h2(p0, p1, F16);
           }
         } else {
 #pragma unroll
@@ -292,7 +294,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 3)
             if (i + 1 >= my_valid) p1 = 0.f;
             rs0 += p0;
             rs1 += p1;
-            pk[i >> 1] = f2_to_h2(p0, p1, a.f16);
+            pk[i >> 1] = f2_to_h2(p0, p1, F16);
           }
         }
         if (!p_free) {
@@ -337,7 +339,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 3)
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             w[i] = f2_to_h2(__uint_as_float(v[ch * 8 + 2 * i]) * inv, __uint_as_float(v[ch * 8 + 2 * i + 1]) * inv,
-                            a.f16);
+                            F16);
           }
           *reinterpret_cast<uint4*>(dst + h * 32 + ch * 8) = make_uint4(w[0], w[1], w[2], w[3]);
         }
@@ -517,14 +519,15 @@ extern "C" int vs_attention(const vs_attention_params* p, vs_stream_t stream_) {
   const int rem = p->max_q_len % QT;
   a.tail = (rem > 0 && rem <= TAIL_MAX_ROWS && p->max_kv_len > 0 && p->max_kv_len <= TAIL_MAX_KEYS)
                ? rem : 0;
-    VS_CONFIGURE_PER_DEVICE(
-    VS_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 SMEM_BYTES));
+  VS_CONFIGURE_PER_DEVICE(
+    VS_CUDA(cudaFuncSetAttribute(attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    VS_CUDA(cudaFuncSetAttribute(attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   );
   const int main_rows = p->max_q_len - a.tail;
   if (main_rows > 0) {
     dim3 grid(ceil_div(main_rows, QT), p->heads, p->items);
-    attention_kernel<<<grid, ATT_THREADS, SMEM_BYTES, to_stream(stream_)>>>(tmQ, tmK, tmV, a);
+    (a.f16 ? attention_kernel<true> : attention_kernel<false>)<<<grid, ATT_THREADS, SMEM_BYTES, to_stream(stream_)>>>(
+        tmQ, tmK, tmV, a);
     VS_LAUNCH_CHECK();
   }
   if (a.tail > 0) {

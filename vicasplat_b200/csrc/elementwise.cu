@@ -274,8 +274,9 @@ __global__ void im2col_kernel(const void* __restrict__ src, int nchw_f32, bf16* 
 
 // bilinear x2 align_corners=True on NHWC bf16; one thread per 8 channels of an output pixel;
 // grid = (segments of an output row, output row, image): no 64-bit index arithmetic
+template <bool f16, bool ADD>
 __global__ void upsample2x_kernel(const bf16* __restrict__ src, const bf16* __restrict__ add,
-                                  bf16* __restrict__ dst, int n, int h, int w, int c, int f16) {
+                                  bf16* __restrict__ dst, int n, int h, int w, int c) {
   const unsigned c8 = c / 8;
   const int ho = 2 * h, wo = 2 * w;
   const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -297,7 +298,7 @@ __global__ void upsample2x_kernel(const bf16* __restrict__ src, const bf16* __re
   uint4 o;
   const size_t oidx = ((static_cast<size_t>(im) * ho + yo) * wo + xo) * c + cc * 8;
   uint4 e = make_uint4(0u, 0u, 0u, 0u);
-  if (add != nullptr) e = __ldg(reinterpret_cast<const uint4*>(add + oidx));
+  if (ADD) e = __ldg(reinterpret_cast<const uint4*>(add + oidx));
   const uint32_t* pa = &a.x; const uint32_t* pb = &b.x; const uint32_t* pc = &cq.x;
   const uint32_t* pd = &d.x; const uint32_t* pe = &e.x; uint32_t* po = &o.x;
 #pragma unroll
@@ -306,7 +307,7 @@ __global__ void upsample2x_kernel(const bf16* __restrict__ src, const bf16* __re
     const float2 fc = h2_to_f2(pc[j], f16), fd = h2_to_f2(pd[j], f16);
     uint32_t r2 = f2_to_h2(w00 * fa.x + w01 * fb.x + w10 * fc.x + w11 * fd.x,
                            w00 * fa.y + w01 * fb.y + w10 * fc.y + w11 * fd.y, f16);
-    if (add != nullptr) {   // the upsampled map is rounded to 16 bits first, like the fused GEMM epilogue does
+    if (ADD) {   // the upsampled map is rounded to 16 bits first, like the fused GEMM epilogue does
       const float2 fu = h2_to_f2(r2, f16);
       const float2 fe = h2_to_f2(pe[j], f16);
       r2 = f2_to_h2(fu.x + fe.x, fu.y + fe.y, f16);
@@ -943,8 +944,8 @@ extern "C" int vs_upsample2x(const void* src, void* dst, int n, int h, int w, in
   if (static_cast<long long>(n) * h * w == 0) return VS_OK;
   VS_REQUIRE(2 * h <= 65535 && n <= 65535, "upsample2x: map too large for the launch grid");
   dim3 grid(blocks_for(static_cast<long long>(2 * w) * (c / 8), 256), 2 * h, n);
-  upsample2x_kernel<<<grid, 256, 0, to_stream(stream)>>>(
-      static_cast<const bf16*>(src), nullptr, static_cast<bf16*>(dst), n, h, w, c, f16);
+  (f16 ? upsample2x_kernel<true, false> : upsample2x_kernel<false, false>)<<<grid, 256, 0, to_stream(stream)>>>(
+      static_cast<const bf16*>(src), nullptr, static_cast<bf16*>(dst), n, h, w, c);
   VS_LAUNCH_CHECK();
   return VS_OK;
 }
@@ -958,8 +959,8 @@ extern "C" int vs_upsample2x_add(const void* src, const void* add, void* dst, in
   if (static_cast<long long>(n) * h * w == 0) return VS_OK;
   VS_REQUIRE(2 * h <= 65535 && n <= 65535, "upsample2x_add: map too large for the launch grid");
   dim3 grid(blocks_for(static_cast<long long>(2 * w) * (c / 8), 256), 2 * h, n);
-  upsample2x_kernel<<<grid, 256, 0, to_stream(stream)>>>(
-      static_cast<const bf16*>(src), static_cast<const bf16*>(add), static_cast<bf16*>(dst), n, h, w, c, f16);
+  (f16 ? upsample2x_kernel<true, true> : upsample2x_kernel<false, true>)<<<grid, 256, 0, to_stream(stream)>>>(
+      static_cast<const bf16*>(src), static_cast<const bf16*>(add), static_cast<bf16*>(dst), n, h, w, c);
   VS_LAUNCH_CHECK();
   return VS_OK;
 }
