@@ -31,3 +31,10 @@ run("K=64 bf16 bias   ", M, 1024, 64, bias=bias, out=torch.empty((M, 1024), devi
 x = torch.randn((M, 1024), device=dev)
 run("K=64 f32 res     ", M, 1024, 64, bias=bias, res1=x, out=x)
 run("K=1024 f32 res   ", 16448, 1024, 1024, bias=bias, res1=x[:16448], out=x[:16448])
+xb = torch.randn((M, 256), device=dev).to(bf)
+run("K=448 N=256 bf16 res", M, 256, 448, bias=bias[:256], res1=xb, out=torch.empty((M, 256), device=dev, dtype=bf))
+run("K=448 N=256 bf16    ", M, 256, 448, bias=bias[:256], out=torch.empty((M, 256), device=dev, dtype=bf))
+b4 = torch.randn((4096,), device=dev)
+run("K=1024 N=4096 gelu  ", 16448, 4096, 1024, bias=b4, act=VS_ACT_GELU, out=torch.empty((16448, 4096), device=dev, dtype=bf))
+run("K=1024 N=3072 bf16  ", 16448, 3072, 1024, bias=b4[:3072], out=torch.empty((16448, 3072), device=dev, dtype=bf))
+run("K=256 N=96 f32      ", M, 96, 256, bias=bias[:96], out=torch.empty((M, 100), device=dev)[:, :96], out_dtype=torch.float32)
