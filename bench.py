@@ -290,11 +290,14 @@ def run_ours(args) -> None:
     def raster_batch(check="deferred"):
         # the camera set-up of all NB * V cameras (sync-free) belongs to the step
         tanfov, view_t, full_t, campos = dec._cameras(ext_all, intr_all, near_all, far_all)
-        for i, s_ in enumerate(scenes):           # one launch chain (all 12 views) per scene
-            c = slice(i * V_TGT, (i + 1) * V_TGT)
-            out = rasterize_views(s_["means"], s_["cov6"], s_["opacities"], shs=s_["harmonics"],
-                                  viewmatrix=view_t[c], projmatrix=full_t[c], campos=campos[c],
-                                  tanfov=tanfov[c], check_overflow=check, **rkw)
+        with rmod.SceneStreams(dev) as ss:        # one launch chain (all 12 views) per scene, scenes
+            for i, s_ in enumerate(scenes):       # round-robin over SceneStreams (what the decoder plugin does)
+                c = slice(i * V_TGT, (i + 1) * V_TGT)
+                with ss.scene(i):
+                    out = rasterize_views(s_["means"], s_["cov6"], s_["opacities"], shs=s_["harmonics"],
+                                          viewmatrix=view_t[c], projmatrix=full_t[c], campos=campos[c],
+                                          tanfov=tanfov[c], check_overflow=check, **rkw)
+                ss.keep(*out)
         return out
 
     def verify_raster():

@@ -19,7 +19,7 @@ from typing import Literal, Optional
 import torch
 from torch import Tensor, nn
 
-from .rasterizer import rasterize_views
+from .rasterizer import SceneStreams, rasterize_views
 
 DepthRenderingMode = Literal["depth", "log", "disparity", "relative_disparity"]
 
@@ -144,18 +144,21 @@ class DecoderSplattingCUDA(nn.Module):
         cov6 = _cov6(cov) if cov6 is None else (cov6.flatten(1, 3) if cov6.ndim > 3 else cov6)
         bg = self.background_color[None].expand(v, 3)
         colors, depths = [], []
-        for i in range(b):
-            sl = slice(i * v, (i + 1) * v)
-            c, _r, d, _a, _n = rasterize_views(
-                means[i], cov6[i], opac[i], shs=sh[i] if use_sh else None,
-                colors_precomp=None if use_sh else sh[i][..., 0], sh_degree=degree,
-                sh_layout="chan_major", viewmatrix=view_t[sl], projmatrix=full_t[sl], campos=campos[sl],
-                tanfov=tanfov[sl], bg=bg, H=h, W=w,
-                theta=None if cam_rot_delta is None else cam_rot_delta[i],
-                rho=None if cam_trans_delta is None else cam_trans_delta[i], want_n_touched=False,
-                check_overflow=check_overflow)
-            colors.append(c)
-            depths.append(d[:, 0])
+        with SceneStreams(means.device) as ss:
+            for i in range(b):
+                sl = slice(i * v, (i + 1) * v)
+                with ss.scene(i):
+                    c, _r, d, _a, _n = rasterize_views(
+                        means[i], cov6[i], opac[i], shs=sh[i] if use_sh else None,
+                        colors_precomp=None if use_sh else sh[i][..., 0], sh_degree=degree,
+                        sh_layout="chan_major", viewmatrix=view_t[sl], projmatrix=full_t[sl], campos=campos[sl],
+                        tanfov=tanfov[sl], bg=bg, H=h, W=w,
+                        theta=None if cam_rot_delta is None else cam_rot_delta[i],
+                        rho=None if cam_trans_delta is None else cam_trans_delta[i], want_n_touched=False,
+                        check_overflow=check_overflow)
+                ss.keep(c, d)
+                colors.append(c)
+                depths.append(d[:, 0])
         color, depth = torch.stack(colors), torch.stack(depths)
         if not return_dict:
             return color, depth

@@ -253,6 +253,55 @@ def render_forward(means, cov6, opac, shs, *, sh_degree, sh_layout, viewmatrix, 
     return color, depth, alpha, st
 
 
+class SceneStreams:
+    """The scenes of a batch are independent launch chains (preprocess -> bin -> sort -> blend): alternating
+    them between the current stream and side streams lets the block scheduler co-run one scene's issue-bound
+    blend with the next scene's memory- / latency-bound binning and sort kernels.
+
+        with SceneStreams(dev) as ss:
+            for i, scene in enumerate(batch):
+                with ss.scene(i):
+                    out.append(rasterize_views(...))
+
+    On exit the current stream waits for the side streams; tensors allocated inside are marked as used by the
+    current stream (``keep``).  VS_RASTER_STREAMS=1 turns the interleaving off (A/B measurements)."""
+    _pool: dict = {}
+
+    def __init__(self, dev, n: Optional[int] = None):
+        import os
+        self.n = n if n is not None else int(os.environ.get("VS_RASTER_STREAMS", "4"))
+        self.dev = dev
+        self.cur = torch.cuda.current_stream(dev)
+        key = (dev.index if dev.index is not None else torch.cuda.current_device(), self.n)
+        if key not in SceneStreams._pool:
+            SceneStreams._pool[key] = [torch.cuda.Stream(dev) for _ in range(max(self.n - 1, 0))]
+        self.side = SceneStreams._pool[key]
+        self.used = set()
+
+    def __enter__(self):
+        return self
+
+    def scene(self, i: int):
+        k = i % max(self.n, 1)
+        if k == 0:
+            return torch.cuda.stream(self.cur)
+        st = self.side[k - 1]
+        if k not in self.used:
+            st.wait_stream(self.cur)
+            self.used.add(k)
+        return torch.cuda.stream(st)
+
+    def keep(self, *tensors):
+        for t in tensors:
+            if isinstance(t, torch.Tensor) and t.is_cuda:
+                t.record_stream(self.cur)
+
+    def __exit__(self, *exc):
+        for k in self.used:
+            self.cur.wait_stream(self.side[k - 1])
+        return False
+
+
 def rasterize_views(means3D, cov6, opacities, *, shs=None, colors_precomp=None, sh_degree=0,
                     sh_layout="coef_major", viewmatrix, projmatrix, campos, tanfov, bg, H, W,
                     theta=None, rho=None, max_pairs: Optional[int] = None,
