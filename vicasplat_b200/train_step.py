@@ -25,7 +25,7 @@ from . import decoder as dec, ops
 from .encoder import VicaSplat
 from .encoder_train import GradReducer
 from .optim import FusedAdamW
-from .rasterizer import render_backward, render_forward, take_deferred, verify_deferred, _deferred
+from .rasterizer import SceneStreams, render_backward, render_forward, take_deferred, verify_deferred, _deferred
 from .train import TrainEngine
 
 
@@ -78,6 +78,30 @@ class TrainStep:
         self.eng.repack()
         return loss
 
+    def _scene(self, b, j, out, override_gaussians, view_t, full_t, campos, tanfov, target, check_overflow, losses,
+               grads, V, Gs, H, W, B):
+        """render scene b (slot j of the micro-batch), its losses, and the render backward into its gradient slice"""
+        d_means, d_cov6, d_sh, d_opac = grads
+        g = slice(j * Gs, (j + 1) * Gs)
+        gauss = dict(means=out["means"][g], cov6=out["cov6"][g], sh=out["sh"][g], opac=out["opac"][g])
+        if override_gaussians is not None:
+            gauss = override_gaussians(b, gauss)
+        cam = slice(b * V, (b + 1) * V)
+        color, _depth, _alpha, st = render_forward(
+            gauss["means"], gauss["cov6"], gauss["opac"], gauss["sh"], sh_degree=4, sh_layout="chan_major",
+            viewmatrix=view_t[cam], projmatrix=full_t[cam], campos=campos[cam], tanfov=tanfov[cam],
+            bg=self.bg, H=H, W=W)
+        if check_overflow:
+            _deferred.append((st.num_pairs, st.max_pairs, st.max_tile, (V, Gs, H, W)))
+        loss, g_color = ops.mse_loss(color, target["image"][b], self.mse_weight / B)
+        losses.append(loss)
+        if self.lpips is not None and self.lpips_weight > 0:
+            ll, gl = self.lpips.loss_and_grad(color, target["image"][b], self.lpips_weight / B)
+            losses.append(ll)
+            g_color.add_(gl)
+        render_backward(st, g_color, out=dict(d_means=d_means[g], d_cov6=d_cov6[g], d_opac=d_opac[g],
+                                              d_sh=d_sh[g].view(Gs, -1)), want_tau=False)
+
     @torch.no_grad()
     def accumulate(self, context: dict, target: dict, override_gaussians=None, check_overflow=True) -> torch.Tensor:
         """Forward + backward of one batch: every ``param.grad`` holds the gradient of the mean loss
@@ -105,27 +129,12 @@ class TrainStep:
             dev = out["raw"].device
             z = lambda *s: torch.zeros((G, *s), dtype=torch.float32, device=dev)
             d_means, d_cov6, d_sh, d_opac = z(3), z(6), z(3, self.model.d_sh), z()
-            for j in range(mb):
-                b = mi * mb + j
-                g = slice(j * Gs, (j + 1) * Gs)
-                gauss = dict(means=out["means"][g], cov6=out["cov6"][g], sh=out["sh"][g], opac=out["opac"][g])
-                if override_gaussians is not None:
-                    gauss = override_gaussians(b, gauss)
-                cam = slice(b * V, (b + 1) * V)
-                color, _depth, _alpha, st = render_forward(
-                    gauss["means"], gauss["cov6"], gauss["opac"], gauss["sh"], sh_degree=4, sh_layout="chan_major",
-                    viewmatrix=view_t[cam], projmatrix=full_t[cam], campos=campos[cam], tanfov=tanfov[cam],
-                    bg=self.bg, H=H, W=W)
-                if check_overflow:
-                    _deferred.append((st.num_pairs, st.max_pairs, st.max_tile, (V, Gs, H, W)))
-                loss, g_color = ops.mse_loss(color, target["image"][b], self.mse_weight / B)
-                losses.append(loss)
-                if self.lpips is not None and self.lpips_weight > 0:
-                    ll, gl = self.lpips.loss_and_grad(color, target["image"][b], self.lpips_weight / B)
-                    losses.append(ll)
-                    g_color.add_(gl)
-                render_backward(st, g_color, out=dict(d_means=d_means[g], d_cov6=d_cov6[g], d_opac=d_opac[g],
-                                                      d_sh=d_sh[g].view(Gs, -1)), want_tau=False)
+            with SceneStreams(dev) as ss:      # the scenes' render / loss / render-backward chains are independent
+                for j in range(mb):
+                    with ss.scene(j):
+                        self._scene(mi * mb + j, j, out, override_gaussians, view_t, full_t, campos, tanfov, target,
+                                    check_overflow, losses, (d_means, d_cov6, d_sh, d_opac), V, Gs, H, W, B)
+                ss.keep(*losses)
             d_pred = None
             if self.camera_weight > 0 and "extrinsics" in context:
                 from .loss import camera_loss
