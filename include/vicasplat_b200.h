@@ -542,8 +542,8 @@ int vs_maxpool2_backward(const void* x, const void* y, const void* dy, const voi
                          int w, int c, int relu_mask, vs_stream_t stream);
 /* One LPIPS layer: per_image[i] += mean over the image's pixels of sum_c w[c] (f0/(|f0|+1e-10) - f1/(|f1|+1e-10))^2
  * (atomics, caller zeroes), and -- if df0 != NULL -- the gradient of grad_scale * (that sum over pixels) w.r.t.
- * f0, already masked by f0 > 0 (the features are post-ReLU), bf16.  f0 / f1: bf16 (pixels, C), hw pixels per
- * image. */
+ * f0, already masked by f0 > 0 (the features are post-ReLU), bf16.  f0 / f1: bf16 (pixels, C), C in {64, 128, 256,
+ * 512}, 16-byte aligned, hw pixels per image (one atomic per 128 pixels when hw % 128 == 0, else one per pixel). */
 int vs_lpips_layer(const void* f0, const void* f1, const float* wlin, int64_t pixels, int C, int hw,
                    float grad_scale, float* per_image, void* df0, vs_stream_t stream);
 
