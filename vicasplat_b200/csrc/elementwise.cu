@@ -272,8 +272,10 @@ __global__ void im2col_kernel(const void* __restrict__ src, int nchw_f32, bf16* 
   *reinterpret_cast<uint4*>(out + row * kpad + col0) = o;
 }
 
-// bilinear x2 align_corners=True on NHWC bf16; one thread per 8 channels of an output pixel;
-// grid = (segments of an output row, output row, image): no 64-bit index arithmetic
+// bilinear x2 align_corners=True on NHWC bf16; one thread per 8 channels of UP2_ROWS vertically adjacent output
+// pixels (one output per thread made the launch block-rate-bound: 262 144 blocks of 256 single-output threads ran
+// at 2.2 TB/s); grid = (segments of an output row, groups of output rows, image): no 64-bit index arithmetic
+constexpr int UP2_ROWS = 4;
 template <bool f16, bool ADD>
 __global__ void upsample2x_kernel(const bf16* __restrict__ src, const bf16* __restrict__ add,
                                   bf16* __restrict__ dst, int n, int h, int w, int c) {
@@ -282,39 +284,48 @@ __global__ void upsample2x_kernel(const bf16* __restrict__ src, const bf16* __re
   const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= static_cast<unsigned>(wo) * c8) return;
   const int xo = idx / c8, cc = idx - xo * c8;
-  const int yo = blockIdx.y, im = blockIdx.z;
+  const int im = blockIdx.z;
   const float sy = ho > 1 ? static_cast<float>(h - 1) / (ho - 1) : 0.f;
   const float sx = wo > 1 ? static_cast<float>(w - 1) / (wo - 1) : 0.f;
-  const float fy = yo * sy, fx = xo * sx;
-  const int y0 = static_cast<int>(fy), x0 = static_cast<int>(fx);
-  const int y1 = min(y0 + 1, h - 1), x1 = min(x0 + 1, w - 1);
-  const float ly = fy - y0, lx = fx - x0;
-  const float w00 = (1 - ly) * (1 - lx), w01 = (1 - ly) * lx, w10 = ly * (1 - lx), w11 = ly * lx;
+  const float fx = xo * sx;
+  const int x0 = static_cast<int>(fx);
+  const int x1 = min(x0 + 1, w - 1);
+  const float lx = fx - x0;
   const bf16* base = src + static_cast<size_t>(im) * h * w * c + cc * 8;
   auto ld = [&](int y, int x) {
     return __ldg(reinterpret_cast<const uint4*>(base + (static_cast<size_t>(y) * w + x) * c));
   };
-  const uint4 a = ld(y0, x0), b = ld(y0, x1), cq = ld(y1, x0), d = ld(y1, x1);
-  uint4 o;
-  const size_t oidx = ((static_cast<size_t>(im) * ho + yo) * wo + xo) * c + cc * 8;
-  uint4 e = make_uint4(0u, 0u, 0u, 0u);
-  if (ADD) e = __ldg(reinterpret_cast<const uint4*>(add + oidx));
-  const uint32_t* pa = &a.x; const uint32_t* pb = &b.x; const uint32_t* pc = &cq.x;
-  const uint32_t* pd = &d.x; const uint32_t* pe = &e.x; uint32_t* po = &o.x;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const float2 fa = h2_to_f2(pa[j], f16), fb = h2_to_f2(pb[j], f16);
-    const float2 fc = h2_to_f2(pc[j], f16), fd = h2_to_f2(pd[j], f16);
-    uint32_t r2 = f2_to_h2(w00 * fa.x + w01 * fb.x + w10 * fc.x + w11 * fd.x,
-                           w00 * fa.y + w01 * fb.y + w10 * fc.y + w11 * fd.y, f16);
-    if (ADD) {   // the upsampled map is rounded to 16 bits first, like the fused GEMM epilogue does
-      const float2 fu = h2_to_f2(r2, f16);
-      const float2 fe = h2_to_f2(pe[j], f16);
-      r2 = f2_to_h2(fu.x + fe.x, fu.y + fe.y, f16);
+  for (int r = 0; r < UP2_ROWS; ++r) {
+    const int yo = blockIdx.y * UP2_ROWS + r;
+    if (yo >= ho) break;
+    const float fy = yo * sy;
+    const int y0 = static_cast<int>(fy);
+    const int y1 = min(y0 + 1, h - 1);
+    const float ly = fy - y0;
+    const float w00 = (1 - ly) * (1 - lx), w01 = (1 - ly) * lx, w10 = ly * (1 - lx), w11 = ly * lx;
+    const uint4 a = ld(y0, x0), b = ld(y0, x1), cq = ld(y1, x0), d = ld(y1, x1);
+    uint4 o;
+    const size_t oidx = ((static_cast<size_t>(im) * ho + yo) * wo + xo) * c + cc * 8;
+    uint4 e = make_uint4(0u, 0u, 0u, 0u);
+    if (ADD) e = __ldg(reinterpret_cast<const uint4*>(add + oidx));
+    const uint32_t* pa = &a.x; const uint32_t* pb = &b.x; const uint32_t* pc = &cq.x;
+    const uint32_t* pd = &d.x; const uint32_t* pe = &e.x; uint32_t* po = &o.x;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 fa = h2_to_f2(pa[j], f16), fb = h2_to_f2(pb[j], f16);
+      const float2 fc = h2_to_f2(pc[j], f16), fd = h2_to_f2(pd[j], f16);
+      uint32_t r2 = f2_to_h2(w00 * fa.x + w01 * fb.x + w10 * fc.x + w11 * fd.x,
+                             w00 * fa.y + w01 * fb.y + w10 * fc.y + w11 * fd.y, f16);
+      if (ADD) {   // the upsampled map is rounded to 16 bits first, like the fused GEMM epilogue does
+        const float2 fu = h2_to_f2(r2, f16);
+        const float2 fe = h2_to_f2(pe[j], f16);
+        r2 = f2_to_h2(fu.x + fe.x, fu.y + fe.y, f16);
+      }
+      po[j] = r2;
     }
-    po[j] = r2;
+    *reinterpret_cast<uint4*>(dst + oidx) = o;
   }
-  *reinterpret_cast<uint4*>(dst + oidx) = o;
 }
 
 __global__ void pixel_shuffle_kernel(const bf16* __restrict__ src, bf16* __restrict__ dst, int n,
@@ -943,7 +954,7 @@ extern "C" int vs_upsample2x(const void* src, void* dst, int n, int h, int w, in
   VS_REQUIRE(c % 8 == 0, "upsample2x: channels must be a multiple of 8");
   if (static_cast<long long>(n) * h * w == 0) return VS_OK;
   VS_REQUIRE(2 * h <= 65535 && n <= 65535, "upsample2x: map too large for the launch grid");
-  dim3 grid(blocks_for(static_cast<long long>(2 * w) * (c / 8), 256), 2 * h, n);
+  dim3 grid(blocks_for(static_cast<long long>(2 * w) * (c / 8), 256), (2 * h + UP2_ROWS - 1) / UP2_ROWS, n);
   (f16 ? upsample2x_kernel<true, false> : upsample2x_kernel<false, false>)<<<grid, 256, 0, to_stream(stream)>>>(
       static_cast<const bf16*>(src), nullptr, static_cast<bf16*>(dst), n, h, w, c);
   VS_LAUNCH_CHECK();
@@ -958,7 +969,7 @@ extern "C" int vs_upsample2x_add(const void* src, const void* add, void* dst, in
   VS_REQUIRE(c % 8 == 0, "upsample2x_add: channels must be a multiple of 8");
   if (static_cast<long long>(n) * h * w == 0) return VS_OK;
   VS_REQUIRE(2 * h <= 65535 && n <= 65535, "upsample2x_add: map too large for the launch grid");
-  dim3 grid(blocks_for(static_cast<long long>(2 * w) * (c / 8), 256), 2 * h, n);
+  dim3 grid(blocks_for(static_cast<long long>(2 * w) * (c / 8), 256), (2 * h + UP2_ROWS - 1) / UP2_ROWS, n);
   (f16 ? upsample2x_kernel<true, true> : upsample2x_kernel<false, true>)<<<grid, 256, 0, to_stream(stream)>>>(
       static_cast<const bf16*>(src), static_cast<const bf16*>(add), static_cast<bf16*>(dst), n, h, w, c);
   VS_LAUNCH_CHECK();
