@@ -5,9 +5,10 @@ losses) + backward + DDP gradient all-reduce (src/main.py:110-115) + nan_to_num 
 
     per micro-batch of scenes
         TrainEngine.forward            encoder: clips -> per-pixel Gaussians + poses (activations kept)
-        per scene   render_forward     V target views of the scene's Gaussians
-                    vs_mse_loss        loss value + dL/dcolour in one pass (LossMse, loss_mse.py:23-31)
-                    render_backward    -> this scene's slice of d means / d cov6 / d SH / d opacity
+        per scene   render_forward     V target views of the scene's Gaussians       (scenes on SceneStreams)
+        vs_mse_loss per scene, LPIPS   loss values + dL/dcolour (LossMse, loss_mse.py:23-31; LossLpips as one
+                                       sweep over the micro-batch's images); camera loss on the predicted poses
+        per scene   render_backward    -> this scene's slice of d means / d cov6 / d SH / d opacity
         TrainEngine.backward           -> parameter gradients (accumulated over the micro-batches); on the
                                        LAST micro-batch every bucket is all-reduced as soon as it is final
     FusedAdamW.step, TrainEngine.repack
@@ -78,10 +79,8 @@ class TrainStep:
         self.eng.repack()
         return loss
 
-    def _scene(self, b, j, out, override_gaussians, view_t, full_t, campos, tanfov, target, check_overflow, losses,
-               grads, V, Gs, H, W, B):
-        """render scene b (slot j of the micro-batch), its losses, and the render backward into its gradient slice"""
-        d_means, d_cov6, d_sh, d_opac = grads
+    def _render(self, b, j, out, override_gaussians, view_t, full_t, campos, tanfov, check_overflow, V, Gs, H, W):
+        """render scene b (slot j of the micro-batch): (colour (V,3,H,W), forward state)"""
         g = slice(j * Gs, (j + 1) * Gs)
         gauss = dict(means=out["means"][g], cov6=out["cov6"][g], sh=out["sh"][g], opac=out["opac"][g])
         if override_gaussians is not None:
@@ -93,14 +92,7 @@ class TrainStep:
             bg=self.bg, H=H, W=W)
         if check_overflow:
             _deferred.append((st.num_pairs, st.max_pairs, st.max_tile, (V, Gs, H, W)))
-        loss, g_color = ops.mse_loss(color, target["image"][b], self.mse_weight / B)
-        losses.append(loss)
-        if self.lpips is not None and self.lpips_weight > 0:
-            ll, gl = self.lpips.loss_and_grad(color, target["image"][b], self.lpips_weight / B)
-            losses.append(ll)
-            g_color.add_(gl)
-        render_backward(st, g_color, out=dict(d_means=d_means[g], d_cov6=d_cov6[g], d_opac=d_opac[g],
-                                              d_sh=d_sh[g].view(Gs, -1)), want_tau=False)
+        return color, st
 
     @torch.no_grad()
     def accumulate(self, context: dict, target: dict, override_gaussians=None, check_overflow=True) -> torch.Tensor:
@@ -129,12 +121,35 @@ class TrainStep:
             dev = out["raw"].device
             z = lambda *s: torch.zeros((G, *s), dtype=torch.float32, device=dev)
             d_means, d_cov6, d_sh, d_opac = z(3), z(6), z(3, self.model.d_sh), z()
-            with SceneStreams(dev) as ss:      # the scenes' render / loss / render-backward chains are independent
+            # the scenes' render and render-backward chains are independent: round-robin over SceneStreams;
+            # the losses sit between them on the current stream, LPIPS as ONE sweep over the micro-batch's
+            # mb * V images (its deep layers have too few rows per scene to fill the GPU)
+            colors, states = [None] * mb, [None] * mb
+            with SceneStreams(dev) as ss:
                 for j in range(mb):
                     with ss.scene(j):
-                        self._scene(mi * mb + j, j, out, override_gaussians, view_t, full_t, campos, tanfov, target,
-                                    check_overflow, losses, (d_means, d_cov6, d_sh, d_opac), V, Gs, H, W, B)
-                ss.keep(*losses)
+                        colors[j], states[j] = self._render(mi * mb + j, j, out, override_gaussians, view_t, full_t,
+                                                            campos, tanfov, check_overflow, V, Gs, H, W)
+                    ss.keep(colors[j])
+            g_colors = []
+            for j in range(mb):
+                loss, g_color = ops.mse_loss(colors[j], target["image"][mi * mb + j], self.mse_weight / B)
+                losses.append(loss)
+                g_colors.append(g_color)
+            if self.lpips is not None and self.lpips_weight > 0:
+                ll, gl = self.lpips.loss_and_grad(torch.cat(colors), target["image"][sl].flatten(0, 1),
+                                                  self.lpips_weight * mb / B)
+                losses.append(ll)
+                for j in range(mb):
+                    g_colors[j].add_(gl[j * V:(j + 1) * V])
+            with SceneStreams(dev) as ss:
+                for j in range(mb):
+                    g = slice(j * Gs, (j + 1) * Gs)
+                    with ss.scene(j):
+                        render_backward(states[j], g_colors[j],
+                                        out=dict(d_means=d_means[g], d_cov6=d_cov6[g], d_opac=d_opac[g],
+                                                 d_sh=d_sh[g].view(Gs, -1)), want_tau=False)
+            del colors, states, g_colors
             d_pred = None
             if self.camera_weight > 0 and "extrinsics" in context:
                 from .loss import camera_loss
