@@ -977,7 +977,23 @@ __global__ void __launch_bounds__(128)
   float dsh[48];
 #pragma unroll
   for (int i = 0; i < 48; ++i) dsh[i] = 0.f;
-  const float* my_sh = shs ? shs + gi * 3 * M : nullptr;
+  // SH coefficients of the warp's 32 Gaussians staged through shared memory with coalesced loads, like the
+  // forward kernel (thread-per-Gaussian reads of the (G, 3, M) array touch 32 lines per instruction, 48 times
+  // per view); the same buffer carries d SH back out at the end
+  extern __shared__ float sh_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int per = 3 * M;
+  float* wsh = sh_smem + static_cast<size_t>(warp) * 32 * per;
+  const int gbase = blockIdx.x * blockDim.x + warp * 32;
+  const int cnt = max(0, min(32, G - gbase)) * per;
+  const size_t set_off = shared_set ? 0 : static_cast<size_t>(blockIdx.y) * G;
+  const float* my_sh = nullptr;
+  if (shs != nullptr) {
+    const float* src = shs + (set_off + gbase) * per;
+    for (int i = lane; i < cnt; i += 32) wsh[i] = __ldg(src + i);
+    __syncwarp();
+    my_sh = wsh + lane * per;
+  }
 
   for (int v = v_begin; v < v_end; ++v) {
     const float* vm = viewm + v * 16;
@@ -1143,19 +1159,29 @@ __global__ void __launch_bounds__(128)
       }
     }
   }
-  if (!live) return;
-  d_means[gi * 3] += dmean[0]; d_means[gi * 3 + 1] += dmean[1]; d_means[gi * 3 + 2] += dmean[2];
+  if (live) {
+    d_means[gi * 3] += dmean[0]; d_means[gi * 3 + 1] += dmean[1]; d_means[gi * 3 + 2] += dmean[2];
 #pragma unroll
-  for (int i = 0; i < 6; ++i) d_cov[gi * 6 + i] += dcov[i];
-  d_opac[gi] += dop;
-  if (has_colors && d_colors != nullptr) {
-    d_colors[gi * 3] += dcol[0]; d_colors[gi * 3 + 1] += dcol[1]; d_colors[gi * 3 + 2] += dcol[2];
-  } else if (d_shs != nullptr) {
+    for (int i = 0; i < 6; ++i) d_cov[gi * 6 + i] += dcov[i];
+    d_opac[gi] += dop;
+    if (has_colors && d_colors != nullptr) {
+      d_colors[gi * 3] += dcol[0]; d_colors[gi * 3 + 1] += dcol[1]; d_colors[gi * 3 + 2] += dcol[2];
+    }
+  }
+  if (!has_colors && d_shs != nullptr && shs != nullptr) {   // warp-uniform
+    __syncwarp();
+    for (int i = lane; i < cnt; i += 32) wsh[i] = 0.f;       // bands above the active degree get no gradient
+    __syncwarp();
+    if (live) {
 #pragma unroll
-    for (int k = 0; k < 16; ++k)
-      if (k < n_sh)
+      for (int k = 0; k < 16; ++k)
+        if (k < n_sh)
 #pragma unroll
-        for (int ch = 0; ch < 3; ++ch) d_shs[gi * 3 * M + k * sh_cs + ch * sh_ch] += dsh[k * 3 + ch];
+          for (int ch = 0; ch < 3; ++ch) wsh[lane * per + k * sh_cs + ch * sh_ch] = dsh[k * 3 + ch];
+    }
+    __syncwarp();
+    float* dst = d_shs + (set_off + gbase) * per;
+    for (int i = lane; i < cnt; i += 32) dst[i] += wsh[i];
   }
 }
 
@@ -1318,7 +1344,8 @@ extern "C" int vs_raster_backward(const vs_raster_bwd_params* p, vs_stream_t str
   int sh_cs = f.sh_stride_coef, sh_ch = f.sh_stride_chan;
   if (sh_cs == 0 && sh_ch == 0) { sh_cs = 3; sh_ch = 1; }
   dim3 grid(ceil_div(f.G, 128), f.gaussians_shared ? 1 : f.V);
-  preprocess_backward_kernel<<<grid, 128, 0, stream>>>(
+  const size_t sh_smem_bytes = f.shs != nullptr ? static_cast<size_t>(128) * 3 * f.sh_M * sizeof(float) : 0;
+  preprocess_backward_kernel<<<grid, 128, sh_smem_bytes, stream>>>(
       f.G, f.V, f.gaussians_shared, f.H, f.W, f.means3D, f.cov3D, f.shs, f.sh_M, sh_cs, sh_ch,
       f.sh_degree, f.colors_precomp != nullptr, f.viewmatrix, f.campos, f.tanfov, f.radii, ws.rgbd,
       gacc, VG, p->dL_dmeans3D, p->dL_dcov3D, p->dL_dopacity, p->dL_dshs, p->dL_dcolors, p->dL_dtau);
