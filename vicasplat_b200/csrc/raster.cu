@@ -948,7 +948,7 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
 // the block, of the camera twist tau = (rho, theta) of the left perturbation W2C <- exp(tau) W2C
 // (src/misc/cam_utils.py:123-142).  Assumes projmatrix = viewmatrix o standard perspective with
 // the given tan(fov), which is how cuda_splatting.py:187-194 builds it.
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 4)   // 128 registers (a few spills) beat 242 at two CTAs per SM: the pass is latency-bound
     preprocess_backward_kernel(int G, int V, int shared_set, int H, int W,
                                const float* __restrict__ means, const float* __restrict__ cov6,
                                const float* __restrict__ shs, int M, int sh_cs, int sh_ch,
