@@ -403,29 +403,36 @@ __global__ void __launch_bounds__(256)
     s_q[threadIdx.x] = h_to_f(reinterpret_cast<const uint16_t*>(Q)[static_cast<long long>(grow) * ldq + head * HD +
                                                                       threadIdx.x], a.f16) * a.scale_log2;
   __syncthreads();
+  // phase 1: 8 lanes per key (one 16-byte load each: a warp instruction touches 4 key rows of 128 B; a thread
+  // per key read 32 different lines per instruction and left ONE thread working on the 257-th key)
   float mx = -INFINITY;
-  for (int j = threadIdx.x; j < nk; j += 256) {
-    const int krow = j < l0 ? s0 + j : s1 + (j - l0);
-    float s = -INFINITY;
-    if (krow < lim) {
-      const uint4* kp = reinterpret_cast<const uint4*>(K + static_cast<long long>(krow) * ldk + head * HD);
-      uint4 kv[8];
+  {
+    const int d8q = (threadIdx.x & 7) * 8, kpart = threadIdx.x >> 3;
+    float q8[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) kv[i] = __ldg(kp + i);
-      s = 0.f;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const uint32_t w[4] = {kv[i].x, kv[i].y, kv[i].z, kv[i].w};
+    for (int i = 0; i < 8; ++i) q8[i] = s_q[d8q + i];
+    for (int j0 = 0; j0 < nk; j0 += 32) {
+      const int j = j0 + kpart;
+      const int krow = j < l0 ? s0 + j : s1 + (j - l0);
+      const bool on = j < nk && krow < lim;
+      float s = 0.f;
+      if (on) {
+        const uint4 t4 = __ldg(reinterpret_cast<const uint4*>(K + static_cast<long long>(krow) * ldk + head * HD + d8q));
+        const uint32_t w[4] = {t4.x, t4.y, t4.z, t4.w};
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const float2 f = h2_to_f2(w[u], a.f16);
-          s = fmaf(s_q[8 * i + 2 * u], f.x, s);
-          s = fmaf(s_q[8 * i + 2 * u + 1], f.y, s);
+          s = fmaf(q8[2 * u], f.x, s);
+          s = fmaf(q8[2 * u + 1], f.y, s);
         }
       }
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      s += __shfl_xor_sync(0xffffffffu, s, 4);
+      if (!on) s = -INFINITY;
+      if (j < nk && (threadIdx.x & 7) == 0) s_p[j] = s;
+      mx = fmaxf(mx, s);
     }
-    s_p[j] = s;
-    mx = fmaxf(mx, s);
   }
   mx = block_reduce(mx, s_red, true);
   const float m_use = mx == -INFINITY ? 0.f : mx;
