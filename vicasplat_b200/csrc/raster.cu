@@ -642,6 +642,32 @@ int launch_tile_sorts(const Workspace& ws, int n_tiles, int key_bits, int id_bit
   return VS_OK;
 }
 
+// Shared-memory loads by 32-bit shared address (computed ONCE per kernel): inside the divergent per-splat
+// loop the compiler rebuilt the generic-to-shared window base (S2R SR_CgaCtaId + LEA) for every access.
+__device__ __forceinline__ uint32_t smem_addr(const void* p) {
+  uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(p));
+  asm volatile("mov.u32 %0, %0;" : "+r"(a));   // opaque: not to be re-materialised inside the loop
+  return a;
+}
+__device__ __forceinline__ float4 lds_f4(uint32_t a) {
+  float4 t;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w) : "r"(a));
+  return t;
+}
+__device__ __forceinline__ float2 lds_f2(uint32_t a) {
+  float2 t;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(t.x), "=f"(t.y) : "r"(a));
+  return t;
+}
+// exp(x) for x <= 0 as ONE ex2.approx of x * log2(e): what __expf does minus its denormal-range fix-up (three
+// more instructions), whose results (< 1e-38) can never reach the alpha >= 1/255 test.  The backward pass
+// recomputes alpha with the same two instructions, so both passes take identical decisions.
+__device__ __forceinline__ float exp_neg(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
+  return y;
+}
+
 // ------------------------------------------------------------------ blend
 // One CTA per 16x16 tile, 8 warps; warp w owns the 8x4-pixel sub-block (w & 1, w >> 1).  The tile's
 // depth-sorted splat list is staged through shared memory in batches of 256 (16-byte gathers of
@@ -683,6 +709,7 @@ __global__ void __launch_bounds__(BLEND_THREADS, 6)  /* <= 40 registers: a blend
   bool done = !inside;
   float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f, D = 0.f, A = 0.f;
   int last_contributor = 0;
+  const uint32_t a_xe = smem_addr(s_xe), a_co = smem_addr(s_co), a_cd = smem_addr(s_cd);
 
   for (int r = 0; r < rounds; ++r) {
     if (__syncthreads_count(done) == BLEND_THREADS) break;
@@ -704,7 +731,7 @@ __global__ void __launch_bounds__(BLEND_THREADS, 6)  /* <= 40 registers: a blend
       if (__all_sync(0xffffffffu, done)) break;
       bool near_me = false;
       if (base + lane < nb) {
-        const float4 xe = s_xe[base + lane];
+        const float4 xe = lds_f4(a_xe + (base + lane) * 16);
         const float ddx = fmaxf(fmaxf(bx0 - xe.x, xe.x - bx1), 0.f);
         const float ddy = fmaxf(fmaxf(by0 - xe.y, xe.y - by1), 0.f);
         near_me = ddx <= xe.z && ddy <= xe.w;
@@ -715,18 +742,18 @@ __global__ void __launch_bounds__(BLEND_THREADS, 6)  /* <= 40 registers: a blend
         todo &= todo - 1;
         bool hit = false;
         if (!done) {
-          const float4 xe = s_xe[j];
-          const float4 co = s_co[j];
+          const float2 xe = lds_f2(a_xe + j * 16);
+          const float4 co = lds_f4(a_co + j * 16);
           const float dx = xe.x - pxf, dy = xe.y - pyf;
           const float power = -0.5f * (co.x * dx * dx + co.z * dy * dy) - co.y * dx * dy;
           if (power <= 0.0f) {
-            const float alpha = fminf(kAlphaMax, co.w * __expf(power));
+            const float alpha = fminf(kAlphaMax, co.w * exp_neg(power));
             if (alpha >= kAlphaMin) {
               const float test_T = T * (1.0f - alpha);
               if (test_T < kTStop) {
                 done = true;
               } else {
-                const float4 cd = s_cd[j];
+                const float4 cd = lds_f4(a_cd + j * 16);
                 const float w = alpha * T;
                 C0 += cd.x * w; C1 += cd.y * w; C2 += cd.z * w;
                 D += cd.w * w;
@@ -861,7 +888,7 @@ __global__ void __launch_bounds__(BLEND_THREADS)
           const float dx = xe.x - pxf, dy = xe.y - pyf;
           const float power = -0.5f * (co.x * dx * dx + co.z * dy * dy) - co.y * dx * dy;
           if (power <= 0.0f) {
-            const float Gv = __expf(power);
+            const float Gv = exp_neg(power);
             const float a_raw = co.w * Gv;
             const float alpha = fminf(kAlphaMax, a_raw);
             if (alpha >= kAlphaMin) {
