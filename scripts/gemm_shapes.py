@@ -12,7 +12,7 @@ for a in d["gemm"]:
     agg[a["meta"]][1] += 1
 tot = sum(v[0] for v in agg.values())
 print(f"# GEMM family: {tot:.3f} ms per 8-scene encoder pass (CUDA events per launch, un-graphed pass, median of the reps)")
-print("# (kind, M, N, K, residual kind, second output, fp32 output) | launches | ms | TF/s executed | share")
+print("# (kind, M, N, K, activation, has residual, fp32 output) | launches | ms | TF/s executed | share")
 fl_tot = 0.0
 for k, (ms, n) in sorted(agg.items(), key=lambda kv: -kv[1][0]):
     m = ast.literal_eval(k)
