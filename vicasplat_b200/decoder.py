@@ -144,7 +144,10 @@ class DecoderSplattingCUDA(nn.Module):
         cov6 = _cov6(cov) if cov6 is None else (cov6.flatten(1, 3) if cov6.ndim > 3 else cov6)
         bg = self.background_color[None].expand(v, 3)
         colors, depths = [], []
-        with SceneStreams(means.device) as ss:
+        # (one stream when autograd records the renders: its backward nodes would otherwise run on the side streams)
+        needs_grad = torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in
+                                                     (means, cov, sh, opac, cov6, cam_rot_delta, cam_trans_delta))
+        with SceneStreams(means.device, n=1 if needs_grad else None) as ss:
             for i in range(b):
                 sl = slice(i * v, (i + 1) * v)
                 with ss.scene(i):
