@@ -688,6 +688,7 @@ def train_leg(args, model, scenes, dev, rank, world, local, barrier) -> dict:
     return dict(
         metric="train_scenes_per_sec_8view_256x256", value=world * B * 1e3 / ms, unit="scenes/s",
         ms_per_step=ms, steps=K, warmup=4, scenes_per_step_per_gpu=B, micro_batch=mb, n_gpus=world,
+        peak_memory_gb=torch.cuda.max_memory_allocated(dev) / 2 ** 30,
         workload=(f"configs[{2 if world == 1 else 3}]: 8-view 256x256 training step, batch {B}/GPU in micro-batches "
                   f"of {mb}: encoder fwd + 12-view render + MSE + raster bwd + encoder bwd (all {n_params} "
                   "trained parameters) + " + ("gradient all-reduce + " if world > 1 else "") +
@@ -743,7 +744,9 @@ def main() -> None:
     ap.add_argument("--train-batch", type=int, default=24,
                     help="scenes per GPU per TRAINING step of the train_step sub-record (BASELINE configs[2]/[3]: "
                          "24); 0 = skip the training leg")
-    ap.add_argument("--train-micro", type=int, default=8, help="scenes per micro-batch of the training step")
+    ap.add_argument("--train-micro", type=int, default=12,
+                    help="scenes per micro-batch of the training step (12 keeps ~6 GB of activations per scene "
+                         "within 180 GB; 24 does not fit)")
     ap.add_argument("--train-steps", type=int, default=3)
     ap.add_argument("--train-lpips", choices=["stand-in", "off"], default="stand-in",
                     help="LPIPS term of the training step: a seeded random VGG16 (the real weights are not in the image)")
