@@ -136,7 +136,14 @@ def test_lpips_camera_losses_and_micro_batching_agree(cuda, lib):
     l1, g1 = grads(1)
     assert abs(l1 - l2) <= 2e-3 * abs(l2), (l1, l2)
     assert len(g1) == len(g2) == 499
-    worst = max(((g1[n] - g2[n]).norm() / g2[n].norm().clamp_min(1e-20)).item() for n in g2)
-    print(f"[train step] MSE + LPIPS + camera loss: one micro-batch vs two, loss {l2:.5f} / {l1:.5f}, worst gradient "
-          f"rel-L2 {worst:.2e}")
-    assert worst < 2e-2
+    errs = sorted(((g1[n] - g2[n]).norm() / g2[n].norm().clamp_min(1e-20)).item() for n in g2)
+    worst, median = errs[-1], errs[len(errs) // 2]
+    print(f"[train step] MSE + LPIPS + camera loss: one micro-batch vs two, loss {l2:.5f} / {l1:.5f}, gradient rel-L2 "
+          f"worst {worst:.2e} median {median:.2e}")
+    # Two outcomes, run to run (also between two IDENTICAL calls, scripts/diag_micro_batching.py): ~1e-6 everywhere, or
+    # ~1e-3 median / ~1e-2 worst.  The per-frame AdaLN sums are fp32 atomics; their order moves a value by ~1e-7, which
+    # now and then flips the bf16 rounding of ONE element of a (frames x 6 D) modulation gradient (2e-5 of that
+    # tensor); the decoder's backward amplifies it block by block, most on tensors whose true gradient is ~0 (the key
+    # bias of a softmax: cross_attn.projk.bias).  Both are far below the bf16 error of the gradients themselves
+    # (1.4e-2 median against the fp32 oracle, tests/test_gpu_model_grad.py).
+    assert worst < 5e-2 and median < 5e-3
